@@ -1,0 +1,209 @@
+"""ctypes binding of libcovidabs.so (include/covidabs.h).
+
+The CUDA library is the product path; there is deliberately no CPU fallback here: if the shared
+library is missing or no GPU is visible, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcovidabs.so")
+
+ABI_VERSION = 1
+NUM_STATS = 12
+MAX_TRIGGERS = 8
+SYNCHRONOUS, SEQUENTIAL = 0, 1
+
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_DOMAIN, ERR_NOGPU = 0, -1, -2, -3, -4, -5
+
+# every symbol include/covidabs.h declares (checked by tests/test_capi_symbols.py)
+EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params", "cabs_set_triggers",
+            "cabs_upload", "cabs_download", "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_history",
+            "cabs_contact_pairs", "cabs_get_info")
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, message):
+        super(NativeError, self).__init__("libcovidabs error {}: {}".format(code, message))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("capacity", C.c_uint64),
+                ("max_cells", C.c_uint64), ("seed", C.c_uint64), ("history_capacity", C.c_uint32),
+                ("flags", C.c_uint32)]
+
+
+class Params(C.Structure):
+    _fields_ = [("length", C.c_double), ("height", C.c_double), ("contagion_distance", C.c_double),
+                ("contagion_rate", C.c_double), ("critical_limit", C.c_double), ("amplitudes", C.c_double * 4),
+                ("minimum_income", C.c_double), ("minimum_expense", C.c_double), ("basic_income", C.c_double * 5),
+                ("age_hospitalization_probs", C.c_double * 9), ("age_severe_probs", C.c_double * 9),
+                ("age_death_probs", C.c_double * 9), ("population_size", C.c_uint64),
+                ("recovering_time", C.c_int32), ("wealth_scale_bits", C.c_int32), ("schedule", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class Trigger(C.Structure):
+    _fields_ = [("metric", C.c_int32), ("op", C.c_int32), ("threshold", C.c_double), ("attribute", C.c_int32),
+                ("reserved", C.c_int32), ("value", C.c_double * 4)]
+
+
+class SoaHost(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("x", C.c_void_p), ("y", C.c_void_p), ("status", C.c_void_p),
+                ("severity", C.c_void_p), ("infected_time", C.c_void_p), ("age", C.c_void_p),
+                ("stratum", C.c_void_p), ("wealth", C.c_void_p), ("id", C.c_void_p)]
+
+
+class Info(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("step", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("grid_origin_x", C.c_int32), ("grid_origin_y", C.c_int32), ("cell_edge", C.c_int32),
+                ("cells_x", C.c_int32), ("cells_y", C.c_int32), ("device_error", C.c_uint32)]
+
+
+_lib = None
+
+
+def load():
+    """Load libcovidabs.so (built by `__graft_entry__.build()` / `python -m covid19_agentbasedsimulation_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("{} is missing: build it with `python -m covid19_agentbasedsimulation_b200.build` "
+                          "(there is no CPU fallback for the agent step)".format(LIB_PATH))
+    lib = C.CDLL(LIB_PATH)
+    P = C.c_void_p
+    lib.cabs_create.argtypes = [C.POINTER(Config), C.POINTER(P)]
+    lib.cabs_destroy.argtypes = [P]
+    lib.cabs_destroy.restype = None
+    lib.cabs_last_error.argtypes = [P]
+    lib.cabs_last_error.restype = C.c_char_p
+    lib.cabs_set_params.argtypes = [P, C.POINTER(Params)]
+    lib.cabs_set_triggers.argtypes = [P, C.POINTER(Trigger), C.c_int]
+    lib.cabs_upload.argtypes = [P, C.POINTER(SoaHost)]
+    lib.cabs_download.argtypes = [P, C.POINTER(SoaHost)]
+    lib.cabs_step.argtypes = [P, C.c_int]
+    lib.cabs_sync.argtypes = [P]
+    lib.cabs_stats.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.cabs_stats_history.argtypes = [P, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]
+    lib.cabs_contact_pairs.argtypes = [P, C.POINTER(C.c_int64), C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.cabs_get_info.argtypes = [P, C.POINTER(Info)]
+    for name in EXPORTED:
+        fn = getattr(lib, name)
+        if name not in ("cabs_destroy", "cabs_last_error"):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+SOA_DTYPES = (("x", np.int32), ("y", np.int32), ("status", np.uint8), ("severity", np.uint8),
+              ("infected_time", np.uint8), ("age", np.uint8), ("stratum", np.uint8), ("wealth", np.float64),
+              ("id", np.uint32))
+
+
+class Handle(object):
+    """Owns one `cabs_sim*`."""
+
+    def __init__(self, capacity, seed=0, device=0, max_cells=0, history_capacity=4096):
+        self._lib = load()
+        self._h = C.c_void_p()
+        cfg = Config(ABI_VERSION, int(device), int(capacity), int(max_cells), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                     int(history_capacity), 0)
+        rc = self._lib.cabs_create(C.byref(cfg), C.byref(self._h))
+        if rc != OK:
+            msg = self._lib.cabs_last_error(None)
+            raise NativeError(rc, msg.decode() if msg else "cabs_create failed")
+        self.capacity = int(capacity)
+
+    def _check(self, rc):
+        if rc != OK:
+            msg = self._lib.cabs_last_error(self._h)
+            raise NativeError(rc, msg.decode() if msg else "?")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.cabs_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, params):
+        self._check(self._lib.cabs_set_params(self._h, C.byref(params)))
+
+    def set_triggers(self, triggers):
+        arr = (Trigger * max(1, len(triggers)))(*triggers)
+        self._check(self._lib.cabs_set_triggers(self._h, arr, len(triggers)))
+
+    @staticmethod
+    def _soa(cols, n):
+        s = SoaHost()
+        s.n = n
+        for name, dt in SOA_DTYPES:
+            a = cols.get(name)
+            if a is None:
+                setattr(s, name, None)
+            else:
+                assert a.dtype == dt and a.flags["C_CONTIGUOUS"] and a.shape == (n,), name
+                setattr(s, name, a.ctypes.data)
+        return s
+
+    def upload(self, cols):
+        """cols: dict of contiguous numpy arrays with the dtypes of SOA_DTYPES ('id' optional)."""
+        n = len(cols["x"])
+        s = self._soa(cols, n)
+        self._check(self._lib.cabs_upload(self._h, C.byref(s)))
+
+    def upload_pointers(self, n, ptrs):
+        """Upload from raw host addresses (e.g. pinned torch tensors): ptrs maps column name -> int address."""
+        s = SoaHost()
+        s.n = n
+        for name, _ in SOA_DTYPES:
+            setattr(s, name, ptrs.get(name))
+        self._check(self._lib.cabs_upload(self._h, C.byref(s)))
+
+    def download(self, n):
+        cols = {name: np.empty(n, dtype=dt) for name, dt in SOA_DTYPES}
+        s = self._soa(cols, n)
+        self._check(self._lib.cabs_download(self._h, C.byref(s)))
+        return cols
+
+    def step(self, nsteps=1):
+        self._check(self._lib.cabs_step(self._h, int(nsteps)))
+
+    def sync(self):
+        self._check(self._lib.cabs_sync(self._h))
+
+    def stats(self):
+        v = (C.c_double * NUM_STATS)()
+        c = (C.c_int64 * 7)()
+        self._check(self._lib.cabs_stats(self._h, v, c))
+        return np.array(v[:], dtype=np.float64), np.array(c[:], dtype=np.int64)
+
+    def stats_history(self, first, count):
+        out = np.empty((int(count), NUM_STATS), dtype=np.float64)
+        self._check(self._lib.cabs_stats_history(self._h, int(first), int(count),
+                                                 out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def contact_pairs(self, capacity=None):
+        cap = int(capacity) if capacity else 1 << 16
+        while True:
+            buf = np.empty((cap, 2), dtype=np.int64)
+            n = C.c_size_t(0)
+            self._check(self._lib.cabs_contact_pairs(self._h, buf.ctypes.data_as(C.POINTER(C.c_int64)), cap,
+                                                     C.byref(n)))
+            if n.value <= cap:
+                return buf[:n.value]
+            cap = int(n.value)
+
+    def info(self):
+        i = Info()
+        self._check(self._lib.cabs_get_info(self._h, C.byref(i)))
+        return {k: getattr(i, k) for k, _ in Info._fields_}

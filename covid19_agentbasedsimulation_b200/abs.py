@@ -1,0 +1,385 @@
+"""Host-side mirror of covid_abs/abs.py: the `Simulation` engine with its per-iteration step on a B200.
+
+Same constructor kwargs, attributes and methods as the reference class (abs.py:13-322); the population
+lives on the GPU as structure of arrays and `execute()` runs the hand-written sm_100a kernels of
+`csrc/` through the C ABI of `include/covidabs.h`.  There is no CPU fallback.
+
+Differences a user can observe (all documented in DESIGN.md):
+  * draws come from Philox4x32-10 keyed (seed, agent, step) instead of numpy's sequential MT19937
+    stream; `seed=None` (default) takes the seed from `np.random`, so `np.random.seed(s)` still makes a
+    run reproducible;
+  * contacts are applied synchronously (an agent infected in a step starts transmitting in the next);
+  * the critical-limit test (abs.py:214-217) reads the statistics of the end of the previous step,
+    which is what the reference's memo holds when `batch_experiment` drives it;
+  * `triggers_population` with Python lambdas cannot run on the device and raise NotImplementedError.
+"""
+import numpy as np
+
+from covid19_agentbasedsimulation_b200 import _native
+from covid19_agentbasedsimulation_b200.agents import (Status, InfectionSeverity, Agent, STATUS_LIST, STATUS_CODE,
+                                                      SEVERITY_LIST, SEVERITY_CODE)
+from covid19_agentbasedsimulation_b200.common import *  # noqa: F401,F403  (the reference does the same, abs.py:6)
+from covid19_agentbasedsimulation_b200.common import (age_hospitalization_probs, age_severe_probs, age_death_probs,
+                                                      lorenz_curve, basic_income)
+
+STAT_KEYS = ("Susceptible", "Infected", "Recovered_Immune", "Death", "Asymptomatic", "Hospitalization", "Severe",
+             "Q1", "Q2", "Q3", "Q4", "Q5")
+_OPS = {'>=': 0, '<=': 1, '>': 2, '<': 3}
+_ATTRS = {'amplitudes': 0, 'contagion_rate': 1, 'contagion_distance': 2, 'critical_limit': 3}
+
+
+def distance(a, b):
+    """abs.py:9-10."""
+    return np.sqrt((a.x - b.x) ** 2 + (a.y - b.y) ** 2)
+
+
+class Trigger(object):
+    """Declarative simulation trigger, evaluated on the device at the end of every step.
+
+    Equivalent of `{'condition': lambda s: s.get_statistics()[metric] <op> threshold, 'attribute': attribute,
+    'action': lambda _: value}` (abs.py:74-84, applied at abs.py:267-271), e.g. the conditional lockdown of
+    run_batch.py:628-643.  Like the reference under `batch_experiment`, the condition sees the statistics
+    memoised after the previous step.
+    """
+
+    def __init__(self, metric, op, threshold, attribute, value):
+        if metric not in STAT_KEYS or op not in _OPS or attribute not in _ATTRS:
+            raise ValueError("unsupported trigger: {} {} {}".format(metric, op, attribute))
+        self.metric, self.op, self.threshold, self.attribute, self.value = metric, op, float(threshold), attribute, value
+
+    def __getitem__(self, key):  # lets code that inspects trigger dicts keep working (abs.py:237-238)
+        return {'attribute': self.attribute, 'condition': None, 'action': None}[key]
+
+
+def amplitude_array(amplitudes):
+    """abs.py:33-36: dict keyed by Status -> [S, I, R, D] array (Death never moves, abs.py:164)."""
+    out = np.zeros(4, dtype=np.float64)
+    for status, value in amplitudes.items():
+        out[STATUS_CODE[status] if isinstance(status, Status) else int(status)] = float(value)
+    out[3] = 0.0
+    return out
+
+
+def wealth_scale_bits(total_wealth):
+    """Fixed-point scale of the Q1..Q5 sums: largest s <= 40 with 1024 * total_wealth * 2**s < 2**62."""
+    tw = max(1.0, float(total_wealth))
+    s = int(np.floor(62 - np.log2(1024.0 * tw)))
+    return max(0, min(40, s))
+
+
+class Simulation(object):
+    def __init__(self, **kwargs):
+        self.population_size = kwargs.get("population_size", 20)
+        '''The number of agents'''
+        self.length = kwargs.get("length", 10)
+        '''The length of the shared environment'''
+        self.height = kwargs.get("height", 10)
+        '''The height of the shared environment'''
+        self.initial_infected_perc = kwargs.get("initial_infected_perc", 0.05)
+        '''The initial percent of population which starts the simulation with the status Infected'''
+        self.initial_immune_perc = kwargs.get("initial_immune_perc", 0.05)
+        '''The initial percent of population which starts the simulation with the status Immune'''
+        self.contagion_distance = kwargs.get("contagion_distance", 1.)
+        '''The minimal distance considered as contact (or exposition)'''
+        self.contagion_rate = kwargs.get("contagion_rate", 0.9)
+        '''The probability of contagion given two agents were in contact'''
+        self.critical_limit = kwargs.get("critical_limit", 0.6)
+        '''The percent of population which the Health System can afford'''
+        self.amplitudes = kwargs.get('amplitudes',
+                                     {Status.Susceptible: 5,
+                                      Status.Recovered_Immune: 5,
+                                      Status.Infected: 5})
+        '''A dictionary with the average mobility of agents inside the shared environment for each status'''
+        self.minimum_income = kwargs.get("minimum_income", 1.0)
+        '''The base (or minimum) daily income, related to the most poor wealth quintile'''
+        self.minimum_expense = kwargs.get("minimum_expense", 1.0)
+        '''The base (or minimum) daily expense, related to the most poor wealth quintile'''
+        self.statistics = None
+        '''A dictionary with the population statistics for the current iteration'''
+        self.triggers_simulation = kwargs.get("triggers_simulation", [])
+        "A dictionary with conditional changes in the Simulation attributes"
+        self.triggers_population = kwargs.get("triggers_population", [])
+        "A dictionary with conditional changes in the Agent attributes"
+        self.total_wealth = kwargs.get("total_wealth", 10 ** 4)
+
+        # ---- new, optional: nothing the reference passes is reinterpreted
+        self.seed = kwargs.get("seed", None)
+        '''Philox seed; None = drawn from np.random at initialize(), so np.random.seed() governs the run'''
+        self.device = kwargs.get("device", 0)
+        '''CUDA device ordinal'''
+        self.placement = kwargs.get("placement", "reference")
+        '''"reference": abs.py:97-114 consumed from np.random in the reference's order; "uniform": x,y ~ U{0..L}'''
+        self.max_cells = kwargs.get("max_cells", 0)
+        self.history_capacity = kwargs.get("history_capacity", 4096)
+
+        self._handle = None
+        self._pushed = None          # last parameter tuple sent to the device
+        self._pushed_triggers = None
+        self._host = None            # cached download of the population (dict of columns)
+        self._agents = None          # cached list of Agent objects
+        self._iteration = 0
+
+    # ------------------------------------------------------------------ reference helpers
+    def _xclip(self, x):
+        return np.clip(int(x), 0, self.length)
+
+    def _yclip(self, y):
+        return np.clip(int(y), 0, self.height)
+
+    def set_amplitudes(self, amp):
+        self.amplitudes = amp
+
+    def append_trigger_simulation(self, condition, attribute, action):
+        """abs.py:74-84.  Python lambdas are evaluated on the host after each step."""
+        self.triggers_simulation.append({'condition': condition, 'attribute': attribute, 'action': action})
+
+    def append_trigger_population(self, condition, attribute, action):
+        """abs.py:86-95.  Accepted for API compatibility; see execute()."""
+        self.triggers_population.append({'condition': condition, 'attribute': attribute, 'action': action})
+
+    def random_position(self):
+        # abs.py:97-101
+        x = self._xclip(self.length / 2 + (np.random.randn(1)[0] * (self.length / 3)))
+        y = self._yclip(self.height / 2 + (np.random.randn(1)[0] * (self.height / 3)))
+        return x, y
+
+    # ------------------------------------------------------------------ population on the device
+    def _ensure_handle(self, n):
+        if self._handle is None or self._handle.capacity < n:
+            if self._handle is not None:
+                self._handle.close()
+            if self.seed is None:
+                self.seed = int(np.random.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(np.random.randint(0, 2 ** 31 - 1))
+            self._handle = _native.Handle(capacity=max(1, n), seed=self.seed, device=self.device,
+                                          max_cells=self.max_cells, history_capacity=self.history_capacity)
+            self._pushed = None
+            self._pushed_triggers = None
+        return self._handle
+
+    def _param_tuple(self):
+        amp = amplitude_array(self.amplitudes)
+        return (float(self.length), float(self.height), float(self.contagion_distance), float(self.contagion_rate),
+                float(self.critical_limit), tuple(amp.tolist()), float(self.minimum_income),
+                float(self.minimum_expense), int(self.population_size), float(self.total_wealth))
+
+    def _push_params(self):
+        """Send the attributes of abs.py:17-49 to the device if user code changed them (abs.py:267-271)."""
+        t = self._param_tuple()
+        if t != self._pushed:
+            p = _native.Params()
+            (p.length, p.height, p.contagion_distance, p.contagion_rate, p.critical_limit, amp, p.minimum_income,
+             p.minimum_expense, pop, tw) = t
+            p.amplitudes[:] = amp
+            p.basic_income[:] = [float(v) for v in basic_income]
+            p.age_hospitalization_probs[:] = age_hospitalization_probs
+            p.age_severe_probs[:] = age_severe_probs
+            p.age_death_probs[:] = age_death_probs
+            p.population_size = max(1, pop)
+            p.recovering_time = 20  # abs.py:225
+            p.wealth_scale_bits = wealth_scale_bits(tw)
+            p.schedule = _native.SYNCHRONOUS
+            self._handle.set_params(p)
+            self._pushed = t
+        decl = [t for t in self.triggers_simulation if isinstance(t, Trigger)]
+        key = tuple((t.metric, t.op, t.threshold, t.attribute, repr(t.value)) for t in decl)
+        if key != self._pushed_triggers:
+            native = []
+            for t in decl:
+                n = _native.Trigger()
+                n.metric, n.op, n.threshold, n.attribute = STAT_KEYS.index(t.metric), _OPS[t.op], t.threshold, _ATTRS[
+                    t.attribute]
+                if t.attribute == 'amplitudes':
+                    n.value[:] = amplitude_array(t.value).tolist()
+                else:
+                    n.value[:] = [float(t.value), 0.0, 0.0, 0.0]
+                native.append(n)
+            self._handle.set_triggers(native)
+            self._pushed_triggers = key
+
+    def set_population_arrays(self, x, y, status, age, stratum, wealth, severity=None, infected_time=None):
+        """Upload a population given as columns (codes of include/covidabs.h); ids = positions."""
+        n = len(x)
+        cols = {
+            "x": np.ascontiguousarray(x, dtype=np.int32), "y": np.ascontiguousarray(y, dtype=np.int32),
+            "status": np.ascontiguousarray(status, dtype=np.uint8),
+            "severity": (np.full(n, 1, dtype=np.uint8) if severity is None
+                         else np.ascontiguousarray(severity, dtype=np.uint8)),
+            "infected_time": (np.zeros(n, dtype=np.uint8) if infected_time is None
+                              else np.ascontiguousarray(infected_time, dtype=np.uint8)),
+            "age": np.ascontiguousarray(np.minimum(age, 255), dtype=np.uint8),
+            "stratum": np.ascontiguousarray(stratum, dtype=np.uint8),
+            "wealth": np.ascontiguousarray(wealth, dtype=np.float64),
+        }
+        self.population_size = n
+        self._ensure_handle(n)
+        self._push_params()
+        self._handle.upload(cols)
+        self._invalidate_host()
+        self.statistics = None
+
+    def _invalidate_host(self):
+        self._host = None
+        self._agents = None
+
+    def _download(self):
+        if self._host is None:
+            if self._handle is None:
+                self._host = {name: np.zeros(0, dtype=dt) for name, dt in _native.SOA_DTYPES}
+            else:
+                self._host = self._handle.download(int(self.population_size))
+        return self._host
+
+    def get_population(self):
+        """Current population as `Agent` objects, materialised from a device download (abs.py:57-63)."""
+        if self._agents is None:
+            h = self._download()
+            self._agents = [Agent(id=int(h["id"][k]), x=int(h["x"][k]), y=int(h["y"][k]),
+                                  status=STATUS_LIST[h["status"][k]],
+                                  infected_status=SEVERITY_LIST[h["severity"][k]],
+                                  infected_time=int(h["infected_time"][k]), age=int(h["age"][k]),
+                                  social_stratum=int(h["stratum"][k]), wealth=float(h["wealth"][k]),
+                                  environment=self) for k in range(len(h["x"]))]
+        return self._agents
+
+    def set_population(self, pop):
+        """Replace the population with a list of Agent-like objects (abs.py:65-69)."""
+        pop = list(pop)
+        self.set_population_arrays(
+            [int(a.x) for a in pop], [int(a.y) for a in pop], [STATUS_CODE[a.status] for a in pop],
+            [int(a.age) for a in pop], [int(a.social_stratum) for a in pop],
+            [float(np.asarray(a.wealth).ravel()[0]) for a in pop],
+            severity=[SEVERITY_CODE[a.infected_status] for a in pop],
+            infected_time=[int(a.infected_time) for a in pop])
+
+    population = property(get_population, set_population)
+
+    # ------------------------------------------------------------------ initialize
+    def create_agent(self, status):
+        """abs.py:103-114 (draw order: x, y, age, stratum)."""
+        x, y = self.random_position()
+        age = int(np.random.beta(2, 5, 1)[0] * 100)
+        social_stratum = int(np.random.rand(1)[0] * 100 // 20)
+        return int(x), int(y), age, social_stratum
+
+    def initialize(self):
+        """Create the population (abs.py:116-139) on the host and upload it."""
+        n = int(self.population_size)
+        n_inf = int(n * self.initial_infected_perc)
+        n_imm = int(n * self.initial_immune_perc)
+        status = np.zeros(n, dtype=np.uint8)
+        status[:n_inf] = STATUS_CODE[Status.Infected]
+        status[n_inf:n_inf + n_imm] = STATUS_CODE[Status.Recovered_Immune]
+        if self.placement == "reference":
+            rows = [self.create_agent(None) for _ in range(n)]
+            cols = np.array(rows, dtype=np.int64).reshape(n, 4)
+            x, y, age, stratum = cols[:, 0], cols[:, 1], cols[:, 2], cols[:, 3]
+        elif self.placement == "uniform":
+            # synthetic uniform lattice placement (large N, no Python loop)
+            if self.seed is None:
+                self.seed = int(np.random.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(np.random.randint(0, 2 ** 31 - 1))
+            rng = np.random.default_rng(self.seed)
+            x = rng.integers(0, int(self.length) + 1, size=n)
+            y = rng.integers(0, int(self.height) + 1, size=n)
+            age = (rng.beta(2, 5, size=n) * 100).astype(np.int64)
+            stratum = rng.integers(0, 5, size=n)
+        else:
+            raise ValueError("placement must be 'reference' or 'uniform'")
+        wealth = np.zeros(n, dtype=np.float64)
+        for quintile in [0, 1, 2, 3, 4]:  # abs.py:134-139
+            total = lorenz_curve[quintile] * self.total_wealth
+            sel = (stratum == quintile) & (age >= 18)
+            qty = max(1.0, float(np.sum(sel)))
+            wealth[sel] = total / qty
+        self.set_population_arrays(x, y, status, age, stratum, wealth)
+        self._iteration = 0
+
+    # ------------------------------------------------------------------ step
+    def _host_triggers(self):
+        return [t for t in self.triggers_simulation if not isinstance(t, Trigger)]
+
+    def execute(self):
+        """One iteration (abs.py:232-273): move, update, contacts on the GPU; simulation triggers after."""
+        if self._handle is None:
+            raise RuntimeError("initialize() or set_population() first")
+        if len(self.triggers_population) > 0:
+            raise NotImplementedError("per-agent Python triggers (abs.py:244-247) cannot run on the device and "
+                                      "there is no CPU fallback; see DESIGN.md (out of scope rows)")
+        self._push_params()
+        self._handle.step(1)
+        self._iteration += 1
+        self._invalidate_host()
+        for trigger in self._host_triggers():  # abs.py:267-271
+            if trigger['condition'](self):
+                attr = trigger['attribute']
+                self.__dict__[attr] = trigger['action'](self.__dict__[attr])
+        self.statistics = None
+
+    def run(self, iterations):
+        """`iterations` x (execute(); get_statistics('all')) -> float64 array [iterations, 12] (key order STAT_KEYS).
+
+        With only declarative triggers the whole run is enqueued at once and the statistics rows come
+        back in one copy; Python-lambda triggers force one host round trip per iteration.
+        """
+        iterations = int(iterations)
+        if self._host_triggers() or iterations > self.history_capacity:
+            rows = np.empty((iterations, len(STAT_KEYS)))
+            for it in range(iterations):
+                self.execute()
+                s = self.get_statistics(kind='all')
+                rows[it] = [s[k] for k in STAT_KEYS]
+            return rows
+        if len(self.triggers_population) > 0:
+            raise NotImplementedError("per-agent Python triggers cannot run on the device")
+        self._push_params()
+        first = self._iteration
+        self._handle.step(iterations)
+        self._iteration += iterations
+        self._invalidate_host()
+        self.statistics = None
+        return self._handle.stats_history(first, iterations)
+
+    # ------------------------------------------------------------------ accessors
+    def get_positions(self):
+        """abs.py:275-277."""
+        h = self._download()
+        return [[int(a), int(b)] for a, b in zip(h["x"], h["y"])]
+
+    def get_description(self, complete=False):
+        """abs.py:279-289."""
+        if complete:
+            return [a.get_description() for a in self.get_population()]
+        h = self._download()
+        return [STATUS_LIST[s].name for s in h["status"]]
+
+    def get_contact_pairs(self):
+        """The pair list of abs.py:253-259 for the current positions, sorted lexicographically (test hook)."""
+        self._push_params()
+        pairs = self._handle.contact_pairs()
+        order = np.lexsort((pairs[:, 1], pairs[:, 0]))
+        return pairs[order]
+
+    def get_statistics(self, kind='info'):
+        """abs.py:291-314: memoised until the end of the next execute()."""
+        if self.statistics is None:
+            if self._handle is None:
+                raise RuntimeError("initialize() or set_population() first")
+            self._push_params()
+            values, _ = self._handle.stats()
+            self.statistics = {k: np.float64(v) for k, v in zip(STAT_KEYS, values)}
+        return self.filter_stats(kind)
+
+    def filter_stats(self, kind):
+        # abs.py:316-322
+        if kind == 'info':
+            return {k: v for k, v in self.statistics.items()
+                    if not k.startswith('Q') and k not in ('Business', 'Government')}
+        elif kind == 'ecom':
+            return {k: v for k, v in self.statistics.items() if k.startswith('Q') or k in ('Business', 'Government')}
+        else:
+            return self.statistics
+
+    def device_info(self):
+        return self._handle.info()
+
+    def __str__(self):
+        return str(self.get_description())

@@ -1,0 +1,410 @@
+// C ABI of the B200-native COVID-ABS step (include/covidabs.h): host orchestration of the kernels
+// in abs_kernels.cuh.  No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/covidabs.h"
+#include "abs_kernels.cuh"
+
+using namespace cabs;
+
+static thread_local std::string g_create_error;
+
+struct cabs_sim {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  uint64_t capacity = 0;
+  unsigned max_cells = 0;
+  unsigned hist_cap = 0;
+  // ping/pong population columns
+  uint32_t *id[2] = {nullptr, nullptr};
+  int *x[2] = {nullptr, nullptr};
+  int *y[2] = {nullptr, nullptr};
+  uint32_t *attr[2] = {nullptr, nullptr};
+  double *w[2] = {nullptr, nullptr};
+  int cur = 0;
+  unsigned *cells = nullptr;    // histogram / cell_start, max_cells + 8 entries
+  unsigned *partial = nullptr;  // scan partials
+  Ctl *ctl = nullptr;
+  StatRecord *history = nullptr;
+  uint8_t *stage = nullptr;     // byte-column staging for upload/download: 5 * capacity
+  uint32_t *stage_id = nullptr;
+  long long *pairs = nullptr;   // contact-pair output buffer (grown on demand)
+  size_t pairs_cap = 0;
+  unsigned long long *pair_count = nullptr;
+  cabs_params params;
+  bool have_params = false;
+  bool cells_dirty = true;      // cell_start does not describe the current positions / distance
+  uint64_t n = 0, step = 0, launches = 0;
+  std::string err;
+};
+
+#define CK(call)                                                                                \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      char buf_[512];                                                                           \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      sim->err = buf_;                                                                          \
+      return CABS_ERR_CUDA;                                                                     \
+    }                                                                                           \
+  } while (0)
+
+static int fail(cabs_sim *sim, int code, const char *msg) {
+  if (sim) sim->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+static inline int agent_blocks(const cabs_sim *sim) { return sim->num_sms * 8; }
+
+#define LAUNCH(kernel, grid, block, ...)                \
+  do {                                                  \
+    kernel<<<(grid), (block), 0, sim->stream>>>(__VA_ARGS__); \
+    sim->launches++;                                    \
+  } while (0)
+
+extern "C" const char *cabs_last_error(const cabs_sim *sim) {
+  return sim ? sim->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" void cabs_destroy(cabs_sim *sim) {
+  if (!sim) return;
+  cudaSetDevice(sim->device);
+  if (sim->stream) cudaStreamSynchronize(sim->stream);
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(sim->id[b]); cudaFree(sim->x[b]); cudaFree(sim->y[b]); cudaFree(sim->attr[b]); cudaFree(sim->w[b]);
+  }
+  cudaFree(sim->cells); cudaFree(sim->partial); cudaFree(sim->ctl); cudaFree(sim->history);
+  cudaFree(sim->stage); cudaFree(sim->stage_id); cudaFree(sim->pairs); cudaFree(sim->pair_count);
+  if (sim->stream) cudaStreamDestroy(sim->stream);
+  delete sim;
+}
+
+static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(sim, CABS_ERR_NOGPU, "no CUDA device visible: the agent step has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(sim, CABS_ERR_INVALID, "device ordinal out of range");
+  sim->device = cfg->device;
+  CK(cudaSetDevice(sim->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, sim->device));
+  sim->num_sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
+  sim->capacity = cfg->capacity ? cfg->capacity : 1;
+  if (sim->capacity >= (1ull << 31)) return fail(sim, CABS_ERR_CAPACITY, "capacity must be < 2^31 agents per device");
+  uint64_t mc = cfg->max_cells;
+  if (mc == 0) {
+    mc = sim->capacity + sim->capacity / 2;
+    if (mc < 4096) mc = 4096;
+    if (mc > (1ull << 24)) mc = 1ull << 24;
+  }
+  if (mc < 64) mc = 64;
+  if (mc > (1ull << 30)) mc = 1ull << 30;
+  sim->max_cells = (unsigned)mc;
+  sim->hist_cap = cfg->history_capacity ? cfg->history_capacity : 4096;
+  const size_t cap = sim->capacity;
+  for (int b = 0; b < 2; ++b) {
+    CK(cudaMalloc(&sim->id[b], cap * sizeof(uint32_t)));
+    CK(cudaMalloc(&sim->x[b], cap * sizeof(int)));
+    CK(cudaMalloc(&sim->y[b], cap * sizeof(int)));
+    CK(cudaMalloc(&sim->attr[b], cap * sizeof(uint32_t)));
+    CK(cudaMalloc(&sim->w[b], cap * sizeof(double)));
+  }
+  CK(cudaMalloc(&sim->cells, ((size_t)sim->max_cells + 8) * sizeof(unsigned)));
+  CK(cudaMalloc(&sim->partial, 1024 * sizeof(unsigned)));
+  CK(cudaMalloc(&sim->ctl, sizeof(Ctl)));
+  CK(cudaMalloc(&sim->history, (size_t)sim->hist_cap * sizeof(StatRecord)));
+  CK(cudaMalloc(&sim->stage, cap * 5));
+  CK(cudaMalloc(&sim->stage_id, cap * sizeof(uint32_t)));
+  CK(cudaMalloc(&sim->pair_count, sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(sim->ctl, 0, sizeof(Ctl), sim->stream));
+  CK(cudaMemsetAsync(sim->history, 0, (size_t)sim->hist_cap * sizeof(StatRecord), sim->stream));
+  LAUNCH(k_init_ctl, 1, 32, sim->ctl, (unsigned)(cfg->seed & 0xFFFFFFFFu), (unsigned)(cfg->seed >> 32), sim->max_cells,
+         sim->hist_cap);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(sim->stream));
+  return CABS_OK;
+}
+
+extern "C" int cabs_create(const cabs_config *cfg, cabs_sim **out) {
+  if (!cfg || !out) return fail(nullptr, CABS_ERR_INVALID, "cabs_create: null argument");
+  if (cfg->abi_version != CABS_ABI_VERSION) return fail(nullptr, CABS_ERR_INVALID, "cabs_create: ABI version mismatch");
+  cabs_sim *sim = new (std::nothrow) cabs_sim();
+  if (!sim) return fail(nullptr, CABS_ERR_INVALID, "cabs_create: out of host memory");
+  const int rc = create_impl(sim, cfg);
+  if (rc != CABS_OK) {
+    g_create_error = sim->err;
+    cabs_destroy(sim);
+    *out = nullptr;
+    return rc;
+  }
+  *out = sim;
+  return CABS_OK;
+}
+
+extern "C" int cabs_set_params(cabs_sim *sim, const cabs_params *p) {
+  if (!sim || !p) return fail(sim, CABS_ERR_INVALID, "cabs_set_params: null argument");
+  if (p->wealth_scale_bits < 0 || p->wealth_scale_bits > 52)
+    return fail(sim, CABS_ERR_INVALID, "wealth_scale_bits must be in [0, 52]");
+  if (p->recovering_time < 0 || p->recovering_time > 250)
+    return fail(sim, CABS_ERR_INVALID, "recovering_time must be in [0, 250] (infected_time is stored in 8 bits)");
+  if (p->schedule != CABS_SYNCHRONOUS) return fail(sim, CABS_ERR_INVALID, "only CABS_SYNCHRONOUS is implemented");
+  if (p->population_size == 0) return fail(sim, CABS_ERR_INVALID, "population_size must be > 0");
+  CK(cudaSetDevice(sim->device));
+  ParamBlock b;
+  for (int k = 0; k < 4; ++k) b.amp[k] = (float)p->amplitudes[k];
+  b.amp[3] = 0.f;
+  b.length = p->length; b.height = p->height; b.contagion_distance = p->contagion_distance;
+  b.rate = p->contagion_rate; b.critical_limit = p->critical_limit; b.min_expense = p->minimum_expense;
+  for (int k = 0; k < 5; ++k) b.bi[k] = p->basic_income[k];
+  for (int k = 0; k < 9; ++k) {
+    b.p_hosp[k] = p->age_hospitalization_probs[k];
+    b.p_sev[k] = p->age_severe_probs[k];
+    b.p_death[k] = p->age_death_probs[k];
+  }
+  b.pop_size = p->population_size;
+  b.recovering_time = p->recovering_time; b.scale_bits = p->wealth_scale_bits; b.schedule = p->schedule;
+  LAUNCH(k_set_params, 1, 32, sim->ctl, b);
+  if (sim->n > 0) LAUNCH(k_replan, 1, 32, sim->ctl, 0);  // amplitudes / distance may have changed the margin
+  CK(cudaGetLastError());
+  sim->params = *p;
+  sim->have_params = true;
+  sim->cells_dirty = true;
+  return CABS_OK;
+}
+
+extern "C" int cabs_set_triggers(cabs_sim *sim, const cabs_trigger *t, int count) {
+  if (!sim || (count > 0 && !t)) return fail(sim, CABS_ERR_INVALID, "cabs_set_triggers: null argument");
+  if (count < 0 || count > CABS_MAX_TRIGGERS) return fail(sim, CABS_ERR_INVALID, "too many triggers");
+  CK(cudaSetDevice(sim->device));
+  TriggerBlock b;
+  memset(&b, 0, sizeof b);
+  b.ntrig = count;
+  for (int k = 0; k < count; ++k) {
+    if (t[k].metric < 0 || t[k].metric >= CABS_NUM_STATS || t[k].op < 0 || t[k].op > 3 || t[k].attribute < 0 ||
+        t[k].attribute > 3)
+      return fail(sim, CABS_ERR_INVALID, "cabs_set_triggers: bad metric/op/attribute");
+    b.trig[k].metric = t[k].metric; b.trig[k].op = t[k].op; b.trig[k].attribute = t[k].attribute;
+    b.trig[k].threshold = t[k].threshold;
+    for (int j = 0; j < 4; ++j) b.trig[k].value[j] = t[k].value[j];
+  }
+  LAUNCH(k_set_triggers, 1, 32, sim->ctl, b);
+  CK(cudaGetLastError());
+  return CABS_OK;
+}
+
+// Build the cell list of the current positions without advancing the simulation.
+static int rebuild_static(cabs_sim *sim) {
+  const int c = sim->cur, o = c ^ 1;
+  const int nb = agent_blocks(sim);
+  LAUNCH(k_bbox, nb, 256, sim->ctl, sim->x[c], sim->y[c]);
+  LAUNCH(k_replan, 1, 32, sim->ctl, 1);
+  LAUNCH(k_clear_cells, nb, 256, sim->ctl, sim->cells);
+  LAUNCH(k_move_count<false>, nb, 256, sim->ctl, sim->id[c], sim->x[c], sim->y[c], sim->attr[c], sim->cells);
+  LAUNCH(k_scan_reduce, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
+  LAUNCH(k_scan_partials, 1, 1024, sim->partial);
+  LAUNCH(k_scan_apply, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
+  LAUNCH(k_update_scatter<false>, nb, 256, sim->ctl, sim->id[c], sim->x[c], sim->y[c], sim->attr[c], sim->w[c],
+         sim->cells, sim->id[o], sim->x[o], sim->y[o], sim->attr[o], sim->w[o]);
+  LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 0);
+  CK(cudaGetLastError());
+  sim->cur = o;
+  sim->cells_dirty = false;
+  return CABS_OK;
+}
+
+extern "C" int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop) {
+  if (!sim || !pop) return fail(sim, CABS_ERR_INVALID, "cabs_upload: null argument");
+  if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_upload: call cabs_set_params first");
+  if (pop->n > sim->capacity) return fail(sim, CABS_ERR_CAPACITY, "cabs_upload: population larger than capacity");
+  const size_t n = pop->n;
+  if (n && (!pop->x || !pop->y || !pop->status || !pop->severity || !pop->infected_time || !pop->age ||
+            !pop->stratum || !pop->wealth))
+    return fail(sim, CABS_ERR_INVALID, "cabs_upload: null column");
+  CK(cudaSetDevice(sim->device));
+  const int c = sim->cur;
+  const size_t cap = sim->capacity;
+  if (n) {
+    CK(cudaMemcpyAsync(sim->x[c], pop->x, n * sizeof(int), cudaMemcpyHostToDevice, sim->stream));
+    CK(cudaMemcpyAsync(sim->y[c], pop->y, n * sizeof(int), cudaMemcpyHostToDevice, sim->stream));
+    CK(cudaMemcpyAsync(sim->w[c], pop->wealth, n * sizeof(double), cudaMemcpyHostToDevice, sim->stream));
+    CK(cudaMemcpyAsync(sim->stage + 0 * cap, pop->status, n, cudaMemcpyHostToDevice, sim->stream));
+    CK(cudaMemcpyAsync(sim->stage + 1 * cap, pop->severity, n, cudaMemcpyHostToDevice, sim->stream));
+    CK(cudaMemcpyAsync(sim->stage + 2 * cap, pop->infected_time, n, cudaMemcpyHostToDevice, sim->stream));
+    CK(cudaMemcpyAsync(sim->stage + 3 * cap, pop->age, n, cudaMemcpyHostToDevice, sim->stream));
+    CK(cudaMemcpyAsync(sim->stage + 4 * cap, pop->stratum, n, cudaMemcpyHostToDevice, sim->stream));
+    if (pop->id) CK(cudaMemcpyAsync(sim->stage_id, pop->id, n * sizeof(uint32_t), cudaMemcpyHostToDevice, sim->stream));
+    LAUNCH(k_pack, agent_blocks(sim), 256, (unsigned)n, sim->stage + 0 * cap, sim->stage + 1 * cap,
+           sim->stage + 2 * cap, sim->stage + 3 * cap, sim->stage + 4 * cap, pop->id ? sim->stage_id : nullptr,
+           sim->attr[c], sim->id[c]);
+  }
+  const unsigned n32 = (unsigned)n;
+  CK(cudaMemcpyAsync(&sim->ctl->n, &n32, sizeof(unsigned), cudaMemcpyHostToDevice, sim->stream));
+  sim->n = n;
+  return rebuild_static(sim);
+}
+
+extern "C" int cabs_download(cabs_sim *sim, cabs_soa_host *pop) {
+  if (!sim || !pop) return fail(sim, CABS_ERR_INVALID, "cabs_download: null argument");
+  if (pop->n < sim->n) return fail(sim, CABS_ERR_CAPACITY, "cabs_download: host buffers smaller than the population");
+  CK(cudaSetDevice(sim->device));
+  const size_t n = sim->n, cap = sim->capacity;
+  pop->n = n;
+  if (n == 0) return CABS_OK;
+  const int c = sim->cur, o = c ^ 1;  // the other copy is free between steps: use it as scratch
+  LAUNCH(k_unpack, agent_blocks(sim), 256, (unsigned)n, 0, sim->id[c], sim->x[c], sim->y[c], sim->attr[c], sim->w[c],
+         sim->x[o], sim->y[o], sim->stage + 0 * cap, sim->stage + 1 * cap, sim->stage + 2 * cap, sim->stage + 3 * cap,
+         sim->stage + 4 * cap, sim->w[o], sim->stage_id);
+  CK(cudaGetLastError());
+  if (pop->x) CK(cudaMemcpyAsync(pop->x, sim->x[o], n * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
+  if (pop->y) CK(cudaMemcpyAsync(pop->y, sim->y[o], n * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
+  if (pop->wealth) CK(cudaMemcpyAsync(pop->wealth, sim->w[o], n * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
+  if (pop->status) CK(cudaMemcpyAsync(pop->status, sim->stage + 0 * cap, n, cudaMemcpyDeviceToHost, sim->stream));
+  if (pop->severity) CK(cudaMemcpyAsync(pop->severity, sim->stage + 1 * cap, n, cudaMemcpyDeviceToHost, sim->stream));
+  if (pop->infected_time)
+    CK(cudaMemcpyAsync(pop->infected_time, sim->stage + 2 * cap, n, cudaMemcpyDeviceToHost, sim->stream));
+  if (pop->age) CK(cudaMemcpyAsync(pop->age, sim->stage + 3 * cap, n, cudaMemcpyDeviceToHost, sim->stream));
+  if (pop->stratum) CK(cudaMemcpyAsync(pop->stratum, sim->stage + 4 * cap, n, cudaMemcpyDeviceToHost, sim->stream));
+  if (pop->id) CK(cudaMemcpyAsync(pop->id, sim->stage_id, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  return CABS_OK;
+}
+
+extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
+  if (!sim || nsteps < 0) return fail(sim, CABS_ERR_INVALID, "cabs_step: bad argument");
+  if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_step: call cabs_set_params first");
+  CK(cudaSetDevice(sim->device));
+  const int nb = agent_blocks(sim);
+  for (int s = 0; s < nsteps; ++s) {
+    const int c = sim->cur, o = c ^ 1;
+    LAUNCH(k_clear_cells, nb, 256, sim->ctl, sim->cells);
+    LAUNCH(k_move_count<true>, nb, 256, sim->ctl, sim->id[c], sim->x[c], sim->y[c], sim->attr[c], sim->cells);
+    LAUNCH(k_scan_reduce, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
+    LAUNCH(k_scan_partials, 1, 1024, sim->partial);
+    LAUNCH(k_scan_apply, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
+    LAUNCH(k_update_scatter<true>, nb, 256, sim->ctl, sim->id[c], sim->x[c], sim->y[c], sim->attr[c], sim->w[c],
+           sim->cells, sim->id[o], sim->x[o], sim->y[o], sim->attr[o], sim->w[o]);
+    LAUNCH(k_contagion, nb, 256, sim->ctl, sim->id[o], sim->x[o], sim->y[o], sim->attr[o], sim->cells);
+    LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 1);
+    sim->cur = o;
+    sim->step++;
+  }
+  CK(cudaGetLastError());
+  sim->cells_dirty = false;
+  return CABS_OK;
+}
+
+static int check_device_error(cabs_sim *sim) {
+  unsigned err = 0;
+  CK(cudaMemcpyAsync(&err, &sim->ctl->err, sizeof(unsigned), cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  if (err & kErrDomain) return fail(sim, CABS_ERR_DOMAIN, "population bounding box exceeds the supported 2^28 lattice units");
+  if (err & kErrOutOfGrid) return fail(sim, CABS_ERR_DOMAIN, "internal: an agent left the planned cell grid");
+  return CABS_OK;
+}
+
+extern "C" int cabs_sync(cabs_sim *sim) {
+  if (!sim) return fail(sim, CABS_ERR_INVALID, "cabs_sync: null handle");
+  CK(cudaSetDevice(sim->device));
+  CK(cudaStreamSynchronize(sim->stream));
+  return check_device_error(sim);
+}
+
+static void convert_record(const cabs_sim *sim, const StatRecord &r, double *values, int64_t *counts) {
+  const double n = (double)sim->params.population_size;
+  for (int k = 0; k < 7; ++k) {
+    values[k] = (double)r.cnt[k] / n;  // abs.py:301-307: count / population_size
+    if (counts) counts[k] = (int64_t)r.cnt[k];
+  }
+  const double scale = (double)(1ull << sim->params.wealth_scale_bits);
+  for (int k = 0; k < 5; ++k) values[7 + k] = (double)r.q[k] / scale;  // abs.py:309-312
+}
+
+extern "C" int cabs_stats(cabs_sim *sim, double *values, int64_t *counts) {
+  if (!sim || !values) return fail(sim, CABS_ERR_INVALID, "cabs_stats: null argument");
+  if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_stats: call cabs_set_params first");
+  CK(cudaSetDevice(sim->device));
+  StatRecord r;
+  CK(cudaMemcpyAsync(&r, &sim->ctl->cur, sizeof r, cudaMemcpyDeviceToHost, sim->stream));
+  const int rc = check_device_error(sim);  // synchronises
+  if (rc != CABS_OK) return rc;
+  convert_record(sim, r, values, counts);
+  return CABS_OK;
+}
+
+extern "C" int cabs_stats_history(cabs_sim *sim, uint64_t first_step, uint64_t count, double *values) {
+  if (!sim || (count && !values)) return fail(sim, CABS_ERR_INVALID, "cabs_stats_history: null argument");
+  if (first_step + count > sim->step) return fail(sim, CABS_ERR_INVALID, "cabs_stats_history: steps not executed yet");
+  if (sim->step - first_step > sim->hist_cap)
+    return fail(sim, CABS_ERR_CAPACITY, "cabs_stats_history: records already overwritten (history_capacity)");
+  CK(cudaSetDevice(sim->device));
+  if (count == 0) return CABS_OK;
+  std::vector<StatRecord> recs(count);
+  uint64_t done = 0;
+  while (done < count) {  // the ring may wrap
+    const uint64_t slot = (first_step + done) % sim->hist_cap;
+    const uint64_t run = std::min<uint64_t>(count - done, sim->hist_cap - slot);
+    CK(cudaMemcpyAsync(recs.data() + done, sim->history + slot, run * sizeof(StatRecord), cudaMemcpyDeviceToHost,
+                       sim->stream));
+    done += run;
+  }
+  const int rc = check_device_error(sim);
+  if (rc != CABS_OK) return rc;
+  for (uint64_t k = 0; k < count; ++k) convert_record(sim, recs[k], values + k * CABS_NUM_STATS, nullptr);
+  return CABS_OK;
+}
+
+extern "C" int cabs_contact_pairs(cabs_sim *sim, int64_t *ij, size_t capacity_pairs, size_t *n_pairs) {
+  if (!sim || !n_pairs || (capacity_pairs && !ij)) return fail(sim, CABS_ERR_INVALID, "cabs_contact_pairs: null argument");
+  CK(cudaSetDevice(sim->device));
+  if (sim->cells_dirty) {
+    const int rc = rebuild_static(sim);
+    if (rc != CABS_OK) return rc;
+  }
+  if (capacity_pairs > sim->pairs_cap) {
+    cudaFree(sim->pairs);
+    sim->pairs = nullptr;
+    sim->pairs_cap = 0;
+    CK(cudaMalloc(&sim->pairs, capacity_pairs * 2 * sizeof(long long)));
+    sim->pairs_cap = capacity_pairs;
+  }
+  CK(cudaMemsetAsync(sim->pair_count, 0, sizeof(unsigned long long), sim->stream));
+  const int c = sim->cur;
+  LAUNCH(k_contact_pairs, agent_blocks(sim), 256, sim->ctl, sim->id[c], sim->x[c], sim->y[c], sim->cells, sim->pairs,
+         (unsigned long long)capacity_pairs, sim->pair_count);
+  CK(cudaGetLastError());
+  unsigned long long total = 0;
+  CK(cudaMemcpyAsync(&total, sim->pair_count, sizeof total, cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  const size_t ncopy = (size_t)std::min<unsigned long long>(total, capacity_pairs);
+  if (ncopy) CK(cudaMemcpy(ij, sim->pairs, ncopy * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+  *n_pairs = (size_t)total;
+  return check_device_error(sim);
+}
+
+extern "C" int cabs_get_info(cabs_sim *sim, cabs_info *info) {
+  if (!sim || !info) return fail(sim, CABS_ERR_INVALID, "cabs_get_info: null argument");
+  CK(cudaSetDevice(sim->device));
+  Ctl h;
+  CK(cudaMemcpyAsync(&h, sim->ctl, sizeof h, cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  info->n = sim->n;
+  info->step = sim->step;
+  info->kernel_launches = sim->launches;
+  info->grid_origin_x = h.built.gx0;
+  info->grid_origin_y = h.built.gy0;
+  info->cell_edge = 1 << h.built.eshift;
+  info->cells_x = h.built.ncx;
+  info->cells_y = h.built.ncy;
+  info->device_error = h.err;
+  return CABS_OK;
+}

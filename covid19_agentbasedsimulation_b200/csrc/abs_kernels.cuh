@@ -1,0 +1,757 @@
+// Device side of the COVID-ABS agent step for sm_100a (B200).
+//
+// Population layout in HBM (structure of arrays, kept physically ordered by cell key):
+//   id   u32   position in the reference's population list (abs.py:15); keys all draws
+//   x,y  i32   lattice position (agents.py:45-47)
+//   attr u32   status[1:0] severity[3:2] stratum[6:4] | infected_time[15:8] | age[23:16]
+//   w    f64   wealth (agents.py:60)
+// Two copies (ping/pong): every step scatters the updated records straight into their
+// cell-sorted slot of the other copy, so the neighbour scan reads contiguous cell ranges.
+//
+// One step (Simulation.execute, abs.py:232-273):
+//   k_clear_cells      zero the cell histogram (L2 resident: <= 2^24 cells)
+//   k_move_count       recompute-only pass: new position of every agent -> cell key -> histogram
+//   k_scan_*           exclusive scan of the histogram = cell starts
+//   k_update_scatter   move + update + economy (abs.py:156-230), partial statistics,
+//                      scatter the record to cell_start[key] + rank
+//   k_contagion        neighbour scan over the 3x3 cells, contact() (abs.py:141-154)
+//   k_finalize         statistics record (abs.py:291-314), triggers (abs.py:267-271), next grid
+#pragma once
+#include <stdint.h>
+
+#include "abs_rng.cuh"
+
+namespace cabs {
+
+constexpr int kMaxTriggers = 8;
+constexpr int kNumStats = 12;
+
+// sticky device error bits
+constexpr uint32_t kErrOutOfGrid = 1u;     // an agent left the planned grid (internal invariant broken)
+constexpr uint32_t kErrDomain = 2u;        // bounding box wider than 2^28
+constexpr uint32_t kErrWealthRange = 4u;   // fixed-point wealth sum would overflow
+
+struct DevTrigger {
+  int metric, op, attribute, pad;
+  double threshold;
+  double value[4];
+};
+
+// Raw statistics of one step: 7 counts (abs.py:300-307) + 5 fixed-point wealth sums (abs.py:309-312)
+struct StatRecord {
+  unsigned long long cnt[7];
+  long long q[5];
+  unsigned long long new_infections;
+  unsigned long long n_resident;
+  unsigned long long pad[2];
+};
+
+struct Grid {
+  int gx0, gy0;       // lattice coordinates of cell (1,1)'s lower corner
+  int eshift;         // cell edge = 1 << eshift lattice units
+  int ncx, ncy;       // cells per row / rows, including one padding cell on each side
+  unsigned ncells;    // ncx * ncy; cell_start has ncells + 1 entries
+};
+
+// Everything the kernels read that can change from step to step lives here (device memory),
+// so that a whole run of steps can be enqueued without the host in the loop.
+struct Ctl {
+  // ---- cell grids: `g` is the one the next build (k_move_count .. k_contagion) uses, planned by
+  //      the previous k_finalize; `built` is the one the current contents of cell_start were built with
+  Grid g, built;
+  int last_bb[4];     // bounding box of the current positions (xmin, xmax, ymin, ymax)
+  unsigned max_cells;
+  // ---- simulation attributes (abs.py:17-49); triggers rewrite them on the device
+  float amp[4];
+  double length, height;
+  double contagion_distance, rate, critical_limit, min_expense;
+  double bi[5];
+  double p_hosp[9], p_sev[9], p_death[9];
+  unsigned long long pop_size;
+  int T;              // largest integer d2 with sqrt(d2) <= contagion_distance, -1: none
+  int recovering_time;
+  int scale_bits;
+  int schedule;
+  unsigned k0, k1;    // Philox key (seed)
+  unsigned step;
+  unsigned n;         // agents resident on this device
+  int crit_active;    // (Severe+Hospitalization)/N >= critical_limit at the end of the previous step
+  // ---- accumulators of the running step
+  unsigned long long cnt[7];
+  long long q[5];
+  unsigned long long newinf;
+  int bb_xmin, bb_xmax, bb_ymin, bb_ymax;
+  unsigned pair_count;
+  // ---- statistics of the previous step (what triggers and the critical-limit test read)
+  StatRecord prev;
+  StatRecord cur;
+  int ntrig;
+  DevTrigger trig[kMaxTriggers];
+  unsigned err;
+  unsigned hist_cap;
+};
+
+// ------------------------------------------------------------------------------------------
+// attribute word helpers
+__device__ __forceinline__ uint32_t attr_status(uint32_t a) { return a & 3u; }
+__device__ __forceinline__ uint32_t attr_severity(uint32_t a) { return (a >> 2) & 3u; }
+__device__ __forceinline__ uint32_t attr_stratum(uint32_t a) { return (a >> 4) & 7u; }
+__device__ __forceinline__ uint32_t attr_time(uint32_t a) { return (a >> 8) & 0xFFu; }
+__device__ __forceinline__ uint32_t attr_age(uint32_t a) { return (a >> 16) & 0xFFu; }
+// Bit 7 marks "became Infected in the last contact phase" (set by k_contagion while the status bits
+// still say Susceptible, so that agents infected in a pass do not transmit in the same pass).  Every
+// other reader folds the mark into the status first.
+constexpr uint32_t kNewlyInfected = 0x80u;
+__device__ __forceinline__ uint32_t attr_normalize(uint32_t a) {
+  return (a & kNewlyInfected) ? ((a & ~(kNewlyInfected | 3u)) | 1u) : a;
+}
+__host__ __device__ __forceinline__ uint32_t attr_pack(uint32_t status, uint32_t sev, uint32_t stratum, uint32_t time,
+                                                       uint32_t age) {
+  return (status & 3u) | ((sev & 3u) << 2) | ((stratum & 7u) << 4) | ((time & 0xFFu) << 8) | ((age & 0xFFu) << 16);
+}
+
+enum : uint32_t { ST_S = 0, ST_I = 1, ST_R = 2, ST_D = 3 };
+enum : uint32_t { SEV_E = 0, SEV_A = 1, SEV_H = 2, SEV_G = 3 };
+
+// Per-block copy of the step-invariant part of Ctl that the agent kernels need.
+struct StepParams {
+  int gx0, gy0, eshift, ncx, ncy;
+  float amp[4];
+  double length, height, rate, min_expense;
+  double bi[5];
+  double p_hosp[9], p_sev[9], p_death[9];
+  int T, recovering_time, scale_bits, crit_active;
+  unsigned k0, k1, step, n;
+};
+
+__device__ __forceinline__ void load_params(StepParams &P, const Ctl *ctl, bool use_built = false) {
+  // one thread fills the shared copy; callers __syncthreads() afterwards
+  const Grid &g = use_built ? ctl->built : ctl->g;
+  P.gx0 = g.gx0; P.gy0 = g.gy0; P.eshift = g.eshift; P.ncx = g.ncx; P.ncy = g.ncy;
+  for (int i = 0; i < 4; ++i) P.amp[i] = ctl->amp[i];
+  P.length = ctl->length; P.height = ctl->height; P.rate = ctl->rate; P.min_expense = ctl->min_expense;
+  for (int i = 0; i < 5; ++i) P.bi[i] = ctl->bi[i];
+  for (int i = 0; i < 9; ++i) { P.p_hosp[i] = ctl->p_hosp[i]; P.p_sev[i] = ctl->p_sev[i]; P.p_death[i] = ctl->p_death[i]; }
+  P.T = ctl->T; P.recovering_time = ctl->recovering_time; P.scale_bits = ctl->scale_bits;
+  P.crit_active = ctl->crit_active;
+  P.k0 = ctl->k0; P.k1 = ctl->k1; P.step = ctl->step; P.n = ctl->n;
+}
+
+// Simulation.move (abs.py:156-189): displacement and reflected position.  `w` = stream-0 words.
+__device__ __forceinline__ void move_agent(const StepParams &P, int x, int y, uint32_t attr, const uint4 &w, int &nx,
+                                           int &ny, int &ix, int &iy, bool &mobile) {
+  const uint32_t st = attr_status(attr), sev = attr_severity(attr);
+  mobile = !(st == ST_D || (st == ST_I && (sev == SEV_H || sev == SEV_G)));  // abs.py:164-167
+  ix = 0;
+  iy = 0;
+  if (mobile) {
+    float z0, z1;
+    normal_pair(w.x, w.y, z0, z1);
+    const float a = P.amp[st];
+    ix = __float2int_rz(__fmul_rn(z0, a));  // int() truncates toward zero (abs.py:174-175)
+    iy = __float2int_rz(__fmul_rn(z1, a));
+  }
+  const int tx = x + ix, ty = y + iy;
+  nx = (tx <= 0 || (double)tx >= P.length) ? x - ix : tx;  // abs.py:177-180: the increment is reflected
+  ny = (ty <= 0 || (double)ty >= P.height) ? y - iy : ty;  // abs.py:182-185
+}
+
+// Cell of a lattice point.  Interior cells are 1..ncx-2 / 1..ncy-2; row/column 0 and the last one
+// are always-empty padding so that the 3x3 neighbourhood never needs a bounds test.
+__device__ __forceinline__ void cell_coords(const StepParams &P, int x, int y, int &cx, int &cy, unsigned *err) {
+  cx = ((x - P.gx0) >> P.eshift) + 1;
+  cy = ((y - P.gy0) >> P.eshift) + 1;
+  if (cx < 1 || cx > P.ncx - 2 || cy < 1 || cy > P.ncy - 2) {
+    atomicOr(err, kErrOutOfGrid);
+    cx = min(max(cx, 1), P.ncx - 2);
+    cy = min(max(cy, 1), P.ncy - 2);
+  }
+}
+__device__ __forceinline__ unsigned cell_key(const StepParams &P, int x, int y, unsigned *err) {
+  int cx, cy;
+  cell_coords(P, x, y, cx, cy, err);
+  return (unsigned)cy * (unsigned)P.ncx + (unsigned)cx;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_clear_cells(const Ctl *__restrict__ ctl, unsigned *__restrict__ cells) {
+  const unsigned m = ctl->g.ncells + 1;
+  const unsigned m4 = m >> 2;
+  uint4 *c4 = reinterpret_cast<uint4 *>(cells);
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < m4; i += stride) c4[i] = make_uint4(0, 0, 0, 0);
+  for (unsigned i = (m4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) cells[i] = 0;
+}
+
+// Pass A: histogram of the cells agents will occupy after this step's move.
+// kAdvance=false builds the cell list of the current positions (used before the first step).
+template <bool kAdvance>
+__global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id,
+                                                    const int *__restrict__ x, const int *__restrict__ y,
+                                                    const uint32_t *__restrict__ attr, unsigned *__restrict__ cells) {
+  __shared__ StepParams P;
+  if (threadIdx.x == 0) load_params(P, ctl);
+  __syncthreads();
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+    int nx = x[i], ny = y[i];
+    if (kAdvance) {
+      const uint32_t a = attr_normalize(attr[i]);
+      const uint4 w = philox4x32_10(id[i], P.step, kStreamAgent, 0u, P.k0, P.k1);
+      int ix, iy;
+      bool mobile;
+      move_agent(P, nx, ny, a, w, nx, ny, ix, iy, mobile);
+    }
+    const unsigned key = cell_key(P, nx, ny, &ctl->err);
+    atomicAdd(&cells[key + 1], 1u);
+  }
+}
+
+// ---- exclusive scan of cells[0 .. ncells] in place, fixed grid of kScanBlocks chunks ----------
+constexpr int kScanBlocks = 592;  // 148 SMs x 4
+constexpr int kScanThreads = 512;
+
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned *warp_sums, unsigned &total) {
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    const unsigned nw = blockDim.x >> 5;
+    unsigned s = (lane < nw) ? warp_sums[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    warp_sums[lane] = s;  // inclusive over warps
+  }
+  __syncthreads();
+  const unsigned base = (wid == 0) ? 0u : warp_sums[wid - 1];
+  total = warp_sums[(blockDim.x >> 5) - 1];
+  const unsigned r = base + inc - v;
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ void scan_chunk(const Ctl *ctl, unsigned &begin, unsigned &end) {
+  const unsigned m = ctl->g.ncells + 1;
+  unsigned chunk = (m + kScanBlocks - 1) / kScanBlocks;
+  chunk = (chunk + 3u) & ~3u;  // keep chunks 16-byte aligned
+  begin = min(m, blockIdx.x * chunk);
+  end = min(m, begin + chunk);
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const Ctl *__restrict__ ctl,
+                                                              const unsigned *__restrict__ cells,
+                                                              unsigned *__restrict__ partial) {
+  __shared__ unsigned warp_sums[32];
+  unsigned begin, end;
+  scan_chunk(ctl, begin, end);
+  unsigned s = 0;
+  for (unsigned i = begin + threadIdx.x; i < end; i += blockDim.x) s += cells[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned t = (threadIdx.x < (blockDim.x >> 5)) ? warp_sums[threadIdx.x] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_partials(unsigned *__restrict__ partial) {
+  __shared__ unsigned warp_sums[32];
+  unsigned total;
+  const unsigned v = (threadIdx.x < kScanBlocks) ? partial[threadIdx.x] : 0u;
+  const unsigned ex = block_exclusive_scan(v, warp_sums, total);
+  if (threadIdx.x < kScanBlocks) partial[threadIdx.x] = ex;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const Ctl *__restrict__ ctl, unsigned *__restrict__ cells,
+                                                             const unsigned *__restrict__ partial) {
+  __shared__ unsigned warp_sums[32];
+  unsigned begin, end;
+  scan_chunk(ctl, begin, end);
+  unsigned carry = partial[blockIdx.x];
+  for (unsigned base = begin; base < end; base += blockDim.x * 4) {
+    const unsigned i = base + threadIdx.x * 4;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (i + 3 < end) {
+      v = *reinterpret_cast<const uint4 *>(cells + i);
+    } else {
+      if (i < end) v.x = cells[i];
+      if (i + 1 < end) v.y = cells[i + 1];
+      if (i + 2 < end) v.z = cells[i + 2];
+    }
+    const unsigned sum = v.x + v.y + v.z + v.w;
+    unsigned total;
+    const unsigned ex = block_exclusive_scan(sum, warp_sums, total) + carry;
+    uint4 o;
+    o.x = ex;
+    o.y = ex + v.x;
+    o.z = o.y + v.y;
+    o.w = o.z + v.z;
+    if (i + 3 < end) {
+      *reinterpret_cast<uint4 *>(cells + i) = o;
+    } else {
+      if (i < end) cells[i] = o.x;
+      if (i + 1 < end) cells[i + 1] = o.y;
+      if (i + 2 < end) cells[i + 2] = o.z;
+    }
+    carry += total;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass B: Simulation.move + Simulation.update (abs.py:156-230) per agent, partial statistics of
+// abs.py:291-314, and the scatter of the record into its cell-sorted slot.
+struct BlockStats {
+  unsigned long long cnt[7];
+  long long q[5];
+  int bb[4];
+};
+
+template <bool kAdvance>
+__global__ void __launch_bounds__(256)
+k_update_scatter(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id, const int *__restrict__ x,
+                 const int *__restrict__ y, const uint32_t *__restrict__ attr, const double *__restrict__ wealth,
+                 unsigned *__restrict__ cells, uint32_t *__restrict__ oid, int *__restrict__ ox, int *__restrict__ oy,
+                 uint32_t *__restrict__ oattr, double *__restrict__ owealth) {
+  __shared__ StepParams P;
+  __shared__ BlockStats B;
+  if (threadIdx.x == 0) {
+    load_params(P, ctl);
+    for (int i = 0; i < 7; ++i) B.cnt[i] = 0;
+    for (int i = 0; i < 5; ++i) B.q[i] = 0;
+    B.bb[0] = B.bb[2] = INT_MAX;
+    B.bb[1] = B.bb[3] = INT_MIN;
+  }
+  __syncthreads();
+  unsigned c_st[4] = {0, 0, 0, 0}, c_sev[3] = {0, 0, 0};
+  long long q[5] = {0, 0, 0, 0, 0};
+  int bxmin = INT_MAX, bxmax = INT_MIN, bymin = INT_MAX, bymax = INT_MIN;
+  const double qscale = (double)(1ull << P.scale_bits);
+
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+    const uint32_t aid = id[i];
+    int nx = x[i], ny = y[i];
+    uint32_t a = attr_normalize(attr[i]);
+    double w = wealth[i];
+    if (kAdvance) {
+      uint32_t st = attr_status(a), sev = attr_severity(a), time = attr_time(a);
+      const uint32_t stratum = attr_stratum(a), age = attr_age(a);
+      const uint4 r0 = philox4x32_10(aid, P.step, kStreamAgent, 0u, P.k0, P.k1);
+      int ix, iy;
+      bool mobile;
+      move_agent(P, nx, ny, a, r0, nx, ny, ix, iy, mobile);
+      const double bi = P.bi[min(stratum, 4u)];
+      if (mobile) {
+        // abs.py:187-189: wealth += sqrt(ix^2+iy^2) * rand * minimum_expense * basic_income[stratum]
+        const double dist = __dsqrt_rn((double)(ix * ix + iy * iy));
+        const double inc = __dmul_rn(__dmul_rn(__dmul_rn(dist, u01(r0.z)), P.min_expense), bi);
+        w = __dadd_rn(w, inc);
+      }
+      // abs.py:191-230
+      if (st != ST_D) {
+        bool pays = true;
+        if (st == ST_I) {
+          time += 1;
+          const uint32_t idx = min(age > 10u ? age / 10u - 1u : 0u, 8u);  // abs.py:204
+          const double u_sub = u01(r0.w);
+          if (sev == SEV_A) {
+            if (P.p_hosp[idx] > u_sub) sev = SEV_H;
+          } else if (sev == SEV_H) {
+            if (P.p_sev[idx] > u_sub) {
+              sev = SEV_G;
+              if (P.crit_active) {  // abs.py:214-217
+                st = ST_D;
+                sev = SEV_A;
+              }
+            }
+          }
+          const uint4 r1 = philox4x32_10(aid, P.step, kStreamAgent2, 0u, P.k0, P.k1);
+          if (P.p_death[idx] > u01(r1.x)) {  // abs.py:219-223
+            st = ST_D;
+            sev = SEV_A;
+            pays = false;
+          } else if ((int)time > P.recovering_time) {  // abs.py:225-228
+            time = 0;
+            st = ST_R;
+            sev = SEV_A;
+          }
+        }
+        if (pays) w = __dadd_rn(w, -__dmul_rn(P.min_expense, bi));  // abs.py:230
+      }
+      a = attr_pack(st, sev, stratum, time, age) | (a & 0xFF000000u);
+    }
+    // partial statistics (abs.py:300-312); infections of this step are added by k_contagion
+    {
+      const uint32_t st = attr_status(a), sev = attr_severity(a);
+      c_st[0] += (st == ST_S); c_st[1] += (st == ST_I); c_st[2] += (st == ST_R); c_st[3] += (st == ST_D);
+      if (st != ST_D) {
+        c_sev[0] += (sev == SEV_A); c_sev[1] += (sev == SEV_H); c_sev[2] += (sev == SEV_G);
+        if (attr_age(a) >= 18u) {
+          const long long f = __double2ll_rn(__dmul_rn(w, qscale));
+          const uint32_t s = attr_stratum(a);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) q[k] += (s == (uint32_t)k) ? f : 0ll;
+        }
+      }
+      bxmin = min(bxmin, nx); bxmax = max(bxmax, nx); bymin = min(bymin, ny); bymax = max(bymax, ny);
+    }
+    const unsigned key = cell_key(P, nx, ny, &ctl->err);
+    const unsigned slot = atomicAdd(&cells[key + 1], 1u);
+    oid[slot] = aid;
+    ox[slot] = nx;
+    oy[slot] = ny;
+    oattr[slot] = a;
+    owealth[slot] = w;
+  }
+  // block reduction: warp shuffles, then shared atomics, then one set of global atomics per block
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c_st[k] += __shfl_xor_sync(0xffffffffu, c_st[k], o);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c_sev[k] += __shfl_xor_sync(0xffffffffu, c_sev[k], o);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+    bxmin = min(bxmin, __shfl_xor_sync(0xffffffffu, bxmin, o));
+    bxmax = max(bxmax, __shfl_xor_sync(0xffffffffu, bxmax, o));
+    bymin = min(bymin, __shfl_xor_sync(0xffffffffu, bymin, o));
+    bymax = max(bymax, __shfl_xor_sync(0xffffffffu, bymax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    for (int k = 0; k < 4; ++k) atomicAdd(&B.cnt[k], (unsigned long long)c_st[k]);
+    for (int k = 0; k < 3; ++k) atomicAdd(&B.cnt[4 + k], (unsigned long long)c_sev[k]);
+    for (int k = 0; k < 5; ++k) atomicAdd((unsigned long long *)&B.q[k], (unsigned long long)q[k]);
+    atomicMin(&B.bb[0], bxmin); atomicMax(&B.bb[1], bxmax); atomicMin(&B.bb[2], bymin); atomicMax(&B.bb[3], bymax);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 7; ++k) atomicAdd(&ctl->cnt[k], B.cnt[k]);
+    for (int k = 0; k < 5; ++k) atomicAdd((unsigned long long *)&ctl->q[k], (unsigned long long)B.q[k]);
+    atomicMin(&ctl->bb_xmin, B.bb[0]); atomicMax(&ctl->bb_xmax, B.bb[1]);
+    atomicMin(&ctl->bb_ymin, B.bb[2]); atomicMax(&ctl->bb_ymax, B.bb[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass C: the contact loop of abs.py:249-265 as a neighbour scan over the sorted population.
+// A Susceptible agent looks at the three cell rows around it; each row's three cells are one
+// contiguous range of the sorted arrays.  contact(): abs.py:141-154 with one draw per pair.
+__global__ void __launch_bounds__(256)
+k_contagion(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id, const int *__restrict__ x,
+            const int *__restrict__ y, uint32_t *__restrict__ attr, const unsigned *__restrict__ cell_start) {
+  __shared__ StepParams P;
+  __shared__ unsigned s_new;
+  if (threadIdx.x == 0) {
+    load_params(P, ctl);
+    s_new = 0;
+  }
+  __syncthreads();
+  unsigned newinf = 0;
+  const unsigned stride = gridDim.x * blockDim.x;
+  if (P.T >= 0) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+      const uint32_t a = attr[i];
+      if (attr_status(a) != ST_S) continue;
+      const int xi = x[i], yi = y[i];
+      const uint32_t idi = id[i];
+      int cx, cy;
+      cell_coords(P, xi, yi, cx, cy, &ctl->err);
+      bool infected = false;
+      for (int dy = -1; dy <= 1 && !infected; ++dy) {
+        const unsigned c = (unsigned)(cy + dy) * (unsigned)P.ncx + (unsigned)cx;
+        const unsigned jb = cell_start[c - 1], je = cell_start[c + 2];
+        for (unsigned j = jb; j < je; ++j) {
+          const uint32_t aj = attr[j];
+          if (attr_status(aj) != ST_I) continue;
+          const long long dx = x[j] - xi, dyy = y[j] - yi;
+          if (dx * dx + dyy * dyy > (long long)P.T) continue;
+          const uint32_t idj = id[j];
+          const uint4 r = philox4x32_10(min(idi, idj), P.step, kStreamContact, max(idi, idj), P.k0, P.k1);
+          if (u01(r.x) <= P.rate) {  // abs.py:150-153
+            infected = true;
+            break;
+          }
+        }
+      }
+      if (infected) {
+        attr[i] = a | kNewlyInfected;  // status bits stay Susceptible during this pass (see attr_normalize)
+        ++newinf;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) newinf += __shfl_xor_sync(0xffffffffu, newinf, o);
+  if ((threadIdx.x & 31) == 0 && newinf) atomicAdd(&s_new, newinf);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_new) atomicAdd(&ctl->newinf, (unsigned long long)s_new);
+}
+
+// ------------------------------------------------------------------------------------------
+// Test hook for the pair loop of abs.py:253-259: every (i, j), i < j, within contagion_distance.
+__global__ void __launch_bounds__(256)
+k_contact_pairs(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id, const int *__restrict__ x,
+                const int *__restrict__ y, const unsigned *__restrict__ cell_start, long long *__restrict__ out,
+                unsigned long long capacity, unsigned long long *__restrict__ count) {
+  __shared__ StepParams P;
+  if (threadIdx.x == 0) load_params(P, ctl, true);
+  __syncthreads();
+  if (P.T < 0) return;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+    const int xi = x[i], yi = y[i];
+    const uint32_t idi = id[i];
+    int cx, cy;
+    cell_coords(P, xi, yi, cx, cy, &ctl->err);
+    for (int dy = -1; dy <= 1; ++dy) {
+      const unsigned c = (unsigned)(cy + dy) * (unsigned)P.ncx + (unsigned)cx;
+      const unsigned jb = cell_start[c - 1], je = cell_start[c + 2];
+      for (unsigned j = jb; j < je; ++j) {
+        const uint32_t idj = id[j];
+        if (idj <= idi) continue;
+        const long long dx = x[j] - xi, dyy = y[j] - yi;
+        if (dx * dx + dyy * dyy > (long long)P.T) continue;
+        const unsigned long long slot = atomicAdd(count, 1ull);
+        if (slot < capacity) {
+          out[2 * slot] = (long long)idi;
+          out[2 * slot + 1] = (long long)idj;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Grid planning: conservative bounding box of where agents can be after the next move.
+__device__ inline void plan_grid(Ctl *ctl, int xmin, int xmax, int ymin, int ymax, bool add_margin) {
+  if (xmin > xmax) { xmin = xmax = 0; ymin = ymax = 0; }  // empty population
+  int margin = 0;
+  if (add_margin) {
+    float amax = 0.f;
+    for (int k = 0; k < 3; ++k) amax = fmaxf(amax, fabsf(ctl->amp[k]));
+    margin = (int)(kMaxAbsNormal * amax) + 2;
+  }
+  const long long x0 = (long long)xmin - margin, x1 = (long long)xmax + margin;
+  const long long y0 = (long long)ymin - margin, y1 = (long long)ymax + margin;
+  if (x1 - x0 >= (1ll << 28) || y1 - y0 >= (1ll << 28) || x0 < -(1ll << 30) || x1 > (1ll << 30) ||
+      y0 < -(1ll << 30) || y1 > (1ll << 30)) {
+    ctl->err |= kErrDomain;
+  }
+  // cell edge: power of two, at least floor(sqrt(T)) so contacts never skip a cell, grown until
+  // the grid fits max_cells (keeps the histogram L2-resident)
+  int eshift = 0;
+  const int T = ctl->T;
+  while (T > 0 && ((1ll << eshift) * (1ll << eshift)) < (long long)T && eshift < 28) ++eshift;
+  // (1<<eshift)^2 >= T  =>  1<<eshift >= sqrt(T) >= any |dx| of a contact
+  for (;;) {
+    const long long ncx = ((x1 - x0) >> eshift) + 3, ncy = ((y1 - y0) >> eshift) + 3;
+    if (ncx * ncy <= (long long)ctl->max_cells || eshift >= 28) {
+      ctl->g.ncx = (int)ncx;
+      ctl->g.ncy = (int)ncy;
+      ctl->g.ncells = (unsigned)min(ncx * ncy, (long long)ctl->max_cells);
+      break;
+    }
+    ++eshift;
+  }
+  ctl->g.eshift = eshift;
+  ctl->g.gx0 = (int)x0;
+  ctl->g.gy0 = (int)y0;
+}
+
+__device__ inline void reset_accumulators(Ctl *ctl) {
+  for (int k = 0; k < 7; ++k) ctl->cnt[k] = 0;
+  for (int k = 0; k < 5; ++k) ctl->q[k] = 0;
+  ctl->newinf = 0;
+  ctl->bb_xmin = INT_MAX; ctl->bb_xmax = INT_MIN; ctl->bb_ymin = INT_MAX; ctl->bb_ymax = INT_MIN;
+}
+
+__device__ inline double stat_value(const Ctl *ctl, const StatRecord &r, int metric) {
+  if (metric < 7) return (double)r.cnt[metric] / (double)ctl->pop_size;
+  return (double)r.q[metric - 7] / (double)(1ull << ctl->scale_bits);
+}
+
+__device__ inline int threshold_T(double r) {
+  // largest integer n with sqrt(n) <= r in binary64; -1 if r < 0 or NaN
+  if (!(r >= 0.0)) return -1;
+  if (r > 16000.0) r = 16000.0;  // d2 must fit int32 for the largest supported box anyway
+  long long n = (long long)floor(r * r);
+  while (__dsqrt_rn((double)(n + 1)) <= r) ++n;
+  while (n >= 0 && __dsqrt_rn((double)n) > r) --n;
+  return (int)n;
+}
+
+// End of Simulation.execute (abs.py:267-273) + the statistics row batch_experiment appends
+// (experiments.py:193-196).  One thread.
+//   record_stats = true : after a real step
+//   record_stats = false: after upload / static rebuild (statistics of the initial state = "previous" stats)
+__global__ void k_finalize(Ctl *ctl, StatRecord *history, int record_stats) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  StatRecord cur;
+  for (int k = 0; k < 7; ++k) cur.cnt[k] = ctl->cnt[k];
+  cur.cnt[ST_S] -= ctl->newinf;  // infections of the contact phase (abs.py:153)
+  cur.cnt[ST_I] += ctl->newinf;
+  for (int k = 0; k < 5; ++k) cur.q[k] = ctl->q[k];
+  cur.new_infections = ctl->newinf;
+  cur.n_resident = ctl->n;
+  cur.pad[0] = cur.pad[1] = 0;
+  if (record_stats) {
+    history[ctl->step % ctl->hist_cap] = cur;
+    // simulation triggers (abs.py:267-271) see the memoised statistics of the previous step
+    for (int t = 0; t < ctl->ntrig; ++t) {
+      const DevTrigger &tr = ctl->trig[t];
+      const double v = stat_value(ctl, ctl->prev, tr.metric);
+      const bool hit = tr.op == 0 ? v >= tr.threshold : tr.op == 1 ? v <= tr.threshold
+                     : tr.op == 2 ? v > tr.threshold : v < tr.threshold;
+      if (!hit) continue;
+      if (tr.attribute == 0) {
+        for (int k = 0; k < 4; ++k) ctl->amp[k] = (float)tr.value[k];
+      } else if (tr.attribute == 1) {
+        ctl->rate = tr.value[0];
+      } else if (tr.attribute == 2) {
+        ctl->contagion_distance = tr.value[0];
+        ctl->T = threshold_T(tr.value[0]);
+      } else if (tr.attribute == 3) {
+        ctl->critical_limit = tr.value[0];
+      }
+    }
+    ctl->step += 1;
+  }
+  ctl->prev = cur;
+  ctl->cur = cur;
+  // abs.py:215: statistics['Severe'] + statistics['Hospitalization'] >= critical_limit
+  const double n = (double)ctl->pop_size;
+  ctl->crit_active = ((double)cur.cnt[6] / n + (double)cur.cnt[5] / n) >= ctl->critical_limit;
+  ctl->built = ctl->g;
+  ctl->last_bb[0] = ctl->bb_xmin; ctl->last_bb[1] = ctl->bb_xmax;
+  ctl->last_bb[2] = ctl->bb_ymin; ctl->last_bb[3] = ctl->bb_ymax;
+  plan_grid(ctl, ctl->bb_xmin, ctl->bb_xmax, ctl->bb_ymin, ctl->bb_ymax, true);
+  reset_accumulators(ctl);
+}
+
+// Bounding box of the resident positions into ctl->bb_* (used once per upload).
+__global__ void __launch_bounds__(256) k_bbox(Ctl *__restrict__ ctl, const int *__restrict__ x,
+                                              const int *__restrict__ y) {
+  int bxmin = INT_MAX, bxmax = INT_MIN, bymin = INT_MAX, bymax = INT_MIN;
+  const unsigned n = ctl->n, stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    bxmin = min(bxmin, x[i]); bxmax = max(bxmax, x[i]); bymin = min(bymin, y[i]); bymax = max(bymax, y[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    bxmin = min(bxmin, __shfl_xor_sync(0xffffffffu, bxmin, o));
+    bxmax = max(bxmax, __shfl_xor_sync(0xffffffffu, bxmax, o));
+    bymin = min(bymin, __shfl_xor_sync(0xffffffffu, bymin, o));
+    bymax = max(bymax, __shfl_xor_sync(0xffffffffu, bymax, o));
+  }
+  if ((threadIdx.x & 31) == 0 && bxmin <= bxmax) {
+    atomicMin(&ctl->bb_xmin, bxmin); atomicMax(&ctl->bb_xmax, bxmax);
+    atomicMin(&ctl->bb_ymin, bymin); atomicMax(&ctl->bb_ymax, bymax);
+  }
+}
+
+// Plan `g` from a bounding box: from_accum = the box k_bbox just reduced (exact, for a static
+// build), otherwise the saved box of the current positions plus one move of margin.
+__global__ void k_replan(Ctl *ctl, int from_accum) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctl->T = threshold_T(ctl->contagion_distance);
+  if (from_accum) {
+    plan_grid(ctl, ctl->bb_xmin, ctl->bb_xmax, ctl->bb_ymin, ctl->bb_ymax, false);
+  } else {
+    plan_grid(ctl, ctl->last_bb[0], ctl->last_bb[1], ctl->last_bb[2], ctl->last_bb[3], true);
+  }
+  reset_accumulators(ctl);
+}
+
+// Host-side parameter block -> Ctl (cabs_set_params / cabs_set_triggers / creation).
+struct ParamBlock {
+  float amp[4];
+  double length, height, contagion_distance, rate, critical_limit, min_expense;
+  double bi[5];
+  double p_hosp[9], p_sev[9], p_death[9];
+  unsigned long long pop_size;
+  int recovering_time, scale_bits, schedule;
+};
+
+__global__ void k_set_params(Ctl *ctl, ParamBlock p) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int k = 0; k < 4; ++k) ctl->amp[k] = p.amp[k];
+  ctl->length = p.length; ctl->height = p.height; ctl->contagion_distance = p.contagion_distance;
+  ctl->rate = p.rate; ctl->critical_limit = p.critical_limit; ctl->min_expense = p.min_expense;
+  for (int k = 0; k < 5; ++k) ctl->bi[k] = p.bi[k];
+  for (int k = 0; k < 9; ++k) { ctl->p_hosp[k] = p.p_hosp[k]; ctl->p_sev[k] = p.p_sev[k]; ctl->p_death[k] = p.p_death[k]; }
+  ctl->pop_size = p.pop_size;
+  ctl->recovering_time = p.recovering_time; ctl->scale_bits = p.scale_bits; ctl->schedule = p.schedule;
+  ctl->T = threshold_T(p.contagion_distance);
+  const double n = (double)ctl->pop_size;
+  ctl->crit_active = ((double)ctl->cur.cnt[6] / n + (double)ctl->cur.cnt[5] / n) >= ctl->critical_limit;
+}
+
+struct TriggerBlock {
+  int ntrig;
+  DevTrigger trig[kMaxTriggers];
+};
+
+__global__ void k_set_triggers(Ctl *ctl, TriggerBlock t) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctl->ntrig = t.ntrig;
+  for (int k = 0; k < kMaxTriggers; ++k) ctl->trig[k] = t.trig[k];
+}
+
+__global__ void k_init_ctl(Ctl *ctl, unsigned k0, unsigned k1, unsigned max_cells, unsigned hist_cap) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctl->k0 = k0; ctl->k1 = k1; ctl->max_cells = max_cells; ctl->hist_cap = hist_cap;
+  ctl->step = 0; ctl->n = 0; ctl->err = 0; ctl->ntrig = 0; ctl->pop_size = 1; ctl->T = -1;
+  reset_accumulators(ctl);
+  plan_grid(ctl, 0, 0, 0, 0, false);
+  ctl->built = ctl->g;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host SoA (separate byte columns, agents.py:44-64) <-> packed device columns.
+__global__ void k_pack(unsigned n, const uint8_t *__restrict__ status, const uint8_t *__restrict__ severity,
+                       const uint8_t *__restrict__ time, const uint8_t *__restrict__ age,
+                       const uint8_t *__restrict__ stratum, const uint32_t *__restrict__ id_in,
+                       uint32_t *__restrict__ attr, uint32_t *__restrict__ id) {
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    attr[i] = attr_pack(status[i], severity[i], stratum[i], time[i], age[i]);
+    id[i] = id_in ? id_in[i] : i;
+  }
+}
+
+// Scatter back to id order (ids must be a permutation of 0..n-1 unless by_slot).
+__global__ void k_unpack(unsigned n, int by_slot, const uint32_t *__restrict__ id, const int *__restrict__ x,
+                         const int *__restrict__ y, const uint32_t *__restrict__ attr,
+                         const double *__restrict__ wealth, int *__restrict__ ox, int *__restrict__ oy,
+                         uint8_t *__restrict__ status, uint8_t *__restrict__ severity, uint8_t *__restrict__ time,
+                         uint8_t *__restrict__ age, uint8_t *__restrict__ stratum, double *__restrict__ owealth,
+                         uint32_t *__restrict__ oid) {
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t a = attr_normalize(attr[i]);
+    const unsigned d = by_slot ? i : id[i];
+    ox[d] = x[i];
+    oy[d] = y[i];
+    status[d] = (uint8_t)attr_status(a);
+    severity[d] = (uint8_t)attr_severity(a);
+    time[d] = (uint8_t)attr_time(a);
+    age[d] = (uint8_t)attr_age(a);
+    stratum[d] = (uint8_t)attr_stratum(a);
+    owealth[d] = wealth[i];
+    oid[d] = id[i];
+  }
+}
+
+}  // namespace cabs

@@ -1,0 +1,173 @@
+/*
+ * covidabs.h -- C ABI of the B200-native COVID-ABS agent step.
+ *
+ * The reference (petroniocandido/COVID19_AgentBasedSimulation) is pure Python and has no FFI of
+ * its own; the seam it offers is the duck type `batch_experiment` drives:
+ *     sim = simulation_type(**kwargs)      covid_abs/experiments.py:185
+ *     sim.initialize()                     covid_abs/experiments.py:186  -> abs.py:116
+ *     sim.execute()                        covid_abs/experiments.py:193  -> abs.py:232
+ *     sim.get_statistics(kind='all')       covid_abs/experiments.py:194  -> abs.py:291
+ * Each entry point below cites the reference code it stands in for.  The Python host layer
+ * (covid19_agentbasedsimulation_b200/abs.py) binds these with ctypes and keeps the covid_abs API.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; the caller owns every host buffer it passes in;
+ *  - every call returns CABS_OK (0) or a negative error code and never throws across the ABI;
+ *    `cabs_last_error` returns the message of the last failing call on that handle;
+ *  - one handle = one CUDA device + one stream; handles are not thread-safe (the reference is
+ *    single-threaded); `cabs_step` only enqueues work, `cabs_stats*`, `cabs_download`,
+ *    `cabs_contact_pairs` and `cabs_sync` wait for it.
+ */
+#ifndef COVIDABS_H
+#define COVIDABS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CABS_ABI_VERSION 1
+
+/* error codes */
+#define CABS_OK 0
+#define CABS_ERR_INVALID (-1)   /* bad argument / handle state                          */
+#define CABS_ERR_CUDA (-2)      /* CUDA runtime error (message has the CUDA string)    */
+#define CABS_ERR_CAPACITY (-3)  /* population / output buffer larger than the capacity */
+#define CABS_ERR_DOMAIN (-4)    /* coordinates outside the supported +-2^28 box        */
+#define CABS_ERR_NOGPU (-5)     /* no CUDA device: there is no CPU fallback            */
+
+/* covid_abs/agents.py:13-16 (declaration order = statistics key order) */
+enum { CABS_SUSCEPTIBLE = 0, CABS_INFECTED = 1, CABS_RECOVERED_IMMUNE = 2, CABS_DEATH = 3 };
+/* covid_abs/agents.py:23-26 */
+enum { CABS_EXPOSED = 0, CABS_ASYMPTOMATIC = 1, CABS_HOSPITALIZATION = 2, CABS_SEVERE = 3 };
+
+/* contact schedule */
+enum {
+  CABS_SYNCHRONOUS = 0, /* one neighbour scan: only agents infected before the contact phase transmit */
+  CABS_SEQUENTIAL = 1   /* abs.py:261-265 order: in-step chains along increasing (i,j) rank           */
+};
+
+/* statistics slots, in the key order of abs.py:300-312 */
+enum {
+  CABS_STAT_SUSCEPTIBLE = 0, CABS_STAT_INFECTED, CABS_STAT_RECOVERED_IMMUNE, CABS_STAT_DEATH,
+  CABS_STAT_ASYMPTOMATIC, CABS_STAT_HOSPITALIZATION, CABS_STAT_SEVERE,
+  CABS_STAT_Q1, CABS_STAT_Q2, CABS_STAT_Q3, CABS_STAT_Q4, CABS_STAT_Q5,
+  CABS_NUM_STATS
+};
+
+typedef struct cabs_sim cabs_sim;
+
+/* creation-time configuration (sizes of the device allocations) */
+typedef struct cabs_config {
+  uint32_t abi_version;      /* CABS_ABI_VERSION                                                  */
+  int32_t device;            /* CUDA device ordinal                                               */
+  uint64_t capacity;         /* max agents resident on this device                                */
+  uint64_t max_cells;        /* cap on cell-list cells (0 = auto: min(2^24, max(4096, 1.5*capacity))) */
+  uint64_t seed;             /* Philox key; draws are keyed (seed, agent id, step)                */
+  uint32_t history_capacity; /* per-step statistics records kept on the device (ring)             */
+  uint32_t flags;            /* reserved, 0                                                       */
+} cabs_config;
+
+/* Simulation attributes a step reads: covid_abs/abs.py:17-49 and covid_abs/common.py:13-27.
+ * May be changed between steps (that is what abs.py:267-271 `triggers_simulation` do). */
+typedef struct cabs_params {
+  double length, height;                 /* abs.py:19-22                                     */
+  double contagion_distance;             /* abs.py:27  (sqrt(dx^2+dy^2) <= d, abs.py:10,258) */
+  double contagion_rate;                 /* abs.py:29                                        */
+  double critical_limit;                 /* abs.py:31                                        */
+  double amplitudes[4];                  /* abs.py:33-36, by status code; Death ignored      */
+  double minimum_income;                 /* abs.py:38 (unused by Simulation, kept for parity) */
+  double minimum_expense;                /* abs.py:40                                        */
+  double basic_income[5];                /* common.py:27                                     */
+  double age_hospitalization_probs[9];   /* common.py:13                                     */
+  double age_severe_probs[9];            /* common.py:14                                     */
+  double age_death_probs[9];             /* common.py:15                                     */
+  uint64_t population_size;              /* abs.py:17: denominator of the status fractions   */
+  int32_t recovering_time;               /* 20 in abs.py:225                                 */
+  int32_t wealth_scale_bits;             /* Q1..Q5 are summed as round(wealth*2^bits) int64  */
+  int32_t schedule;                      /* CABS_SYNCHRONOUS / CABS_SEQUENTIAL               */
+  int32_t reserved;
+} cabs_params;
+
+/* Declarative form of one abs.py:74-84 simulation trigger, evaluated on the device at the end of
+ * every step against the statistics of the previous step (what the reference's memo holds when
+ * batch_experiment drives it, abs.py:273,298 + experiments.py:193-194):
+ *     if stats[metric] <op> threshold:  attribute = value                                         */
+enum { CABS_OP_GE = 0, CABS_OP_LE = 1, CABS_OP_GT = 2, CABS_OP_LT = 3 };
+enum { CABS_ATTR_AMPLITUDES = 0, CABS_ATTR_CONTAGION_RATE = 1, CABS_ATTR_CONTAGION_DISTANCE = 2,
+       CABS_ATTR_CRITICAL_LIMIT = 3 };
+typedef struct cabs_trigger {
+  int32_t metric;    /* CABS_STAT_*                                   */
+  int32_t op;        /* CABS_OP_*                                     */
+  double threshold;
+  int32_t attribute; /* CABS_ATTR_*                                   */
+  int32_t reserved;
+  double value[4];   /* amplitudes[4] by status code, else value[0]   */
+} cabs_trigger;
+#define CABS_MAX_TRIGGERS 8
+
+/* The population as structure of arrays on the host: the fields of covid_abs/agents.py:44-64 that
+ * the step reads.  `id` may be NULL on upload (ids 0..n-1 = list order of abs.py:15). */
+typedef struct cabs_soa_host {
+  uint64_t n;
+  int32_t *x, *y;          /* agents.py:45-47 (integer lattice) */
+  uint8_t *status;         /* agents.py:49  CABS_SUSCEPTIBLE..CABS_DEATH       */
+  uint8_t *severity;       /* agents.py:52  CABS_EXPOSED..CABS_SEVERE          */
+  uint8_t *infected_time;  /* agents.py:54                                     */
+  uint8_t *age;            /* agents.py:56                                     */
+  uint8_t *stratum;        /* agents.py:58  0..4                               */
+  double *wealth;          /* agents.py:60                                     */
+  uint32_t *id;            /* position in the reference's population list      */
+} cabs_soa_host;
+
+typedef struct cabs_info {
+  uint64_t n;               /* agents resident                          */
+  uint64_t step;            /* steps executed so far                    */
+  uint64_t kernel_launches; /* CUDA kernels launched by this handle     */
+  int32_t grid_origin_x, grid_origin_y, cell_edge, cells_x, cells_y;
+  uint32_t device_error;    /* sticky device-side error bits            */
+} cabs_info;
+
+/* Replaces Simulation.__init__ (abs.py:14-49): allocates the device-side population. */
+int cabs_create(const cabs_config *cfg, cabs_sim **out);
+/* Releases everything the handle owns. */
+void cabs_destroy(cabs_sim *sim);
+/* Message of the last error on this handle (or of the last failed cabs_create when sim == NULL). */
+const char *cabs_last_error(const cabs_sim *sim);
+
+/* Sets the attributes of abs.py:17-49; callable between steps (abs.py:267-271). */
+int cabs_set_params(cabs_sim *sim, const cabs_params *params);
+/* Installs up to CABS_MAX_TRIGGERS device-side simulation triggers (abs.py:74-84, 267-271). */
+int cabs_set_triggers(cabs_sim *sim, const cabs_trigger *triggers, int count);
+
+/* Replaces set_population (abs.py:65-69) / the list built by initialize (abs.py:116-139). */
+int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop);
+/* Replaces get_population (abs.py:57-63): writes the population back in id order. */
+int cabs_download(cabs_sim *sim, cabs_soa_host *pop);
+
+/* Replaces `nsteps` calls of Simulation.execute (abs.py:232-273): move, update, contacts,
+ * triggers.  Asynchronous. */
+int cabs_step(cabs_sim *sim, int nsteps);
+/* Waits for the enqueued steps. */
+int cabs_sync(cabs_sim *sim);
+
+/* Replaces get_statistics(kind='all') (abs.py:291-314) for the current state.
+ * `values`: CABS_NUM_STATS doubles in abs.py key order; `counts` (optional): the 7 raw counts. */
+int cabs_stats(cabs_sim *sim, double *values, int64_t *counts);
+/* Statistics after each of steps [first_step, first_step+count) (the rows batch_experiment appends,
+ * experiments.py:193-196); `values` holds count*CABS_NUM_STATS doubles. */
+int cabs_stats_history(cabs_sim *sim, uint64_t first_step, uint64_t count, double *values);
+
+/* Test hook for the pair loop of abs.py:253-259: all (i, j), i < j (ids), with
+ * sqrt(dx^2+dy^2) <= contagion_distance on the current positions, in unspecified order.
+ * Writes min(*n_pairs, capacity_pairs) pairs as ij[2k], ij[2k+1]; *n_pairs = total found. */
+int cabs_contact_pairs(cabs_sim *sim, int64_t *ij, size_t capacity_pairs, size_t *n_pairs);
+
+int cabs_get_info(cabs_sim *sim, cabs_info *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COVIDABS_H */
