@@ -247,9 +247,12 @@ extern "C" int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop) {
            sim->stage + 2 * cap, sim->stage + 3 * cap, sim->stage + 4 * cap, pop->id ? sim->stage_id : nullptr,
            sim->attr[c], sim->id[c]);
   }
-  const unsigned n32 = (unsigned)n;
+  // a new population starts a new run: step counter (part of the draw key) back to 0
+  const unsigned n32 = (unsigned)n, zero = 0;
   CK(cudaMemcpyAsync(&sim->ctl->n, &n32, sizeof(unsigned), cudaMemcpyHostToDevice, sim->stream));
+  CK(cudaMemcpyAsync(&sim->ctl->step, &zero, sizeof(unsigned), cudaMemcpyHostToDevice, sim->stream));
   sim->n = n;
+  sim->step = 0;
   return rebuild_static(sim);
 }
 
