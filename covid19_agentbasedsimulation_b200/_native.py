@@ -21,7 +21,8 @@ OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_DOMAIN, ERR_NOGPU = 0, -1, -2, -3, 
 # every symbol include/covidabs.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params", "cabs_set_triggers",
             "cabs_upload", "cabs_download", "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_history",
-            "cabs_contact_pairs", "cabs_get_info")
+            "cabs_contact_pairs", "cabs_get_info", "cabs_event_record", "cabs_event_elapsed_ms",
+            "cabs_profile_enable", "cabs_profile_read")
 
 
 class NativeError(RuntimeError):
@@ -63,6 +64,10 @@ class Info(C.Structure):
                 ("cells_x", C.c_int32), ("cells_y", C.c_int32), ("device_error", C.c_uint32)]
 
 
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_uint64), ("total_ms", C.c_double)]
+
+
 _lib = None
 
 
@@ -91,6 +96,10 @@ def load():
     lib.cabs_stats_history.argtypes = [P, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]
     lib.cabs_contact_pairs.argtypes = [P, C.POINTER(C.c_int64), C.c_size_t, C.POINTER(C.c_size_t)]
     lib.cabs_get_info.argtypes = [P, C.POINTER(Info)]
+    lib.cabs_event_record.argtypes = [P, C.c_int]
+    lib.cabs_event_elapsed_ms.argtypes = [P, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    lib.cabs_profile_enable.argtypes = [P, C.c_int]
+    lib.cabs_profile_read.argtypes = [P, C.POINTER(KernelTime), C.c_int, C.POINTER(C.c_int)]
     for name in EXPORTED:
         fn = getattr(lib, name)
         if name not in ("cabs_destroy", "cabs_last_error"):
@@ -207,3 +216,21 @@ class Handle(object):
         i = Info()
         self._check(self._lib.cabs_get_info(self._h, C.byref(i)))
         return {k: getattr(i, k) for k, _ in Info._fields_}
+
+    def event_record(self, slot):
+        self._check(self._lib.cabs_event_record(self._h, int(slot)))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_double(0)
+        self._check(self._lib.cabs_event_elapsed_ms(self._h, int(a), int(b), C.byref(ms)))
+        return ms.value
+
+    def profile_enable(self, on=True):
+        self._check(self._lib.cabs_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel name: (launches, total_ms)} since profiling was enabled / last read."""
+        arr = (KernelTime * 32)()
+        n = C.c_int(0)
+        self._check(self._lib.cabs_profile_read(self._h, arr, 32, C.byref(n)))
+        return {arr[i].name.decode(): (int(arr[i].launches), float(arr[i].total_ms)) for i in range(n.value)}

@@ -43,8 +43,26 @@ struct cabs_sim {
   bool have_params = false;
   bool cells_dirty = true;      // cell_start does not describe the current positions / distance
   uint64_t n = 0, step = 0, launches = 0;
+  cudaEvent_t events[CABS_NUM_EVENTS] = {};
+  // per-kernel profiling: events[i] is recorded before launch i of the current batch, names[i] its kernel
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<const char *> prof_names;
+  size_t prof_used = 0;
   std::string err;
 };
+
+static void prof_mark(cabs_sim *sim, const char *name) {
+  if (sim->prof_used == sim->prof_events.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    sim->prof_events.push_back(e);
+    sim->prof_names.push_back(name);
+  }
+  sim->prof_names[sim->prof_used] = name;
+  cudaEventRecord(sim->prof_events[sim->prof_used], sim->stream);
+  sim->prof_used++;
+}
 
 #define CK(call)                                                                                \
   do {                                                                                          \
@@ -67,6 +85,7 @@ static inline int agent_blocks(const cabs_sim *sim) { return sim->num_sms * 8; }
 
 #define LAUNCH(kernel, grid, block, ...)                \
   do {                                                  \
+    if (sim->profiling) prof_mark(sim, #kernel);        \
     kernel<<<(grid), (block), 0, sim->stream>>>(__VA_ARGS__); \
     sim->launches++;                                    \
   } while (0)
@@ -84,6 +103,8 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
   }
   cudaFree(sim->cells); cudaFree(sim->partial); cudaFree(sim->ctl); cudaFree(sim->history);
   cudaFree(sim->stage); cudaFree(sim->stage_id); cudaFree(sim->pairs); cudaFree(sim->pair_count);
+  for (cudaEvent_t e : sim->events) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
   if (sim->stream) cudaStreamDestroy(sim->stream);
   delete sim;
 }
@@ -301,6 +322,7 @@ extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
     sim->cur = o;
     sim->step++;
   }
+  if (sim->profiling) prof_mark(sim, nullptr);  // closing timestamp of the batch
   CK(cudaGetLastError());
   sim->cells_dirty = false;
   return CABS_OK;
@@ -409,5 +431,61 @@ extern "C" int cabs_get_info(cabs_sim *sim, cabs_info *info) {
   info->cells_x = h.built.ncx;
   info->cells_y = h.built.ncy;
   info->device_error = h.err;
+  return CABS_OK;
+}
+
+extern "C" int cabs_event_record(cabs_sim *sim, int slot) {
+  if (!sim || slot < 0 || slot >= CABS_NUM_EVENTS) return fail(sim, CABS_ERR_INVALID, "cabs_event_record: bad slot");
+  CK(cudaSetDevice(sim->device));
+  if (!sim->events[slot]) CK(cudaEventCreate(&sim->events[slot]));
+  CK(cudaEventRecord(sim->events[slot], sim->stream));
+  return CABS_OK;
+}
+
+extern "C" int cabs_event_elapsed_ms(cabs_sim *sim, int a, int b, double *ms) {
+  if (!sim || !ms || a < 0 || b < 0 || a >= CABS_NUM_EVENTS || b >= CABS_NUM_EVENTS || !sim->events[a] ||
+      !sim->events[b])
+    return fail(sim, CABS_ERR_INVALID, "cabs_event_elapsed_ms: bad slot");
+  CK(cudaSetDevice(sim->device));
+  CK(cudaEventSynchronize(sim->events[b]));
+  float f = 0.f;
+  CK(cudaEventElapsedTime(&f, sim->events[a], sim->events[b]));
+  *ms = (double)f;
+  return CABS_OK;
+}
+
+extern "C" int cabs_profile_enable(cabs_sim *sim, int on) {
+  if (!sim) return fail(sim, CABS_ERR_INVALID, "cabs_profile_enable: null handle");
+  CK(cudaSetDevice(sim->device));
+  CK(cudaStreamSynchronize(sim->stream));
+  sim->profiling = on != 0;
+  sim->prof_used = 0;
+  return CABS_OK;
+}
+
+extern "C" int cabs_profile_read(cabs_sim *sim, cabs_kernel_time *out, int capacity, int *count) {
+  if (!sim || !out || !count) return fail(sim, CABS_ERR_INVALID, "cabs_profile_read: null argument");
+  CK(cudaSetDevice(sim->device));
+  CK(cudaStreamSynchronize(sim->stream));
+  int n = 0;
+  for (size_t i = 0; i + 1 < sim->prof_used; ++i) {
+    const char *name = sim->prof_names[i];
+    if (!name) continue;  // closing mark of a batch: the gap to the next batch is host time, not a kernel
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, sim->prof_events[i], sim->prof_events[i + 1]));
+    int k = 0;
+    for (; k < n; ++k)
+      if (strncmp(out[k].name, name, sizeof(out[k].name) - 1) == 0) break;
+    if (k == n) {
+      if (n == capacity) continue;
+      memset(&out[n], 0, sizeof(out[n]));
+      strncpy(out[n].name, name, sizeof(out[n].name) - 1);
+      ++n;
+    }
+    out[k].launches += 1;
+    out[k].total_ms += (double)ms;
+  }
+  *count = n;
+  sim->prof_used = 0;
   return CABS_OK;
 }

@@ -167,6 +167,23 @@ int cabs_contact_pairs(cabs_sim *sim, int64_t *ij, size_t capacity_pairs, size_t
 
 int cabs_get_info(cabs_sim *sim, cabs_info *info);
 
+/* Measurement support (no reference counterpart: the reference has no timing code).
+ * CUDA events on the handle's own stream, so that a caller can bracket any sequence of calls above
+ * (uploads, steps, statistics reads) with device-side timestamps. */
+#define CABS_NUM_EVENTS 8
+int cabs_event_record(cabs_sim *sim, int slot);
+int cabs_event_elapsed_ms(cabs_sim *sim, int slot_begin, int slot_end, double *ms); /* waits for slot_end */
+
+/* Per-kernel device times: while enabled, every kernel launch of cabs_step is bracketed by events.
+ * cabs_profile_read waits, then returns up to `capacity` entries (kernel name, launches, total ms) and resets. */
+typedef struct cabs_kernel_time {
+  char name[32];
+  uint64_t launches;
+  double total_ms;
+} cabs_kernel_time;
+int cabs_profile_enable(cabs_sim *sim, int on);
+int cabs_profile_read(cabs_sim *sim, cabs_kernel_time *out, int capacity, int *count);
+
 #ifdef __cplusplus
 }
 #endif
