@@ -23,12 +23,10 @@ struct cabs_sim {
   uint64_t capacity = 0;
   unsigned max_cells = 0;
   unsigned hist_cap = 0;
-  // ping/pong population columns
-  uint32_t *id[2] = {nullptr, nullptr};
-  int *x[2] = {nullptr, nullptr};
-  int *y[2] = {nullptr, nullptr};
-  uint32_t *attr[2] = {nullptr, nullptr};
+  // ping/pong population: 16-byte hot records {x, y, attr, id} + wealth; per-step displacement
+  uint4 *hot[2] = {nullptr, nullptr};
   double *w[2] = {nullptr, nullptr};
+  uint32_t *disp = nullptr;
   int cur = 0;
   unsigned *cells = nullptr;    // histogram / cell_start, max_cells + 8 entries
   unsigned *partial = nullptr;  // scan partials
@@ -99,8 +97,9 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
   cudaSetDevice(sim->device);
   if (sim->stream) cudaStreamSynchronize(sim->stream);
   for (int b = 0; b < 2; ++b) {
-    cudaFree(sim->id[b]); cudaFree(sim->x[b]); cudaFree(sim->y[b]); cudaFree(sim->attr[b]); cudaFree(sim->w[b]);
+    cudaFree(sim->hot[b]); cudaFree(sim->w[b]);
   }
+  cudaFree(sim->disp);
   cudaFree(sim->cells); cudaFree(sim->partial); cudaFree(sim->ctl); cudaFree(sim->history);
   cudaFree(sim->stage); cudaFree(sim->stage_id); cudaFree(sim->pairs); cudaFree(sim->pair_count);
   for (cudaEvent_t e : sim->events) if (e) cudaEventDestroy(e);
@@ -134,12 +133,10 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   sim->hist_cap = cfg->history_capacity ? cfg->history_capacity : 4096;
   const size_t cap = sim->capacity;
   for (int b = 0; b < 2; ++b) {
-    CK(cudaMalloc(&sim->id[b], cap * sizeof(uint32_t)));
-    CK(cudaMalloc(&sim->x[b], cap * sizeof(int)));
-    CK(cudaMalloc(&sim->y[b], cap * sizeof(int)));
-    CK(cudaMalloc(&sim->attr[b], cap * sizeof(uint32_t)));
+    CK(cudaMalloc(&sim->hot[b], cap * sizeof(uint4)));
     CK(cudaMalloc(&sim->w[b], cap * sizeof(double)));
   }
+  CK(cudaMalloc(&sim->disp, cap * sizeof(uint32_t)));
   CK(cudaMalloc(&sim->cells, ((size_t)sim->max_cells + 8) * sizeof(unsigned)));
   CK(cudaMalloc(&sim->partial, 1024 * sizeof(unsigned)));
   CK(cudaMalloc(&sim->ctl, sizeof(Ctl)));
@@ -180,6 +177,9 @@ extern "C" int cabs_set_params(cabs_sim *sim, const cabs_params *p) {
     return fail(sim, CABS_ERR_INVALID, "recovering_time must be in [0, 250] (infected_time is stored in 8 bits)");
   if (p->schedule != CABS_SYNCHRONOUS) return fail(sim, CABS_ERR_INVALID, "only CABS_SYNCHRONOUS is implemented");
   if (p->population_size == 0) return fail(sim, CABS_ERR_INVALID, "population_size must be > 0");
+  for (int k = 0; k < 3; ++k)
+    if (!(p->amplitudes[k] >= -5000.0 && p->amplitudes[k] <= 5000.0))
+      return fail(sim, CABS_ERR_INVALID, "amplitudes must be within +-5000 (displacements are stored in 16 bits)");
   CK(cudaSetDevice(sim->device));
   ParamBlock b;
   for (int k = 0; k < 4; ++k) b.amp[k] = (float)p->amplitudes[k];
@@ -217,6 +217,10 @@ extern "C" int cabs_set_triggers(cabs_sim *sim, const cabs_trigger *t, int count
     b.trig[k].metric = t[k].metric; b.trig[k].op = t[k].op; b.trig[k].attribute = t[k].attribute;
     b.trig[k].threshold = t[k].threshold;
     for (int j = 0; j < 4; ++j) b.trig[k].value[j] = t[k].value[j];
+    if (t[k].attribute == CABS_ATTR_AMPLITUDES)
+      for (int j = 0; j < 3; ++j)
+        if (!(t[k].value[j] >= -5000.0 && t[k].value[j] <= 5000.0))
+          return fail(sim, CABS_ERR_INVALID, "trigger amplitudes must be within +-5000");
   }
   LAUNCH(k_set_triggers, 1, 32, sim->ctl, b);
   CK(cudaGetLastError());
@@ -227,15 +231,15 @@ extern "C" int cabs_set_triggers(cabs_sim *sim, const cabs_trigger *t, int count
 static int rebuild_static(cabs_sim *sim) {
   const int c = sim->cur, o = c ^ 1;
   const int nb = agent_blocks(sim);
-  LAUNCH(k_bbox, nb, 256, sim->ctl, sim->x[c], sim->y[c]);
+  LAUNCH(k_bbox, nb, 256, sim->ctl, sim->hot[c]);
   LAUNCH(k_replan, 1, 32, sim->ctl, 1);
   LAUNCH(k_clear_cells, nb, 256, sim->ctl, sim->cells);
-  LAUNCH(k_move_count<false>, nb, 256, sim->ctl, sim->id[c], sim->x[c], sim->y[c], sim->attr[c], sim->cells);
+  LAUNCH(k_move_count<false>, nb, 256, sim->ctl, sim->hot[c], sim->disp, sim->cells);
   LAUNCH(k_scan_reduce, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
   LAUNCH(k_scan_partials, 1, 1024, sim->partial);
   LAUNCH(k_scan_apply, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
-  LAUNCH(k_update_scatter<false>, nb, 256, sim->ctl, sim->id[c], sim->x[c], sim->y[c], sim->attr[c], sim->w[c],
-         sim->cells, sim->id[o], sim->x[o], sim->y[o], sim->attr[o], sim->w[o]);
+  LAUNCH(k_update_scatter<false>, nb, 256, sim->ctl, sim->hot[c], sim->w[c], sim->disp, sim->cells, sim->hot[o],
+         sim->w[o]);
   LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 0);
   CK(cudaGetLastError());
   sim->cur = o;
@@ -254,9 +258,10 @@ extern "C" int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop) {
   CK(cudaSetDevice(sim->device));
   const int c = sim->cur;
   const size_t cap = sim->capacity;
+  int *sx = reinterpret_cast<int *>(sim->hot[c ^ 1]), *sy = sx + cap;  // the other copy is free: scratch
   if (n) {
-    CK(cudaMemcpyAsync(sim->x[c], pop->x, n * sizeof(int), cudaMemcpyHostToDevice, sim->stream));
-    CK(cudaMemcpyAsync(sim->y[c], pop->y, n * sizeof(int), cudaMemcpyHostToDevice, sim->stream));
+    CK(cudaMemcpyAsync(sx, pop->x, n * sizeof(int), cudaMemcpyHostToDevice, sim->stream));
+    CK(cudaMemcpyAsync(sy, pop->y, n * sizeof(int), cudaMemcpyHostToDevice, sim->stream));
     CK(cudaMemcpyAsync(sim->w[c], pop->wealth, n * sizeof(double), cudaMemcpyHostToDevice, sim->stream));
     CK(cudaMemcpyAsync(sim->stage + 0 * cap, pop->status, n, cudaMemcpyHostToDevice, sim->stream));
     CK(cudaMemcpyAsync(sim->stage + 1 * cap, pop->severity, n, cudaMemcpyHostToDevice, sim->stream));
@@ -264,9 +269,9 @@ extern "C" int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop) {
     CK(cudaMemcpyAsync(sim->stage + 3 * cap, pop->age, n, cudaMemcpyHostToDevice, sim->stream));
     CK(cudaMemcpyAsync(sim->stage + 4 * cap, pop->stratum, n, cudaMemcpyHostToDevice, sim->stream));
     if (pop->id) CK(cudaMemcpyAsync(sim->stage_id, pop->id, n * sizeof(uint32_t), cudaMemcpyHostToDevice, sim->stream));
-    LAUNCH(k_pack, agent_blocks(sim), 256, (unsigned)n, sim->stage + 0 * cap, sim->stage + 1 * cap,
+    LAUNCH(k_pack, agent_blocks(sim), 256, (unsigned)n, sx, sy, sim->stage + 0 * cap, sim->stage + 1 * cap,
            sim->stage + 2 * cap, sim->stage + 3 * cap, sim->stage + 4 * cap, pop->id ? sim->stage_id : nullptr,
-           sim->attr[c], sim->id[c]);
+           sim->hot[c]);
   }
   // a new population starts a new run: step counter (part of the draw key) back to 0
   const unsigned n32 = (unsigned)n, zero = 0;
@@ -285,12 +290,13 @@ extern "C" int cabs_download(cabs_sim *sim, cabs_soa_host *pop) {
   pop->n = n;
   if (n == 0) return CABS_OK;
   const int c = sim->cur, o = c ^ 1;  // the other copy is free between steps: use it as scratch
-  LAUNCH(k_unpack, agent_blocks(sim), 256, (unsigned)n, 0, sim->id[c], sim->x[c], sim->y[c], sim->attr[c], sim->w[c],
-         sim->x[o], sim->y[o], sim->stage + 0 * cap, sim->stage + 1 * cap, sim->stage + 2 * cap, sim->stage + 3 * cap,
-         sim->stage + 4 * cap, sim->w[o], sim->stage_id);
+  int *sx = reinterpret_cast<int *>(sim->hot[o]), *sy = sx + cap;
+  LAUNCH(k_unpack, agent_blocks(sim), 256, (unsigned)n, 0, sim->hot[c], sim->w[c], sx, sy, sim->stage + 0 * cap,
+         sim->stage + 1 * cap, sim->stage + 2 * cap, sim->stage + 3 * cap, sim->stage + 4 * cap, sim->w[o],
+         sim->stage_id);
   CK(cudaGetLastError());
-  if (pop->x) CK(cudaMemcpyAsync(pop->x, sim->x[o], n * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
-  if (pop->y) CK(cudaMemcpyAsync(pop->y, sim->y[o], n * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
+  if (pop->x) CK(cudaMemcpyAsync(pop->x, sx, n * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
+  if (pop->y) CK(cudaMemcpyAsync(pop->y, sy, n * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
   if (pop->wealth) CK(cudaMemcpyAsync(pop->wealth, sim->w[o], n * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
   if (pop->status) CK(cudaMemcpyAsync(pop->status, sim->stage + 0 * cap, n, cudaMemcpyDeviceToHost, sim->stream));
   if (pop->severity) CK(cudaMemcpyAsync(pop->severity, sim->stage + 1 * cap, n, cudaMemcpyDeviceToHost, sim->stream));
@@ -311,13 +317,13 @@ extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
   for (int s = 0; s < nsteps; ++s) {
     const int c = sim->cur, o = c ^ 1;
     LAUNCH(k_clear_cells, nb, 256, sim->ctl, sim->cells);
-    LAUNCH(k_move_count<true>, nb, 256, sim->ctl, sim->id[c], sim->x[c], sim->y[c], sim->attr[c], sim->cells);
+    LAUNCH(k_move_count<true>, nb, 256, sim->ctl, sim->hot[c], sim->disp, sim->cells);
     LAUNCH(k_scan_reduce, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
     LAUNCH(k_scan_partials, 1, 1024, sim->partial);
     LAUNCH(k_scan_apply, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
-    LAUNCH(k_update_scatter<true>, nb, 256, sim->ctl, sim->id[c], sim->x[c], sim->y[c], sim->attr[c], sim->w[c],
-           sim->cells, sim->id[o], sim->x[o], sim->y[o], sim->attr[o], sim->w[o]);
-    LAUNCH(k_contagion, nb, 256, sim->ctl, sim->id[o], sim->x[o], sim->y[o], sim->attr[o], sim->cells);
+    LAUNCH(k_update_scatter<true>, nb, 256, sim->ctl, sim->hot[c], sim->w[c], sim->disp, sim->cells, sim->hot[o],
+           sim->w[o]);
+    LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells);
     LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 1);
     sim->cur = o;
     sim->step++;
@@ -404,7 +410,7 @@ extern "C" int cabs_contact_pairs(cabs_sim *sim, int64_t *ij, size_t capacity_pa
   }
   CK(cudaMemsetAsync(sim->pair_count, 0, sizeof(unsigned long long), sim->stream));
   const int c = sim->cur;
-  LAUNCH(k_contact_pairs, agent_blocks(sim), 256, sim->ctl, sim->id[c], sim->x[c], sim->y[c], sim->cells, sim->pairs,
+  LAUNCH(k_contact_pairs, agent_blocks(sim), 256, sim->ctl, sim->hot[c], sim->cells, sim->pairs,
          (unsigned long long)capacity_pairs, sim->pair_count);
   CK(cudaGetLastError());
   unsigned long long total = 0;

@@ -1,11 +1,14 @@
 // Device side of the COVID-ABS agent step for sm_100a (B200).
 //
 // Population layout in HBM (structure of arrays, kept physically ordered by cell key):
-//   id   u32   position in the reference's population list (abs.py:15); keys all draws
-//   x,y  i32   lattice position (agents.py:45-47)
-//   attr u32   status[1:0] severity[3:2] stratum[6:4] | infected_time[15:8] | age[23:16]
+//   hot  uint4 {x, y, attr, id}: what the cell-list build and the neighbour scan read; one 128-bit
+//              load/store per agent, two records per 32-byte sector
+//        x,y   i32  lattice position (agents.py:45-47)
+//        attr  u32  status[1:0] severity[3:2] stratum[6:4] new[7] | infected_time[15:8] | age[23:16]
+//        id    u32  position in the reference's population list (abs.py:15); keys all draws
 //   w    f64   wealth (agents.py:60)
-// Two copies (ping/pong): every step scatters the updated records straight into their
+//   disp u32   this step's displacement (ix, iy as int16 pair), written by pass A, read by pass B
+// Two copies of hot/w (ping/pong): every step scatters the updated records straight into their
 // cell-sorted slot of the other copy, so the neighbour scan reads contiguous cell ranges.
 //
 // One step (Simulation.execute, abs.py:232-273):
@@ -76,6 +79,12 @@ struct Ctl {
   unsigned step;
   unsigned n;         // agents resident on this device
   int crit_active;    // (Severe+Hospitalization)/N >= critical_limit at the end of the previous step
+  // The probability tests compare a table entry with u = (w + 0.5) * 2^-32 (w = 32 random bits); both
+  // sides are exact in binary64, so each test is an integer comparison of w with a precomputed bound:
+  //   p > u   <=>  w <  ceil(p * 2^32 - 0.5)          (abs.py:209,212,220)
+  //   u <= r  <=>  w <= floor(r * 2^32 - 0.5)         (abs.py:152)
+  long long thr_hosp[9], thr_sev[9], thr_death[9];
+  long long thr_rate;
   // ---- accumulators of the running step
   unsigned long long cnt[7];
   long long q[5];
@@ -117,10 +126,11 @@ enum : uint32_t { SEV_E = 0, SEV_A = 1, SEV_H = 2, SEV_G = 3 };
 struct StepParams {
   int gx0, gy0, eshift, ncx, ncy;
   float amp[4];
-  double length, height, rate, min_expense;
+  double length, height, min_expense;
   double bi[5];
-  double p_hosp[9], p_sev[9], p_death[9];
-  int T, recovering_time, scale_bits, crit_active;
+  long long thr_hosp[9], thr_sev[9], thr_death[9];
+  long long thr_rate;
+  int T, reach, recovering_time, scale_bits, crit_active;
   unsigned k0, k1, step, n;
 };
 
@@ -129,10 +139,19 @@ __device__ __forceinline__ void load_params(StepParams &P, const Ctl *ctl, bool 
   const Grid &g = use_built ? ctl->built : ctl->g;
   P.gx0 = g.gx0; P.gy0 = g.gy0; P.eshift = g.eshift; P.ncx = g.ncx; P.ncy = g.ncy;
   for (int i = 0; i < 4; ++i) P.amp[i] = ctl->amp[i];
-  P.length = ctl->length; P.height = ctl->height; P.rate = ctl->rate; P.min_expense = ctl->min_expense;
+  P.length = ctl->length; P.height = ctl->height; P.min_expense = ctl->min_expense;
   for (int i = 0; i < 5; ++i) P.bi[i] = ctl->bi[i];
-  for (int i = 0; i < 9; ++i) { P.p_hosp[i] = ctl->p_hosp[i]; P.p_sev[i] = ctl->p_sev[i]; P.p_death[i] = ctl->p_death[i]; }
-  P.T = ctl->T; P.recovering_time = ctl->recovering_time; P.scale_bits = ctl->scale_bits;
+  for (int i = 0; i < 9; ++i) {
+    P.thr_hosp[i] = ctl->thr_hosp[i]; P.thr_sev[i] = ctl->thr_sev[i]; P.thr_death[i] = ctl->thr_death[i];
+  }
+  P.thr_rate = ctl->thr_rate;
+  P.T = ctl->T;
+  // reach = floor(sqrt(T)): the largest |dx| a contact can have
+  int reach = P.T > 0 ? (int)__dsqrt_rn((double)P.T) : 0;
+  while ((long long)reach * reach > (long long)P.T) --reach;
+  while ((long long)(reach + 1) * (reach + 1) <= (long long)P.T) ++reach;
+  P.reach = reach;
+  P.recovering_time = ctl->recovering_time; P.scale_bits = ctl->scale_bits;
   P.crit_active = ctl->crit_active;
   P.k0 = ctl->k0; P.k1 = ctl->k1; P.step = ctl->step; P.n = ctl->n;
 }
@@ -183,24 +202,26 @@ __global__ void k_clear_cells(const Ctl *__restrict__ ctl, unsigned *__restrict_
   for (unsigned i = (m4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) cells[i] = 0;
 }
 
-// Pass A: histogram of the cells agents will occupy after this step's move.
-// kAdvance=false builds the cell list of the current positions (used before the first step).
+// Pass A: where will every agent be after this step's move?  Writes the displacement (for pass B)
+// and counts the agent in the histogram of its destination cell.
+// kAdvance=false builds the cell list of the current positions (upload / contact-pair hook).
 template <bool kAdvance>
-__global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id,
-                                                    const int *__restrict__ x, const int *__restrict__ y,
-                                                    const uint32_t *__restrict__ attr, unsigned *__restrict__ cells) {
+__global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot,
+                                                    uint32_t *__restrict__ disp, unsigned *__restrict__ cells) {
   __shared__ StepParams P;
   if (threadIdx.x == 0) load_params(P, ctl);
   __syncthreads();
   const unsigned stride = gridDim.x * blockDim.x;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-    int nx = x[i], ny = y[i];
+    const uint4 h = __ldg(&hot[i]);
+    int nx = (int)h.x, ny = (int)h.y;
     if (kAdvance) {
-      const uint32_t a = attr_normalize(attr[i]);
-      const uint4 w = philox4x32_10(id[i], P.step, kStreamAgent, 0u, P.k0, P.k1);
+      const uint32_t a = attr_normalize(h.z);
+      const uint4 w = philox4x32_10(h.w, P.step, kStreamAgent, 0u, P.k0, P.k1);
       int ix, iy;
       bool mobile;
       move_agent(P, nx, ny, a, w, nx, ny, ix, iy, mobile);
+      disp[i] = ((uint32_t)ix & 0xFFFFu) | ((uint32_t)iy << 16);
     }
     const unsigned key = cell_key(P, nx, ny, &ctl->err);
     atomicAdd(&cells[key + 1], 1u);
@@ -320,11 +341,10 @@ struct BlockStats {
 };
 
 template <bool kAdvance>
-__global__ void __launch_bounds__(256)
-k_update_scatter(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id, const int *__restrict__ x,
-                 const int *__restrict__ y, const uint32_t *__restrict__ attr, const double *__restrict__ wealth,
-                 unsigned *__restrict__ cells, uint32_t *__restrict__ oid, int *__restrict__ ox, int *__restrict__ oy,
-                 uint32_t *__restrict__ oattr, double *__restrict__ owealth) {
+__global__ void __launch_bounds__(256, 3)
+k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const double *__restrict__ wealth,
+                 const uint32_t *__restrict__ disp, unsigned *__restrict__ cells, uint4 *__restrict__ ohot,
+                 double *__restrict__ owealth) {
   __shared__ StepParams P;
   __shared__ BlockStats B;
   if (threadIdx.x == 0) {
@@ -335,24 +355,32 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id, const i
     B.bb[1] = B.bb[3] = INT_MIN;
   }
   __syncthreads();
-  unsigned c_st[4] = {0, 0, 0, 0}, c_sev[3] = {0, 0, 0};
+  // per-thread partial statistics: 16-bit fields (a thread sees far fewer than 65535 agents per launch
+  // for any population the 2^31 capacity allows: n / (gridDim * 256) < 2^31 / (148*8*256))
+  unsigned long long c_st = 0, c_sev = 0;  // status S,I,R,D and severity A,H,G counts
   long long q[5] = {0, 0, 0, 0, 0};
   int bxmin = INT_MAX, bxmax = INT_MIN, bymin = INT_MAX, bymax = INT_MIN;
   const double qscale = (double)(1ull << P.scale_bits);
 
   const unsigned stride = gridDim.x * blockDim.x;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-    const uint32_t aid = id[i];
-    int nx = x[i], ny = y[i];
-    uint32_t a = attr_normalize(attr[i]);
-    double w = wealth[i];
+    const uint4 h = __ldg(&hot[i]);
+    double w = __ldg(&wealth[i]);
+    int nx = (int)h.x, ny = (int)h.y;
+    uint32_t a = attr_normalize(h.z);
+    const uint32_t aid = h.w;
     if (kAdvance) {
+      const uint32_t d = __ldg(&disp[i]);
+      const int ix = (int)(short)(d & 0xFFFFu), iy = (int)(short)(d >> 16);
       uint32_t st = attr_status(a), sev = attr_severity(a), time = attr_time(a);
       const uint32_t stratum = attr_stratum(a), age = attr_age(a);
+      const bool mobile = !(st == ST_D || (st == ST_I && (sev == SEV_H || sev == SEV_G)));  // abs.py:164-167
       const uint4 r0 = philox4x32_10(aid, P.step, kStreamAgent, 0u, P.k0, P.k1);
-      int ix, iy;
-      bool mobile;
-      move_agent(P, nx, ny, a, r0, nx, ny, ix, iy, mobile);
+      {  // abs.py:177-185 with the displacement pass A drew (immobile agents have ix = iy = 0)
+        const int tx = nx + ix, ty = ny + iy;
+        nx = (tx <= 0 || (double)tx >= P.length) ? nx - ix : tx;
+        ny = (ty <= 0 || (double)ty >= P.height) ? ny - iy : ty;
+      }
       const double bi = P.bi[min(stratum, 4u)];
       if (mobile) {
         // abs.py:187-189: wealth += sqrt(ix^2+iy^2) * rand * minimum_expense * basic_income[stratum]
@@ -366,20 +394,20 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id, const i
         if (st == ST_I) {
           time += 1;
           const uint32_t idx = min(age > 10u ? age / 10u - 1u : 0u, 8u);  // abs.py:204
-          const double u_sub = u01(r0.w);
+          const long long w_sub = (long long)r0.w;
           if (sev == SEV_A) {
-            if (P.p_hosp[idx] > u_sub) sev = SEV_H;
+            if (w_sub < P.thr_hosp[idx]) sev = SEV_H;  // age_hospitalization_probs[idx] > u (abs.py:209)
           } else if (sev == SEV_H) {
-            if (P.p_sev[idx] > u_sub) {
+            if (w_sub < P.thr_sev[idx]) {              // age_severe_probs[idx] > u (abs.py:212)
               sev = SEV_G;
-              if (P.crit_active) {  // abs.py:214-217
+              if (P.crit_active) {                     // abs.py:214-217
                 st = ST_D;
                 sev = SEV_A;
               }
             }
           }
           const uint4 r1 = philox4x32_10(aid, P.step, kStreamAgent2, 0u, P.k0, P.k1);
-          if (P.p_death[idx] > u01(r1.x)) {  // abs.py:219-223
+          if ((long long)r1.x < P.thr_death[idx]) {    // age_death_probs[idx] > u (abs.py:219-223)
             st = ST_D;
             sev = SEV_A;
             pays = false;
@@ -396,9 +424,9 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id, const i
     // partial statistics (abs.py:300-312); infections of this step are added by k_contagion
     {
       const uint32_t st = attr_status(a), sev = attr_severity(a);
-      c_st[0] += (st == ST_S); c_st[1] += (st == ST_I); c_st[2] += (st == ST_R); c_st[3] += (st == ST_D);
+      c_st += 1ull << (16 * st);
       if (st != ST_D) {
-        c_sev[0] += (sev == SEV_A); c_sev[1] += (sev == SEV_H); c_sev[2] += (sev == SEV_G);
+        c_sev += (sev != SEV_E) ? (1ull << (16 * (sev - 1))) : 0ull;
         if (attr_age(a) >= 18u) {
           const long long f = __double2ll_rn(__dmul_rn(w, qscale));
           const uint32_t s = attr_stratum(a);
@@ -410,31 +438,32 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id, const i
     }
     const unsigned key = cell_key(P, nx, ny, &ctl->err);
     const unsigned slot = atomicAdd(&cells[key + 1], 1u);
-    oid[slot] = aid;
-    ox[slot] = nx;
-    oy[slot] = ny;
-    oattr[slot] = a;
+    ohot[slot] = make_uint4((uint32_t)nx, (uint32_t)ny, a, aid);
     owealth[slot] = w;
   }
-  // block reduction: warp shuffles, then shared atomics, then one set of global atomics per block
+  // block reduction: per-warp shared atomics, then one set of global atomics per block
+  {
+    unsigned long long cnt[7];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+    for (int k = 0; k < 4; ++k) cnt[k] = (c_st >> (16 * k)) & 0xFFFFull;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) c_st[k] += __shfl_xor_sync(0xffffffffu, c_st[k], o);
+    for (int k = 0; k < 3; ++k) cnt[4 + k] = (c_sev >> (16 * k)) & 0xFFFFull;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) c_sev[k] += __shfl_xor_sync(0xffffffffu, c_sev[k], o);
+    for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
-    bxmin = min(bxmin, __shfl_xor_sync(0xffffffffu, bxmin, o));
-    bxmax = max(bxmax, __shfl_xor_sync(0xffffffffu, bxmax, o));
-    bymin = min(bymin, __shfl_xor_sync(0xffffffffu, bymin, o));
-    bymax = max(bymax, __shfl_xor_sync(0xffffffffu, bymax, o));
-  }
-  if ((threadIdx.x & 31) == 0) {
-    for (int k = 0; k < 4; ++k) atomicAdd(&B.cnt[k], (unsigned long long)c_st[k]);
-    for (int k = 0; k < 3; ++k) atomicAdd(&B.cnt[4 + k], (unsigned long long)c_sev[k]);
-    for (int k = 0; k < 5; ++k) atomicAdd((unsigned long long *)&B.q[k], (unsigned long long)q[k]);
-    atomicMin(&B.bb[0], bxmin); atomicMax(&B.bb[1], bxmax); atomicMin(&B.bb[2], bymin); atomicMax(&B.bb[3], bymax);
+      for (int k = 0; k < 7; ++k) cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], o);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+      bxmin = min(bxmin, __shfl_xor_sync(0xffffffffu, bxmin, o));
+      bxmax = max(bxmax, __shfl_xor_sync(0xffffffffu, bxmax, o));
+      bymin = min(bymin, __shfl_xor_sync(0xffffffffu, bymin, o));
+      bymax = max(bymax, __shfl_xor_sync(0xffffffffu, bymax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      for (int k = 0; k < 7; ++k) atomicAdd(&B.cnt[k], cnt[k]);
+      for (int k = 0; k < 5; ++k) atomicAdd((unsigned long long *)&B.q[k], (unsigned long long)q[k]);
+      atomicMin(&B.bb[0], bxmin); atomicMax(&B.bb[1], bxmax); atomicMin(&B.bb[2], bymin); atomicMax(&B.bb[3], bymax);
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -446,12 +475,21 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id, const i
 }
 
 // ------------------------------------------------------------------------------------------
-// Pass C: the contact loop of abs.py:249-265 as a neighbour scan over the sorted population.
-// A Susceptible agent looks at the three cell rows around it; each row's three cells are one
-// contiguous range of the sorted arrays.  contact(): abs.py:141-154 with one draw per pair.
+// Cells a contact of the agent at (x, y) can be in: columns [clo, chi] of rows [rlo, rhi].  Only the
+// cells that intersect [x - reach, x + reach] x [y - reach, y + reach] (reach = floor(sqrt(T)) <= cell
+// edge); each row's columns are one contiguous slot range [cell_start[row*ncx+clo], cell_start[row*ncx+chi+1]).
+__device__ __forceinline__ void contact_cells(const StepParams &P, int x, int y, int &clo, int &chi, int &rlo,
+                                              int &rhi) {
+  clo = min(max(((x - P.reach - P.gx0) >> P.eshift) + 1, 0), P.ncx - 1);
+  chi = min(max(((x + P.reach - P.gx0) >> P.eshift) + 1, 0), P.ncx - 1);
+  rlo = min(max(((y - P.reach - P.gy0) >> P.eshift) + 1, 0), P.ncy - 1);
+  rhi = min(max(((y + P.reach - P.gy0) >> P.eshift) + 1, 0), P.ncy - 1);
+}
+
+// Pass C: the contact loop of abs.py:249-265 as a neighbour scan over the sorted population;
+// contact() = abs.py:141-154 with one draw per pair.
 __global__ void __launch_bounds__(256)
-k_contagion(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id, const int *__restrict__ x,
-            const int *__restrict__ y, uint32_t *__restrict__ attr, const unsigned *__restrict__ cell_start) {
+k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start) {
   __shared__ StepParams P;
   __shared__ unsigned s_new;
   if (threadIdx.x == 0) {
@@ -463,31 +501,30 @@ k_contagion(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id, const int *_
   const unsigned stride = gridDim.x * blockDim.x;
   if (P.T >= 0) {
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-      const uint32_t a = attr[i];
-      if (attr_status(a) != ST_S) continue;
-      const int xi = x[i], yi = y[i];
-      const uint32_t idi = id[i];
-      int cx, cy;
-      cell_coords(P, xi, yi, cx, cy, &ctl->err);
+      const uint4 h = hot[i];
+      if (attr_status(h.z) != ST_S || (h.z & kNewlyInfected)) continue;
+      const int xi = (int)h.x, yi = (int)h.y;
+      int clo, chi, rlo, rhi;
+      contact_cells(P, xi, yi, clo, chi, rlo, rhi);
       bool infected = false;
-      for (int dy = -1; dy <= 1 && !infected; ++dy) {
-        const unsigned c = (unsigned)(cy + dy) * (unsigned)P.ncx + (unsigned)cx;
-        const unsigned jb = cell_start[c - 1], je = cell_start[c + 2];
+      for (int row = rlo; row <= rhi && !infected; ++row) {
+        const unsigned base = (unsigned)row * (unsigned)P.ncx;
+        const unsigned jb = cell_start[base + clo], je = cell_start[base + chi + 1];
         for (unsigned j = jb; j < je; ++j) {
-          const uint32_t aj = attr[j];
-          if (attr_status(aj) != ST_I) continue;
-          const long long dx = x[j] - xi, dyy = y[j] - yi;
-          if (dx * dx + dyy * dyy > (long long)P.T) continue;
-          const uint32_t idj = id[j];
-          const uint4 r = philox4x32_10(min(idi, idj), P.step, kStreamContact, max(idi, idj), P.k0, P.k1);
-          if (u01(r.x) <= P.rate) {  // abs.py:150-153
+          const uint4 c = hot[j];
+          if (attr_status(c.z) != ST_I) continue;  // newly infected still read Susceptible here
+          const long long dx = (int)c.x - xi, dy = (int)c.y - yi;
+          if (dx * dx + dy * dy > (long long)P.T) continue;
+          const uint4 r = philox4x32_10(min(h.w, c.w), P.step, kStreamContact, max(h.w, c.w), P.k0, P.k1);
+          if ((long long)r.x <= P.thr_rate) {  // contagion_test <= contagion_rate (abs.py:150-153)
             infected = true;
             break;
           }
         }
       }
       if (infected) {
-        attr[i] = a | kNewlyInfected;  // status bits stay Susceptible during this pass (see attr_normalize)
+        // status bits stay Susceptible during this pass (see attr_normalize)
+        reinterpret_cast<uint32_t *>(&hot[i])[2] = h.z | kNewlyInfected;
         ++newinf;
       }
     }
@@ -502,31 +539,30 @@ k_contagion(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id, const int *_
 // ------------------------------------------------------------------------------------------
 // Test hook for the pair loop of abs.py:253-259: every (i, j), i < j, within contagion_distance.
 __global__ void __launch_bounds__(256)
-k_contact_pairs(Ctl *__restrict__ ctl, const uint32_t *__restrict__ id, const int *__restrict__ x,
-                const int *__restrict__ y, const unsigned *__restrict__ cell_start, long long *__restrict__ out,
-                unsigned long long capacity, unsigned long long *__restrict__ count) {
+k_contact_pairs(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
+                long long *__restrict__ out, unsigned long long capacity, unsigned long long *__restrict__ count) {
   __shared__ StepParams P;
   if (threadIdx.x == 0) load_params(P, ctl, true);
   __syncthreads();
   if (P.T < 0) return;
   const unsigned stride = gridDim.x * blockDim.x;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-    const int xi = x[i], yi = y[i];
-    const uint32_t idi = id[i];
-    int cx, cy;
-    cell_coords(P, xi, yi, cx, cy, &ctl->err);
-    for (int dy = -1; dy <= 1; ++dy) {
-      const unsigned c = (unsigned)(cy + dy) * (unsigned)P.ncx + (unsigned)cx;
-      const unsigned jb = cell_start[c - 1], je = cell_start[c + 2];
+    const uint4 h = hot[i];
+    const int xi = (int)h.x, yi = (int)h.y;
+    int clo, chi, rlo, rhi;
+    contact_cells(P, xi, yi, clo, chi, rlo, rhi);
+    for (int row = rlo; row <= rhi; ++row) {
+      const unsigned base = (unsigned)row * (unsigned)P.ncx;
+      const unsigned jb = cell_start[base + clo], je = cell_start[base + chi + 1];
       for (unsigned j = jb; j < je; ++j) {
-        const uint32_t idj = id[j];
-        if (idj <= idi) continue;
-        const long long dx = x[j] - xi, dyy = y[j] - yi;
-        if (dx * dx + dyy * dyy > (long long)P.T) continue;
+        const uint4 c = hot[j];
+        if (c.w <= h.w) continue;
+        const long long dx = (int)c.x - xi, dy = (int)c.y - yi;
+        if (dx * dx + dy * dy > (long long)P.T) continue;
         const unsigned long long slot = atomicAdd(count, 1ull);
         if (slot < capacity) {
-          out[2 * slot] = (long long)idi;
-          out[2 * slot + 1] = (long long)idj;
+          out[2 * slot] = (long long)h.w;
+          out[2 * slot + 1] = (long long)c.w;
         }
       }
     }
@@ -582,6 +618,15 @@ __device__ inline double stat_value(const Ctl *ctl, const StatRecord &r, int met
   return (double)r.q[metric - 7] / (double)(1ull << ctl->scale_bits);
 }
 
+__device__ inline long long prob_bound_lt(double p) {   // p > u  <=>  w < bound
+  const double t = ceil(p * 4294967296.0 - 0.5);
+  return t <= 0.0 ? 0ll : t >= 4294967296.0 ? 4294967296ll : (long long)t;
+}
+__device__ inline long long prob_bound_le(double r) {   // u <= r  <=>  w <= bound
+  const double t = floor(r * 4294967296.0 - 0.5);
+  return !(t >= 0.0) ? -1ll : t >= 4294967295.0 ? 4294967295ll : (long long)t;
+}
+
 __device__ inline int threshold_T(double r) {
   // largest integer n with sqrt(n) <= r in binary64; -1 if r < 0 or NaN
   if (!(r >= 0.0)) return -1;
@@ -619,6 +664,7 @@ __global__ void k_finalize(Ctl *ctl, StatRecord *history, int record_stats) {
         for (int k = 0; k < 4; ++k) ctl->amp[k] = (float)tr.value[k];
       } else if (tr.attribute == 1) {
         ctl->rate = tr.value[0];
+        ctl->thr_rate = prob_bound_le(tr.value[0]);
       } else if (tr.attribute == 2) {
         ctl->contagion_distance = tr.value[0];
         ctl->T = threshold_T(tr.value[0]);
@@ -641,12 +687,13 @@ __global__ void k_finalize(Ctl *ctl, StatRecord *history, int record_stats) {
 }
 
 // Bounding box of the resident positions into ctl->bb_* (used once per upload).
-__global__ void __launch_bounds__(256) k_bbox(Ctl *__restrict__ ctl, const int *__restrict__ x,
-                                              const int *__restrict__ y) {
+__global__ void __launch_bounds__(256) k_bbox(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot) {
   int bxmin = INT_MAX, bxmax = INT_MIN, bymin = INT_MAX, bymax = INT_MIN;
   const unsigned n = ctl->n, stride = gridDim.x * blockDim.x;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    bxmin = min(bxmin, x[i]); bxmax = max(bxmax, x[i]); bymin = min(bymin, y[i]); bymax = max(bymax, y[i]);
+    const uint4 h = hot[i];
+    bxmin = min(bxmin, (int)h.x); bxmax = max(bxmax, (int)h.x);
+    bymin = min(bymin, (int)h.y); bymax = max(bymax, (int)h.y);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -690,7 +737,13 @@ __global__ void k_set_params(Ctl *ctl, ParamBlock p) {
   ctl->length = p.length; ctl->height = p.height; ctl->contagion_distance = p.contagion_distance;
   ctl->rate = p.rate; ctl->critical_limit = p.critical_limit; ctl->min_expense = p.min_expense;
   for (int k = 0; k < 5; ++k) ctl->bi[k] = p.bi[k];
-  for (int k = 0; k < 9; ++k) { ctl->p_hosp[k] = p.p_hosp[k]; ctl->p_sev[k] = p.p_sev[k]; ctl->p_death[k] = p.p_death[k]; }
+  for (int k = 0; k < 9; ++k) {
+    ctl->p_hosp[k] = p.p_hosp[k]; ctl->p_sev[k] = p.p_sev[k]; ctl->p_death[k] = p.p_death[k];
+    ctl->thr_hosp[k] = prob_bound_lt(p.p_hosp[k]);
+    ctl->thr_sev[k] = prob_bound_lt(p.p_sev[k]);
+    ctl->thr_death[k] = prob_bound_lt(p.p_death[k]);
+  }
+  ctl->thr_rate = prob_bound_le(p.rate);
   ctl->pop_size = p.pop_size;
   ctl->recovering_time = p.recovering_time; ctl->scale_bits = p.scale_bits; ctl->schedule = p.schedule;
   ctl->T = threshold_T(p.contagion_distance);
@@ -719,38 +772,38 @@ __global__ void k_init_ctl(Ctl *ctl, unsigned k0, unsigned k1, unsigned max_cell
 }
 
 // ------------------------------------------------------------------------------------------
-// Host SoA (separate byte columns, agents.py:44-64) <-> packed device columns.
-__global__ void k_pack(unsigned n, const uint8_t *__restrict__ status, const uint8_t *__restrict__ severity,
+// Host SoA (separate columns, agents.py:44-64) <-> device records.
+__global__ void k_pack(unsigned n, const int *__restrict__ x, const int *__restrict__ y,
+                       const uint8_t *__restrict__ status, const uint8_t *__restrict__ severity,
                        const uint8_t *__restrict__ time, const uint8_t *__restrict__ age,
                        const uint8_t *__restrict__ stratum, const uint32_t *__restrict__ id_in,
-                       uint32_t *__restrict__ attr, uint32_t *__restrict__ id) {
+                       uint4 *__restrict__ hot) {
   const unsigned stride = gridDim.x * blockDim.x;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    attr[i] = attr_pack(status[i], severity[i], stratum[i], time[i], age[i]);
-    id[i] = id_in ? id_in[i] : i;
+    hot[i] = make_uint4((uint32_t)x[i], (uint32_t)y[i], attr_pack(status[i], severity[i], stratum[i], time[i], age[i]),
+                        id_in ? id_in[i] : i);
   }
 }
 
 // Scatter back to id order (ids must be a permutation of 0..n-1 unless by_slot).
-__global__ void k_unpack(unsigned n, int by_slot, const uint32_t *__restrict__ id, const int *__restrict__ x,
-                         const int *__restrict__ y, const uint32_t *__restrict__ attr,
-                         const double *__restrict__ wealth, int *__restrict__ ox, int *__restrict__ oy,
-                         uint8_t *__restrict__ status, uint8_t *__restrict__ severity, uint8_t *__restrict__ time,
-                         uint8_t *__restrict__ age, uint8_t *__restrict__ stratum, double *__restrict__ owealth,
-                         uint32_t *__restrict__ oid) {
+__global__ void k_unpack(unsigned n, int by_slot, const uint4 *__restrict__ hot, const double *__restrict__ wealth,
+                         int *__restrict__ ox, int *__restrict__ oy, uint8_t *__restrict__ status,
+                         uint8_t *__restrict__ severity, uint8_t *__restrict__ time, uint8_t *__restrict__ age,
+                         uint8_t *__restrict__ stratum, double *__restrict__ owealth, uint32_t *__restrict__ oid) {
   const unsigned stride = gridDim.x * blockDim.x;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint32_t a = attr_normalize(attr[i]);
-    const unsigned d = by_slot ? i : id[i];
-    ox[d] = x[i];
-    oy[d] = y[i];
+    const uint4 h = hot[i];
+    const uint32_t a = attr_normalize(h.z);
+    const unsigned d = by_slot ? i : h.w;
+    ox[d] = (int)h.x;
+    oy[d] = (int)h.y;
     status[d] = (uint8_t)attr_status(a);
     severity[d] = (uint8_t)attr_severity(a);
     time[d] = (uint8_t)attr_time(a);
     age[d] = (uint8_t)attr_age(a);
     stratum[d] = (uint8_t)attr_stratum(a);
     owealth[d] = wealth[i];
-    oid[d] = id[i];
+    oid[d] = h.w;
   }
 }
 
