@@ -27,6 +27,7 @@ struct cabs_sim {
   uint4 *hot[2] = {nullptr, nullptr};
   double *w[2] = {nullptr, nullptr};
   uint32_t *disp = nullptr;
+  double *sqrt_tab = nullptr;   // exact sqrt of small integers (income of abs.py:187)
   int cur = 0;
   unsigned *cells = nullptr;    // histogram / cell_start, max_cells + 8 entries
   unsigned *partial = nullptr;  // scan partials
@@ -100,6 +101,7 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
     cudaFree(sim->hot[b]); cudaFree(sim->w[b]);
   }
   cudaFree(sim->disp);
+  cudaFree(sim->sqrt_tab);
   cudaFree(sim->cells); cudaFree(sim->partial); cudaFree(sim->ctl); cudaFree(sim->history);
   cudaFree(sim->stage); cudaFree(sim->stage_id); cudaFree(sim->pairs); cudaFree(sim->pair_count);
   for (cudaEvent_t e : sim->events) if (e) cudaEventDestroy(e);
@@ -137,6 +139,7 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
     CK(cudaMalloc(&sim->w[b], cap * sizeof(double)));
   }
   CK(cudaMalloc(&sim->disp, cap * sizeof(uint32_t)));
+  CK(cudaMalloc(&sim->sqrt_tab, kSqrtTable * sizeof(double)));
   CK(cudaMalloc(&sim->cells, ((size_t)sim->max_cells + 8) * sizeof(unsigned)));
   CK(cudaMalloc(&sim->partial, 1024 * sizeof(unsigned)));
   CK(cudaMalloc(&sim->ctl, sizeof(Ctl)));
@@ -146,8 +149,8 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   CK(cudaMalloc(&sim->pair_count, sizeof(unsigned long long)));
   CK(cudaMemsetAsync(sim->ctl, 0, sizeof(Ctl), sim->stream));
   CK(cudaMemsetAsync(sim->history, 0, (size_t)sim->hist_cap * sizeof(StatRecord), sim->stream));
-  LAUNCH(k_init_ctl, 1, 32, sim->ctl, (unsigned)(cfg->seed & 0xFFFFFFFFu), (unsigned)(cfg->seed >> 32), sim->max_cells,
-         sim->hist_cap);
+  LAUNCH(k_init_ctl, 1, 256, sim->ctl, (unsigned)(cfg->seed & 0xFFFFFFFFu), (unsigned)(cfg->seed >> 32),
+         sim->max_cells, sim->hist_cap, sim->sqrt_tab);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(sim->stream));
   return CABS_OK;
@@ -239,7 +242,7 @@ static int rebuild_static(cabs_sim *sim) {
   LAUNCH(k_scan_partials, 1, 1024, sim->partial);
   LAUNCH(k_scan_apply, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
   LAUNCH(k_update_scatter<false>, nb, 256, sim->ctl, sim->hot[c], sim->w[c], sim->disp, sim->cells, sim->hot[o],
-         sim->w[o]);
+         sim->w[o], sim->sqrt_tab);
   LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 0);
   CK(cudaGetLastError());
   sim->cur = o;
@@ -322,7 +325,7 @@ extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
     LAUNCH(k_scan_partials, 1, 1024, sim->partial);
     LAUNCH(k_scan_apply, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
     LAUNCH(k_update_scatter<true>, nb, 256, sim->ctl, sim->hot[c], sim->w[c], sim->disp, sim->cells, sim->hot[o],
-           sim->w[o]);
+           sim->w[o], sim->sqrt_tab);
     LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells);
     LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 1);
     sim->cur = o;

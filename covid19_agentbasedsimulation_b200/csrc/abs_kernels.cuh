@@ -131,6 +131,7 @@ struct StepParams {
   long long thr_hosp[9], thr_sev[9], thr_death[9];
   long long thr_rate;
   int T, reach, recovering_time, scale_bits, crit_active;
+  int len_i, hei_i;  // x >= length  <=>  x >= ceil(length) for integer x (abs.py:177,182)
   unsigned k0, k1, step, n;
 };
 
@@ -140,6 +141,8 @@ __device__ __forceinline__ void load_params(StepParams &P, const Ctl *ctl, bool 
   P.gx0 = g.gx0; P.gy0 = g.gy0; P.eshift = g.eshift; P.ncx = g.ncx; P.ncy = g.ncy;
   for (int i = 0; i < 4; ++i) P.amp[i] = ctl->amp[i];
   P.length = ctl->length; P.height = ctl->height; P.min_expense = ctl->min_expense;
+  P.len_i = (int)fmin(fmax(ceil(ctl->length), -2147483647.0), 2147483647.0);
+  P.hei_i = (int)fmin(fmax(ceil(ctl->height), -2147483647.0), 2147483647.0);
   for (int i = 0; i < 5; ++i) P.bi[i] = ctl->bi[i];
   for (int i = 0; i < 9; ++i) {
     P.thr_hosp[i] = ctl->thr_hosp[i]; P.thr_sev[i] = ctl->thr_sev[i]; P.thr_death[i] = ctl->thr_death[i];
@@ -171,8 +174,8 @@ __device__ __forceinline__ void move_agent(const StepParams &P, int x, int y, ui
     iy = __float2int_rz(__fmul_rn(z1, a));
   }
   const int tx = x + ix, ty = y + iy;
-  nx = (tx <= 0 || (double)tx >= P.length) ? x - ix : tx;  // abs.py:177-180: the increment is reflected
-  ny = (ty <= 0 || (double)ty >= P.height) ? y - iy : ty;  // abs.py:182-185
+  nx = (tx <= 0 || tx >= P.len_i) ? x - ix : tx;  // abs.py:177-180: the increment is reflected
+  ny = (ty <= 0 || ty >= P.hei_i) ? y - iy : ty;  // abs.py:182-185
 }
 
 // Cell of a lattice point.  Interior cells are 1..ncx-2 / 1..ncy-2; row/column 0 and the last one
@@ -340,13 +343,24 @@ struct BlockStats {
   int bb[4];
 };
 
+#ifndef CABS_B_MINBLOCKS
+#define CABS_B_MINBLOCKS 3
+#endif
+#ifndef CABS_B_PREFETCH
+#define CABS_B_PREFETCH 1
+#endif
+constexpr int kSqrtTable = 4096;  // sqrt(d2) for d2 < 4096, exact (IEEE sqrt), filled once by k_init_ctl
+
 template <bool kAdvance>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, CABS_B_MINBLOCKS)
 k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const double *__restrict__ wealth,
                  const uint32_t *__restrict__ disp, unsigned *__restrict__ cells, uint4 *__restrict__ ohot,
-                 double *__restrict__ owealth) {
+                 double *__restrict__ owealth, const double *__restrict__ sqrt_tab) {
   __shared__ StepParams P;
   __shared__ BlockStats B;
+  __shared__ long long s_q[5][256];  // per-thread Q1..Q5 partial sums (abs.py:309-312), no bank conflicts
+#pragma unroll
+  for (int k = 0; k < 5; ++k) s_q[k][threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     load_params(P, ctl);
     for (int i = 0; i < 7; ++i) B.cnt[i] = 0;
@@ -358,33 +372,60 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
   // per-thread partial statistics: 16-bit fields (a thread sees far fewer than 65535 agents per launch
   // for any population the 2^31 capacity allows: n / (gridDim * 256) < 2^31 / (148*8*256))
   unsigned long long c_st = 0, c_sev = 0;  // status S,I,R,D and severity A,H,G counts
-  long long q[5] = {0, 0, 0, 0, 0};
   int bxmin = INT_MAX, bxmax = INT_MIN, bymin = INT_MAX, bymax = INT_MIN;
   const double qscale = (double)(1ull << P.scale_bits);
 
   const unsigned stride = gridDim.x * blockDim.x;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  // software pipeline: the next agent's columns are requested before this agent's arithmetic starts
+  uint4 h_next = make_uint4(0, 0, 0, 0);
+  double w_next = 0.0;
+  uint32_t d_next = 0;
+#if CABS_B_PREFETCH
+  if (i < P.n) {
+    h_next = __ldg(&hot[i]);
+    w_next = __ldg(&wealth[i]);
+    if (kAdvance) d_next = __ldg(&disp[i]);
+  }
+#endif
+  for (; i < P.n; i += stride) {
+#if CABS_B_PREFETCH
+    const uint4 h = h_next;
+    double w = w_next;
+    const uint32_t d = d_next;
+    if (i + stride < P.n) {
+      h_next = __ldg(&hot[i + stride]);
+      w_next = __ldg(&wealth[i + stride]);
+      if (kAdvance) d_next = __ldg(&disp[i + stride]);
+    }
+#else
     const uint4 h = __ldg(&hot[i]);
     double w = __ldg(&wealth[i]);
+    const uint32_t d = kAdvance ? __ldg(&disp[i]) : 0u;
+#endif
     int nx = (int)h.x, ny = (int)h.y;
     uint32_t a = attr_normalize(h.z);
     const uint32_t aid = h.w;
+    const int ix = (int)(short)(d & 0xFFFFu), iy = (int)(short)(d >> 16);
+    if (kAdvance) {  // abs.py:177-185 with the displacement pass A drew (immobile agents have ix = iy = 0)
+      const int tx = nx + ix, ty = ny + iy;
+      nx = (tx <= 0 || tx >= P.len_i) ? nx - ix : tx;
+      ny = (ty <= 0 || ty >= P.hei_i) ? ny - iy : ty;
+    }
+    // the destination slot only needs the new position: claim it now so that the round trip to the
+    // L2-resident cell table overlaps the arithmetic below
+    const unsigned key = cell_key(P, nx, ny, &ctl->err);
+    const unsigned slot = atomicAdd(&cells[key + 1], 1u);
     if (kAdvance) {
-      const uint32_t d = __ldg(&disp[i]);
-      const int ix = (int)(short)(d & 0xFFFFu), iy = (int)(short)(d >> 16);
       uint32_t st = attr_status(a), sev = attr_severity(a), time = attr_time(a);
       const uint32_t stratum = attr_stratum(a), age = attr_age(a);
       const bool mobile = !(st == ST_D || (st == ST_I && (sev == SEV_H || sev == SEV_G)));  // abs.py:164-167
       const uint4 r0 = philox4x32_10(aid, P.step, kStreamAgent, 0u, P.k0, P.k1);
-      {  // abs.py:177-185 with the displacement pass A drew (immobile agents have ix = iy = 0)
-        const int tx = nx + ix, ty = ny + iy;
-        nx = (tx <= 0 || (double)tx >= P.length) ? nx - ix : tx;
-        ny = (ty <= 0 || (double)ty >= P.height) ? ny - iy : ty;
-      }
       const double bi = P.bi[min(stratum, 4u)];
       if (mobile) {
         // abs.py:187-189: wealth += sqrt(ix^2+iy^2) * rand * minimum_expense * basic_income[stratum]
-        const double dist = __dsqrt_rn((double)(ix * ix + iy * iy));
+        const int d2 = ix * ix + iy * iy;
+        const double dist = d2 < kSqrtTable ? __ldg(&sqrt_tab[d2]) : __dsqrt_rn((double)d2);
         const double inc = __dmul_rn(__dmul_rn(__dmul_rn(dist, u01(r0.z)), P.min_expense), bi);
         w = __dadd_rn(w, inc);
       }
@@ -428,22 +469,20 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
       if (st != ST_D) {
         c_sev += (sev != SEV_E) ? (1ull << (16 * (sev - 1))) : 0ull;
         if (attr_age(a) >= 18u) {
-          const long long f = __double2ll_rn(__dmul_rn(w, qscale));
-          const uint32_t s = attr_stratum(a);
-#pragma unroll
-          for (int k = 0; k < 5; ++k) q[k] += (s == (uint32_t)k) ? f : 0ll;
+          s_q[min(attr_stratum(a), 4u)][threadIdx.x] += __double2ll_rn(__dmul_rn(w, qscale));
         }
       }
       bxmin = min(bxmin, nx); bxmax = max(bxmax, nx); bymin = min(bymin, ny); bymax = max(bymax, ny);
     }
-    const unsigned key = cell_key(P, nx, ny, &ctl->err);
-    const unsigned slot = atomicAdd(&cells[key + 1], 1u);
     ohot[slot] = make_uint4((uint32_t)nx, (uint32_t)ny, a, aid);
     owealth[slot] = w;
   }
   // block reduction: per-warp shared atomics, then one set of global atomics per block
   {
     unsigned long long cnt[7];
+    long long q[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) q[k] = s_q[k][threadIdx.x];
 #pragma unroll
     for (int k = 0; k < 4; ++k) cnt[k] = (c_st >> (16 * k)) & 0xFFFFull;
 #pragma unroll
@@ -762,7 +801,9 @@ __global__ void k_set_triggers(Ctl *ctl, TriggerBlock t) {
   for (int k = 0; k < kMaxTriggers; ++k) ctl->trig[k] = t.trig[k];
 }
 
-__global__ void k_init_ctl(Ctl *ctl, unsigned k0, unsigned k1, unsigned max_cells, unsigned hist_cap) {
+__global__ void k_init_ctl(Ctl *ctl, unsigned k0, unsigned k1, unsigned max_cells, unsigned hist_cap,
+                           double *sqrt_tab) {
+  for (int d2 = threadIdx.x; d2 < kSqrtTable; d2 += blockDim.x) sqrt_tab[d2] = __dsqrt_rn((double)d2);
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ctl->k0 = k0; ctl->k1 = k1; ctl->max_cells = max_cells; ctl->hist_cap = hist_cap;
   ctl->step = 0; ctl->n = 0; ctl->err = 0; ctl->ntrig = 0; ctl->pop_size = 1; ctl->T = -1;
