@@ -28,12 +28,9 @@ B_ALG = 147.0  # algorithmic bytes per agent-update of the whole step (SURVEY.md
 # algorithmic bytes per agent of each kernel of THIS implementation (DESIGN.md "Kernels"): columns the kernel
 # must read/write once, c = cells per agent (1.25 at config 3)
 KERNEL_BYTES = {
-    "k_update_scatter<true>": lambda c: 24 + 24 + 8,      # R id,x,y,attr,wealth; W the same; cell_start RMW
-    "k_move_count<true>": lambda c: 16 + 8,               # R id,x,y,attr; histogram RMW
-    "k_contagion": lambda c: 12 + 4 * c + 1,              # R x,y,attr; R cell_start; W attr of the newly infected
-    "k_scan_reduce": lambda c: 4 * c,
-    "k_scan_apply": lambda c: 8 * c,
-    "k_clear_cells": lambda c: 4 * c,
+    "k_move_count<true>": lambda c: 16 + 8 + 8,               # R id,x,y,attr; W displacement,rank; histogram RMW
+    "k_scan_cells": lambda c: 8 * c,                          # R + W the cell table
+    "k_update_scatter<true>": lambda c: 32 + 4 + 24 + 4 * c,  # R record,wealth,aux; R cell_start; W record,wealth; zero old table
 }
 
 
@@ -185,7 +182,7 @@ def run_ours(args, rank, world, local_rank):
     low = {Status.Susceptible: 1.5, Status.Recovered_Immune: 1.5, Status.Infected: 1.5}
     high = {Status.Susceptible: 5, Status.Recovered_Immune: 5, Status.Infected: 5}
     triggers = [Trigger('Infected', '>=', .2, 'amplitudes', low), Trigger('Infected', '<=', .05, 'amplitudes', high)]
-    sim = Simulation(seed=rank, device=local_rank, triggers_simulation=triggers,
+    sim = Simulation(seed=rank, device=local_rank, triggers_simulation=triggers, max_cells=args.max_cells,
                      history_capacity=max(4096, args.steps + args.warmup + 64), **kw)
     # population in pinned host memory (also the source of the end-to-end leg)
     x, y, age, stratum = build_population(n, side, seed=rank)
@@ -327,6 +324,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
     ap.add_argument("--ref-sample", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-cells", type=int, default=0, help="cap on cell-list cells (0 = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

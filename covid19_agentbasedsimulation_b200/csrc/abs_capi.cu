@@ -26,11 +26,13 @@ struct cabs_sim {
   // ping/pong population: 16-byte hot records {x, y, attr, id} + wealth; per-step displacement
   uint4 *hot[2] = {nullptr, nullptr};
   double *w[2] = {nullptr, nullptr};
-  uint32_t *disp = nullptr;
+  uint2 *aux = nullptr;         // {displacement, rank in destination cell}: pass A -> pass B
   double *sqrt_tab = nullptr;   // exact sqrt of small integers (income of abs.py:187)
   int cur = 0;
-  unsigned *cells = nullptr;    // histogram / cell_start, max_cells + 8 entries
-  unsigned *partial = nullptr;  // scan partials
+  unsigned *cells[2] = {nullptr, nullptr};  // histogram / cell_start (ping/pong), max_cells + 8 entries each
+  int tab = 0;                  // table the next build uses (mirrors Ctl::cur_table)
+  unsigned long long *tile_state = nullptr;  // look-back state of the scan
+  unsigned *inf_list = nullptr; // slots of the Infected agents (sources of the contact pass)
   Ctl *ctl = nullptr;
   StatRecord *history = nullptr;
   uint8_t *stage = nullptr;     // byte-column staging for upload/download: 5 * capacity
@@ -82,12 +84,13 @@ static int fail(cabs_sim *sim, int code, const char *msg) {
 
 static inline int agent_blocks(const cabs_sim *sim) { return sim->num_sms * 8; }
 
-#define LAUNCH(kernel, grid, block, ...)                \
+#define LAUNCH_AS(name, kernel, grid, block, ...)        \
   do {                                                  \
-    if (sim->profiling) prof_mark(sim, #kernel);        \
+    if (sim->profiling) prof_mark(sim, name);           \
     kernel<<<(grid), (block), 0, sim->stream>>>(__VA_ARGS__); \
     sim->launches++;                                    \
   } while (0)
+#define LAUNCH(kernel, grid, block, ...) LAUNCH_AS(#kernel, kernel, grid, block, __VA_ARGS__)
 
 extern "C" const char *cabs_last_error(const cabs_sim *sim) {
   return sim ? sim->err.c_str() : g_create_error.c_str();
@@ -100,9 +103,10 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
   for (int b = 0; b < 2; ++b) {
     cudaFree(sim->hot[b]); cudaFree(sim->w[b]);
   }
-  cudaFree(sim->disp);
+  cudaFree(sim->aux);
   cudaFree(sim->sqrt_tab);
-  cudaFree(sim->cells); cudaFree(sim->partial); cudaFree(sim->ctl); cudaFree(sim->history);
+  cudaFree(sim->cells[0]); cudaFree(sim->cells[1]); cudaFree(sim->tile_state); cudaFree(sim->inf_list);
+  cudaFree(sim->ctl); cudaFree(sim->history);
   cudaFree(sim->stage); cudaFree(sim->stage_id); cudaFree(sim->pairs); cudaFree(sim->pair_count);
   for (cudaEvent_t e : sim->events) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
@@ -125,7 +129,7 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   if (sim->capacity >= (1ull << 31)) return fail(sim, CABS_ERR_CAPACITY, "capacity must be < 2^31 agents per device");
   uint64_t mc = cfg->max_cells;
   if (mc == 0) {
-    mc = sim->capacity + sim->capacity / 2;
+    mc = sim->capacity / 2;  // about one cell per 2..8 agents: the table stays a small fraction of the records
     if (mc < 4096) mc = 4096;
     if (mc > (1ull << 24)) mc = 1ull << 24;
   }
@@ -138,10 +142,14 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
     CK(cudaMalloc(&sim->hot[b], cap * sizeof(uint4)));
     CK(cudaMalloc(&sim->w[b], cap * sizeof(double)));
   }
-  CK(cudaMalloc(&sim->disp, cap * sizeof(uint32_t)));
+  CK(cudaMalloc(&sim->aux, cap * sizeof(uint2)));
+  CK(cudaMalloc(&sim->inf_list, cap * sizeof(unsigned)));
   CK(cudaMalloc(&sim->sqrt_tab, kSqrtTable * sizeof(double)));
-  CK(cudaMalloc(&sim->cells, ((size_t)sim->max_cells + 8) * sizeof(unsigned)));
-  CK(cudaMalloc(&sim->partial, 1024 * sizeof(unsigned)));
+  for (int b = 0; b < 2; ++b) {
+    CK(cudaMalloc(&sim->cells[b], ((size_t)sim->max_cells + 8) * sizeof(unsigned)));
+    CK(cudaMemsetAsync(sim->cells[b], 0, ((size_t)sim->max_cells + 8) * sizeof(unsigned), sim->stream));
+  }
+  CK(cudaMalloc(&sim->tile_state, ((size_t)sim->max_cells / kScanTile + 2) * sizeof(unsigned long long)));
   CK(cudaMalloc(&sim->ctl, sizeof(Ctl)));
   CK(cudaMalloc(&sim->history, (size_t)sim->hist_cap * sizeof(StatRecord)));
   CK(cudaMalloc(&sim->stage, cap * 5));
@@ -230,22 +238,32 @@ extern "C" int cabs_set_triggers(cabs_sim *sim, const cabs_trigger *t, int count
   return CABS_OK;
 }
 
-// Build the cell list of the current positions without advancing the simulation.
-static int rebuild_static(cabs_sim *sim) {
-  const int c = sim->cur, o = c ^ 1;
+// One build of the cell-sorted population: kAdvance = a real step, otherwise the cell list of the
+// current positions (upload / contact-pair hook) without advancing the simulation.
+template <bool kAdvance>
+static void enqueue_build(cabs_sim *sim) {
+  const int c = sim->cur, o = c ^ 1, t = sim->tab;
   const int nb = agent_blocks(sim);
-  LAUNCH(k_bbox, nb, 256, sim->ctl, sim->hot[c]);
-  LAUNCH(k_replan, 1, 32, sim->ctl, 1);
-  LAUNCH(k_clear_cells, nb, 256, sim->ctl, sim->cells);
-  LAUNCH(k_move_count<false>, nb, 256, sim->ctl, sim->hot[c], sim->disp, sim->cells);
-  LAUNCH(k_scan_reduce, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
-  LAUNCH(k_scan_partials, 1, 1024, sim->partial);
-  LAUNCH(k_scan_apply, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
-  LAUNCH(k_update_scatter<false>, nb, 256, sim->ctl, sim->hot[c], sim->w[c], sim->disp, sim->cells, sim->hot[o],
-         sim->w[o], sim->sqrt_tab);
-  LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 0);
-  CK(cudaGetLastError());
+  LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl, sim->hot[c], sim->aux, sim->cells[t], sim->tile_state);
+  LAUNCH(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
+  LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", k_update_scatter<kAdvance>, nb, 256, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t],
+         sim->cells[t ^ 1], sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab);
+  if (kAdvance) {
+    LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, nullptr, nullptr,
+           sim->history, 1);
+  } else {
+    LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 0);
+  }
   sim->cur = o;
+  sim->tab = t ^ 1;
+}
+
+static int rebuild_static(cabs_sim *sim) {
+  const int nb = agent_blocks(sim);
+  LAUNCH(k_bbox, nb, 256, sim->ctl, sim->hot[sim->cur]);
+  LAUNCH(k_replan, 1, 32, sim->ctl, 1);
+  enqueue_build<false>(sim);
+  CK(cudaGetLastError());
   sim->cells_dirty = false;
   return CABS_OK;
 }
@@ -316,19 +334,8 @@ extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
   if (!sim || nsteps < 0) return fail(sim, CABS_ERR_INVALID, "cabs_step: bad argument");
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_step: call cabs_set_params first");
   CK(cudaSetDevice(sim->device));
-  const int nb = agent_blocks(sim);
   for (int s = 0; s < nsteps; ++s) {
-    const int c = sim->cur, o = c ^ 1;
-    LAUNCH(k_clear_cells, nb, 256, sim->ctl, sim->cells);
-    LAUNCH(k_move_count<true>, nb, 256, sim->ctl, sim->hot[c], sim->disp, sim->cells);
-    LAUNCH(k_scan_reduce, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
-    LAUNCH(k_scan_partials, 1, 1024, sim->partial);
-    LAUNCH(k_scan_apply, kScanBlocks, kScanThreads, sim->ctl, sim->cells, sim->partial);
-    LAUNCH(k_update_scatter<true>, nb, 256, sim->ctl, sim->hot[c], sim->w[c], sim->disp, sim->cells, sim->hot[o],
-           sim->w[o], sim->sqrt_tab);
-    LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells);
-    LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 1);
-    sim->cur = o;
+    enqueue_build<true>(sim);
     sim->step++;
   }
   if (sim->profiling) prof_mark(sim, nullptr);  // closing timestamp of the batch
@@ -413,7 +420,7 @@ extern "C" int cabs_contact_pairs(cabs_sim *sim, int64_t *ij, size_t capacity_pa
   }
   CK(cudaMemsetAsync(sim->pair_count, 0, sizeof(unsigned long long), sim->stream));
   const int c = sim->cur;
-  LAUNCH(k_contact_pairs, agent_blocks(sim), 256, sim->ctl, sim->hot[c], sim->cells, sim->pairs,
+  LAUNCH(k_contact_pairs, agent_blocks(sim), 256, sim->ctl, sim->hot[c], sim->cells[sim->tab ^ 1], sim->pairs,
          (unsigned long long)capacity_pairs, sim->pair_count);
   CK(cudaGetLastError());
   unsigned long long total = 0;

@@ -1,25 +1,31 @@
 // Device side of the COVID-ABS agent step for sm_100a (B200).
 //
 // Population layout in HBM (structure of arrays, kept physically ordered by cell key):
-//   hot  uint4 {x, y, attr, id}: what the cell-list build and the neighbour scan read; one 128-bit
+//   hot  uint4 {x, y, attr, id}: what the cell-list build and the contact scan read; one 128-bit
 //              load/store per agent, two records per 32-byte sector
 //        x,y   i32  lattice position (agents.py:45-47)
 //        attr  u32  status[1:0] severity[3:2] stratum[6:4] new[7] | infected_time[15:8] | age[23:16]
 //        id    u32  position in the reference's population list (abs.py:15); keys all draws
 //   w    f64   wealth (agents.py:60)
-//   disp u32   this step's displacement (ix, iy as int16 pair), written by pass A, read by pass B
+//   aux  uint2 {displacement (ix, iy as int16 pair), rank inside the destination cell}: written by
+//              pass A, read by pass B
 // Two copies of hot/w (ping/pong): every step scatters the updated records straight into their
-// cell-sorted slot of the other copy, so the neighbour scan reads contiguous cell ranges.
+// cell-sorted slot of the other copy, so the contact scan reads contiguous cell ranges.
+// Two cell tables (ping/pong): pass B of a step zeroes the table of the step before, so the
+// histogram of the next step starts clean without a separate clearing pass.
 //
-// One step (Simulation.execute, abs.py:232-273):
-//   k_clear_cells      zero the cell histogram (L2 resident: <= 2^24 cells)
-//   k_move_count       recompute-only pass: new position of every agent -> cell key -> histogram
-//   k_scan_*           exclusive scan of the histogram = cell starts
-//   k_update_scatter   move + update + economy (abs.py:156-230), partial statistics,
-//                      scatter the record to cell_start[key] + rank
-//   k_contagion        neighbour scan over the 3x3 cells, contact() (abs.py:141-154)
-//   k_finalize         statistics record (abs.py:291-314), triggers (abs.py:267-271), next grid
+// One step (Simulation.execute, abs.py:232-273), four launches:
+//   k_move_count       pass A: new position of every agent -> cell key -> histogram; the value the
+//                      atomic returns is the agent's rank inside its cell
+//   k_scan_cells       single-pass exclusive scan (decoupled look-back) of the histogram = cell starts
+//   k_update_scatter   pass B: move + update + economy (abs.py:156-230), partial statistics
+//                      (abs.py:291-314), record -> slot cell_start[key] + rank, list of the slots
+//                      that hold Infected agents
+//   k_contagion        pass C: contact() (abs.py:141-154) pushed from the Infected agents to the
+//                      Susceptible ones in reach; the last block to finish closes the step:
+//                      statistics record, triggers (abs.py:267-271), grid of the next step
 #pragma once
+#include <limits.h>
 #include <stdint.h>
 
 #include "abs_rng.cuh"
@@ -33,6 +39,7 @@ constexpr int kNumStats = 12;
 constexpr uint32_t kErrOutOfGrid = 1u;     // an agent left the planned grid (internal invariant broken)
 constexpr uint32_t kErrDomain = 2u;        // bounding box wider than 2^28
 constexpr uint32_t kErrWealthRange = 4u;   // fixed-point wealth sum would overflow
+constexpr uint32_t kErrExchange = 8u;      // slab exchange buffer overflow (migrants / ghosts)
 
 struct DevTrigger {
   int metric, op, attribute, pad;
@@ -60,10 +67,12 @@ struct Grid {
 // so that a whole run of steps can be enqueued without the host in the loop.
 struct Ctl {
   // ---- cell grids: `g` is the one the next build (k_move_count .. k_contagion) uses, planned by
-  //      the previous k_finalize; `built` is the one the current contents of cell_start were built with
+  //      the previous step's closing; `built` is the one the current cell table was built with
   Grid g, built;
   int last_bb[4];     // bounding box of the current positions (xmin, xmax, ymin, ymax)
   unsigned max_cells;
+  unsigned cells_used[2];  // entries of each cell table that may be non-zero
+  int cur_table;           // table the build in flight / the last build uses
   // ---- simulation attributes (abs.py:17-49); triggers rewrite them on the device
   float amp[4];
   double length, height;
@@ -85,12 +94,18 @@ struct Ctl {
   //   u <= r  <=>  w <= floor(r * 2^32 - 0.5)         (abs.py:152)
   long long thr_hosp[9], thr_sev[9], thr_death[9];
   long long thr_rate;
+  // ---- slab decomposition: this device owns lattice columns [slab_lo, slab_hi)
+  int slab_lo, slab_hi;
+  int n_ranks;        // 1: no decomposition
   // ---- accumulators of the running step
   unsigned long long cnt[7];
   long long q[5];
   unsigned long long newinf;
   int bb_xmin, bb_xmax, bb_ymin, bb_ymax;
-  unsigned pair_count;
+  unsigned n_inf;          // entries of the Infected-slot list
+  unsigned n_next;         // agents resident after this step's migration
+  unsigned scan_ticket;    // next tile of the scan
+  unsigned done_ticket;    // blocks of k_contagion that have finished
   // ---- statistics of the previous step (what triggers and the critical-limit test read)
   StatRecord prev;
   StatRecord cur;
@@ -126,7 +141,7 @@ enum : uint32_t { SEV_E = 0, SEV_A = 1, SEV_H = 2, SEV_G = 3 };
 struct StepParams {
   int gx0, gy0, eshift, ncx, ncy;
   float amp[4];
-  double length, height, min_expense;
+  double min_expense;
   double bi[5];
   long long thr_hosp[9], thr_sev[9], thr_death[9];
   long long thr_rate;
@@ -140,7 +155,7 @@ __device__ __forceinline__ void load_params(StepParams &P, const Ctl *ctl, bool 
   const Grid &g = use_built ? ctl->built : ctl->g;
   P.gx0 = g.gx0; P.gy0 = g.gy0; P.eshift = g.eshift; P.ncx = g.ncx; P.ncy = g.ncy;
   for (int i = 0; i < 4; ++i) P.amp[i] = ctl->amp[i];
-  P.length = ctl->length; P.height = ctl->height; P.min_expense = ctl->min_expense;
+  P.min_expense = ctl->min_expense;
   P.len_i = (int)fmin(fmax(ceil(ctl->length), -2147483647.0), 2147483647.0);
   P.hei_i = (int)fmin(fmax(ceil(ctl->height), -2147483647.0), 2147483647.0);
   for (int i = 0; i < 5; ++i) P.bi[i] = ctl->bi[i];
@@ -159,11 +174,11 @@ __device__ __forceinline__ void load_params(StepParams &P, const Ctl *ctl, bool 
   P.k0 = ctl->k0; P.k1 = ctl->k1; P.step = ctl->step; P.n = ctl->n;
 }
 
-// Simulation.move (abs.py:156-189): displacement and reflected position.  `w` = stream-0 words.
-__device__ __forceinline__ void move_agent(const StepParams &P, int x, int y, uint32_t attr, const uint4 &w, int &nx,
-                                           int &ny, int &ix, int &iy, bool &mobile) {
+// Simulation.move (abs.py:156-189): displacement of this step.  `w` = stream-0 words.
+__device__ __forceinline__ void draw_displacement(const StepParams &P, uint32_t attr, const uint4 &w, int &ix,
+                                                  int &iy) {
   const uint32_t st = attr_status(attr), sev = attr_severity(attr);
-  mobile = !(st == ST_D || (st == ST_I && (sev == SEV_H || sev == SEV_G)));  // abs.py:164-167
+  const bool mobile = !(st == ST_D || (st == ST_I && (sev == SEV_H || sev == SEV_G)));  // abs.py:164-167
   ix = 0;
   iy = 0;
   if (mobile) {
@@ -173,164 +188,163 @@ __device__ __forceinline__ void move_agent(const StepParams &P, int x, int y, ui
     ix = __float2int_rz(__fmul_rn(z0, a));  // int() truncates toward zero (abs.py:174-175)
     iy = __float2int_rz(__fmul_rn(z1, a));
   }
+}
+// abs.py:177-185: the increment, not the position, is reflected
+__device__ __forceinline__ void apply_displacement(const StepParams &P, int x, int y, int ix, int iy, int &nx,
+                                                   int &ny) {
   const int tx = x + ix, ty = y + iy;
-  nx = (tx <= 0 || tx >= P.len_i) ? x - ix : tx;  // abs.py:177-180: the increment is reflected
-  ny = (ty <= 0 || ty >= P.hei_i) ? y - iy : ty;  // abs.py:182-185
+  nx = (tx <= 0 || tx >= P.len_i) ? x - ix : tx;
+  ny = (ty <= 0 || ty >= P.hei_i) ? y - iy : ty;
 }
 
 // Cell of a lattice point.  Interior cells are 1..ncx-2 / 1..ncy-2; row/column 0 and the last one
-// are always-empty padding so that the 3x3 neighbourhood never needs a bounds test.
-__device__ __forceinline__ void cell_coords(const StepParams &P, int x, int y, int &cx, int &cy, unsigned *err) {
-  cx = ((x - P.gx0) >> P.eshift) + 1;
-  cy = ((y - P.gy0) >> P.eshift) + 1;
+// are always-empty padding so that the neighbourhood of a cell never needs a bounds test.
+__device__ __forceinline__ unsigned cell_key(const StepParams &P, int x, int y, unsigned *err) {
+  int cx = ((x - P.gx0) >> P.eshift) + 1;
+  int cy = ((y - P.gy0) >> P.eshift) + 1;
   if (cx < 1 || cx > P.ncx - 2 || cy < 1 || cy > P.ncy - 2) {
     atomicOr(err, kErrOutOfGrid);
     cx = min(max(cx, 1), P.ncx - 2);
     cy = min(max(cy, 1), P.ncy - 2);
   }
-}
-__device__ __forceinline__ unsigned cell_key(const StepParams &P, int x, int y, unsigned *err) {
-  int cx, cy;
-  cell_coords(P, x, y, cx, cy, err);
   return (unsigned)cy * (unsigned)P.ncx + (unsigned)cx;
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void k_clear_cells(const Ctl *__restrict__ ctl, unsigned *__restrict__ cells) {
-  const unsigned m = ctl->g.ncells + 1;
-  const unsigned m4 = m >> 2;
-  uint4 *c4 = reinterpret_cast<uint4 *>(cells);
-  const unsigned stride = gridDim.x * blockDim.x;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < m4; i += stride) c4[i] = make_uint4(0, 0, 0, 0);
-  for (unsigned i = (m4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) cells[i] = 0;
-}
-
-// Pass A: where will every agent be after this step's move?  Writes the displacement (for pass B)
-// and counts the agent in the histogram of its destination cell.
+// Pass A: where will every agent be after this step's move?  Writes the displacement and the rank
+// inside the destination cell (for pass B) and counts the agent in the histogram of that cell.
 // kAdvance=false builds the cell list of the current positions (upload / contact-pair hook).
+constexpr int kScanTile = 4096;      // histogram entries per scan tile (512 threads x 8)
+constexpr int kScanThreads = 512;
+
 template <bool kAdvance>
 __global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot,
-                                                    uint32_t *__restrict__ disp, unsigned *__restrict__ cells) {
+                                                    uint2 *__restrict__ aux, unsigned *__restrict__ cells,
+                                                    unsigned long long *__restrict__ tile_state) {
   __shared__ StepParams P;
   if (threadIdx.x == 0) load_params(P, ctl);
   __syncthreads();
   const unsigned stride = gridDim.x * blockDim.x;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  // side job: reset the look-back state of the scan that follows
+  {
+    const unsigned ntiles = ((unsigned)P.ncx * (unsigned)P.ncy + 1u + kScanTile - 1) / kScanTile;
+    for (unsigned t = tid; t < ntiles; t += stride) tile_state[t] = 0ull;
+  }
+  for (unsigned i = tid; i < P.n; i += stride) {
     const uint4 h = __ldg(&hot[i]);
     int nx = (int)h.x, ny = (int)h.y;
+    uint32_t d = 0;
     if (kAdvance) {
       const uint32_t a = attr_normalize(h.z);
       const uint4 w = philox4x32_10(h.w, P.step, kStreamAgent, 0u, P.k0, P.k1);
       int ix, iy;
-      bool mobile;
-      move_agent(P, nx, ny, a, w, nx, ny, ix, iy, mobile);
-      disp[i] = ((uint32_t)ix & 0xFFFFu) | ((uint32_t)iy << 16);
+      draw_displacement(P, a, w, ix, iy);
+      apply_displacement(P, nx, ny, ix, iy, nx, ny);
+      d = ((uint32_t)ix & 0xFFFFu) | ((uint32_t)iy << 16);
     }
     const unsigned key = cell_key(P, nx, ny, &ctl->err);
-    atomicAdd(&cells[key + 1], 1u);
+    const unsigned rank = atomicAdd(&cells[key], 1u);
+    aux[i] = make_uint2(d, rank);
   }
 }
 
-// ---- exclusive scan of cells[0 .. ncells] in place, fixed grid of kScanBlocks chunks ----------
-constexpr int kScanBlocks = 592;  // 148 SMs x 4
-constexpr int kScanThreads = 512;
+// ------------------------------------------------------------------------------------------
+// Exclusive scan of cells[0 .. ncells] in place, one pass: every tile publishes its sum, then its
+// inclusive prefix, and looks back over the tiles before it (decoupled look-back).  Tiles are taken
+// in ticket order so that every tile a block waits for is already running or done.
+//   tile_state: bits 63..62 = 0 nothing, 1 tile sum, 2 inclusive prefix; bits 31..0 = value
+constexpr unsigned long long kTileSum = 1ull << 62, kTilePrefix = 2ull << 62;
 
-__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned *warp_sums, unsigned &total) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_cells(Ctl *__restrict__ ctl, unsigned *__restrict__ cells,
+                                                             unsigned long long *__restrict__ tile_state) {
+  __shared__ unsigned warp_sums[kScanThreads / 32];
+  __shared__ unsigned s_tile, s_prefix;
+  const unsigned m = ctl->g.ncells + 1;
+  const unsigned ntiles = (m + kScanTile - 1) / kScanTile;
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  unsigned inc = v;
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ctl->scan_ticket, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    if (tile >= ntiles) break;
+    const unsigned base = tile * kScanTile + threadIdx.x * 8;
+    unsigned v[8];
+    if (base + 8 <= m) {
+      const uint4 a = *reinterpret_cast<const uint4 *>(cells + base);
+      const uint4 b = *reinterpret_cast<const uint4 *>(cells + base + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) warp_sums[wid] = inc;
-  __syncthreads();
-  if (wid == 0) {
-    const unsigned nw = blockDim.x >> 5;
-    unsigned s = (lane < nw) ? warp_sums[lane] : 0u;
+      for (int k = 0; k < 8; ++k) v[k] = (base + k < m) ? cells[base + k] : 0u;
+    }
+    unsigned sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += v[k];
+    unsigned inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned t = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += t;
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
     }
-    warp_sums[lane] = s;  // inclusive over warps
-  }
-  __syncthreads();
-  const unsigned base = (wid == 0) ? 0u : warp_sums[wid - 1];
-  total = warp_sums[(blockDim.x >> 5) - 1];
-  const unsigned r = base + inc - v;
-  __syncthreads();
-  return r;
-}
-
-__device__ __forceinline__ void scan_chunk(const Ctl *ctl, unsigned &begin, unsigned &end) {
-  const unsigned m = ctl->g.ncells + 1;
-  unsigned chunk = (m + kScanBlocks - 1) / kScanBlocks;
-  chunk = (chunk + 3u) & ~3u;  // keep chunks 16-byte aligned
-  begin = min(m, blockIdx.x * chunk);
-  end = min(m, begin + chunk);
-}
-
-__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const Ctl *__restrict__ ctl,
-                                                              const unsigned *__restrict__ cells,
-                                                              unsigned *__restrict__ partial) {
-  __shared__ unsigned warp_sums[32];
-  unsigned begin, end;
-  scan_chunk(ctl, begin, end);
-  unsigned s = 0;
-  for (unsigned i = begin + threadIdx.x; i < end; i += blockDim.x) s += cells[i];
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned s = (lane < kScanThreads / 32) ? warp_sums[lane] : 0u;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    unsigned t = (threadIdx.x < (blockDim.x >> 5)) ? warp_sums[threadIdx.x] : 0u;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += t;
+      }
+      if (lane < kScanThreads / 32) warp_sums[lane] = s;  // inclusive over warps
+      const unsigned total = __shfl_sync(0xffffffffu, s, kScanThreads / 32 - 1);
+      // publish, then look back (warp 0: lane l inspects tile - 1 - l of the current window)
+      unsigned prefix = 0;
+      if (tile == 0) {
+        if (lane == 0) atomicExch(&tile_state[0], kTilePrefix | total);
+      } else {
+        if (lane == 0) atomicExch(&tile_state[tile], kTileSum | total);
+        int look = (int)tile - 1;
+        for (;;) {
+          const int idx = look - (int)lane;
+          unsigned long long st = kTilePrefix;  // tiles before 0 count as a zero prefix
+          if (idx >= 0) {
+            do {
+              st = *reinterpret_cast<volatile unsigned long long *>(&tile_state[idx]);
+            } while ((st >> 62) == 0ull);
+          }
+          const unsigned is_prefix = __ballot_sync(0xffffffffu, (st >> 62) == 2ull);
+          const unsigned val = (unsigned)(st & 0xFFFFFFFFull);
+          // sum the window up to and including the nearest tile that knows its inclusive prefix
+          const int stop = is_prefix ? __ffs(is_prefix) - 1 : 31;
+          unsigned contrib = ((int)lane <= stop) ? val : 0u;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (threadIdx.x == 0) partial[blockIdx.x] = t;
-  }
-}
-
-__global__ void __launch_bounds__(1024) k_scan_partials(unsigned *__restrict__ partial) {
-  __shared__ unsigned warp_sums[32];
-  unsigned total;
-  const unsigned v = (threadIdx.x < kScanBlocks) ? partial[threadIdx.x] : 0u;
-  const unsigned ex = block_exclusive_scan(v, warp_sums, total);
-  if (threadIdx.x < kScanBlocks) partial[threadIdx.x] = ex;
-}
-
-__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const Ctl *__restrict__ ctl, unsigned *__restrict__ cells,
-                                                             const unsigned *__restrict__ partial) {
-  __shared__ unsigned warp_sums[32];
-  unsigned begin, end;
-  scan_chunk(ctl, begin, end);
-  unsigned carry = partial[blockIdx.x];
-  for (unsigned base = begin; base < end; base += blockDim.x * 4) {
-    const unsigned i = base + threadIdx.x * 4;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (i + 3 < end) {
-      v = *reinterpret_cast<const uint4 *>(cells + i);
-    } else {
-      if (i < end) v.x = cells[i];
-      if (i + 1 < end) v.y = cells[i + 1];
-      if (i + 2 < end) v.z = cells[i + 2];
+          for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+          prefix += contrib;
+          if (is_prefix) break;
+          look -= 32;
+        }
+        if (lane == 0) atomicExch(&tile_state[tile], kTilePrefix | (unsigned long long)(prefix + total));
+      }
+      if (lane == 0) s_prefix = prefix;
     }
-    const unsigned sum = v.x + v.y + v.z + v.w;
-    unsigned total;
-    const unsigned ex = block_exclusive_scan(sum, warp_sums, total) + carry;
-    uint4 o;
-    o.x = ex;
-    o.y = ex + v.x;
-    o.z = o.y + v.y;
-    o.w = o.z + v.z;
-    if (i + 3 < end) {
-      *reinterpret_cast<uint4 *>(cells + i) = o;
-    } else {
-      if (i < end) cells[i] = o.x;
-      if (i + 1 < end) cells[i + 1] = o.y;
-      if (i + 2 < end) cells[i + 2] = o.z;
+    __syncthreads();
+    unsigned ex = s_prefix + (wid ? warp_sums[wid - 1] : 0u) + inc - sum;
+    unsigned o8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      o8[k] = ex;
+      ex += v[k];
     }
-    carry += total;
+    if (base + 8 <= m) {
+      *reinterpret_cast<uint4 *>(cells + base) = make_uint4(o8[0], o8[1], o8[2], o8[3]);
+      *reinterpret_cast<uint4 *>(cells + base + 4) = make_uint4(o8[4], o8[5], o8[6], o8[7]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (base + k < m) cells[base + k] = o8[k];
+    }
+    __syncthreads();  // s_tile / warp_sums are reused by the next tile
   }
 }
 
@@ -346,19 +360,67 @@ struct BlockStats {
 #ifndef CABS_B_MINBLOCKS
 #define CABS_B_MINBLOCKS 3
 #endif
-#ifndef CABS_B_PREFETCH
-#define CABS_B_PREFETCH 1
-#endif
 constexpr int kSqrtTable = 4096;  // sqrt(d2) for d2 < 4096, exact (IEEE sqrt), filled once by k_init_ctl
+
+// One agent's move + update + economy (abs.py:156-230).  ix, iy: this step's displacement.
+__device__ __forceinline__ void advance_agent(const StepParams &P, uint32_t aid, int ix, int iy, uint32_t &a,
+                                              double &w, const double *__restrict__ sqrt_tab) {
+  uint32_t st = attr_status(a), sev = attr_severity(a), time = attr_time(a);
+  const uint32_t stratum = attr_stratum(a), age = attr_age(a);
+  const bool mobile = !(st == ST_D || (st == ST_I && (sev == SEV_H || sev == SEV_G)));  // abs.py:164-167
+  const uint4 r0 = philox4x32_10(aid, P.step, kStreamAgent, 0u, P.k0, P.k1);
+  const double bi = P.bi[min(stratum, 4u)];
+  if (mobile) {
+    // abs.py:187-189: wealth += sqrt(ix^2+iy^2) * rand * minimum_expense * basic_income[stratum]
+    const int d2 = ix * ix + iy * iy;
+    const double dist = d2 < kSqrtTable ? __ldg(&sqrt_tab[d2]) : __dsqrt_rn((double)d2);
+    const double inc = __dmul_rn(__dmul_rn(__dmul_rn(dist, u01(r0.z)), P.min_expense), bi);
+    w = __dadd_rn(w, inc);
+  }
+  // abs.py:191-230
+  if (st != ST_D) {
+    bool pays = true;
+    if (st == ST_I) {
+      time += 1;
+      const uint32_t idx = min(age > 10u ? age / 10u - 1u : 0u, 8u);  // abs.py:204
+      const long long w_sub = (long long)r0.w;
+      if (sev == SEV_A) {
+        if (w_sub < P.thr_hosp[idx]) sev = SEV_H;  // age_hospitalization_probs[idx] > u (abs.py:209)
+      } else if (sev == SEV_H) {
+        if (w_sub < P.thr_sev[idx]) {              // age_severe_probs[idx] > u (abs.py:212)
+          sev = SEV_G;
+          if (P.crit_active) {                     // abs.py:214-217
+            st = ST_D;
+            sev = SEV_A;
+          }
+        }
+      }
+      const uint4 r1 = philox4x32_10(aid, P.step, kStreamAgent2, 0u, P.k0, P.k1);
+      if ((long long)r1.x < P.thr_death[idx]) {    // age_death_probs[idx] > u (abs.py:219-223)
+        st = ST_D;
+        sev = SEV_A;
+        pays = false;
+      } else if ((int)time > P.recovering_time) {  // abs.py:225-228
+        time = 0;
+        st = ST_R;
+        sev = SEV_A;
+      }
+    }
+    if (pays) w = __dadd_rn(w, -__dmul_rn(P.min_expense, bi));  // abs.py:230
+  }
+  a = attr_pack(st, sev, stratum, time, age) | (a & 0xFF000000u);
+}
 
 template <bool kAdvance>
 __global__ void __launch_bounds__(256, CABS_B_MINBLOCKS)
 k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const double *__restrict__ wealth,
-                 const uint32_t *__restrict__ disp, unsigned *__restrict__ cells, uint4 *__restrict__ ohot,
-                 double *__restrict__ owealth, const double *__restrict__ sqrt_tab) {
+                 const uint2 *__restrict__ aux, const unsigned *__restrict__ cell_start,
+                 unsigned *__restrict__ stale_cells, uint4 *__restrict__ ohot, double *__restrict__ owealth,
+                 unsigned *__restrict__ inf_list, const double *__restrict__ sqrt_tab) {
   __shared__ StepParams P;
   __shared__ BlockStats B;
   __shared__ long long s_q[5][256];  // per-thread Q1..Q5 partial sums (abs.py:309-312), no bank conflicts
+  __shared__ unsigned s_stale;
 #pragma unroll
   for (int k = 0; k < 5; ++k) s_q[k][threadIdx.x] = 0;
   if (threadIdx.x == 0) {
@@ -367,8 +429,18 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     for (int i = 0; i < 5; ++i) B.q[i] = 0;
     B.bb[0] = B.bb[2] = INT_MAX;
     B.bb[1] = B.bb[3] = INT_MIN;
+    s_stale = ctl->cells_used[ctl->cur_table ^ 1];
   }
   __syncthreads();
+  // side job: zero the cell table of the step before (the next step's histogram)
+  {
+    const unsigned m = s_stale, m4 = m >> 2;
+    uint4 *c4 = reinterpret_cast<uint4 *>(stale_cells);
+    const unsigned chunk = (m4 + gridDim.x - 1) / gridDim.x;
+    const unsigned b0 = min(m4, blockIdx.x * chunk), b1 = min(m4, b0 + chunk);
+    for (unsigned i = b0 + threadIdx.x; i < b1; i += blockDim.x) c4[i] = make_uint4(0, 0, 0, 0);
+    if (blockIdx.x == 0 && threadIdx.x < (m & 3u)) stale_cells[(m4 << 2) + threadIdx.x] = 0;
+  }
   // per-thread partial statistics: 16-bit fields (a thread sees far fewer than 65535 agents per launch
   // for any population the 2^31 capacity allows: n / (gridDim * 256) < 2^31 / (148*8*256))
   unsigned long long c_st = 0, c_sev = 0;  // status S,I,R,D and severity A,H,G counts
@@ -376,95 +448,41 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
   const double qscale = (double)(1ull << P.scale_bits);
 
   const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned lane = threadIdx.x & 31;
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   // software pipeline: the next agent's columns are requested before this agent's arithmetic starts
   uint4 h_next = make_uint4(0, 0, 0, 0);
   double w_next = 0.0;
-  uint32_t d_next = 0;
-#if CABS_B_PREFETCH
+  uint2 x_next = make_uint2(0, 0);
   if (i < P.n) {
     h_next = __ldg(&hot[i]);
     w_next = __ldg(&wealth[i]);
-    if (kAdvance) d_next = __ldg(&disp[i]);
+    x_next = __ldg(&aux[i]);
   }
-#endif
-  for (; i < P.n; i += stride) {
-#if CABS_B_PREFETCH
+  // every lane of a warp runs the same number of iterations (full-mask ballots below)
+  for (unsigned i0 = i - lane; i0 < P.n; i0 += stride, i += stride) {
+    const bool valid = i < P.n;
     const uint4 h = h_next;
     double w = w_next;
-    const uint32_t d = d_next;
+    const uint2 ax = x_next;
     if (i + stride < P.n) {
       h_next = __ldg(&hot[i + stride]);
       w_next = __ldg(&wealth[i + stride]);
-      if (kAdvance) d_next = __ldg(&disp[i + stride]);
+      x_next = __ldg(&aux[i + stride]);
     }
-#else
-    const uint4 h = __ldg(&hot[i]);
-    double w = __ldg(&wealth[i]);
-    const uint32_t d = kAdvance ? __ldg(&disp[i]) : 0u;
-#endif
     int nx = (int)h.x, ny = (int)h.y;
     uint32_t a = attr_normalize(h.z);
     const uint32_t aid = h.w;
-    const int ix = (int)(short)(d & 0xFFFFu), iy = (int)(short)(d >> 16);
-    if (kAdvance) {  // abs.py:177-185 with the displacement pass A drew (immobile agents have ix = iy = 0)
-      const int tx = nx + ix, ty = ny + iy;
-      nx = (tx <= 0 || tx >= P.len_i) ? nx - ix : tx;
-      ny = (ty <= 0 || ty >= P.hei_i) ? ny - iy : ty;
-    }
-    // the destination slot only needs the new position: claim it now so that the round trip to the
-    // L2-resident cell table overlaps the arithmetic below
-    const unsigned key = cell_key(P, nx, ny, &ctl->err);
-    const unsigned slot = atomicAdd(&cells[key + 1], 1u);
-    if (kAdvance) {
-      uint32_t st = attr_status(a), sev = attr_severity(a), time = attr_time(a);
-      const uint32_t stratum = attr_stratum(a), age = attr_age(a);
-      const bool mobile = !(st == ST_D || (st == ST_I && (sev == SEV_H || sev == SEV_G)));  // abs.py:164-167
-      const uint4 r0 = philox4x32_10(aid, P.step, kStreamAgent, 0u, P.k0, P.k1);
-      const double bi = P.bi[min(stratum, 4u)];
-      if (mobile) {
-        // abs.py:187-189: wealth += sqrt(ix^2+iy^2) * rand * minimum_expense * basic_income[stratum]
-        const int d2 = ix * ix + iy * iy;
-        const double dist = d2 < kSqrtTable ? __ldg(&sqrt_tab[d2]) : __dsqrt_rn((double)d2);
-        const double inc = __dmul_rn(__dmul_rn(__dmul_rn(dist, u01(r0.z)), P.min_expense), bi);
-        w = __dadd_rn(w, inc);
-      }
-      // abs.py:191-230
-      if (st != ST_D) {
-        bool pays = true;
-        if (st == ST_I) {
-          time += 1;
-          const uint32_t idx = min(age > 10u ? age / 10u - 1u : 0u, 8u);  // abs.py:204
-          const long long w_sub = (long long)r0.w;
-          if (sev == SEV_A) {
-            if (w_sub < P.thr_hosp[idx]) sev = SEV_H;  // age_hospitalization_probs[idx] > u (abs.py:209)
-          } else if (sev == SEV_H) {
-            if (w_sub < P.thr_sev[idx]) {              // age_severe_probs[idx] > u (abs.py:212)
-              sev = SEV_G;
-              if (P.crit_active) {                     // abs.py:214-217
-                st = ST_D;
-                sev = SEV_A;
-              }
-            }
-          }
-          const uint4 r1 = philox4x32_10(aid, P.step, kStreamAgent2, 0u, P.k0, P.k1);
-          if ((long long)r1.x < P.thr_death[idx]) {    // age_death_probs[idx] > u (abs.py:219-223)
-            st = ST_D;
-            sev = SEV_A;
-            pays = false;
-          } else if ((int)time > P.recovering_time) {  // abs.py:225-228
-            time = 0;
-            st = ST_R;
-            sev = SEV_A;
-          }
-        }
-        if (pays) w = __dadd_rn(w, -__dmul_rn(P.min_expense, bi));  // abs.py:230
-      }
-      a = attr_pack(st, sev, stratum, time, age) | (a & 0xFF000000u);
-    }
+    const int ix = (int)(short)(ax.x & 0xFFFFu), iy = (int)(short)(ax.x >> 16);
+    if (kAdvance) apply_displacement(P, nx, ny, ix, iy, nx, ny);
+    // the destination slot only needs the new position: ask for the cell start now so that the
+    // round trip to the L2-resident table overlaps the arithmetic below
+    unsigned slot = 0;
+    if (valid) slot = __ldg(&cell_start[cell_key(P, nx, ny, &ctl->err)]) + ax.y;
+    if (kAdvance && valid) advance_agent(P, aid, ix, iy, a, w, sqrt_tab);
     // partial statistics (abs.py:300-312); infections of this step are added by k_contagion
-    {
-      const uint32_t st = attr_status(a), sev = attr_severity(a);
+    const uint32_t st = attr_status(a), sev = attr_severity(a);
+    if (valid) {
       c_st += 1ull << (16 * st);
       if (st != ST_D) {
         c_sev += (sev != SEV_E) ? (1ull << (16 * (sev - 1))) : 0ull;
@@ -473,9 +491,18 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
         }
       }
       bxmin = min(bxmin, nx); bxmax = max(bxmax, nx); bymin = min(bymin, ny); bymax = max(bymax, ny);
+      ohot[slot] = make_uint4((uint32_t)nx, (uint32_t)ny, a, aid);
+      owealth[slot] = w;
     }
-    ohot[slot] = make_uint4((uint32_t)nx, (uint32_t)ny, a, aid);
-    owealth[slot] = w;
+    // slots of the agents that can transmit in this step's contact phase (warp-aggregated append)
+    const bool is_inf = valid && st == ST_I;
+    const unsigned m_inf = __ballot_sync(0xffffffffu, is_inf);
+    if (m_inf) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(&ctl->n_inf, (unsigned)__popc(m_inf));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (is_inf) inf_list[base + __popc(m_inf & ((1u << lane) - 1u))] = slot;
+    }
   }
   // block reduction: per-warp shared atomics, then one set of global atomics per block
   {
@@ -498,7 +525,7 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
       bymin = min(bymin, __shfl_xor_sync(0xffffffffu, bymin, o));
       bymax = max(bymax, __shfl_xor_sync(0xffffffffu, bymax, o));
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
       for (int k = 0; k < 7; ++k) atomicAdd(&B.cnt[k], cnt[k]);
       for (int k = 0; k < 5; ++k) atomicAdd((unsigned long long *)&B.q[k], (unsigned long long)q[k]);
       atomicMin(&B.bb[0], bxmin); atomicMax(&B.bb[1], bxmax); atomicMin(&B.bb[2], bymin); atomicMax(&B.bb[3], bymax);
@@ -506,10 +533,14 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int k = 0; k < 7; ++k) atomicAdd(&ctl->cnt[k], B.cnt[k]);
-    for (int k = 0; k < 5; ++k) atomicAdd((unsigned long long *)&ctl->q[k], (unsigned long long)B.q[k]);
-    atomicMin(&ctl->bb_xmin, B.bb[0]); atomicMax(&ctl->bb_xmax, B.bb[1]);
-    atomicMin(&ctl->bb_ymin, B.bb[2]); atomicMax(&ctl->bb_ymax, B.bb[3]);
+    for (int k = 0; k < 7; ++k)
+      if (B.cnt[k]) atomicAdd(&ctl->cnt[k], B.cnt[k]);
+    for (int k = 0; k < 5; ++k)
+      if (B.q[k]) atomicAdd((unsigned long long *)&ctl->q[k], (unsigned long long)B.q[k]);
+    if (B.bb[0] <= B.bb[1]) {
+      atomicMin(&ctl->bb_xmin, B.bb[0]); atomicMax(&ctl->bb_xmax, B.bb[1]);
+      atomicMin(&ctl->bb_ymin, B.bb[2]); atomicMax(&ctl->bb_ymax, B.bb[3]);
+    }
   }
 }
 
@@ -525,46 +556,48 @@ __device__ __forceinline__ void contact_cells(const StepParams &P, int x, int y,
   rhi = min(max(((y + P.reach - P.gy0) >> P.eshift) + 1, 0), P.ncy - 1);
 }
 
-// Pass C: the contact loop of abs.py:249-265 as a neighbour scan over the sorted population;
-// contact() = abs.py:141-154 with one draw per pair.
+__device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats);
+
+// Pass C: the contact loop of abs.py:249-265 pushed from the agents that were Infected before this
+// contact phase (the list pass B wrote) to the Susceptible agents in reach; contact() = abs.py:141-154
+// with one draw per pair, keyed on the pair so that the result does not depend on who scans whom.
+//   src == nullptr: the sources are the slots in inf_list (count ctl->n_inf);
+//   src != nullptr: the sources are the records src[0 .. n_src) (ghost Infected agents of a neighbour slab).
 __global__ void __launch_bounds__(256)
-k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start) {
+k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
+            const unsigned *__restrict__ inf_list, const uint4 *__restrict__ src, const unsigned *__restrict__ n_src,
+            StatRecord *__restrict__ history, int close) {
   __shared__ StepParams P;
-  __shared__ unsigned s_new;
+  __shared__ unsigned s_new, s_count;
   if (threadIdx.x == 0) {
     load_params(P, ctl);
     s_new = 0;
+    s_count = src ? *n_src : ctl->n_inf;
   }
   __syncthreads();
   unsigned newinf = 0;
   const unsigned stride = gridDim.x * blockDim.x;
   if (P.T >= 0) {
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-      const uint4 h = hot[i];
-      if (attr_status(h.z) != ST_S || (h.z & kNewlyInfected)) continue;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < s_count; t += stride) {
+      const uint4 h = src ? src[t] : hot[inf_list[t]];
       const int xi = (int)h.x, yi = (int)h.y;
       int clo, chi, rlo, rhi;
       contact_cells(P, xi, yi, clo, chi, rlo, rhi);
-      bool infected = false;
-      for (int row = rlo; row <= rhi && !infected; ++row) {
+      for (int row = rlo; row <= rhi; ++row) {
         const unsigned base = (unsigned)row * (unsigned)P.ncx;
         const unsigned jb = cell_start[base + clo], je = cell_start[base + chi + 1];
         for (unsigned j = jb; j < je; ++j) {
           const uint4 c = hot[j];
-          if (attr_status(c.z) != ST_I) continue;  // newly infected still read Susceptible here
+          if ((c.z & (3u | kNewlyInfected)) != ST_S) continue;  // only a still Susceptible agent can be infected
           const long long dx = (int)c.x - xi, dy = (int)c.y - yi;
           if (dx * dx + dy * dy > (long long)P.T) continue;
           const uint4 r = philox4x32_10(min(h.w, c.w), P.step, kStreamContact, max(h.w, c.w), P.k0, P.k1);
           if ((long long)r.x <= P.thr_rate) {  // contagion_test <= contagion_rate (abs.py:150-153)
-            infected = true;
-            break;
+            // status bits stay Susceptible during this pass (see attr_normalize)
+            const uint32_t old = atomicOr(reinterpret_cast<uint32_t *>(&hot[j]) + 2, kNewlyInfected);
+            if (!(old & kNewlyInfected)) ++newinf;
           }
         }
-      }
-      if (infected) {
-        // status bits stay Susceptible during this pass (see attr_normalize)
-        reinterpret_cast<uint32_t *>(&hot[i])[2] = h.z | kNewlyInfected;
-        ++newinf;
       }
     }
   }
@@ -572,7 +605,18 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
   for (int o = 16; o > 0; o >>= 1) newinf += __shfl_xor_sync(0xffffffffu, newinf, o);
   if ((threadIdx.x & 31) == 0 && newinf) atomicAdd(&s_new, newinf);
   __syncthreads();
-  if (threadIdx.x == 0 && s_new) atomicAdd(&ctl->newinf, (unsigned long long)s_new);
+  if (threadIdx.x == 0) {
+    if (s_new) atomicAdd(&ctl->newinf, (unsigned long long)s_new);
+    if (close) {
+      // the last block to get here has seen every other block's contribution
+      __threadfence();
+      const unsigned ticket = atomicAdd(&ctl->done_ticket, 1u);
+      if (ticket == gridDim.x - 1) {
+        __threadfence();
+        close_step(ctl, history, 1);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -625,7 +669,7 @@ __device__ inline void plan_grid(Ctl *ctl, int xmin, int xmax, int ymin, int yma
     ctl->err |= kErrDomain;
   }
   // cell edge: power of two, at least floor(sqrt(T)) so contacts never skip a cell, grown until
-  // the grid fits max_cells (keeps the histogram L2-resident)
+  // the grid fits max_cells (keeps the cell table L2-resident)
   int eshift = 0;
   const int T = ctl->T;
   while (T > 0 && ((1ll << eshift) * (1ll << eshift)) < (long long)T && eshift < 28) ++eshift;
@@ -650,6 +694,9 @@ __device__ inline void reset_accumulators(Ctl *ctl) {
   for (int k = 0; k < 5; ++k) ctl->q[k] = 0;
   ctl->newinf = 0;
   ctl->bb_xmin = INT_MAX; ctl->bb_xmax = INT_MIN; ctl->bb_ymin = INT_MAX; ctl->bb_ymax = INT_MIN;
+  ctl->n_inf = 0;
+  ctl->scan_ticket = 0;
+  ctl->done_ticket = 0;
 }
 
 __device__ inline double stat_value(const Ctl *ctl, const StatRecord &r, int metric) {
@@ -676,18 +723,23 @@ __device__ inline int threshold_T(double r) {
   return (int)n;
 }
 
+// accumulators other blocks updated with atomics: read them from L2, not from a stale L1 line
+__device__ __forceinline__ unsigned long long ld_acc(const unsigned long long *p) { return __ldcg(p); }
+__device__ __forceinline__ long long ld_acc(const long long *p) { return __ldcg(p); }
+__device__ __forceinline__ int ld_acc(const int *p) { return __ldcg(p); }
+
 // End of Simulation.execute (abs.py:267-273) + the statistics row batch_experiment appends
 // (experiments.py:193-196).  One thread.
-//   record_stats = true : after a real step
-//   record_stats = false: after upload / static rebuild (statistics of the initial state = "previous" stats)
-__global__ void k_finalize(Ctl *ctl, StatRecord *history, int record_stats) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+//   record_stats = 1 : after a real step
+//   record_stats = 0 : after upload / static rebuild (statistics of the initial state = "previous" stats)
+__device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats) {
   StatRecord cur;
-  for (int k = 0; k < 7; ++k) cur.cnt[k] = ctl->cnt[k];
-  cur.cnt[ST_S] -= ctl->newinf;  // infections of the contact phase (abs.py:153)
-  cur.cnt[ST_I] += ctl->newinf;
-  for (int k = 0; k < 5; ++k) cur.q[k] = ctl->q[k];
-  cur.new_infections = ctl->newinf;
+  const unsigned long long newinf = ld_acc(&ctl->newinf);
+  for (int k = 0; k < 7; ++k) cur.cnt[k] = ld_acc(&ctl->cnt[k]);
+  cur.cnt[ST_S] -= newinf;  // infections of the contact phase (abs.py:153)
+  cur.cnt[ST_I] += newinf;
+  for (int k = 0; k < 5; ++k) cur.q[k] = ld_acc(&ctl->q[k]);
+  cur.new_infections = newinf;
   cur.n_resident = ctl->n;
   cur.pad[0] = cur.pad[1] = 0;
   if (record_stats) {
@@ -718,11 +770,21 @@ __global__ void k_finalize(Ctl *ctl, StatRecord *history, int record_stats) {
   // abs.py:215: statistics['Severe'] + statistics['Hospitalization'] >= critical_limit
   const double n = (double)ctl->pop_size;
   ctl->crit_active = ((double)cur.cnt[6] / n + (double)cur.cnt[5] / n) >= ctl->critical_limit;
+  // the table this build used stays valid (contact-pair hook) until the next build's pass B zeroes it
+  ctl->cells_used[ctl->cur_table] = ctl->g.ncells + 1;
+  ctl->cur_table ^= 1;
   ctl->built = ctl->g;
-  ctl->last_bb[0] = ctl->bb_xmin; ctl->last_bb[1] = ctl->bb_xmax;
-  ctl->last_bb[2] = ctl->bb_ymin; ctl->last_bb[3] = ctl->bb_ymax;
-  plan_grid(ctl, ctl->bb_xmin, ctl->bb_xmax, ctl->bb_ymin, ctl->bb_ymax, true);
+  const int bx0 = ld_acc(&ctl->bb_xmin), bx1 = ld_acc(&ctl->bb_xmax);
+  const int by0 = ld_acc(&ctl->bb_ymin), by1 = ld_acc(&ctl->bb_ymax);
+  ctl->last_bb[0] = bx0; ctl->last_bb[1] = bx1; ctl->last_bb[2] = by0; ctl->last_bb[3] = by1;
+  plan_grid(ctl, bx0, bx1, by0, by1, true);
   reset_accumulators(ctl);
+  __threadfence();
+}
+
+__global__ void k_finalize(Ctl *ctl, StatRecord *history, int record_stats) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  close_step(ctl, history, record_stats);
 }
 
 // Bounding box of the resident positions into ctl->bb_* (used once per upload).
@@ -758,6 +820,13 @@ __global__ void k_replan(Ctl *ctl, int from_accum) {
     plan_grid(ctl, ctl->last_bb[0], ctl->last_bb[1], ctl->last_bb[2], ctl->last_bb[3], true);
   }
   reset_accumulators(ctl);
+}
+
+// Zero the first `used` entries of a cell table (static rebuilds; the step path clears inside pass B).
+__global__ void k_clear_table(Ctl *__restrict__ ctl, unsigned *__restrict__ cells, int which) {
+  const unsigned m = ctl->cells_used[which];
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) cells[i] = 0;
 }
 
 // Host-side parameter block -> Ctl (cabs_set_params / cabs_set_triggers / creation).
@@ -807,6 +876,10 @@ __global__ void k_init_ctl(Ctl *ctl, unsigned k0, unsigned k1, unsigned max_cell
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ctl->k0 = k0; ctl->k1 = k1; ctl->max_cells = max_cells; ctl->hist_cap = hist_cap;
   ctl->step = 0; ctl->n = 0; ctl->err = 0; ctl->ntrig = 0; ctl->pop_size = 1; ctl->T = -1;
+  ctl->cells_used[0] = ctl->cells_used[1] = 0;
+  ctl->cur_table = 0;
+  ctl->n_ranks = 1;
+  ctl->slab_lo = INT_MIN; ctl->slab_hi = INT_MAX;
   reset_accumulators(ctl);
   plan_grid(ctl, 0, 0, 0, 0, false);
   ctl->built = ctl->g;
