@@ -129,7 +129,7 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   if (sim->capacity >= (1ull << 31)) return fail(sim, CABS_ERR_CAPACITY, "capacity must be < 2^31 agents per device");
   uint64_t mc = cfg->max_cells;
   if (mc == 0) {
-    mc = sim->capacity / 2;  // about one cell per 2..8 agents: the table stays a small fraction of the records
+    mc = sim->capacity / 8;  // about one cell per 8..32 agents: the table stays a small fraction of the records
     if (mc < 4096) mc = 4096;
     if (mc > (1ull << 24)) mc = 1ull << 24;
   }
@@ -138,11 +138,15 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   sim->max_cells = (unsigned)mc;
   sim->hist_cap = cfg->history_capacity ? cfg->history_capacity : 4096;
   const size_t cap = sim->capacity;
+  const size_t capp = cap + kPad;  // the agent passes load whole tiles
   for (int b = 0; b < 2; ++b) {
-    CK(cudaMalloc(&sim->hot[b], cap * sizeof(uint4)));
-    CK(cudaMalloc(&sim->w[b], cap * sizeof(double)));
+    CK(cudaMalloc(&sim->hot[b], capp * sizeof(uint4)));
+    CK(cudaMalloc(&sim->w[b], capp * sizeof(double)));
+    CK(cudaMemsetAsync(sim->hot[b], 0, capp * sizeof(uint4), sim->stream));
+    CK(cudaMemsetAsync(sim->w[b], 0, capp * sizeof(double), sim->stream));
   }
-  CK(cudaMalloc(&sim->aux, cap * sizeof(uint2)));
+  CK(cudaMalloc(&sim->aux, capp * sizeof(uint2)));
+  CK(cudaMemsetAsync(sim->aux, 0, capp * sizeof(uint2), sim->stream));
   CK(cudaMalloc(&sim->inf_list, cap * sizeof(unsigned)));
   CK(cudaMalloc(&sim->sqrt_tab, kSqrtTable * sizeof(double)));
   for (int b = 0; b < 2; ++b) {
@@ -246,7 +250,7 @@ static void enqueue_build(cabs_sim *sim) {
   const int nb = agent_blocks(sim);
   LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl, sim->hot[c], sim->aux, sim->cells[t], sim->tile_state);
   LAUNCH(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
-  LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", k_update_scatter<kAdvance>, nb, 256, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t],
+  LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", k_update_scatter<kAdvance>, nb, kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t],
          sim->cells[t ^ 1], sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab);
   if (kAdvance) {
     LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, nullptr, nullptr,

@@ -210,6 +210,47 @@ __device__ __forceinline__ unsigned cell_key(const StepParams &P, int x, int y, 
   return (unsigned)cy * (unsigned)P.ncx + (unsigned)cx;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Bulk asynchronous copies (TMA, cp.async.bulk) global -> shared, completion on an mbarrier.  The agent
+// passes stream their input columns through a ring of shared-memory stages this way: the loads cost no
+// registers and run several tiles ahead of the arithmetic.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int kTile = 256;    // agents per tile = consumer threads per block of the agent passes
+constexpr int kPad = kTile;   // every per-agent array is allocated with this many spare elements (whole-tile loads)
+constexpr int kConsumerWarps = kTile / 32;
+constexpr int kAgentThreads = kTile + 32;  // + one producer warp that only issues the bulk loads
+
 // ------------------------------------------------------------------------------------------
 // Pass A: where will every agent be after this step's move?  Writes the displacement and the rank
 // inside the destination cell (for pass B) and counts the agent in the histogram of that cell.
@@ -217,6 +258,8 @@ __device__ __forceinline__ unsigned cell_key(const StepParams &P, int x, int y, 
 constexpr int kScanTile = 4096;      // histogram entries per scan tile (512 threads x 8)
 constexpr int kScanThreads = 512;
 
+// Pass A reads one 16-byte column with plenty of resident warps, so plain vectorised loads (one agent
+// ahead) do as well as staged ones; pass B, which streams three columns at low occupancy, stages them.
 template <bool kAdvance>
 __global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot,
                                                     uint2 *__restrict__ aux, unsigned *__restrict__ cells,
@@ -228,11 +271,19 @@ __global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
   // side job: reset the look-back state of the scan that follows
   {
-    const unsigned ntiles = ((unsigned)P.ncx * (unsigned)P.ncy + 1u + kScanTile - 1) / kScanTile;
-    for (unsigned t = tid; t < ntiles; t += stride) tile_state[t] = 0ull;
+    const unsigned nscan = ((unsigned)P.ncx * (unsigned)P.ncy + 1u + kScanTile - 1) / kScanTile;
+    for (unsigned t = tid; t < nscan; t += stride) tile_state[t] = 0ull;
   }
+  // the rank an atomic returns is stored one iteration later, so that its round trip to L2 overlaps
+  // the next agent's arithmetic
+  bool pending = false;
+  unsigned p_i = 0, p_rank = 0;
+  uint32_t p_d = 0;
+  uint4 h_next = make_uint4(0, 0, 0, 0);
+  if (tid < P.n) h_next = __ldg(&hot[tid]);
   for (unsigned i = tid; i < P.n; i += stride) {
-    const uint4 h = __ldg(&hot[i]);
+    const uint4 h = h_next;
+    if (i + stride < P.n) h_next = __ldg(&hot[i + stride]);
     int nx = (int)h.x, ny = (int)h.y;
     uint32_t d = 0;
     if (kAdvance) {
@@ -244,9 +295,13 @@ __global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const
       d = ((uint32_t)ix & 0xFFFFu) | ((uint32_t)iy << 16);
     }
     const unsigned key = cell_key(P, nx, ny, &ctl->err);
-    const unsigned rank = atomicAdd(&cells[key], 1u);
-    aux[i] = make_uint2(d, rank);
+    if (pending) aux[p_i] = make_uint2(p_d, p_rank);
+    p_rank = atomicAdd(&cells[key], 1u);
+    p_d = d;
+    p_i = i;
+    pending = true;
   }
+  if (pending) aux[p_i] = make_uint2(p_d, p_rank);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -411,18 +466,30 @@ __device__ __forceinline__ void advance_agent(const StepParams &P, uint32_t aid,
   a = attr_pack(st, sev, stratum, time, age) | (a & 0xFF000000u);
 }
 
+constexpr int kStagesB = 4;
+struct alignas(128) StageB {
+  uint4 hot[kTile];
+  double w[kTile];
+  uint2 aux[kTile];
+};
+
 template <bool kAdvance>
-__global__ void __launch_bounds__(256, CABS_B_MINBLOCKS)
+__global__ void __launch_bounds__(kAgentThreads, CABS_B_MINBLOCKS)
 k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const double *__restrict__ wealth,
                  const uint2 *__restrict__ aux, const unsigned *__restrict__ cell_start,
                  unsigned *__restrict__ stale_cells, uint4 *__restrict__ ohot, double *__restrict__ owealth,
                  unsigned *__restrict__ inf_list, const double *__restrict__ sqrt_tab) {
   __shared__ StepParams P;
   __shared__ BlockStats B;
-  __shared__ long long s_q[5][256];  // per-thread Q1..Q5 partial sums (abs.py:309-312), no bank conflicts
+  __shared__ long long s_q[5][kTile];  // per-thread Q1..Q5 partial sums (abs.py:309-312), no bank conflicts
   __shared__ unsigned s_stale;
+  __shared__ StageB s_in[kStagesB];
+  __shared__ uint64_t s_full[kStagesB], s_empty[kStagesB];
+  const bool producer = threadIdx.x >= kTile;
+  if (!producer) {
 #pragma unroll
-  for (int k = 0; k < 5; ++k) s_q[k][threadIdx.x] = 0;
+    for (int k = 0; k < 5; ++k) s_q[k][threadIdx.x] = 0;
+  }
   if (threadIdx.x == 0) {
     load_params(P, ctl);
     for (int i = 0; i < 7; ++i) B.cnt[i] = 0;
@@ -430,15 +497,34 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     B.bb[0] = B.bb[2] = INT_MAX;
     B.bb[1] = B.bb[3] = INT_MIN;
     s_stale = ctl->cells_used[ctl->cur_table ^ 1];
+    for (int k = 0; k < kStagesB; ++k) {
+      mbar_init(&s_full[k], 1);
+      mbar_init(&s_empty[k], kConsumerWarps);
+    }
+    mbar_fence_init();
   }
   __syncthreads();
+  const unsigned ntiles = (P.n + kTile - 1) / kTile;
+  constexpr unsigned kStageBytes = kTile * (sizeof(uint4) + sizeof(double) + sizeof(uint2));
+  if (threadIdx.x == kTile) {
+    // producer: keeps the ring of stages full; a stage is refilled as soon as all consumer warps released it
+    unsigned k = 0;
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+      const unsigned s = k % kStagesB;
+      if (k >= kStagesB) mbar_wait(&s_empty[s], ((k / kStagesB) - 1u) & 1u);
+      mbar_expect_tx(&s_full[s], kStageBytes);
+      bulk_load(s_in[s].hot, hot + (size_t)tile * kTile, kTile * sizeof(uint4), &s_full[s]);
+      bulk_load(s_in[s].w, wealth + (size_t)tile * kTile, kTile * sizeof(double), &s_full[s]);
+      bulk_load(s_in[s].aux, aux + (size_t)tile * kTile, kTile * sizeof(uint2), &s_full[s]);
+    }
+  }
   // side job: zero the cell table of the step before (the next step's histogram)
-  {
+  if (!producer) {
     const unsigned m = s_stale, m4 = m >> 2;
     uint4 *c4 = reinterpret_cast<uint4 *>(stale_cells);
     const unsigned chunk = (m4 + gridDim.x - 1) / gridDim.x;
     const unsigned b0 = min(m4, blockIdx.x * chunk), b1 = min(m4, b0 + chunk);
-    for (unsigned i = b0 + threadIdx.x; i < b1; i += blockDim.x) c4[i] = make_uint4(0, 0, 0, 0);
+    for (unsigned i = b0 + threadIdx.x; i < b1; i += kTile) c4[i] = make_uint4(0, 0, 0, 0);
     if (blockIdx.x == 0 && threadIdx.x < (m & 3u)) stale_cells[(m4 << 2) + threadIdx.x] = 0;
   }
   // per-thread partial statistics: 16-bit fields (a thread sees far fewer than 65535 agents per launch
@@ -446,30 +532,19 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
   unsigned long long c_st = 0, c_sev = 0;  // status S,I,R,D and severity A,H,G counts
   int bxmin = INT_MAX, bxmax = INT_MIN, bymin = INT_MAX, bymax = INT_MIN;
   const double qscale = (double)(1ull << P.scale_bits);
-
-  const unsigned stride = gridDim.x * blockDim.x;
   const unsigned lane = threadIdx.x & 31;
-  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  // software pipeline: the next agent's columns are requested before this agent's arithmetic starts
-  uint4 h_next = make_uint4(0, 0, 0, 0);
-  double w_next = 0.0;
-  uint2 x_next = make_uint2(0, 0);
-  if (i < P.n) {
-    h_next = __ldg(&hot[i]);
-    w_next = __ldg(&wealth[i]);
-    x_next = __ldg(&aux[i]);
-  }
-  // every lane of a warp runs the same number of iterations (full-mask ballots below)
-  for (unsigned i0 = i - lane; i0 < P.n; i0 += stride, i += stride) {
+
+  unsigned k = 0;
+  for (unsigned tile = blockIdx.x; tile < ntiles && !producer; tile += gridDim.x, ++k) {
+    const unsigned s = k % kStagesB;
+    mbar_wait(&s_full[s], (k / kStagesB) & 1u);
+    const uint4 h = s_in[s].hot[threadIdx.x];
+    double w = s_in[s].w[threadIdx.x];
+    const uint2 ax = s_in[s].aux[threadIdx.x];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[s]);  // this warp is done with the stage
+    const unsigned i = tile * kTile + threadIdx.x;
     const bool valid = i < P.n;
-    const uint4 h = h_next;
-    double w = w_next;
-    const uint2 ax = x_next;
-    if (i + stride < P.n) {
-      h_next = __ldg(&hot[i + stride]);
-      w_next = __ldg(&wealth[i + stride]);
-      x_next = __ldg(&aux[i + stride]);
-    }
     int nx = (int)h.x, ny = (int)h.y;
     uint32_t a = attr_normalize(h.z);
     const uint32_t aid = h.w;
@@ -505,7 +580,7 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     }
   }
   // block reduction: per-warp shared atomics, then one set of global atomics per block
-  {
+  if (!producer) {
     unsigned long long cnt[7];
     long long q[5];
 #pragma unroll
