@@ -22,7 +22,10 @@ OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_DOMAIN, ERR_NOGPU = 0, -1, -2, -3, 
 EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params", "cabs_set_triggers",
             "cabs_upload", "cabs_download", "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_history",
             "cabs_contact_pairs", "cabs_get_info", "cabs_event_record", "cabs_event_elapsed_ms",
-            "cabs_profile_enable", "cabs_profile_read")
+            "cabs_profile_enable", "cabs_profile_read", "cabs_set_slab", "cabs_slab_phase", "cabs_set_stream")
+
+SLAB_ROW, MIGRANT_BYTES, GHOST_BYTES, EXCHANGE_HEADER_BYTES = 16, 32, 16, 32
+INT32_MIN, INT32_MAX = -2 ** 31, 2 ** 31 - 1
 
 
 class NativeError(RuntimeError):
@@ -64,6 +67,13 @@ class Info(C.Structure):
                 ("cells_x", C.c_int32), ("cells_y", C.c_int32), ("device_error", C.c_uint32)]
 
 
+class Slab(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("n_ranks", C.c_int32), ("x_lo", C.c_int32), ("x_hi", C.c_int32),
+                ("migrant_capacity", C.c_uint32), ("ghost_capacity", C.c_uint32),
+                ("migrant_send", C.c_void_p * 2), ("migrant_recv", C.c_void_p * 2),
+                ("ghost_send", C.c_void_p * 2), ("ghost_recv", C.c_void_p * 2), ("stats_rows", C.c_void_p)]
+
+
 class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_uint64), ("total_ms", C.c_double)]
 
@@ -100,6 +110,9 @@ def load():
     lib.cabs_event_elapsed_ms.argtypes = [P, C.c_int, C.c_int, C.POINTER(C.c_double)]
     lib.cabs_profile_enable.argtypes = [P, C.c_int]
     lib.cabs_profile_read.argtypes = [P, C.POINTER(KernelTime), C.c_int, C.POINTER(C.c_int)]
+    lib.cabs_set_slab.argtypes = [P, C.POINTER(Slab)]
+    lib.cabs_slab_phase.argtypes = [P, C.c_int, C.c_int]
+    lib.cabs_set_stream.argtypes = [P, C.c_void_p]
     for name in EXPORTED:
         fn = getattr(lib, name)
         if name not in ("cabs_destroy", "cabs_last_error"):
@@ -181,7 +194,18 @@ class Handle(object):
         cols = {name: np.empty(n, dtype=dt) for name, dt in SOA_DTYPES}
         s = self._soa(cols, n)
         self._check(self._lib.cabs_download(self._h, C.byref(s)))
+        if s.n != n:
+            cols = {k: v[:s.n] for k, v in cols.items()}
         return cols
+
+    def set_slab(self, slab):
+        self._check(self._lib.cabs_set_slab(self._h, C.byref(slab)))
+
+    def slab_phase(self, phase, advance=True):
+        self._check(self._lib.cabs_slab_phase(self._h, int(phase), 1 if advance else 0))
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.cabs_set_stream(self._h, C.c_void_p(int(cuda_stream) or None)))
 
     def step(self, nsteps=1):
         self._check(self._lib.cabs_step(self._h, int(nsteps)))

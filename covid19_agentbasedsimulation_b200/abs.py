@@ -156,6 +156,10 @@ class Simulation(object):
             self._pushed_triggers = None
         return self._handle
 
+    def _targets(self):
+        """Handles that hold a part of this population (several in slab mode)."""
+        return [self._handle]
+
     def _param_tuple(self):
         amp = amplitude_array(self.amplitudes)
         return (float(self.length), float(self.height), float(self.contagion_distance), float(self.contagion_rate),
@@ -178,7 +182,8 @@ class Simulation(object):
             p.recovering_time = 20  # abs.py:225
             p.wealth_scale_bits = wealth_scale_bits(tw)
             p.schedule = _native.SYNCHRONOUS
-            self._handle.set_params(p)
+            for h in self._targets():
+                h.set_params(p)
             self._pushed = t
         decl = [t for t in self.triggers_simulation if isinstance(t, Trigger)]
         key = tuple((t.metric, t.op, t.threshold, t.attribute, repr(t.value)) for t in decl)
@@ -193,7 +198,8 @@ class Simulation(object):
                 else:
                     n.value[:] = [float(t.value), 0.0, 0.0, 0.0]
                 native.append(n)
-            self._handle.set_triggers(native)
+            for h in self._targets():
+                h.set_triggers(native)
             self._pushed_triggers = key
 
     def set_population_arrays(self, x, y, status, age, stratum, wealth, severity=None, infected_time=None):

@@ -33,6 +33,11 @@ struct cabs_sim {
   int tab = 0;                  // table the next build uses (mirrors Ctl::cur_table)
   unsigned long long *tile_state = nullptr;  // look-back state of the scan
   unsigned *inf_list = nullptr; // slots of the Infected agents (sources of the contact pass)
+  // slab decomposition
+  bool slab_on = false;
+  cabs_slab slab;
+  unsigned *emig_list = nullptr, *imm_rank = nullptr;
+  cudaStream_t own_stream = nullptr;
   Ctl *ctl = nullptr;
   StatRecord *history = nullptr;
   uint8_t *stage = nullptr;     // byte-column staging for upload/download: 5 * capacity
@@ -100,12 +105,14 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
   if (!sim) return;
   cudaSetDevice(sim->device);
   if (sim->stream) cudaStreamSynchronize(sim->stream);
+  if (sim->own_stream) sim->stream = sim->own_stream;
   for (int b = 0; b < 2; ++b) {
     cudaFree(sim->hot[b]); cudaFree(sim->w[b]);
   }
   cudaFree(sim->aux);
   cudaFree(sim->sqrt_tab);
   cudaFree(sim->cells[0]); cudaFree(sim->cells[1]); cudaFree(sim->tile_state); cudaFree(sim->inf_list);
+  cudaFree(sim->emig_list); cudaFree(sim->imm_rank);
   cudaFree(sim->ctl); cudaFree(sim->history);
   cudaFree(sim->stage); cudaFree(sim->stage_id); cudaFree(sim->pairs); cudaFree(sim->pair_count);
   for (cudaEvent_t e : sim->events) if (e) cudaEventDestroy(e);
@@ -125,6 +132,7 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   CK(cudaGetDeviceProperties(&prop, sim->device));
   sim->num_sms = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
+  sim->own_stream = sim->stream;
   sim->capacity = cfg->capacity ? cfg->capacity : 1;
   if (sim->capacity >= (1ull << 31)) return fail(sim, CABS_ERR_CAPACITY, "capacity must be < 2^31 agents per device");
   uint64_t mc = cfg->max_cells;
@@ -162,7 +170,7 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   CK(cudaMemsetAsync(sim->ctl, 0, sizeof(Ctl), sim->stream));
   CK(cudaMemsetAsync(sim->history, 0, (size_t)sim->hist_cap * sizeof(StatRecord), sim->stream));
   LAUNCH(k_init_ctl, 1, 256, sim->ctl, (unsigned)(cfg->seed & 0xFFFFFFFFu), (unsigned)(cfg->seed >> 32),
-         sim->max_cells, sim->hist_cap, sim->sqrt_tab);
+         sim->max_cells, sim->hist_cap, (unsigned)sim->capacity, sim->sqrt_tab);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(sim->stream));
   return CABS_OK;
@@ -248,13 +256,12 @@ template <bool kAdvance>
 static void enqueue_build(cabs_sim *sim) {
   const int c = sim->cur, o = c ^ 1, t = sim->tab;
   const int nb = agent_blocks(sim);
-  LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl, sim->hot[c], sim->aux, sim->cells[t], sim->tile_state);
+  LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl, sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list);
   LAUNCH(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
   LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", k_update_scatter<kAdvance>, nb, kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t],
-         sim->cells[t ^ 1], sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab);
+         sim->cells[t ^ 1], sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, nullptr, nullptr);
   if (kAdvance) {
-    LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, nullptr, nullptr,
-           sim->history, 1);
+    LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, nullptr, sim->history, 1);
   } else {
     LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 0);
   }
@@ -269,6 +276,126 @@ static int rebuild_static(cabs_sim *sim) {
   enqueue_build<false>(sim);
   CK(cudaGetLastError());
   sim->cells_dirty = false;
+  return CABS_OK;
+}
+
+
+// ---- slab decomposition -------------------------------------------------------------------------
+extern "C" int cabs_set_stream(cabs_sim *sim, void *cuda_stream) {
+  if (!sim) return fail(sim, CABS_ERR_INVALID, "cabs_set_stream: null handle");
+  CK(cudaSetDevice(sim->device));
+  CK(cudaStreamSynchronize(sim->stream));
+  sim->stream = (cudaStream_t)cuda_stream;  // NULL is CUDA's default stream
+  return CABS_OK;
+}
+
+extern "C" int cabs_set_slab(cabs_sim *sim, const cabs_slab *slab) {
+  if (!sim || !slab) return fail(sim, CABS_ERR_INVALID, "cabs_set_slab: null argument");
+  if (slab->n_ranks < 1 || slab->rank < 0 || slab->rank >= slab->n_ranks || slab->x_lo >= slab->x_hi)
+    return fail(sim, CABS_ERR_INVALID, "cabs_set_slab: bad rank / bounds");
+  if (slab->migrant_capacity == 0 || slab->ghost_capacity == 0 || !slab->stats_rows)
+    return fail(sim, CABS_ERR_INVALID, "cabs_set_slab: capacities and stats_rows are required");
+  for (int d = 0; d < 2; ++d)
+    if (!slab->migrant_send[d] || !slab->migrant_recv[d] || !slab->ghost_send[d] || !slab->ghost_recv[d])
+      return fail(sim, CABS_ERR_INVALID, "cabs_set_slab: null exchange buffer");
+  CK(cudaSetDevice(sim->device));
+  CK(cudaStreamSynchronize(sim->stream));
+  cudaFree(sim->emig_list); cudaFree(sim->imm_rank);
+  sim->emig_list = sim->imm_rank = nullptr;
+  CK(cudaMalloc(&sim->emig_list, 2 * (size_t)slab->migrant_capacity * sizeof(unsigned)));
+  CK(cudaMalloc(&sim->imm_rank, 2 * (size_t)slab->migrant_capacity * sizeof(unsigned)));
+  sim->slab = *slab;
+  sim->slab_on = true;
+  LAUNCH(k_set_slab, 1, 32, sim->ctl, slab->rank, slab->n_ranks, slab->x_lo, slab->x_hi, slab->migrant_capacity,
+         slab->ghost_capacity);
+  if (sim->n > 0) LAUNCH(k_replan, 1, 32, sim->ctl, 0);
+  CK(cudaGetLastError());
+  sim->cells_dirty = true;
+  return CABS_OK;
+}
+
+template <bool kAdvance>
+static int slab_phase(cabs_sim *sim, int phase) {
+  const cabs_slab &sl = sim->slab;
+  const int c = sim->cur, o = c ^ 1, t = sim->tab;
+  const int nb = agent_blocks(sim), nbs = sim->num_sms;  // the exchange kernels see few records
+  ExchangeHeader *ms[2] = {(ExchangeHeader *)sl.migrant_send[0], (ExchangeHeader *)sl.migrant_send[1]};
+  ExchangeHeader *mr[2] = {(ExchangeHeader *)sl.migrant_recv[0], (ExchangeHeader *)sl.migrant_recv[1]};
+  ExchangeHeader *gs[2] = {(ExchangeHeader *)sl.ghost_send[0], (ExchangeHeader *)sl.ghost_send[1]};
+  ExchangeHeader *gr[2] = {(ExchangeHeader *)sl.ghost_recv[0], (ExchangeHeader *)sl.ghost_recv[1]};
+  switch (phase) {
+    case 0:
+      for (int d = 0; d < 2; ++d) {
+        CK(cudaMemsetAsync(ms[d], 0, sizeof(ExchangeHeader), sim->stream));
+        CK(cudaMemsetAsync(gs[d], 0, sizeof(ExchangeHeader), sim->stream));
+      }
+      // no neighbour on an outer side: nothing will be written into those receive buffers
+      if (sl.rank == 0) {
+        CK(cudaMemsetAsync(mr[0], 0, sizeof(ExchangeHeader), sim->stream));
+        CK(cudaMemsetAsync(gr[0], 0, sizeof(ExchangeHeader), sim->stream));
+      }
+      if (sl.rank == sl.n_ranks - 1) {
+        CK(cudaMemsetAsync(mr[1], 0, sizeof(ExchangeHeader), sim->stream));
+        CK(cudaMemsetAsync(gr[1], 0, sizeof(ExchangeHeader), sim->stream));
+      }
+      if (!kAdvance) {
+        LAUNCH(k_bbox, nb, 256, sim->ctl, sim->hot[c]);
+        LAUNCH(k_replan, 1, 32, sim->ctl, 1);
+      }
+      LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl,
+                sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list);
+      LAUNCH_AS("k_pack_emigrants", k_pack_emigrants<kAdvance>, nbs, 256, sim->ctl, sim->hot[c], sim->w[c], sim->aux,
+                sim->emig_list, ms[0], ms[1], sim->sqrt_tab);
+      break;
+    case 1:
+      LAUNCH(k_count_immigrants, nbs, 256, sim->ctl, mr[0], mr[1], sim->cells[t], sim->imm_rank);
+      LAUNCH(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
+      LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", k_update_scatter<kAdvance>, nb,
+                kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t], sim->cells[t ^ 1],
+                sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, gs[0], gs[1]);
+      LAUNCH(k_scatter_immigrants, nbs, 256, sim->ctl, mr[0], mr[1], sim->cells[t], sim->imm_rank, sim->hot[o],
+             sim->w[o], sim->inf_list, gs[0], gs[1]);
+      break;
+    case 2:
+      if (kAdvance) {
+        LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, nullptr, sim->history, 0);
+        LAUNCH_AS("k_contagion(ghosts)", k_contagion, nbs, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list,
+                  gr[0], sim->history, 0);
+        LAUNCH_AS("k_contagion(ghosts)", k_contagion, nbs, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list,
+                  gr[1], sim->history, 0);
+      }
+      LAUNCH(k_slab_export, 1, 32, sim->ctl, (long long *)sl.stats_rows);
+      break;
+    case 3:
+      LAUNCH(k_slab_close, 1, 32, sim->ctl, (const long long *)sl.stats_rows, sim->cells[t], sim->history,
+             kAdvance ? 1 : 0);
+      sim->cur = o;
+      sim->tab = t ^ 1;
+      if (kAdvance) sim->step++;
+      sim->cells_dirty = false;
+      break;
+    default:
+      return fail(sim, CABS_ERR_INVALID, "cabs_slab_phase: phase must be 0..3");
+  }
+  CK(cudaGetLastError());
+  return CABS_OK;
+}
+
+extern "C" int cabs_slab_phase(cabs_sim *sim, int phase, int advance) {
+  if (!sim) return fail(sim, CABS_ERR_INVALID, "cabs_slab_phase: null handle");
+  if (!sim->slab_on) return fail(sim, CABS_ERR_INVALID, "cabs_slab_phase: call cabs_set_slab first");
+  if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_slab_phase: call cabs_set_params first");
+  CK(cudaSetDevice(sim->device));
+  return advance ? slab_phase<true>(sim, phase) : slab_phase<false>(sim, phase);
+}
+
+// number of resident agents (changes on the device when agents migrate between slabs)
+static int refresh_n(cabs_sim *sim) {
+  if (!sim->slab_on) return CABS_OK;
+  unsigned n = 0;
+  CK(cudaMemcpyAsync(&n, &sim->ctl->n, sizeof n, cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  sim->n = n;
   return CABS_OK;
 }
 
@@ -304,19 +431,28 @@ extern "C" int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop) {
   CK(cudaMemcpyAsync(&sim->ctl->step, &zero, sizeof(unsigned), cudaMemcpyHostToDevice, sim->stream));
   sim->n = n;
   sim->step = 0;
+  if (sim->slab_on) {  // the caller drives the four phases of the first build (advance = 0)
+    sim->cells_dirty = true;
+    CK(cudaGetLastError());
+    return CABS_OK;
+  }
   return rebuild_static(sim);
 }
 
 extern "C" int cabs_download(cabs_sim *sim, cabs_soa_host *pop) {
   if (!sim || !pop) return fail(sim, CABS_ERR_INVALID, "cabs_download: null argument");
-  if (pop->n < sim->n) return fail(sim, CABS_ERR_CAPACITY, "cabs_download: host buffers smaller than the population");
   CK(cudaSetDevice(sim->device));
+  {
+    const int rc = refresh_n(sim);
+    if (rc != CABS_OK) return rc;
+  }
+  if (pop->n < sim->n) return fail(sim, CABS_ERR_CAPACITY, "cabs_download: host buffers smaller than the population");
   const size_t n = sim->n, cap = sim->capacity;
   pop->n = n;
   if (n == 0) return CABS_OK;
   const int c = sim->cur, o = c ^ 1;  // the other copy is free between steps: use it as scratch
   int *sx = reinterpret_cast<int *>(sim->hot[o]), *sy = sx + cap;
-  LAUNCH(k_unpack, agent_blocks(sim), 256, (unsigned)n, 0, sim->hot[c], sim->w[c], sx, sy, sim->stage + 0 * cap,
+  LAUNCH(k_unpack, agent_blocks(sim), 256, (unsigned)n, sim->slab_on ? 1 : 0, sim->hot[c], sim->w[c], sx, sy, sim->stage + 0 * cap,
          sim->stage + 1 * cap, sim->stage + 2 * cap, sim->stage + 3 * cap, sim->stage + 4 * cap, sim->w[o],
          sim->stage_id);
   CK(cudaGetLastError());
@@ -337,6 +473,7 @@ extern "C" int cabs_download(cabs_sim *sim, cabs_soa_host *pop) {
 extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
   if (!sim || nsteps < 0) return fail(sim, CABS_ERR_INVALID, "cabs_step: bad argument");
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_step: call cabs_set_params first");
+  if (sim->slab_on) return fail(sim, CABS_ERR_INVALID, "cabs_step: a slab handle is stepped with cabs_slab_phase");
   CK(cudaSetDevice(sim->device));
   for (int s = 0; s < nsteps; ++s) {
     enqueue_build<true>(sim);
@@ -354,6 +491,8 @@ static int check_device_error(cabs_sim *sim) {
   CK(cudaStreamSynchronize(sim->stream));
   if (err & kErrDomain) return fail(sim, CABS_ERR_DOMAIN, "population bounding box exceeds the supported 2^28 lattice units");
   if (err & kErrOutOfGrid) return fail(sim, CABS_ERR_DOMAIN, "internal: an agent left the planned cell grid");
+  if (err & kErrExchange)
+    return fail(sim, CABS_ERR_CAPACITY, "slab exchange overflow: more migrants / ghosts / residents than the buffers hold");
   return CABS_OK;
 }
 
@@ -412,6 +551,7 @@ extern "C" int cabs_contact_pairs(cabs_sim *sim, int64_t *ij, size_t capacity_pa
   if (!sim || !n_pairs || (capacity_pairs && !ij)) return fail(sim, CABS_ERR_INVALID, "cabs_contact_pairs: null argument");
   CK(cudaSetDevice(sim->device));
   if (sim->cells_dirty) {
+    if (sim->slab_on) return fail(sim, CABS_ERR_INVALID, "cabs_contact_pairs: run a slab build first");
     const int rc = rebuild_static(sim);
     if (rc != CABS_OK) return rc;
   }
@@ -442,6 +582,7 @@ extern "C" int cabs_get_info(cabs_sim *sim, cabs_info *info) {
   Ctl h;
   CK(cudaMemcpyAsync(&h, sim->ctl, sizeof h, cudaMemcpyDeviceToHost, sim->stream));
   CK(cudaStreamSynchronize(sim->stream));
+  if (sim->slab_on) sim->n = h.n;
   info->n = sim->n;
   info->step = sim->step;
   info->kernel_launches = sim->launches;

@@ -96,14 +96,17 @@ struct Ctl {
   long long thr_rate;
   // ---- slab decomposition: this device owns lattice columns [slab_lo, slab_hi)
   int slab_lo, slab_hi;
-  int n_ranks;        // 1: no decomposition
+  int n_ranks, rank;  // n_ranks 1: no decomposition
+  unsigned capacity;  // records the population arrays hold
+  unsigned mig_cap, ghost_cap;  // records per exchange buffer
+  int overflow;       // residents + immigrants would not fit `capacity`: the scatter passes stand down
   // ---- accumulators of the running step
   unsigned long long cnt[7];
   long long q[5];
   unsigned long long newinf;
   int bb_xmin, bb_xmax, bb_ymin, bb_ymax;
   unsigned n_inf;          // entries of the Infected-slot list
-  unsigned n_next;         // agents resident after this step's migration
+  unsigned n_emig;         // agents that leave this slab in the running step
   unsigned scan_ticket;    // next tile of the scan
   unsigned done_ticket;    // blocks of k_contagion that have finished
   // ---- statistics of the previous step (what triggers and the critical-limit test read)
@@ -147,6 +150,7 @@ struct StepParams {
   long long thr_rate;
   int T, reach, recovering_time, scale_bits, crit_active;
   int len_i, hei_i;  // x >= length  <=>  x >= ceil(length) for integer x (abs.py:177,182)
+  int slab_lo, slab_hi, overflow;
   unsigned k0, k1, step, n;
 };
 
@@ -171,6 +175,7 @@ __device__ __forceinline__ void load_params(StepParams &P, const Ctl *ctl, bool 
   P.reach = reach;
   P.recovering_time = ctl->recovering_time; P.scale_bits = ctl->scale_bits;
   P.crit_active = ctl->crit_active;
+  P.slab_lo = ctl->slab_lo; P.slab_hi = ctl->slab_hi; P.overflow = ctl->overflow;
   P.k0 = ctl->k0; P.k1 = ctl->k1; P.step = ctl->step; P.n = ctl->n;
 }
 
@@ -210,6 +215,24 @@ __device__ __forceinline__ unsigned cell_key(const StepParams &P, int x, int y, 
   return (unsigned)cy * (unsigned)P.ncx + (unsigned)cx;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Slab decomposition.  A device owns the lattice columns [slab_lo, slab_hi).  Agents whose
+// move takes them out of the slab travel to the neighbour as complete post-update records (exchange 1,
+// before the cell-list scan, so that the receiver can count them in its histogram); Infected agents within
+// reach of a slab edge are sent as ghosts (exchange 2) and push their contacts on the neighbour's side.
+// Exchange buffers (caller-allocated device memory): a 32-byte header {count} followed by the records.
+constexpr unsigned kEmigrant = 0xFFFFFFFFu;  // aux rank of an agent that leaves the slab
+struct alignas(32) MigrantRecord {
+  uint4 hot;
+  double w;
+  unsigned long long pad;
+};
+struct alignas(32) ExchangeHeader {
+  unsigned count;
+  unsigned pad[7];
+};
+constexpr int kSlabRow = 16;  // int64 values per rank in the statistics all-gather
 
 // ------------------------------------------------------------------------------------------
 // Bulk asynchronous copies (TMA, cp.async.bulk) global -> shared, completion on an mbarrier.  The agent
@@ -263,7 +286,8 @@ constexpr int kScanThreads = 512;
 template <bool kAdvance>
 __global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot,
                                                     uint2 *__restrict__ aux, unsigned *__restrict__ cells,
-                                                    unsigned long long *__restrict__ tile_state) {
+                                                    unsigned long long *__restrict__ tile_state,
+                                                    unsigned *__restrict__ emig_list) {
   __shared__ StepParams P;
   if (threadIdx.x == 0) load_params(P, ctl);
   __syncthreads();
@@ -293,6 +317,14 @@ __global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const
       draw_displacement(P, a, w, ix, iy);
       apply_displacement(P, nx, ny, ix, iy, nx, ny);
       d = ((uint32_t)ix & 0xFFFFu) | ((uint32_t)iy << 16);
+    }
+    if (nx < P.slab_lo || nx >= P.slab_hi) {
+      // leaves the slab: k_pack_emigrants finishes its step and hands it to the neighbour
+      const unsigned e = atomicAdd(&ctl->n_emig, 1u);
+      if (e < 2u * ctl->mig_cap) emig_list[e] = i;
+      else atomicOr(&ctl->err, kErrExchange);
+      aux[i] = make_uint2(d, kEmigrant);
+      continue;
     }
     const unsigned key = cell_key(P, nx, ny, &ctl->err);
     if (pending) aux[p_i] = make_uint2(p_d, p_rank);
@@ -466,6 +498,23 @@ __device__ __forceinline__ void advance_agent(const StepParams &P, uint32_t aid,
   a = attr_pack(st, sev, stratum, time, age) | (a & 0xFF000000u);
 }
 
+// An Infected agent within reach of a slab edge also pushes its contacts on the neighbour's side.
+__device__ __forceinline__ void send_ghost(Ctl *ctl, const StepParams &P, const uint4 &rec,
+                                           ExchangeHeader *__restrict__ ghost_left,
+                                           ExchangeHeader *__restrict__ ghost_right) {
+  const int x = (int)rec.x;
+  if (P.slab_lo != INT_MIN && (long long)x - P.reach < (long long)P.slab_lo && P.T >= 0) {
+    const unsigned g = atomicAdd(&ghost_left->count, 1u);
+    if (g < ctl->ghost_cap) reinterpret_cast<uint4 *>(ghost_left + 1)[g] = rec;
+    else atomicOr(&ctl->err, kErrExchange);
+  }
+  if (P.slab_hi != INT_MAX && (long long)x + P.reach >= (long long)P.slab_hi && P.T >= 0) {
+    const unsigned g = atomicAdd(&ghost_right->count, 1u);
+    if (g < ctl->ghost_cap) reinterpret_cast<uint4 *>(ghost_right + 1)[g] = rec;
+    else atomicOr(&ctl->err, kErrExchange);
+  }
+}
+
 constexpr int kStagesB = 4;
 struct alignas(128) StageB {
   uint4 hot[kTile];
@@ -478,7 +527,8 @@ __global__ void __launch_bounds__(kAgentThreads, CABS_B_MINBLOCKS)
 k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const double *__restrict__ wealth,
                  const uint2 *__restrict__ aux, const unsigned *__restrict__ cell_start,
                  unsigned *__restrict__ stale_cells, uint4 *__restrict__ ohot, double *__restrict__ owealth,
-                 unsigned *__restrict__ inf_list, const double *__restrict__ sqrt_tab) {
+                 unsigned *__restrict__ inf_list, const double *__restrict__ sqrt_tab,
+                 ExchangeHeader *__restrict__ ghost_left, ExchangeHeader *__restrict__ ghost_right) {
   __shared__ StepParams P;
   __shared__ BlockStats B;
   __shared__ long long s_q[5][kTile];  // per-thread Q1..Q5 partial sums (abs.py:309-312), no bank conflicts
@@ -544,7 +594,7 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[s]);  // this warp is done with the stage
     const unsigned i = tile * kTile + threadIdx.x;
-    const bool valid = i < P.n;
+    const bool valid = i < P.n && ax.y != kEmigrant && !P.overflow;
     int nx = (int)h.x, ny = (int)h.y;
     uint32_t a = attr_normalize(h.z);
     const uint32_t aid = h.w;
@@ -576,7 +626,10 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
       unsigned base = 0;
       if (lane == 0) base = atomicAdd(&ctl->n_inf, (unsigned)__popc(m_inf));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (is_inf) inf_list[base + __popc(m_inf & ((1u << lane) - 1u))] = slot;
+      if (is_inf) {
+        inf_list[base + __popc(m_inf & ((1u << lane) - 1u))] = slot;
+        send_ghost(ctl, P, make_uint4((uint32_t)nx, (uint32_t)ny, a, aid), ghost_left, ghost_right);
+      }
     }
   }
   // block reduction: per-warp shared atomics, then one set of global atomics per block
@@ -620,6 +673,114 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
 }
 
 // ------------------------------------------------------------------------------------------
+// Slab exchange 1, sender side: the agents pass A found leaving the slab finish their step here
+// (abs.py:156-230) and are appended, as complete records, to the buffer of the neighbour they move to.
+template <bool kAdvance>
+__global__ void __launch_bounds__(256)
+k_pack_emigrants(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const double *__restrict__ wealth,
+                 const uint2 *__restrict__ aux, const unsigned *__restrict__ emig_list,
+                 ExchangeHeader *__restrict__ send_left, ExchangeHeader *__restrict__ send_right,
+                 const double *__restrict__ sqrt_tab) {
+  __shared__ StepParams P;
+  if (threadIdx.x == 0) load_params(P, ctl);
+  __syncthreads();
+  const unsigned count = min(ctl->n_emig, 2u * ctl->mig_cap);
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+    const unsigned i = emig_list[t];
+    const uint4 h = hot[i];
+    double w = wealth[i];
+    const uint2 ax = aux[i];
+    int nx = (int)h.x, ny = (int)h.y;
+    uint32_t a = attr_normalize(h.z);
+    const int ix = (int)(short)(ax.x & 0xFFFFu), iy = (int)(short)(ax.x >> 16);
+    if (kAdvance) {
+      apply_displacement(P, nx, ny, ix, iy, nx, ny);
+      advance_agent(P, h.w, ix, iy, a, w, sqrt_tab);
+    }
+    ExchangeHeader *dst = nx < P.slab_lo ? send_left : send_right;
+    const unsigned k = atomicAdd(&dst->count, 1u);
+    if (k < ctl->mig_cap) {
+      MigrantRecord r;
+      r.hot = make_uint4((uint32_t)nx, (uint32_t)ny, a, h.w);
+      r.w = w;
+      r.pad = 0;
+      reinterpret_cast<MigrantRecord *>(dst + 1)[k] = r;
+    } else {
+      atomicOr(&ctl->err, kErrExchange);
+    }
+  }
+}
+
+// Slab exchange 1, receiver side, before the scan: count the immigrants in the histogram and keep
+// their ranks; check that residents + immigrants fit.
+__global__ void __launch_bounds__(256)
+k_count_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ recv_left,
+                   const ExchangeHeader *__restrict__ recv_right, unsigned *__restrict__ cells,
+                   unsigned *__restrict__ imm_rank) {
+  __shared__ StepParams P;
+  if (threadIdx.x == 0) load_params(P, ctl);
+  __syncthreads();
+  const unsigned cap = ctl->mig_cap;
+  const unsigned nl = min(recv_left->count, cap), nr = min(recv_right->count, cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (recv_left->count > cap || recv_right->count > cap) atomicOr(&ctl->err, kErrExchange);
+    const unsigned long long total = (unsigned long long)P.n - min(ctl->n_emig, P.n) + nl + nr;
+    if (total > ctl->capacity) {
+      ctl->overflow = 1;
+      atomicOr(&ctl->err, kErrExchange);
+    }
+  }
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < nl + nr; t += gridDim.x * blockDim.x) {
+    const MigrantRecord *src = t < nl ? reinterpret_cast<const MigrantRecord *>(recv_left + 1) + t
+                                      : reinterpret_cast<const MigrantRecord *>(recv_right + 1) + (t - nl);
+    const uint4 h = src->hot;
+    imm_rank[t] = atomicAdd(&cells[cell_key(P, (int)h.x, (int)h.y, &ctl->err)], 1u);
+  }
+}
+
+// Slab exchange 1, receiver side, after the scan: the immigrants take their slots; statistics, Infected
+// list and ghosts exactly as pass B does for the residents (every agent is counted once, by the device
+// that owns it after the move).
+__global__ void __launch_bounds__(256)
+k_scatter_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ recv_left,
+                     const ExchangeHeader *__restrict__ recv_right, const unsigned *__restrict__ cell_start,
+                     const unsigned *__restrict__ imm_rank, uint4 *__restrict__ ohot, double *__restrict__ owealth,
+                     unsigned *__restrict__ inf_list, ExchangeHeader *__restrict__ ghost_left,
+                     ExchangeHeader *__restrict__ ghost_right) {
+  __shared__ StepParams P;
+  if (threadIdx.x == 0) load_params(P, ctl);
+  __syncthreads();
+  if (P.overflow) return;
+  const unsigned cap = ctl->mig_cap;
+  const unsigned nl = min(recv_left->count, cap), nr = min(recv_right->count, cap);
+  const double qscale = (double)(1ull << P.scale_bits);
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < nl + nr; t += gridDim.x * blockDim.x) {
+    const MigrantRecord *src = t < nl ? reinterpret_cast<const MigrantRecord *>(recv_left + 1) + t
+                                      : reinterpret_cast<const MigrantRecord *>(recv_right + 1) + (t - nl);
+    const uint4 h = src->hot;
+    const double w = src->w;
+    const int nx = (int)h.x, ny = (int)h.y;
+    const uint32_t a = h.z, st = attr_status(a), sev = attr_severity(a);
+    const unsigned slot = cell_start[cell_key(P, nx, ny, &ctl->err)] + imm_rank[t];
+    atomicAdd(&ctl->cnt[st], 1ull);
+    if (st != ST_D) {
+      if (sev != SEV_E) atomicAdd(&ctl->cnt[3 + sev], 1ull);
+      if (attr_age(a) >= 18u)
+        atomicAdd((unsigned long long *)&ctl->q[min(attr_stratum(a), 4u)],
+                  (unsigned long long)__double2ll_rn(__dmul_rn(w, qscale)));
+    }
+    atomicMin(&ctl->bb_xmin, nx); atomicMax(&ctl->bb_xmax, nx);
+    atomicMin(&ctl->bb_ymin, ny); atomicMax(&ctl->bb_ymax, ny);
+    ohot[slot] = h;
+    owealth[slot] = w;
+    if (st == ST_I) {
+      inf_list[atomicAdd(&ctl->n_inf, 1u)] = slot;
+      send_ghost(ctl, P, h, ghost_left, ghost_right);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Cells a contact of the agent at (x, y) can be in: columns [clo, chi] of rows [rlo, rhi].  Only the
 // cells that intersect [x - reach, x + reach] x [y - reach, y + reach] (reach = floor(sqrt(T)) <= cell
 // edge); each row's columns are one contiguous slot range [cell_start[row*ncx+clo], cell_start[row*ncx+chi+1]).
@@ -636,20 +797,21 @@ __device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats);
 // Pass C: the contact loop of abs.py:249-265 pushed from the agents that were Infected before this
 // contact phase (the list pass B wrote) to the Susceptible agents in reach; contact() = abs.py:141-154
 // with one draw per pair, keyed on the pair so that the result does not depend on who scans whom.
-//   src == nullptr: the sources are the slots in inf_list (count ctl->n_inf);
-//   src != nullptr: the sources are the records src[0 .. n_src) (ghost Infected agents of a neighbour slab).
+//   ghosts == nullptr: the sources are the slots in inf_list (count ctl->n_inf);
+//   ghosts != nullptr: the sources are the records of that exchange buffer (Infected agents of a neighbour slab).
 __global__ void __launch_bounds__(256)
 k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
-            const unsigned *__restrict__ inf_list, const uint4 *__restrict__ src, const unsigned *__restrict__ n_src,
+            const unsigned *__restrict__ inf_list, const ExchangeHeader *__restrict__ ghosts,
             StatRecord *__restrict__ history, int close) {
   __shared__ StepParams P;
   __shared__ unsigned s_new, s_count;
   if (threadIdx.x == 0) {
     load_params(P, ctl);
     s_new = 0;
-    s_count = src ? *n_src : ctl->n_inf;
+    s_count = ghosts ? min(ghosts->count, ctl->ghost_cap) : ctl->n_inf;
   }
   __syncthreads();
+  const uint4 *src = ghosts ? reinterpret_cast<const uint4 *>(ghosts + 1) : nullptr;
   unsigned newinf = 0;
   const unsigned stride = gridDim.x * blockDim.x;
   if (P.T >= 0) {
@@ -737,8 +899,12 @@ __device__ inline void plan_grid(Ctl *ctl, int xmin, int xmax, int ymin, int yma
     for (int k = 0; k < 3; ++k) amax = fmaxf(amax, fabsf(ctl->amp[k]));
     margin = (int)(kMaxAbsNormal * amax) + 2;
   }
-  const long long x0 = (long long)xmin - margin, x1 = (long long)xmax + margin;
+  long long x0 = (long long)xmin - margin, x1 = (long long)xmax + margin;
   const long long y0 = (long long)ymin - margin, y1 = (long long)ymax + margin;
+  // a slab's residents and immigrants are inside [slab_lo, slab_hi) by construction
+  if (ctl->slab_lo != INT_MIN) x0 = ctl->slab_lo;
+  if (ctl->slab_hi != INT_MAX) x1 = (long long)ctl->slab_hi - 1;
+  if (x1 < x0) x1 = x0;
   if (x1 - x0 >= (1ll << 28) || y1 - y0 >= (1ll << 28) || x0 < -(1ll << 30) || x1 > (1ll << 30) ||
       y0 < -(1ll << 30) || y1 > (1ll << 30)) {
     ctl->err |= kErrDomain;
@@ -770,6 +936,7 @@ __device__ inline void reset_accumulators(Ctl *ctl) {
   ctl->newinf = 0;
   ctl->bb_xmin = INT_MAX; ctl->bb_xmax = INT_MIN; ctl->bb_ymin = INT_MAX; ctl->bb_ymax = INT_MIN;
   ctl->n_inf = 0;
+  ctl->n_emig = 0;
   ctl->scan_ticket = 0;
   ctl->done_ticket = 0;
 }
@@ -809,6 +976,7 @@ __device__ __forceinline__ int ld_acc(const int *p) { return __ldcg(p); }
 //   record_stats = 0 : after upload / static rebuild (statistics of the initial state = "previous" stats)
 __device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats) {
   StatRecord cur;
+  ctl->overflow = 0;
   const unsigned long long newinf = ld_acc(&ctl->newinf);
   for (int k = 0; k < 7; ++k) cur.cnt[k] = ld_acc(&ctl->cnt[k]);
   cur.cnt[ST_S] -= newinf;  // infections of the contact phase (abs.py:153)
@@ -860,6 +1028,50 @@ __device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats) {
 __global__ void k_finalize(Ctl *ctl, StatRecord *history, int record_stats) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   close_step(ctl, history, record_stats);
+}
+
+// Slab mode: a build ends with  k_slab_export -> all-gather of the rows -> k_slab_close  instead of the
+// in-kernel closing: statistics are summed and the y-range is joined over the slabs, so every device
+// takes the same trigger / critical-limit decisions and plans a grid that holds its future immigrants.
+__global__ void k_slab_export(Ctl *ctl, long long *rows) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  long long *r = rows + (size_t)ctl->rank * kSlabRow;
+  for (int k = 0; k < 7; ++k) r[k] = (long long)ctl->cnt[k];
+  for (int k = 0; k < 5; ++k) r[7 + k] = ctl->q[k];
+  r[12] = (long long)ctl->newinf;
+  r[13] = ctl->bb_ymin;
+  r[14] = ctl->bb_ymax;
+  r[15] = (long long)ctl->err;
+}
+
+__global__ void k_slab_close(Ctl *ctl, const long long *rows, const unsigned *cell_start, StatRecord *history,
+                             int record_stats) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int k = 0; k < 7; ++k) ctl->cnt[k] = 0;
+  for (int k = 0; k < 5; ++k) ctl->q[k] = 0;
+  ctl->newinf = 0;
+  int ymin = INT_MAX, ymax = INT_MIN;
+  for (int g = 0; g < ctl->n_ranks; ++g) {
+    const long long *r = rows + (size_t)g * kSlabRow;
+    for (int k = 0; k < 7; ++k) ctl->cnt[k] += (unsigned long long)r[k];
+    for (int k = 0; k < 5; ++k) ctl->q[k] += r[7 + k];
+    ctl->newinf += (unsigned long long)r[12];
+    if (r[13] <= r[14]) {
+      ymin = min(ymin, (int)r[13]);
+      ymax = max(ymax, (int)r[14]);
+    }
+    ctl->err |= (unsigned)r[15];  // an exchange overflow anywhere invalidates the run everywhere
+  }
+  if (ymin <= ymax) {
+    ctl->bb_ymin = ymin;
+    ctl->bb_ymax = ymax;
+    if (ctl->bb_xmin > ctl->bb_xmax) {  // no resident here at the moment: any x inside the slab will do
+      ctl->bb_xmin = ctl->bb_xmax = ctl->slab_lo != INT_MIN ? ctl->slab_lo : ctl->slab_hi - 1;
+    }
+  }
+  const unsigned n_next = cell_start[ctl->g.ncells];  // residents that stayed + immigrants
+  close_step(ctl, history, record_stats);
+  ctl->n = n_next;
 }
 
 // Bounding box of the resident positions into ctl->bb_* (used once per upload).
@@ -945,16 +1157,23 @@ __global__ void k_set_triggers(Ctl *ctl, TriggerBlock t) {
   for (int k = 0; k < kMaxTriggers; ++k) ctl->trig[k] = t.trig[k];
 }
 
+__global__ void k_set_slab(Ctl *ctl, int rank, int n_ranks, int lo, int hi, unsigned mig_cap, unsigned ghost_cap) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctl->rank = rank; ctl->n_ranks = n_ranks; ctl->slab_lo = lo; ctl->slab_hi = hi;
+  ctl->mig_cap = mig_cap; ctl->ghost_cap = ghost_cap;
+}
+
 __global__ void k_init_ctl(Ctl *ctl, unsigned k0, unsigned k1, unsigned max_cells, unsigned hist_cap,
-                           double *sqrt_tab) {
+                           unsigned capacity, double *sqrt_tab) {
   for (int d2 = threadIdx.x; d2 < kSqrtTable; d2 += blockDim.x) sqrt_tab[d2] = __dsqrt_rn((double)d2);
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  ctl->k0 = k0; ctl->k1 = k1; ctl->max_cells = max_cells; ctl->hist_cap = hist_cap;
+  ctl->k0 = k0; ctl->k1 = k1; ctl->max_cells = max_cells; ctl->hist_cap = hist_cap; ctl->capacity = capacity;
   ctl->step = 0; ctl->n = 0; ctl->err = 0; ctl->ntrig = 0; ctl->pop_size = 1; ctl->T = -1;
   ctl->cells_used[0] = ctl->cells_used[1] = 0;
   ctl->cur_table = 0;
-  ctl->n_ranks = 1;
+  ctl->n_ranks = 1; ctl->rank = 0;
   ctl->slab_lo = INT_MIN; ctl->slab_hi = INT_MAX;
+  ctl->overflow = 0; ctl->mig_cap = 0; ctl->ghost_cap = 0;
   reset_accumulators(ctl);
   plan_grid(ctl, 0, 0, 0, 0, false);
   ctl->built = ctl->g;

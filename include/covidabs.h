@@ -167,6 +167,36 @@ int cabs_contact_pairs(cabs_sim *sim, int64_t *ij, size_t capacity_pairs, size_t
 
 int cabs_get_info(cabs_sim *sim, cabs_info *info);
 
+/* ---- slab decomposition over the GPUs of one box (no reference counterpart: the reference is one
+ * process).  A handle owns the lattice columns [x_lo, x_hi); the caller owns the
+ * exchange buffers (device memory) and moves them between neighbours (NCCL send/recv, or plain copies
+ * when several slabs share a device) between the phases of a build:
+ *     phase 0   pass A, emigrants packed            -> exchange migrants  (send[d] -> neighbour's recv[1-d])
+ *     phase 1   immigrants counted, scan, pass B    -> exchange ghosts    (same pattern)
+ *     phase 2   contacts (local + ghosts), export   -> all-gather stats_rows (row `rank` is this handle's)
+ *     phase 3   close: global statistics, triggers, next grid
+ * advance = 1: a simulation step (Simulation.execute, abs.py:232-273); 0: build the cell list of the current
+ * positions (after cabs_upload).  Buffers: 32-byte header {uint32 count} + capacity records (migrants 32 B,
+ * ghosts 16 B).  Index 0 = towards lower x, 1 = towards higher x.  With a slab configured, cabs_download
+ * returns the resident agents in storage order with their ids, and cabs_contact_pairs only local pairs. */
+typedef struct cabs_slab {
+  int32_t rank, n_ranks;
+  int32_t x_lo, x_hi;                   /* INT32_MIN / INT32_MAX on an open side */
+  uint32_t migrant_capacity, ghost_capacity;
+  void *migrant_send[2], *migrant_recv[2];
+  void *ghost_send[2], *ghost_recv[2];
+  void *stats_rows;                     /* n_ranks x CABS_SLAB_ROW int64 */
+} cabs_slab;
+#define CABS_SLAB_ROW 16
+#define CABS_MIGRANT_BYTES 32
+#define CABS_GHOST_BYTES 16
+#define CABS_EXCHANGE_HEADER_BYTES 32
+int cabs_set_slab(cabs_sim *sim, const cabs_slab *slab);
+int cabs_slab_phase(cabs_sim *sim, int phase, int advance);
+/* Run on the caller's CUDA stream (e.g. the one its collectives are ordered on; NULL = CUDA's default stream)
+ * instead of the handle's own. */
+int cabs_set_stream(cabs_sim *sim, void *cuda_stream);
+
 /* Measurement support (no reference counterpart: the reference has no timing code).
  * CUDA events on the handle's own stream, so that a caller can bracket any sequence of calls above
  * (uploads, steps, statistics reads) with device-side timestamps. */
