@@ -93,15 +93,6 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_population(n_agents, side, seed):
-    rng = np.random.default_rng(seed)
-    x = rng.integers(0, side + 1, size=n_agents, dtype=np.int32)
-    y = rng.integers(0, side + 1, size=n_agents, dtype=np.int32)
-    age = (rng.beta(2, 5, size=n_agents) * 100).astype(np.uint8)
-    stratum = rng.integers(0, 5, size=n_agents, dtype=np.uint8)
-    return x, y, age, stratum
-
-
 def cpu_baseline(sample_agents, steps, kw_full):
     """The CPU restatement (oracle/sync_oracle.py, numpy, 1 thread) on a bounded sample of the same workload:
     same density, rates and triggers, `sample_agents` agents."""
@@ -158,14 +149,34 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def make_population(n, x_lo, x_hi, side, seed, id0, total_wealth_per_agent):
+    """Synthetic uniform placement of n agents with x in [x_lo, x_hi] (one slab)."""
+    rng = np.random.default_rng(seed)
+    x = rng.integers(x_lo, x_hi + 1, size=n, dtype=np.int32)
+    y = rng.integers(0, side + 1, size=n, dtype=np.int32)
+    age = (rng.beta(2, 5, size=n) * 100).astype(np.uint8)
+    stratum = rng.integers(0, 5, size=n, dtype=np.uint8)
+    status = np.zeros(n, dtype=np.uint8)
+    status[:int(n * 0.01)] = 1
+    status[int(n * 0.01):int(n * 0.02)] = 2
+    from covid19_agentbasedsimulation_b200.common import lorenz_curve
+    wealth = np.zeros(n)
+    for q in range(5):   # abs.py:134-139 with total_wealth proportional to the population
+        sel = (stratum == q) & (age >= 18)
+        wealth[sel] = lorenz_curve[q] * total_wealth_per_agent * n / max(1.0, float(sel.sum()))
+    return {"x": x, "y": y, "status": status, "severity": np.ones(n, dtype=np.uint8),
+            "infected_time": np.zeros(n, dtype=np.uint8), "age": age, "stratum": stratum, "wealth": wealth,
+            "id": (np.arange(n, dtype=np.int64) + id0).astype(np.uint32)}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from covid19_agentbasedsimulation_b200 import build
     build.build_library()
-    from covid19_agentbasedsimulation_b200.abs import Simulation, Trigger, wealth_scale_bits
+    from covid19_agentbasedsimulation_b200.abs import Simulation, Trigger
     from covid19_agentbasedsimulation_b200.agents import Status
-    from covid19_agentbasedsimulation_b200.common import lorenz_curve
+    from covid19_agentbasedsimulation_b200.slab import SlabSimulation, slab_bounds
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -176,63 +187,96 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n = args.agents
-    kw = workload_kwargs(n)
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = args.agents                      # per GPU (weak scaling: the domain grows with the number of GPUs)
+    kw = workload_kwargs(n * world)
     side = kw["length"]
     low = {Status.Susceptible: 1.5, Status.Recovered_Immune: 1.5, Status.Infected: 1.5}
     high = {Status.Susceptible: 5, Status.Recovered_Immune: 5, Status.Infected: 5}
     triggers = [Trigger('Infected', '>=', .2, 'amplitudes', low), Trigger('Infected', '<=', .05, 'amplitudes', high)]
-    sim = Simulation(seed=rank, device=local_rank, triggers_simulation=triggers, max_cells=args.max_cells,
-                     history_capacity=max(4096, args.steps + args.warmup + 64), **kw)
-    # population in pinned host memory (also the source of the end-to-end leg)
-    x, y, age, stratum = build_population(n, side, seed=rank)
-    status = np.zeros(n, dtype=np.uint8)
-    status[:int(n * 0.01)] = 1
-    status[int(n * 0.01):int(n * 0.02)] = 2
-    wealth = np.zeros(n)
-    for q in range(5):
-        sel = (stratum == q) & (age >= 18)
-        wealth[sel] = lorenz_curve[q] * kw["total_wealth"] / max(1.0, float(sel.sum()))
-    cols = {"x": x, "y": y, "status": status, "severity": np.ones(n, dtype=np.uint8),
-            "infected_time": np.zeros(n, dtype=np.uint8), "age": age, "stratum": stratum, "wealth": wealth}
+    common = dict(seed=0, device=local_rank, triggers_simulation=triggers, max_cells=args.max_cells,
+                  history_capacity=max(4096, args.steps + args.warmup + 64), **kw)
+    if world == 1:
+        sim = Simulation(**common)
+        x_lo, x_hi = 0, side
+    else:
+        sim = SlabSimulation(distributed=True, slab_devices=[local_rank], **common)
+        lo, hi = slab_bounds(side, world)[rank]
+        x_lo, x_hi = max(lo, 0), min(hi - 1, side)
+    # this rank's agents in pinned host memory (also the source of the end-to-end leg)
+    cols = make_population(n, x_lo, x_hi, side, seed=rank, id0=rank * n, total_wealth_per_agent=1e4 / 20)
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in cols.items()}
     ptrs = {k: t.data_ptr() for k, t in pinned.items()}
     h2d_bytes = sum(t.numel() * t.element_size() for t in pinned.values())
 
-    sim._ensure_handle(n)
-    sim._push_params()
-    h = sim._handle
-    h.upload_pointers(n, ptrs)
+    if world == 1:
+        sim._ensure_handle(n)
+        sim._push_params()
+        h = sim._handle
+
+        def upload():
+            h.upload_pointers(n, ptrs)
+
+        def step(k):
+            h.step(k)
+    else:
+        sim.population_size = n * world
+        sim._create([n])
+        h = sim._handle
+
+        def upload():
+            h.upload_pointers(n, ptrs)
+            sim._build(advance=False)
+
+        def step(k):
+            for _ in range(k):
+                sim._build(advance=True)
+
+    def timed(fn):
+        """Device time of fn() on the stream the library runs on, ms."""
+        if world == 1:
+            h.event_record(0)
+            fn()
+            h.event_record(1)
+            return h.event_elapsed_ms(0, 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    upload()
     h.sync()
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps
-    h.step(args.warmup)
+    step(args.warmup)
     h.sync()
     launches0 = h.info()["kernel_launches"]
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    h.event_record(0)
-    h.step(args.steps)
-    h.event_record(1)
-    ms = h.event_elapsed_ms(0, 1)
+    ms = timed(lambda: step(args.steps))
     barrier()
     clocks = sampler.stop()
     launches = h.info()["kernel_launches"] - launches0
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms)
     value = world * n * args.steps / (ms * 1e-3)
     stats_last = h.stats()[0]
 
     # ---- per-kernel device times (events around every launch), same steady state
     h.profile_enable(True)
-    h.step(args.steps)
+    step(args.steps)
     prof = h.profile_read()
     h.profile_enable(False)
     info = h.info()
-    cells_per_agent = info["cells_x"] * info["cells_y"] / float(n)
+    cells_per_agent = info["cells_x"] * info["cells_y"] / float(max(1, info["n"]))
     kernels = {}
     for name, (cnt, tot) in prof.items():
         avg = tot / cnt
@@ -260,27 +304,20 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end through the C ABI with HOST buffers: every step uploads the population from pinned
     #      host memory (set_population, abs.py:65-69), executes, and reads the statistics back (abs.py:291-314)
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    h.upload_pointers(n, ptrs)
-    h.step(1)
-    h.stats()
-    barrier()
-    h.event_record(2)
-    for _ in range(e2e_steps):
-        h.upload_pointers(n, ptrs)
-        h.step(1)
+
+    def e2e_once():
+        upload()
+        step(1)
         h.stats()
-    h.event_record(3)
-    e2e_ms = h.event_elapsed_ms(2, 3)
+
+    e2e_once()
     barrier()
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks(timed(lambda: [e2e_once() for _ in range(e2e_steps)]))
+    barrier()
     e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
 
     line = None
     if rank == 0:
-        base_value, base_dt = (None, None)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             base_value, base_dt = cpu_baseline(args.cpu_sample, 5, kw)
@@ -291,13 +328,17 @@ def run_ours(args, rank, world, local_rank):
             "metric": "agent-updates/sec", "value": value, "unit": "agent-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i32/u8/f64", "data": "synthetic",
-            "config": {"workload": "config3: Simulation 1e7 agents/GPU, conditional lockdown + masks, synthetic "
-                                   "uniform placement (BASELINE.json configs[2])",
-                       "agents_per_gpu": n, "length": side, "height": side, "contagion_distance": 0.05,
-                       "contagion_rate": 0.1, "cache": "working set {:.0f} MB >> 126 MB L2 (inputs larger than L2)"
-                       .format((48.0 * n + 4 * info["cells_x"] * info["cells_y"]) / 1e6),
+            "config": {"workload": ("config3: Simulation 1e7 agents, conditional lockdown + masks, synthetic uniform "
+                                    "placement (BASELINE.json configs[2])" if world == 1 else
+                                    "config4-style: one Simulation of {} agents slab-partitioned over {} GPUs, migrant + "
+                                    "ghost exchange and statistics all-gather over NCCL every step, conditional lockdown "
+                                    "+ masks (BASELINE.json configs[3] at {} agents/GPU)".format(n * world, world, n)),
+                       "agents_per_gpu": n, "agents": n * world, "length": side, "height": side,
+                       "contagion_distance": 0.05, "contagion_rate": 0.1,
+                       "cache": "working set {:.0f} MB per GPU >> 126 MB L2 (inputs larger than L2)"
+                       .format((56.0 * n + 8 * info["cells_x"] * info["cells_y"]) / 1e6),
                        "cell_edge": info["cell_edge"], "cells": info["cells_x"] * info["cells_y"],
-                       "multi_gpu": "independent replicas" if world > 1 else "single device"},
+                       "multi_gpu": "x-slabs, torch.distributed NCCL" if world > 1 else "single device"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "agent-updates/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 12 * 8 + 7 * 8 + 4, "steps": e2e_steps,

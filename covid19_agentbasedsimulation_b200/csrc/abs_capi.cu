@@ -261,7 +261,8 @@ static void enqueue_build(cabs_sim *sim) {
   LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", k_update_scatter<kAdvance>, nb, kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t],
          sim->cells[t ^ 1], sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, nullptr, nullptr);
   if (kAdvance) {
-    LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, nullptr, sim->history, 1);
+    LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, nullptr, nullptr, sim->history,
+           nullptr, 1);
   } else {
     LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 0);
   }
@@ -304,6 +305,12 @@ extern "C" int cabs_set_slab(cabs_sim *sim, const cabs_slab *slab) {
   sim->emig_list = sim->imm_rank = nullptr;
   CK(cudaMalloc(&sim->emig_list, 2 * (size_t)slab->migrant_capacity * sizeof(unsigned)));
   CK(cudaMalloc(&sim->imm_rank, 2 * (size_t)slab->migrant_capacity * sizeof(unsigned)));
+  for (int d = 0; d < 2; ++d) {  // headers start at count 0; outer-side receive buffers are never written again
+    CK(cudaMemsetAsync(slab->migrant_send[d], 0, sizeof(ExchangeHeader), sim->stream));
+    CK(cudaMemsetAsync(slab->migrant_recv[d], 0, sizeof(ExchangeHeader), sim->stream));
+    CK(cudaMemsetAsync(slab->ghost_send[d], 0, sizeof(ExchangeHeader), sim->stream));
+    CK(cudaMemsetAsync(slab->ghost_recv[d], 0, sizeof(ExchangeHeader), sim->stream));
+  }
   sim->slab = *slab;
   sim->slab_on = true;
   LAUNCH(k_set_slab, 1, 32, sim->ctl, slab->rank, slab->n_ranks, slab->x_lo, slab->x_hi, slab->migrant_capacity,
@@ -325,19 +332,6 @@ static int slab_phase(cabs_sim *sim, int phase) {
   ExchangeHeader *gr[2] = {(ExchangeHeader *)sl.ghost_recv[0], (ExchangeHeader *)sl.ghost_recv[1]};
   switch (phase) {
     case 0:
-      for (int d = 0; d < 2; ++d) {
-        CK(cudaMemsetAsync(ms[d], 0, sizeof(ExchangeHeader), sim->stream));
-        CK(cudaMemsetAsync(gs[d], 0, sizeof(ExchangeHeader), sim->stream));
-      }
-      // no neighbour on an outer side: nothing will be written into those receive buffers
-      if (sl.rank == 0) {
-        CK(cudaMemsetAsync(mr[0], 0, sizeof(ExchangeHeader), sim->stream));
-        CK(cudaMemsetAsync(gr[0], 0, sizeof(ExchangeHeader), sim->stream));
-      }
-      if (sl.rank == sl.n_ranks - 1) {
-        CK(cudaMemsetAsync(mr[1], 0, sizeof(ExchangeHeader), sim->stream));
-        CK(cudaMemsetAsync(gr[1], 0, sizeof(ExchangeHeader), sim->stream));
-      }
       if (!kAdvance) {
         LAUNCH(k_bbox, nb, 256, sim->ctl, sim->hot[c]);
         LAUNCH(k_replan, 1, 32, sim->ctl, 1);
@@ -358,17 +352,15 @@ static int slab_phase(cabs_sim *sim, int phase) {
       break;
     case 2:
       if (kAdvance) {
-        LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, nullptr, sim->history, 0);
-        LAUNCH_AS("k_contagion(ghosts)", k_contagion, nbs, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list,
-                  gr[0], sim->history, 0);
-        LAUNCH_AS("k_contagion(ghosts)", k_contagion, nbs, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list,
-                  gr[1], sim->history, 0);
+        LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, gr[0], gr[1], sim->history,
+               (long long *)sl.stats_rows, 2);
+      } else {
+        LAUNCH(k_slab_export, 1, 32, sim->ctl, (long long *)sl.stats_rows);
       }
-      LAUNCH(k_slab_export, 1, 32, sim->ctl, (long long *)sl.stats_rows);
       break;
     case 3:
       LAUNCH(k_slab_close, 1, 32, sim->ctl, (const long long *)sl.stats_rows, sim->cells[t], sim->history,
-             kAdvance ? 1 : 0);
+             kAdvance ? 1 : 0, ms[0], ms[1], gs[0], gs[1]);
       sim->cur = o;
       sim->tab = t ^ 1;
       if (kAdvance) sim->step++;
@@ -377,6 +369,7 @@ static int slab_phase(cabs_sim *sim, int phase) {
     default:
       return fail(sim, CABS_ERR_INVALID, "cabs_slab_phase: phase must be 0..3");
   }
+  if (sim->profiling) prof_mark(sim, nullptr);  // the exchange that follows is not a kernel of this library
   CK(cudaGetLastError());
   return CABS_OK;
 }

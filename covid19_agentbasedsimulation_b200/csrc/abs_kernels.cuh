@@ -793,30 +793,38 @@ __device__ __forceinline__ void contact_cells(const StepParams &P, int x, int y,
 }
 
 __device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats);
+__device__ void slab_export(Ctl *ctl, long long *rows);
 
 // Pass C: the contact loop of abs.py:249-265 pushed from the agents that were Infected before this
-// contact phase (the list pass B wrote) to the Susceptible agents in reach; contact() = abs.py:141-154
-// with one draw per pair, keyed on the pair so that the result does not depend on who scans whom.
-//   ghosts == nullptr: the sources are the slots in inf_list (count ctl->n_inf);
-//   ghosts != nullptr: the sources are the records of that exchange buffer (Infected agents of a neighbour slab).
+// contact phase to the Susceptible agents in reach; contact() = abs.py:141-154 with one draw per pair,
+// keyed on the pair so that the result does not depend on who scans whom.  Sources: the slots pass B
+// listed, then (slab mode) the ghost records received from the two neighbour slabs.
+//   finish = 1: the last block to finish closes the step (one device);
+//   finish = 2: the last block exports this slab's partial statistics row (slab mode).
 __global__ void __launch_bounds__(256)
 k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
-            const unsigned *__restrict__ inf_list, const ExchangeHeader *__restrict__ ghosts,
-            StatRecord *__restrict__ history, int close) {
+            const unsigned *__restrict__ inf_list, const ExchangeHeader *__restrict__ ghosts_left,
+            const ExchangeHeader *__restrict__ ghosts_right, StatRecord *__restrict__ history,
+            long long *__restrict__ rows, int finish) {
   __shared__ StepParams P;
-  __shared__ unsigned s_new, s_count;
+  __shared__ unsigned s_new, s_local, s_left, s_right;
   if (threadIdx.x == 0) {
     load_params(P, ctl);
     s_new = 0;
-    s_count = ghosts ? min(ghosts->count, ctl->ghost_cap) : ctl->n_inf;
+    s_local = ctl->n_inf;
+    s_left = ghosts_left ? min(ghosts_left->count, ctl->ghost_cap) : 0u;
+    s_right = ghosts_right ? min(ghosts_right->count, ctl->ghost_cap) : 0u;
   }
   __syncthreads();
-  const uint4 *src = ghosts ? reinterpret_cast<const uint4 *>(ghosts + 1) : nullptr;
   unsigned newinf = 0;
   const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned total = s_local + s_left + s_right;
   if (P.T >= 0) {
-    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < s_count; t += stride) {
-      const uint4 h = src ? src[t] : hot[inf_list[t]];
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+      uint4 h;
+      if (t < s_local) h = hot[inf_list[t]];
+      else if (t < s_local + s_left) h = reinterpret_cast<const uint4 *>(ghosts_left + 1)[t - s_local];
+      else h = reinterpret_cast<const uint4 *>(ghosts_right + 1)[t - s_local - s_left];
       const int xi = (int)h.x, yi = (int)h.y;
       int clo, chi, rlo, rhi;
       contact_cells(P, xi, yi, clo, chi, rlo, rhi);
@@ -844,13 +852,14 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
   __syncthreads();
   if (threadIdx.x == 0) {
     if (s_new) atomicAdd(&ctl->newinf, (unsigned long long)s_new);
-    if (close) {
+    if (finish) {
       // the last block to get here has seen every other block's contribution
       __threadfence();
       const unsigned ticket = atomicAdd(&ctl->done_ticket, 1u);
       if (ticket == gridDim.x - 1) {
         __threadfence();
-        close_step(ctl, history, 1);
+        if (finish == 1) close_step(ctl, history, 1);
+        else slab_export(ctl, rows);
       }
     }
   }
@@ -1033,20 +1042,26 @@ __global__ void k_finalize(Ctl *ctl, StatRecord *history, int record_stats) {
 // Slab mode: a build ends with  k_slab_export -> all-gather of the rows -> k_slab_close  instead of the
 // in-kernel closing: statistics are summed and the y-range is joined over the slabs, so every device
 // takes the same trigger / critical-limit decisions and plans a grid that holds its future immigrants.
+__device__ void slab_export(Ctl *ctl, long long *rows) {
+  long long *r = rows + (size_t)ctl->rank * kSlabRow;
+  for (int k = 0; k < 7; ++k) r[k] = (long long)ld_acc(&ctl->cnt[k]);
+  for (int k = 0; k < 5; ++k) r[7 + k] = ld_acc(&ctl->q[k]);
+  r[12] = (long long)ld_acc(&ctl->newinf);
+  r[13] = ld_acc(&ctl->bb_ymin);
+  r[14] = ld_acc(&ctl->bb_ymax);
+  r[15] = (long long)atomicOr(&ctl->err, 0u);
+}
+
 __global__ void k_slab_export(Ctl *ctl, long long *rows) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  long long *r = rows + (size_t)ctl->rank * kSlabRow;
-  for (int k = 0; k < 7; ++k) r[k] = (long long)ctl->cnt[k];
-  for (int k = 0; k < 5; ++k) r[7 + k] = ctl->q[k];
-  r[12] = (long long)ctl->newinf;
-  r[13] = ctl->bb_ymin;
-  r[14] = ctl->bb_ymax;
-  r[15] = (long long)ctl->err;
+  slab_export(ctl, rows);
 }
 
 __global__ void k_slab_close(Ctl *ctl, const long long *rows, const unsigned *cell_start, StatRecord *history,
-                             int record_stats) {
+                             int record_stats, ExchangeHeader *s0, ExchangeHeader *s1, ExchangeHeader *s2,
+                             ExchangeHeader *s3) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  s0->count = 0; s1->count = 0; s2->count = 0; s3->count = 0;  // this slab's send buffers start the next build empty
   for (int k = 0; k < 7; ++k) ctl->cnt[k] = 0;
   for (int k = 0; k < 5; ++k) ctl->q[k] = 0;
   ctl->newinf = 0;

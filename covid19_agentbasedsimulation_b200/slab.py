@@ -125,7 +125,7 @@ class DistComm(object):
     def gather_rows(self):
         import torch.distributed as dist
         mine = self.b.rows[self.rank].clone()
-        dist.all_gather_into_tensor(self.b.rows.view(-1), mine)
+        dist.all_gather([self.b.rows[g] for g in range(self.world)], mine)
 
 
 class SlabSimulation(Simulation):
@@ -225,7 +225,11 @@ class SlabSimulation(Simulation):
             self.population_size = n if population_size is None else int(population_size)
             owner = owner_of(x, self.length, self.n_slabs)
             parts = [{k: np.ascontiguousarray(v[owner == r]) for k, v in cols.items()} for r in self.my_ranks]
-        self._create([len(p["x"]) for p in parts])
+        counts = [len(p["x"]) for p in parts]
+        if not self._handles or any(h.capacity < c for h, c in zip(self._handles, counts)):
+            self._create(counts)
+        else:
+            self._push_params()
         for h, p in zip(self._handles, parts):
             h.upload(p)
         self._build(advance=False)

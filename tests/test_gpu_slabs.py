@@ -83,3 +83,18 @@ def test_migrant_overflow_is_reported(native_lib):
     sim.execute()
     with pytest.raises(_native.NativeError):
         sim.get_statistics('all')
+
+
+def test_two_process_nccl_slabs_match_single_device(native_lib):
+    """One slab per process over NCCL (needs >= 2 GPUs; skipped on a one-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dist_slab_check.py")]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=600)
+    assert res.returncode == 0 and "DIST_SLAB_CHECK OK" in res.stdout, res.stdout[-3000:]
