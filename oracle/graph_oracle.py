@@ -83,7 +83,7 @@ class GraphDraws(object):
         """low, up (np.random.randint(-1, 1), graph_abs.py:290-291) and the contagion word (294) of a pair."""
         lo, hi = (a, b) if a < b else (b, a)
         w = self.words(lo, it, ST_CONTACT, hi)
-        return -int(int(w[0]) >> 31), -int(int(w[1]) >> 31), int(w[2])
+        return -1 + (int(w[0]) >> 31), -1 + (int(w[1]) >> 31), int(w[2])
 
 
 def prob_bound_lt(p):
