@@ -22,7 +22,12 @@ OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_DOMAIN, ERR_NOGPU = 0, -1, -2, -3, 
 EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params", "cabs_set_triggers",
             "cabs_upload", "cabs_download", "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_history",
             "cabs_contact_pairs", "cabs_get_info", "cabs_event_record", "cabs_event_elapsed_ms",
-            "cabs_profile_enable", "cabs_profile_read", "cabs_set_slab", "cabs_slab_phase", "cabs_set_stream")
+            "cabs_profile_enable", "cabs_profile_read", "cabs_set_slab", "cabs_slab_phase", "cabs_set_stream",
+            "cabs_graph_create", "cabs_graph_destroy", "cabs_graph_last_error", "cabs_graph_upload", "cabs_graph_run",
+            "cabs_graph_sync", "cabs_graph_stats", "cabs_graph_download", "cabs_graph_last_run_ms")
+
+GRAPH_NUM_STATS, GRAPH_MAX_BUSINESS = 14, 16
+GRAPH_MODE_NONE, GRAPH_MODE_LOCKDOWN, GRAPH_MODE_CONDITIONAL_LOCKDOWN, GRAPH_MODE_VERTICAL_ISOLATION = 0, 1, 2, 3
 
 SLAB_ROW, MIGRANT_BYTES, GHOST_BYTES, EXCHANGE_HEADER_BYTES = 16, 32, 16, 32
 INT32_MIN, INT32_MAX = -2 ** 31, 2 ** 31 - 1
@@ -78,6 +83,44 @@ class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_uint64), ("total_ms", C.c_double)]
 
 
+class GraphConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("n_sims", C.c_uint32), ("max_persons", C.c_uint32),
+                ("max_houses", C.c_uint32), ("max_business", C.c_uint32), ("history_capacity", C.c_uint32),
+                ("cell_capacity", C.c_uint32)]
+
+
+class GraphParams(C.Structure):
+    _fields_ = [("amplitudes", C.c_double * 4), ("basic_income", C.c_double * 5), ("minimum_income", C.c_double),
+                ("minimum_expense", C.c_double), ("total_wealth", C.c_double), ("critical_limit", C.c_double),
+                ("contagion_distance", C.c_double), ("contagion_rate", C.c_double), ("business_distance", C.c_double),
+                ("age_hospitalization_probs", C.c_double * 9), ("age_severe_probs", C.c_double * 9),
+                ("age_death_probs", C.c_double * 9), ("population_size", C.c_uint64), ("seed", C.c_uint64),
+                ("incubation_time", C.c_int32), ("contagion_time", C.c_int32), ("recovering_time", C.c_int32),
+                ("mode", C.c_int32), ("sleep", C.c_int32), ("money_bits", C.c_int32)]
+
+
+# (field, numpy dtype) of the array columns of cabs_graph_world, in declaration order
+GRAPH_PERSON_COLS = (("px", np.int32), ("py", np.int32), ("status", np.uint8), ("severity", np.uint8),
+                     ("infected_time", np.uint8), ("age", np.uint8), ("stratum", np.uint8), ("active", np.uint8),
+                     ("isolated", np.uint8), ("house", np.int32), ("employer", np.int32), ("hire_seq", np.int32),
+                     ("pwealth", np.float64))
+GRAPH_HOUSE_COLS = (("hx", np.int32), ("hy", np.int32), ("hstratum", np.int32), ("hsize", np.int32),
+                    ("hwealth", np.float64), ("hfixed", np.float64), ("hincomes", np.float64), ("hexpenses", np.float64))
+GRAPH_BUSINESS_COLS = (("bx", np.int32), ("by", np.int32), ("bstratum", np.int32), ("bstocks", np.int32),
+                       ("bsales", np.int32), ("bnum_employees", np.int32), ("bprice", np.float64),
+                       ("bwealth", np.float64), ("bfixed", np.float64), ("bincomes", np.float64))
+GRAPH_SCALARS = (("gov_x", C.c_int32), ("gov_y", C.c_int32), ("health_x", C.c_int32), ("health_y", C.c_int32),
+                 ("gov_wealth", C.c_double), ("gov_price", C.c_double), ("gov_fixed", C.c_double),
+                 ("health_wealth", C.c_double), ("health_fixed", C.c_double), ("health_expenses", C.c_double),
+                 ("iteration", C.c_int32), ("reserved2", C.c_int32))
+
+
+class GraphWorld(C.Structure):
+    _fields_ = ([("n_persons", C.c_int32), ("n_houses", C.c_int32), ("n_business", C.c_int32), ("reserved", C.c_int32)] +
+                [(k, C.c_void_p) for k, _ in GRAPH_PERSON_COLS] + [(k, C.c_void_p) for k, _ in GRAPH_HOUSE_COLS] +
+                [(k, C.c_void_p) for k, _ in GRAPH_BUSINESS_COLS] + list(GRAPH_SCALARS))
+
+
 _lib = None
 
 
@@ -113,9 +156,20 @@ def load():
     lib.cabs_set_slab.argtypes = [P, C.POINTER(Slab)]
     lib.cabs_slab_phase.argtypes = [P, C.c_int, C.c_int]
     lib.cabs_set_stream.argtypes = [P, C.c_void_p]
+    lib.cabs_graph_create.argtypes = [C.POINTER(GraphConfig), C.POINTER(P)]
+    lib.cabs_graph_destroy.argtypes = [P]
+    lib.cabs_graph_destroy.restype = None
+    lib.cabs_graph_last_error.argtypes = [P]
+    lib.cabs_graph_last_error.restype = C.c_char_p
+    lib.cabs_graph_upload.argtypes = [P, C.c_uint32, C.POINTER(GraphWorld), C.POINTER(GraphParams)]
+    lib.cabs_graph_run.argtypes = [P, C.c_int]
+    lib.cabs_graph_sync.argtypes = [P]
+    lib.cabs_graph_stats.argtypes = [P, C.c_uint32, C.c_int64, C.c_uint32, C.POINTER(C.c_double)]
+    lib.cabs_graph_download.argtypes = [P, C.c_uint32, C.POINTER(GraphWorld)]
+    lib.cabs_graph_last_run_ms.argtypes = [P, C.POINTER(C.c_double)]
     for name in EXPORTED:
         fn = getattr(lib, name)
-        if name not in ("cabs_destroy", "cabs_last_error"):
+        if name not in ("cabs_destroy", "cabs_last_error", "cabs_graph_destroy", "cabs_graph_last_error"):
             fn.restype = C.c_int
     _lib = lib
     return lib
@@ -258,3 +312,94 @@ class Handle(object):
         n = C.c_int(0)
         self._check(self._lib.cabs_profile_read(self._h, arr, 32, C.byref(n)))
         return {arr[i].name.decode(): (int(arr[i].launches), float(arr[i].total_ms)) for i in range(n.value)}
+
+
+class GraphHandle(object):
+    """Owns one `cabs_graph*`: `n_sims` GraphSimulation worlds of the same capacity on one device."""
+
+    def __init__(self, n_sims, max_persons, max_houses, max_business, device=0, history_capacity=2048,
+                 cell_capacity=0):
+        self._lib = load()
+        self._h = C.c_void_p()
+        cfg = GraphConfig(ABI_VERSION, int(device), int(n_sims), int(max_persons), int(max_houses), int(max_business),
+                          int(history_capacity), int(cell_capacity))
+        rc = self._lib.cabs_graph_create(C.byref(cfg), C.byref(self._h))
+        if rc != OK:
+            msg = self._lib.cabs_graph_last_error(None)
+            raise NativeError(rc, msg.decode() if msg else "cabs_graph_create failed")
+        self.n_sims, self.max_persons, self.max_houses, self.max_business = (int(n_sims), int(max_persons),
+                                                                             int(max_houses), int(max_business))
+        self._sizes = {}
+
+    def _check(self, rc):
+        if rc != OK:
+            msg = self._lib.cabs_graph_last_error(self._h)
+            raise NativeError(rc, msg.decode() if msg else "?")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.cabs_graph_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _world_struct(world, keep):
+        """dict of arrays / scalars (keys of cabs_graph_world) -> GraphWorld; `keep` holds the converted arrays."""
+        w = GraphWorld()
+        w.n_persons, w.n_houses, w.n_business = len(world["px"]), len(world["hx"]), len(world["bx"])
+        for cols, n in ((GRAPH_PERSON_COLS, w.n_persons), (GRAPH_HOUSE_COLS, w.n_houses),
+                        (GRAPH_BUSINESS_COLS, w.n_business)):
+            for name, dt in cols:
+                a = world.get(name)
+                a = np.zeros(n, dtype=dt) if a is None else np.ascontiguousarray(a, dtype=dt)
+                assert a.shape == (n,), name
+                keep.append(a)
+                setattr(w, name, a.ctypes.data)
+        for name, _ in GRAPH_SCALARS:
+            if name != "reserved2":
+                setattr(w, name, world.get(name, -1 if name == "iteration" else 0))
+        return w
+
+    def upload(self, sim, world, params):
+        keep = []
+        w = self._world_struct(world, keep)
+        self._check(self._lib.cabs_graph_upload(self._h, int(sim), C.byref(w), C.byref(params)))
+        self._sizes[int(sim)] = (w.n_persons, w.n_houses, w.n_business)
+
+    def run(self, iterations):
+        self._check(self._lib.cabs_graph_run(self._h, int(iterations)))
+
+    def sync(self):
+        self._check(self._lib.cabs_graph_sync(self._h))
+
+    def last_run_ms(self):
+        ms = C.c_double(0)
+        self._check(self._lib.cabs_graph_last_run_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def stats(self, sim, first, count):
+        out = np.empty((int(count), GRAPH_NUM_STATS), dtype=np.float64)
+        self._check(self._lib.cabs_graph_stats(self._h, int(sim), int(first), int(count),
+                                               out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def download(self, sim):
+        n, nh, nb = self._sizes[int(sim)]
+        world = {}
+        for cols, m in ((GRAPH_PERSON_COLS, n), (GRAPH_HOUSE_COLS, nh), (GRAPH_BUSINESS_COLS, nb)):
+            for name, dt in cols:
+                world[name] = np.zeros(m, dtype=dt)
+        keep = []
+        w = self._world_struct(world, keep)
+        for (name, _), a in zip(GRAPH_PERSON_COLS + GRAPH_HOUSE_COLS + GRAPH_BUSINESS_COLS, keep):
+            world[name] = a
+        self._check(self._lib.cabs_graph_download(self._h, int(sim), C.byref(w)))
+        for name, _ in GRAPH_SCALARS:
+            if name != "reserved2":
+                world[name] = getattr(w, name)
+        return world

@@ -1,0 +1,799 @@
+// Device side of the GraphSimulation step (covid_abs/network/graph_abs.py:190-324) for sm_100a.
+//
+// One thread block owns one simulation and stays resident for a whole run of hourly iterations
+// (`k_graph_run`): the reference's configs are small populations stepped thousands of times (1 440 hourly
+// iterations, run_batch.py:384), which is launch-latency bound if every hour is a sequence of kernels, and
+// scenario x seed ensembles are thousands of independent simulations -- one block
+// each fills the GPU with no inter-block communication at all.  Business, government and healthcare
+// accounts live in shared memory for the whole run; persons and houses stream from global memory (L2).
+//
+// Phases of one executed hour (block-wide barriers between them):
+//   1 persons     on_person_move / routine move (network/agents.py:293-342), daily Person.update (362-415),
+//                 purchase requests (graph_abs.py:230-233) -> one event word per person
+//   2 stocks      Business.supply / checkin stock arithmetic (network/agents.py:82-93,101-102) resolved in the
+//                 reference's person order with a block-wide scan of the max-plus maps s -> max(s + a, m)
+//   3 accounts    Business/House/Government daily update and monthly accounting (network/agents.py:108-168,227-245)
+//   4 contacts    cell list over the block's persons, contact() pushed from the contagious persons
+//                 (graph_abs.py:256-300)
+//   5 statistics  GraphSimulation.get_statistics (graph_abs.py:302-324) -> one row of the history
+//
+// Money that several threads add to is 64-bit fixed point (`money_bits` fractional bits, every flow rounded
+// to nearest-even once), so the sums do not depend on the order of the additions; oracle/graph_oracle.py
+// does the same and the two agree bit for bit.  Draws: Philox4x32-10, counter (entity, iteration, stream, aux).
+#pragma once
+#include <limits.h>
+#include <stdint.h>
+
+#include "abs_rng.cuh"
+
+namespace cabs {
+namespace graph {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxBusiness = 16;
+constexpr int kStats = 14;
+
+enum : uint32_t { S_ = 0, I_ = 1, R_ = 2, D_ = 3 };
+enum : uint32_t { SEV_E_ = 0, SEV_A_ = 1, SEV_H_ = 2, SEV_G_ = 3 };
+enum : int { MODE_NONE = 0, MODE_LOCKDOWN = 1, MODE_CONDITIONAL = 2, MODE_VERTICAL = 3 };
+// draw streams: shared contract with oracle/graph_oracle.py
+enum : uint32_t { ST_MOVE = 0, ST_UPDATE = 1, ST_HOSP_MOVE = 2, ST_DEATH_MOVE = 3, ST_CONTACT = 4, ST_GOV = 5,
+                  ST_ACCOUNT = 6, ST_SHOP = 16 };
+constexpr uint32_t kGovId = 0xFFFFFFFFu, kBusinessId0 = 0xFFFF0000u;
+
+// person attribute word: status[1:0] severity[3:2] stratum[6:4] new[7] infected_time[15:8] age[23:16]
+//                        active[24] isolated[25]
+constexpr uint32_t kNew = 0x80u, kActive = 1u << 24, kIsolated = 1u << 25;
+__device__ __forceinline__ uint32_t a_status(uint32_t a) { return a & 3u; }
+__device__ __forceinline__ uint32_t a_sev(uint32_t a) { return (a >> 2) & 3u; }
+__device__ __forceinline__ uint32_t a_stratum(uint32_t a) { return (a >> 4) & 7u; }
+__device__ __forceinline__ uint32_t a_time(uint32_t a) { return (a >> 8) & 0xFFu; }
+__device__ __forceinline__ uint32_t a_age(uint32_t a) { return (a >> 16) & 0xFFu; }
+__device__ __forceinline__ uint32_t a_set(uint32_t a, uint32_t st, uint32_t sev, uint32_t time) {
+  return (a & 0xFFFF0070u) | (st & 3u) | ((sev & 3u) << 2) | ((time & 0xFFu) << 8);
+}
+
+// Per-simulation descriptor (device memory).  Arrays are this simulation's segments.
+struct Sim {
+  int n, nh, nb;
+  // persons
+  int *px, *py;
+  uint32_t *attr;
+  int *house, *employer, *hire_seq;
+  long long *pwealth;
+  unsigned long long *events;   // scratch: one nibble per business (0 none, 1..9 request, 15 check-in)
+  // houses
+  int *hx, *hy, *hstratum, *hsize;
+  long long *hwealth, *hfixed, *hincomes, *hexpenses;
+  // businesses
+  int *bx, *by, *bstratum, *bstocks, *bsales, *bnum;
+  double *bprice;
+  long long *bwealth, *bfixed, *bincomes;
+  // government / healthcare
+  int gov_x, gov_y, health_x, health_y;
+  long long gov_wealth, gov_fixed, health_wealth, health_fixed, health_expenses;
+  double gov_price;
+  // parameters (graph_abs.py:13-32, abs.py:17-49, common.py:13-27)
+  double amp[4];
+  double bi[5];
+  double min_income, min_expense, total_wealth, critical_limit, pop_size, scale;
+  long long thr_hosp[9], thr_sev[9], thr_death[9], thr_rate;
+  int T, T_bus, reach, incubation, contagion_time, recovering;
+  int mode, sleep;
+  unsigned k0, k1;
+  // run state
+  int iteration;          // graph_abs.py:25 starts at -1
+  int next_hire_seq;
+  double prev_infected, prev_hosp_severe;   // memo of the previous executed hour (statistics fractions)
+  // contact cell list scratch
+  unsigned *cell_count;   // cell_cap + 1
+  unsigned *cell_items;   // n
+  unsigned *contagious;   // n
+  int cell_cap;
+  // output
+  double *history;        // hist_cap rows of kStats doubles, row = iteration % hist_cap
+  int hist_cap;
+  unsigned err;
+};
+
+__device__ __forceinline__ long long fx(double v, double scale) { return __double2ll_rn(__dmul_rn(v, scale)); }
+__device__ __forceinline__ double fl(long long v, double scale) { return __ddiv_rn((double)v, scale); }
+__device__ __forceinline__ int trunc_add(int base, float z, double sigma) {
+  // int(base + normal(0, sigma)) of network/agents.py:304-305,323-324,339-340,349-350
+  return __double2int_rz(__dadd_rn((double)base, __dmul_rn((double)z, sigma)));
+}
+__device__ __forceinline__ uint32_t mulhi_pick(uint32_t w, uint32_t n) { return __umulhi(w, n); }
+__device__ __forceinline__ void atom_add(long long *p, long long v) {
+  atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
+}
+
+// block-wide helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ long long block_sum(long long v, long long *s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  long long t = 0;
+  for (int k = 0; k < kWarps; ++k) t += s_red[k];
+  return t;
+}
+
+// shared state of one block / simulation
+struct Shared {
+  long long bwealth[kMaxBusiness], bfixed[kMaxBusiness], bincomes[kMaxBusiness];
+  int bstocks[kMaxBusiness], bsales[kMaxBusiness], bnum[kMaxBusiness], bx[kMaxBusiness], by[kMaxBusiness];
+  double bprice[kMaxBusiness];
+  long long gov_wealth, health_wealth, health_expenses;
+  long long red[kWarps];
+  long long acc[8];
+  int wa[kWarps][kMaxBusiness], wm[kWarps][kMaxBusiness];   // per-warp max-plus totals
+  unsigned present;          // businesses with an event in the current chunk
+  int bb[4];
+  unsigned n_contagious;
+  unsigned cnt[8];
+  int sel;                   // result slot of block-wide selections
+  int next_hire_seq;
+};
+
+constexpr int kNegInf = -(1 << 29);
+
+// compose max-plus maps: apply (a1, m1) first, then (a2, m2):  s -> max(max(s + a1, m1) + a2, m2)
+__device__ __forceinline__ void compose(int a1, int m1, int a2, int m2, int &a, int &m) {
+  a = a1 + a2;
+  m = max(m1 > kNegInf / 2 ? m1 + a2 : kNegInf, m2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Person moves (network/agents.py:293-342).  Return the business checked in at (move_to_work) or -1.
+struct PersonCtx {
+  const Sim *S;
+  Shared *sh;
+  uint32_t it;
+  double scale;
+};
+
+__device__ __forceinline__ double person_expenses(const Sim &S, uint32_t a) { return __dmul_rn(S.bi[min(a_stratum(a), 4u)], S.min_expense); }
+__device__ __forceinline__ double person_incomes(const Sim &S, uint32_t a) {
+  return (a & kActive) ? __dmul_rn(S.bi[min(a_stratum(a), 4u)], S.min_income) : 0.0;
+}
+
+__device__ __forceinline__ void house_checkin(const Sim &S, int h, uint32_t a) {   // network/agents.py:202-207
+  const long long v = fx(__ddiv_rn(person_expenses(S, a), 720.0), S.scale);
+  atom_add(&S.hwealth[h], -v);
+  atom_add(&S.hexpenses[h], v);
+}
+
+__device__ __forceinline__ void move_freely(const Sim &S, uint32_t i, uint32_t it, uint32_t stream, uint32_t a, int &x,
+                                            int &y) {
+  if (a_sev(a) != SEV_A_) return;
+  const uint4 w = philox4x32_10(i, it, stream, 0u, S.k0, S.k1);
+  float z0, z1;
+  normal_pair(w.x, w.y, z0, z1);
+  const double amp = S.amp[a_status(a)];
+  x = trunc_add(x, z0, amp);
+  y = trunc_add(y, z1, amp);
+}
+
+__device__ __forceinline__ void move_to_home(const Sim &S, uint32_t i, uint32_t it, uint32_t stream, uint32_t a, int h,
+                                             int &x, int &y) {
+  if (a_sev(a) != SEV_A_) return;
+  if (h >= 0) {
+    house_checkin(S, h, a);
+    const uint4 w = philox4x32_10(i, it, stream, 0u, S.k0, S.k1);
+    float z0, z1;
+    normal_pair(w.x, w.y, z0, z1);
+    x = trunc_add(S.hx[h], z0, 0.25);
+    y = trunc_add(S.hy[h], z1, 0.25);
+  } else {
+    atom_add(&S.pwealth[i], -fx(__ddiv_rn(person_incomes(S, a), 720.0), S.scale));
+    move_freely(S, i, it, stream, a, x, y);
+  }
+}
+
+// Person.supply (network/agents.py:286-291): income goes to the house, or to the person if homeless
+__device__ __forceinline__ void person_supply(const Sim &S, uint32_t i, int h, long long v) {
+  if (h >= 0) {
+    atom_add(&S.hwealth[h], v);
+    atom_add(&S.hincomes[h], v);
+  } else {
+    atom_add(&S.pwealth[i], v);
+  }
+}
+__device__ __forceinline__ void person_demand(const Sim &S, uint32_t i, int h, long long v) {   // 279-284
+  if (h >= 0) {
+    atom_add(&S.hwealth[h], -v);
+    atom_add(&S.hexpenses[h], v);
+  } else {
+    atom_add(&S.pwealth[i], -v);
+  }
+}
+
+// Business.fire (network/agents.py:44-53)
+__device__ __forceinline__ void fire(const Sim &S, Shared &sh, int b, uint32_t i, uint32_t a) {
+  S.employer[i] = -1;
+  S.hire_seq[i] = -1;
+  const long long v = fx(person_incomes(S, a), S.scale);
+  person_supply(S, i, S.house[i], v);
+  atom_add(&sh.bwealth[b], -v);
+  atomicSub(&sh.bnum[b], 1);
+  atom_add(&sh.bfixed[b], -fx(__dmul_rn(__ddiv_rn(person_expenses(S, a), 720.0), 24.0), S.scale));
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_graph_run(Sim *sims, int iterations) {
+  Sim &S = sims[blockIdx.x];
+  __shared__ Shared sh;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = S.n, nh = S.nh, nb = S.nb;
+  const double scale = S.scale;
+
+  // ---- load the accounts that live in shared memory for the run
+  if (tid < nb) {
+    sh.bwealth[tid] = S.bwealth[tid]; sh.bfixed[tid] = S.bfixed[tid]; sh.bincomes[tid] = S.bincomes[tid];
+    sh.bstocks[tid] = S.bstocks[tid]; sh.bsales[tid] = S.bsales[tid]; sh.bnum[tid] = S.bnum[tid];
+    sh.bx[tid] = S.bx[tid]; sh.by[tid] = S.by[tid]; sh.bprice[tid] = S.bprice[tid];
+  }
+  if (tid == 0) {
+    sh.gov_wealth = S.gov_wealth; sh.health_wealth = S.health_wealth; sh.health_expenses = S.health_expenses;
+    sh.next_hire_seq = S.next_hire_seq;
+  }
+  __syncthreads();
+
+  int it = S.iteration;
+  double prev_infected = S.prev_infected, prev_hs = S.prev_hosp_severe;
+
+  for (int step = 0; step < iterations; ++step) {
+    ++it;                                                                       // graph_abs.py:192
+    const int hour = it % 24, day = it / 24;
+    const bool bed = hour < 8, work = hour >= 8 && hour < 16, free_t = hour >= 17, lunch = hour == 12;
+    const bool new_day = hour == 0, work_day = (day % 7 + 1) != 1 && (day % 7 + 1) != 7;
+    const bool new_month = (day % 30 + 1) == 1 && hour == 0;
+    double *row = S.history + (size_t)(it % S.hist_cap) * kStats;
+    if (S.sleep && !new_day && bed) {                                           // run_batch.py:8-13 (on_execute)
+      // the reference returns before anything changes; batch_experiment re-reads the same statistics
+      const double *prev_row = S.history + (size_t)((it + S.hist_cap - 1) % S.hist_cap) * kStats;
+      if (tid < kStats) row[tid] = prev_row[tid];
+      __syncthreads();
+      continue;
+    }
+    const bool lock_all = S.mode == MODE_LOCKDOWN || (S.mode == MODE_CONDITIONAL && prev_infected > 0.05);
+    const bool crit_active = prev_hs >= S.critical_limit;                        // network/agents.py:389-390
+    const bool monthly = it > 1 && new_month;
+    if (tid == 0) {
+      sh.bb[0] = sh.bb[2] = INT_MAX; sh.bb[1] = sh.bb[3] = INT_MIN;
+      sh.n_contagious = 0;
+    }
+    __syncthreads();
+
+    // ================= phase 1: persons (graph_abs.py:210-233) =================
+    int bxmin = INT_MAX, bxmax = INT_MIN, bymin = INT_MAX, bymax = INT_MIN;
+    for (int i = tid; i < n; i += kThreads) {
+      uint32_t a = S.attr[i];
+      int x = S.px[i], y = S.py[i];
+      unsigned long long ev = 0ull;
+      if (a_status(a) != D_) {
+        const int h = S.house[i];
+        int checked_in = -1;
+        // ---- on_person_move (run_batch.py:16-50) or the default routine (graph_abs.py:212-220)
+        if (lock_all || (S.mode == MODE_VERTICAL && !(a & kActive))) {
+          if (h >= 0) house_checkin(S, h, a);
+        } else if ((a & kIsolated) || bed) {
+          move_to_home(S, i, it, ST_MOVE, a, h, x, y);
+        } else if (lunch || free_t || !work_day) {
+          move_freely(S, i, it, ST_MOVE, a, x, y);
+        } else if (work_day && work) {                                           // move_to_work, 293-310
+          if (a_sev(a) == SEV_A_ && (a & kActive)) {
+            const int b = S.employer[i];
+            if (b >= 0) {
+              const uint4 w = philox4x32_10(i, it, ST_MOVE, 0u, S.k0, S.k1);
+              float z0, z1;
+              normal_pair(w.x, w.y, z0, z1);
+              x = trunc_add(sh.bx[b], z0, 0.25);
+              y = trunc_add(sh.by[b], z1, 0.25);
+              atom_add(&sh.bwealth[b], -fx(__ddiv_rn(person_expenses(S, a), 720.0), scale));   // checkin, 101-103
+              checked_in = b;
+            } else {
+              move_freely(S, i, it, ST_MOVE, a, x, y);
+            }
+          }
+        }
+        // ---- daily health update (network/agents.py:362-415)
+        if (new_day && a_status(a) == I_) {
+          uint32_t st = I_, sev = a_sev(a), time = a_time(a) + 1;
+          const uint32_t age = a_age(a);
+          const uint32_t ix = min(age > 10u ? age / 10u - 1u : 0u, 8u);
+          const uint4 u = philox4x32_10(i, it, ST_UPDATE, 0u, S.k0, S.k1);
+          if (sev == SEV_A_) {
+            if ((long long)u.x < S.thr_hosp[ix]) {
+              sev = SEV_H_;
+              const uint4 w = philox4x32_10(i, it, ST_HOSP_MOVE, 0u, S.k0, S.k1);   // move_to(healthcare), 344-354
+              float z0, z1;
+              normal_pair(w.x, w.y, z0, z1);
+              x = trunc_add(S.health_x, z0, 0.25);
+              y = trunc_add(S.health_y, z1, 0.25);
+              atom_add(&sh.health_expenses, fx(person_expenses(S, a), scale));       // checkin, 104-105
+            }
+          } else if (sev == SEV_H_) {
+            if ((long long)u.x < S.thr_sev[ix]) {
+              sev = SEV_G_;
+              if (crit_active) {                                                     // 388-401
+                st = D_;
+                sev = SEV_A_;
+                if (h >= 0) {                                                        // remove_mate, 196-200
+                  atom_add(&S.hwealth[h], -fx(__ddiv_rn(fl(S.pwealth[i], scale), 2.0), scale));
+                  atomicSub(&S.hsize[h], 1);
+                  atom_add(&S.hfixed[h], -fx(__dmul_rn(__ddiv_rn(person_expenses(S, a), 720.0), 24.0), scale));
+                } else {
+                  atom_add(&sh.gov_wealth, -fx(person_expenses(S, a), scale));
+                }
+                const int b = S.employer[i];
+                if (b >= 0) fire(S, sh, b, i, a);
+                else atom_add(&sh.gov_wealth, -fx(person_expenses(S, a), scale));
+              }
+            }
+          }
+          bool died = false;
+          if ((long long)u.y < S.thr_death[ix]) {                                    // 403-408
+            st = D_;
+            sev = SEV_A_;
+            a = a_set(a, st, sev, time);
+            move_to_home(S, i, it, ST_DEATH_MOVE, a, h, x, y);
+            died = true;
+          }
+          if (!died && (int)time > S.recovering) {                                   // 410-413
+            time = 0;
+            st = R_;
+            sev = SEV_A_;
+          }
+          a = a_set(a, st, sev, time);
+        }
+        // ---- purchase requests at every business in reach other than the employer (graph_abs.py:230-233)
+        if (checked_in >= 0) ev |= 15ull << (4 * checked_in);
+        if (a_sev(a) == SEV_A_) {
+          const int emp = S.employer[i];
+          uint4 q4 = make_uint4(0, 0, 0, 0);
+          int have = -1;
+          for (int b = 0; b < nb; ++b) {
+            const long long dx = sh.bx[b] - x, dy = sh.by[b] - y;
+            if (b == emp || dx * dx + dy * dy > (long long)S.T_bus) continue;
+            if (have != (b >> 2)) {
+              q4 = philox4x32_10(i, it, ST_SHOP + (b >> 2), 0u, S.k0, S.k1);
+              have = b >> 2;
+            }
+            const uint32_t w = (b & 3) == 0 ? q4.x : (b & 3) == 1 ? q4.y : (b & 3) == 2 ? q4.z : q4.w;
+            ev |= (unsigned long long)(1u + mulhi_pick(w, 9u)) << (4 * b);            // np.random.randint(1, 10)
+          }
+        }
+        S.attr[i] = a;
+        S.px[i] = x;
+        S.py[i] = y;
+      }
+      S.events[i] = ev;
+      bxmin = min(bxmin, x); bxmax = max(bxmax, x); bymin = min(bymin, y); bymax = max(bymax, y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bxmin = min(bxmin, __shfl_xor_sync(0xffffffffu, bxmin, o)); bxmax = max(bxmax, __shfl_xor_sync(0xffffffffu, bxmax, o));
+      bymin = min(bymin, __shfl_xor_sync(0xffffffffu, bymin, o)); bymax = max(bymax, __shfl_xor_sync(0xffffffffu, bymax, o));
+    }
+    if (lane == 0 && bxmin <= bxmax) {
+      atomicMin(&sh.bb[0], bxmin); atomicMax(&sh.bb[1], bxmax); atomicMin(&sh.bb[2], bymin); atomicMax(&sh.bb[3], bymax);
+    }
+    __syncthreads();
+
+    // ================= phase 2: stocks in person order (network/agents.py:82-93,101-102) =================
+    for (int base = 0; base < n; base += kThreads) {
+      const int i = base + tid;
+      const unsigned long long ev = i < n ? S.events[i] : 0ull;
+      if (tid == 0) sh.present = 0;
+      __syncthreads();
+      unsigned mine = 0;
+      for (int b = 0; b < nb; ++b)
+        if ((ev >> (4 * b)) & 15ull) mine |= 1u << b;
+      mine = __reduce_or_sync(0xffffffffu, mine);
+      if (lane == 0 && mine) atomicOr(&sh.present, mine);
+      __syncthreads();
+      const unsigned present = sh.present;
+      __syncthreads();   // everyone has read it before the next chunk resets it
+      if (!present) continue;
+      int ea[kMaxBusiness], em[kMaxBusiness];  // inclusive prefix inside the warp, per business
+      for (int b = 0; b < nb; ++b) {
+        if (!((present >> b) & 1u)) continue;
+        const unsigned nib = (unsigned)((ev >> (4 * b)) & 15ull);
+        int a = nib == 15u ? 1 : -(int)nib;
+        int m = (nib >= 1u && nib <= 9u) ? 0 : kNegInf;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int pa = __shfl_up_sync(0xffffffffu, a, o), pm = __shfl_up_sync(0xffffffffu, m, o);
+          if (lane >= o) compose(pa, pm, a, m, a, m);
+        }
+        ea[b] = a;
+        em[b] = m;
+        if (lane == 31) {
+          sh.wa[wid][b] = a;
+          sh.wm[wid][b] = m;
+        }
+      }
+      __syncthreads();
+      for (int b = 0; b < nb; ++b) {
+        if (!((present >> b) & 1u)) continue;
+        const unsigned nib = (unsigned)((ev >> (4 * b)) & 15ull);
+        // stock before this warp = carry through the earlier warps of the chunk
+        int s0 = sh.bstocks[b];
+        for (int w = 0; w < wid; ++w) s0 = max(s0 + sh.wa[w][b], sh.wm[w][b]);
+        const int after = max(s0 + ea[b], em[b]);
+        // exclusive prefix = inclusive prefix of the lane before
+        const int pa = __shfl_up_sync(0xffffffffu, ea[b], 1), pm = __shfl_up_sync(0xffffffffu, em[b], 1);
+        if (nib >= 1u && nib <= 9u) {
+          const int before = lane == 0 ? s0 : max(s0 + pa, pm);
+          const int taken = before - after;                                           // min(qty, stocks)
+          const uint32_t a = S.attr[i];
+          const long long value = fx(__dmul_rn(__dmul_rn(sh.bprice[b], (double)a_stratum(a)), (double)taken), scale);
+          person_demand(S, i, S.house[i], value);
+          atom_add(&sh.bwealth[b], value);
+          atom_add(&sh.bincomes[b], value);
+          atomicAdd(&sh.bsales[b], taken);
+        }
+      }
+      __syncthreads();
+      if (tid < nb && ((present >> tid) & 1u)) {
+        int s0 = sh.bstocks[tid];
+        for (int w = 0; w < kWarps; ++w) s0 = max(s0 + sh.wa[w][tid], sh.wm[w][tid]);
+        sh.bstocks[tid] = s0;
+      }
+      __syncthreads();
+    }
+
+    // ================= phase 3: accounts (graph_abs.py:235-254) =================
+    // ---- businesses: daily update (network/agents.py:147-153)
+    if (new_day && tid < nb) {
+      atom_add(&sh.gov_wealth, fx(__ddiv_rn(fl(sh.bfixed[tid], scale), 3.0), scale));
+      atom_add(&sh.bwealth[tid], -sh.bfixed[tid]);
+    }
+    __syncthreads();
+    // ---- businesses: monthly accounting, one after the other (network/agents.py:115-145)
+    if (monthly) {
+      for (int b = 0; b < nb; ++b) {
+        long long labor = 0;
+        for (int i = tid; i < n; i += kThreads) {                                     // demand(), 55-76
+          if (S.employer[i] != b) continue;
+          const uint32_t a = S.attr[i];
+          if (a_status(a) == D_ || a_sev(a) != SEV_A_) continue;
+          const long long v = fx(person_incomes(S, a), scale);
+          person_supply(S, i, S.house[i], v);
+          labor += v;
+        }
+        labor = block_sum(labor, sh.red);
+        __syncthreads();
+        if (tid == 0) {
+          sh.bwealth[b] -= labor;
+          const long long tax = fx(__dadd_rn(__dmul_rn(S.gov_price, (double)sh.bnum[b]),
+                                             __ddiv_rn(fl(sh.bincomes[b], scale), 20.0)), scale);   // taxes(), 108-113
+          sh.gov_wealth += tax;
+          sh.bwealth[b] -= tax;
+          const double lt = __dadd_rn(fl(labor, scale), fl(tax, scale)), inc = fl(sh.bincomes[b], scale);
+          sh.sel = __dmul_rn(2.0, lt) < inc ? 1 : (lt > inc ? 2 : 0);                   // 1 hire, 2 fire
+        }
+        __syncthreads();
+        const int action = sh.sel;
+        __syncthreads();
+        const uint4 w = philox4x32_10(kBusinessId0 + b, it, ST_ACCOUNT, 0u, S.k0, S.k1);
+        if (action == 1) {
+          // ---- hire the ix-th unemployed person in population order (graph_abs.py:43-45)
+          long long cnt = 0;
+          for (int i = tid; i < n; i += kThreads) {
+            const uint32_t a = S.attr[i];
+            cnt += (S.employer[i] < 0 && (a & kActive) && a_status(a) != D_ && a_sev(a) == SEV_A_) ? 1 : 0;
+          }
+          cnt = block_sum(cnt, sh.red);
+          __syncthreads();
+          if (cnt > 0) {
+            const int target = (int)mulhi_pick(w.x, (uint32_t)cnt);
+            // ordered search: chunks of kThreads persons, running count
+            int seen = 0;
+            if (tid == 0) sh.sel = -1;
+            __syncthreads();
+            for (int base = 0; base < n; base += kThreads) {
+              const int i = base + tid;
+              bool u = false;
+              if (i < n) {
+                const uint32_t a = S.attr[i];
+                u = S.employer[i] < 0 && (a & kActive) && a_status(a) != D_ && a_sev(a) == SEV_A_;
+              }
+              const unsigned bal = __ballot_sync(0xffffffffu, u);
+              if (lane == 0) sh.wa[wid][0] = __popc(bal);
+              __syncthreads();
+              int before = seen;
+              for (int k = 0; k < wid; ++k) before += sh.wa[k][0];
+              const int my = before + __popc(bal & ((1u << lane) - 1u));
+              if (u && my == target) sh.sel = i;
+              int total = 0;
+              for (int k = 0; k < kWarps; ++k) total += sh.wa[k][0];
+              seen += total;
+              __syncthreads();
+              if (sh.sel >= 0) break;
+            }
+            if (tid == 0 && sh.sel >= 0) {                                             // hire(), 36-42
+              const int i = sh.sel;
+              const uint32_t a = S.attr[i];
+              S.employer[i] = b;
+              S.hire_seq[i] = sh.next_hire_seq++;
+              sh.bnum[b] += 1;
+              sh.bfixed[b] += fx(__dmul_rn(__ddiv_rn(person_expenses(S, a), 720.0), 24.0), scale);
+            }
+            __syncthreads();
+          }
+        } else if (action == 2 && sh.bnum[b] > 0) {
+          // ---- fire the ix-th employee in list (= hire) order: smallest v with #(hire_seq <= v) > ix
+          const int target = (int)mulhi_pick(w.x, (uint32_t)sh.bnum[b]);
+          long long members = 0;
+          for (int i = tid; i < n; i += kThreads) members += S.employer[i] == b ? 1 : 0;
+          members = block_sum(members, sh.red);
+          __syncthreads();
+          if (target < members) {
+            int lo = 0, hi = sh.next_hire_seq;    // answer in [lo, hi)
+            while (hi - lo > 1) {
+              const int mid = lo + (hi - lo) / 2;  // count employees with hire_seq < mid
+              long long c = 0;
+              for (int i = tid; i < n; i += kThreads) c += (S.employer[i] == b && S.hire_seq[i] < mid) ? 1 : 0;
+              c = block_sum(c, sh.red);
+              __syncthreads();
+              if (c > target) hi = mid; else lo = mid;
+            }
+            for (int i = tid; i < n; i += kThreads)
+              if (S.employer[i] == b && S.hire_seq[i] == lo) fire(S, sh, b, i, S.attr[i]);
+            __syncthreads();
+          }
+        }
+        if (tid == 0) {
+          sh.bincomes[b] = 0;
+          sh.bsales[b] = 0;
+        }
+        __syncthreads();
+      }
+    }
+    // ---- houses (network/agents.py:227-245)
+    if (new_day || monthly) {
+      long long gov = 0;
+      for (int h = tid; h < nh; h += kThreads) {
+        if (S.hsize[h] <= 0) continue;
+        if (new_day) gov += fx(__ddiv_rn(fl(S.hfixed[h], scale), 10.0), scale);
+        if (monthly) {
+          const long long tax = fx(__dadd_rn(__dmul_rn(S.gov_price, (double)S.hsize[h]),
+                                             __ddiv_rn(fl(S.hexpenses[h], scale), 10.0)), scale);
+          gov += tax;
+          S.hwealth[h] -= tax;
+          S.hincomes[h] = 0;
+          S.hexpenses[h] = 0;
+        }
+      }
+      gov = block_sum(gov, sh.red);
+      if (tid == 0) sh.gov_wealth += gov;
+      __syncthreads();
+    }
+    // ---- government and healthcare (network/agents.py:147-166, 132-139)
+    if (new_day && tid == 0) {
+      const uint4 w = philox4x32_10(kGovId, it, ST_GOV, 0u, S.k0, S.k1);
+      const int b = (int)mulhi_pick(w.x, (uint32_t)nb);
+      const int q = min(1 + (int)mulhi_pick(w.y, 9u), sh.bstocks[b]);
+      const long long value = fx(__dmul_rn(__dmul_rn(sh.bprice[b], 4.0), (double)q), scale);   // buys as stratum 4
+      sh.gov_wealth -= value;
+      sh.bwealth[b] += value;
+      sh.bincomes[b] += value;
+      sh.bstocks[b] -= q;
+      sh.bsales[b] += q;
+      sh.gov_wealth += fx(__ddiv_rn(fl(S.health_fixed, scale), 3.0), scale);                   // healthcare.update()
+      sh.health_wealth -= S.health_fixed;
+    }
+    __syncthreads();
+    if (monthly) {
+      long long paid = 0;
+      for (int i = tid; i < n; i += kThreads) {
+        const uint32_t a = S.attr[i];
+        if (a_status(a) == D_ || a_sev(a) != SEV_A_) continue;
+        const int h = S.house[i];
+        const long long v = fx(person_expenses(S, a), scale);
+        if (h < 0) {                                                                    // homeless
+          person_supply(S, i, h, v);
+          paid += v;
+        }
+        if (S.employer[i] < 0 && (a & kActive)) {                                       // unemployed
+          person_supply(S, i, h, v);
+          paid += v;
+        }
+      }
+      paid = block_sum(paid, sh.red);
+      if (tid == 0) {
+        const long long labor = sh.health_expenses;                                     // demand(healthcare)
+        sh.health_wealth += labor;
+        sh.gov_wealth -= labor + paid;
+      }
+      __syncthreads();
+    }
+
+    // ================= phase 4: contacts (graph_abs.py:256-300) =================
+    if (S.T >= 0) {
+      // cell grid over the bounding box, edge a power of two >= reach, grown to fit cell_cap
+      int eshift = 0;
+      while ((1 << eshift) < S.reach) ++eshift;
+      const int x0 = sh.bb[0], y0 = sh.bb[2];
+      int ncx, ncy;
+      for (;;) {
+        ncx = ((sh.bb[1] - x0) >> eshift) + 3;
+        ncy = ((sh.bb[3] - y0) >> eshift) + 3;
+        if ((long long)ncx * ncy <= (long long)S.cell_cap || eshift >= 30) break;
+        ++eshift;
+      }
+      const int ncells = (int)min((long long)ncx * ncy, (long long)S.cell_cap);
+      if (n > 0 && sh.bb[0] <= sh.bb[1]) {
+        for (int c = tid; c <= ncells; c += kThreads) S.cell_count[c] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += kThreads) {
+          const int cx = ((S.px[i] - x0) >> eshift) + 1, cy = ((S.py[i] - y0) >> eshift) + 1;
+          atomicAdd(&S.cell_count[cy * ncx + cx], 1u);
+          const uint32_t a = S.attr[i];
+          // sources: Infected persons whose infected_time can fall inside the window for some (low, up)
+          if (a_status(a) == I_ && (int)a_time(a) >= S.incubation - 1 && (int)a_time(a) <= S.contagion_time)
+            S.contagious[atomicAdd(&sh.n_contagious, 1u)] = i;
+        }
+        __syncthreads();
+        // exclusive scan of cell_count[0..ncells] (chunked, running carry)
+        unsigned carry = 0;
+        for (int base = 0; base <= ncells; base += kThreads) {
+          const int c = base + tid;
+          const unsigned v = c <= ncells ? S.cell_count[c] : 0u;
+          unsigned inc = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+          }
+          if (lane == 31) sh.wa[wid][0] = (int)inc;
+          __syncthreads();
+          unsigned before = carry, total = 0;
+          for (int k = 0; k < kWarps; ++k) {
+            if (k < wid) before += (unsigned)sh.wa[k][0];
+            total += (unsigned)sh.wa[k][0];
+          }
+          if (c <= ncells) S.cell_count[c] = before + inc - v;
+          carry += total;
+          __syncthreads();
+        }
+        // fill: cell_count[c] is advanced to the end of cell c, i.e. becomes the start of cell c + 1
+        for (int i = tid; i < n; i += kThreads) {
+          const int cx = ((S.px[i] - x0) >> eshift) + 1, cy = ((S.py[i] - y0) >> eshift) + 1;
+          S.cell_items[atomicAdd(&S.cell_count[cy * ncx + cx], 1u)] = i;
+        }
+        __syncthreads();
+        // after the fill, items of cell c are [c == 0 ? 0 : cell_count[c - 1], cell_count[c])
+        const unsigned nsrc = sh.n_contagious;
+        for (unsigned t = tid; t < nsrc; t += kThreads) {
+          const int j = (int)S.contagious[t];
+          const int xj = S.px[j], yj = S.py[j], tj = (int)a_time(S.attr[j]);
+          const int clo = max(((xj - S.reach - x0) >> eshift) + 1, 0), chi = min(((xj + S.reach - x0) >> eshift) + 1, ncx - 1);
+          const int rlo = max(((yj - S.reach - y0) >> eshift) + 1, 0), rhi = min(((yj + S.reach - y0) >> eshift) + 1, ncy - 1);
+          for (int r = rlo; r <= rhi; ++r) {
+            const int c0 = r * ncx + clo, c1 = r * ncx + chi;
+            const unsigned jb = c0 == 0 ? 0u : S.cell_count[c0 - 1], je = S.cell_count[c1];
+            for (unsigned k = jb; k < je; ++k) {
+              const int s = (int)S.cell_items[k];
+              const uint32_t as = S.attr[s];
+              if ((as & (3u | kNew)) != S_) continue;
+              const long long dx = S.px[s] - xj, dy = S.py[s] - yj;
+              if (dx * dx + dy * dy > (long long)S.T) continue;
+              const uint4 w = philox4x32_10((uint32_t)min(s, j), it, ST_CONTACT, (uint32_t)max(s, j), S.k0, S.k1);
+              const int low = -1 + (int)(w.x >> 31), up = -1 + (int)(w.y >> 31);       // np.random.randint(-1, 1)
+              if (tj >= S.incubation + low && tj <= S.contagion_time + up && (long long)w.z <= S.thr_rate)
+                atomicOr(&S.attr[s], kNew);                                            // graph_abs.py:292-297
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+
+    // ================= phase 5: statistics (graph_abs.py:302-324) =================
+    {
+      unsigned c_st[4] = {0, 0, 0, 0}, c_sev[3] = {0, 0, 0};
+      for (int i = tid; i < n; i += kThreads) {
+        uint32_t a = S.attr[i];
+        if (a & kNew) {                       // contact() rewrote the status (only the status, graph_abs.py:297-298)
+          a = (a & ~(kNew | 3u)) | I_;
+          S.attr[i] = a;
+        }
+        c_st[a_status(a)]++;
+        if (a_status(a) != D_ && a_sev(a) != SEV_E_) c_sev[a_sev(a) - 1]++;
+      }
+      long long q[5] = {0, 0, 0, 0, 0};
+      for (int h = tid; h < nh; h += kThreads) {
+        const int s = S.hstratum[h];
+        if (s >= 0 && s < 5) q[s] += S.hwealth[h];
+      }
+      if (tid < 8) sh.cnt[tid] = 0;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned v = __reduce_add_sync(0xffffffffu, c_st[k]);
+        if (lane == 0 && v) atomicAdd(&sh.cnt[k], v);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const unsigned v = __reduce_add_sync(0xffffffffu, c_sev[k]);
+        if (lane == 0 && v) atomicAdd(&sh.cnt[4 + k], v);
+      }
+      for (int k = 0; k < 5; ++k) {
+        const long long t = block_sum(q[k], sh.red);
+        if (tid == 0) sh.acc[k] = t;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        long long bsum = 0;
+        for (int b = 0; b < nb; ++b) bsum += sh.bwealth[b];
+        for (int k = 0; k < 5; ++k) row[k] = __ddiv_rn(fl(sh.acc[k], scale), S.total_wealth);
+        row[5] = __ddiv_rn(fl(bsum, scale), S.total_wealth);
+        row[6] = __ddiv_rn(fl(sh.gov_wealth, scale), S.total_wealth);
+        for (int k = 0; k < 7; ++k) row[7 + k] = __ddiv_rn((double)sh.cnt[k], S.pop_size);
+      }
+      __syncthreads();
+      prev_infected = __ddiv_rn((double)sh.cnt[1], S.pop_size);
+      prev_hs = __dadd_rn(__ddiv_rn((double)sh.cnt[6], S.pop_size), __ddiv_rn((double)sh.cnt[5], S.pop_size));
+      __syncthreads();
+    }
+  }
+
+  // ---- write the shared accounts back
+  if (tid < nb) {
+    S.bwealth[tid] = sh.bwealth[tid]; S.bfixed[tid] = sh.bfixed[tid]; S.bincomes[tid] = sh.bincomes[tid];
+    S.bstocks[tid] = sh.bstocks[tid]; S.bsales[tid] = sh.bsales[tid]; S.bnum[tid] = sh.bnum[tid];
+  }
+  if (tid == 0) {
+    S.gov_wealth = sh.gov_wealth; S.health_wealth = sh.health_wealth; S.health_expenses = sh.health_expenses;
+    S.next_hire_seq = sh.next_hire_seq;
+    S.iteration = it;
+    S.prev_infected = prev_infected;
+    S.prev_hosp_severe = prev_hs;
+  }
+}
+
+// Statistics of the initial state (row -1 is never read by batch_experiment, but get_statistics() before the
+// first execute() and the first hour's memo need it): same reduction as phase 5, one block per simulation.
+__global__ void __launch_bounds__(kThreads) k_graph_initial_stats(Sim *sims, double *rows) {
+  Sim &S = sims[blockIdx.x];
+  __shared__ long long red[kWarps];
+  __shared__ long long acc[12];
+  const int tid = threadIdx.x;
+  long long v[12] = {0};
+  for (int i = tid; i < S.n; i += kThreads) {
+    const uint32_t a = S.attr[i];
+    v[a_status(a)]++;
+    if (a_status(a) != D_ && a_sev(a) != SEV_E_) v[3 + a_sev(a)]++;
+  }
+  for (int h = tid; h < S.nh; h += kThreads) {
+    const int s = S.hstratum[h];
+    if (s >= 0 && s < 5) v[7 + s] += S.hwealth[h];
+  }
+  for (int k = 0; k < 12; ++k) {
+    const long long t = block_sum(v[k], red);
+    if (tid == 0) acc[k] = t;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double *row = rows + (size_t)blockIdx.x * kStats;
+    long long bsum = 0;
+    for (int b = 0; b < S.nb; ++b) bsum += S.bwealth[b];
+    for (int k = 0; k < 5; ++k) row[k] = __ddiv_rn(fl(acc[7 + k], S.scale), S.total_wealth);
+    row[5] = __ddiv_rn(fl(bsum, S.scale), S.total_wealth);
+    row[6] = __ddiv_rn(fl(S.gov_wealth, S.scale), S.total_wealth);
+    for (int k = 0; k < 7; ++k) row[7 + k] = __ddiv_rn((double)acc[k], S.pop_size);
+    S.prev_infected = row[8];
+    S.prev_hosp_severe = __dadd_rn(row[13], row[12]);
+    // the row before the first iteration: a slept first hour copies it
+    double *h = S.history + (size_t)((S.iteration + S.hist_cap) % S.hist_cap) * kStats;
+    for (int k = 0; k < kStats; ++k) h[k] = row[k];
+  }
+}
+
+}  // namespace graph
+}  // namespace cabs

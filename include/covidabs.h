@@ -214,6 +214,87 @@ typedef struct cabs_kernel_time {
 int cabs_profile_enable(cabs_sim *sim, int on);
 int cabs_profile_read(cabs_sim *sim, cabs_kernel_time *out, int capacity, int *count);
 
+
+/* ======================================================================================================
+ * GraphSimulation (covid_abs/network/graph_abs.py): the hourly routine model with houses, businesses,
+ * government and healthcare.  One handle holds `n_sims` independent simulations of the same capacity (a
+ * scenario x seed ensemble, or a single one); one thread block per simulation runs a whole batch of
+ * iterations.  The world is built on the host (GraphSimulation.initialize, graph_abs.py:89-188) and
+ * uploaded as structure of arrays; every array below is indexed like the reference's lists
+ * (population, houses, business).
+ * ====================================================================================================== */
+typedef struct cabs_graph cabs_graph;
+
+enum { CABS_GRAPH_MODE_NONE = 0,                 /* run_batch.py scenario1: routine only                  */
+       CABS_GRAPH_MODE_LOCKDOWN = 1,             /* run_batch.py:16-19  on_person_move = lockdown         */
+       CABS_GRAPH_MODE_CONDITIONAL_LOCKDOWN = 2, /* run_batch.py:22-26  lockdown while Infected > .05     */
+       CABS_GRAPH_MODE_VERTICAL_ISOLATION = 3 }; /* run_batch.py:45-50  lockdown of the Inactive          */
+/* partial isolation (run_batch.py:31-42) is the per-person `isolated` column with any mode */
+
+#define CABS_GRAPH_NUM_STATS 14  /* Q1..Q5, Business, Government, S, I, R, D, Asymptomatic, Hospitalization, Severe
+                                    = key order of graph_abs.py:305-322 and of the published CSVs */
+#define CABS_GRAPH_MAX_BUSINESS 16
+
+typedef struct cabs_graph_config {
+  uint32_t abi_version;
+  int32_t device;
+  uint32_t n_sims;
+  uint32_t max_persons, max_houses, max_business; /* per simulation */
+  uint32_t history_capacity;                      /* statistics rows kept per simulation (ring)            */
+  uint32_t cell_capacity;                         /* cells of the contact grid per simulation (0 = auto)   */
+} cabs_graph_config;
+
+/* graph_abs.py:13-32 + abs.py:17-49 + common.py:13-27 */
+typedef struct cabs_graph_params {
+  double amplitudes[4];            /* by status code                                             */
+  double basic_income[5];
+  double minimum_income, minimum_expense, total_wealth, critical_limit;
+  double contagion_distance, contagion_rate, business_distance;
+  double age_hospitalization_probs[9], age_severe_probs[9], age_death_probs[9];
+  uint64_t population_size;        /* denominator of the status fractions (graph_abs.py:315-322) */
+  uint64_t seed;                   /* Philox key                                                  */
+  int32_t incubation_time, contagion_time, recovering_time;
+  int32_t mode;                    /* CABS_GRAPH_MODE_*                                           */
+  int32_t sleep;                   /* run_batch.py:8-13: skip hours 1..7 of every day             */
+  int32_t money_bits;              /* fractional bits of the fixed-point accounts                 */
+} cabs_graph_params;
+
+typedef struct cabs_graph_world {
+  int32_t n_persons, n_houses, n_business, reserved;
+  /* persons (network/agents.py:256-274) */
+  int32_t *px, *py;
+  uint8_t *status, *severity, *infected_time, *age, *stratum, *active, *isolated;
+  int32_t *house, *employer, *hire_seq; /* -1 = none; hire_seq = position order in employer.employees */
+  double *pwealth;
+  /* houses (network/agents.py:171-184) */
+  int32_t *hx, *hy, *hstratum, *hsize;
+  double *hwealth, *hfixed, *hincomes, *hexpenses;
+  /* businesses (network/agents.py:14-31) */
+  int32_t *bx, *by, *bstratum, *bstocks, *bsales, *bnum_employees;
+  double *bprice, *bwealth, *bfixed, *bincomes;
+  /* government and healthcare (graph_abs.py:95-102) */
+  int32_t gov_x, gov_y, health_x, health_y;
+  double gov_wealth, gov_price, gov_fixed, health_wealth, health_fixed, health_expenses;
+  int32_t iteration;               /* graph_abs.py:25: -1 before the first execute()              */
+  int32_t reserved2;
+} cabs_graph_world;
+
+int cabs_graph_create(const cabs_graph_config *cfg, cabs_graph **out);
+void cabs_graph_destroy(cabs_graph *g);
+const char *cabs_graph_last_error(const cabs_graph *g);
+/* Replaces the lists GraphSimulation.initialize builds (graph_abs.py:89-188) for simulation `sim`. */
+int cabs_graph_upload(cabs_graph *g, uint32_t sim, const cabs_graph_world *world, const cabs_graph_params *params);
+/* Replaces `iterations` calls of GraphSimulation.execute (graph_abs.py:190-276) on every simulation. Asynchronous. */
+int cabs_graph_run(cabs_graph *g, int iterations);
+int cabs_graph_sync(cabs_graph *g);
+/* Replaces get_statistics(kind='all') (graph_abs.py:302-324): rows after iterations
+ * [first_iteration, first_iteration + count); first_iteration = -1 is the initial state. */
+int cabs_graph_stats(cabs_graph *g, uint32_t sim, int64_t first_iteration, uint32_t count, double *rows);
+/* Current state of simulation `sim` (caller-allocated arrays of at least the uploaded sizes). */
+int cabs_graph_download(cabs_graph *g, uint32_t sim, cabs_graph_world *world);
+/* Device time of the last cabs_graph_run (CUDA events on the handle's stream); waits for it. */
+int cabs_graph_last_run_ms(cabs_graph *g, double *ms);
+
 #ifdef __cplusplus
 }
 #endif

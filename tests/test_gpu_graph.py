@@ -1,0 +1,102 @@
+"""GraphSimulation on the GPU (through the C ABI) against the oracle and the reference's golden trajectories."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from graph_util import product_world, oracle_world, sim_kwargs
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "graph_*.json")))
+
+
+def _compare_state(sim, orc):
+    w = sim.world()
+    for k, o in (("px", orc.px), ("py", orc.py), ("status", orc.status), ("severity", orc.severity),
+                 ("infected_time", orc.time), ("employer", orc.employer), ("hire_seq", orc.hire_seq),
+                 ("hsize", orc.hsize), ("bstocks", orc.bstocks), ("bsales", orc.bsales), ("bnum_employees", orc.bnum)):
+        assert np.array_equal(np.asarray(w[k]).astype(np.int64), o), k
+    for k, o in (("pwealth", orc.pwealth), ("hwealth", orc.hwealth), ("hfixed", orc.hfixed), ("hincomes", orc.hincomes),
+                 ("hexpenses", orc.hexpenses), ("bwealth", orc.bwealth), ("bfixed", orc.bfixed),
+                 ("bincomes", orc.bincomes)):
+        assert np.array_equal(np.rint(np.asarray(w[k]) * orc.scale).astype(np.int64), o), k
+    assert int(round(w["gov_wealth"] * orc.scale)) == orc.gov["wealth"]
+    assert int(round(w["health_wealth"] * orc.scale)) == orc.health["wealth"]
+    assert int(round(w["health_expenses"] * orc.scale)) == orc.health["expenses"]
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-5] for p in GOLDEN])
+def test_reference_trajectories(native_lib, path):
+    """The fixtures were produced by the unmodified reference under keyed draws: same epidemiological rows exactly,
+    money rows to fixed-point rounding; and bit equality with the oracle in every column."""
+    from covid19_agentbasedsimulation_b200.network.graph_abs import GraphSimulation, GRAPH_STAT_KEYS
+    from oracle.graph_oracle import GraphOracle
+    fix = json.load(open(path))
+    p = fix["world"]["params"]
+    sim = GraphSimulation(seed=fix["seed"], history_capacity=1024, **sim_kwargs(p))
+    sim.set_world(product_world(fix["world"]), mode=p["mode"], sleep=p["sleep"])
+    init = sim.get_statistics('all')
+    orc = GraphOracle(fix["world"], seed=fix["seed"])
+    assert [float(init[k]) for k in GRAPH_STAT_KEYS] == [orc.stats[k] for k in GRAPH_STAT_KEYS]
+    rows = sim.run(fix["iterations"])
+    gold = np.array(fix["rows"])
+    assert np.array_equal(rows[:, 7:], gold[:, 7:])
+    assert np.allclose(rows[:, :7], gold[:, :7], rtol=0, atol=1e-9)
+    for it in range(fix["iterations"]):
+        st = orc.execute()
+        assert rows[it].tolist() == [st[k] for k in GRAPH_STAT_KEYS], it
+    _compare_state(sim, orc)
+    assert sim.world()["px"].tolist() == fix["final"]["px"] and sim.world()["status"].tolist() == fix["final"]["status"]
+
+
+@pytest.mark.parametrize("scenario,n", [("scenario1", 1500), ("scenario3", 1000), ("scenario6", 800)])
+def test_built_world_stepwise_equals_batched_equals_oracle(native_lib, scenario, n):
+    from covid19_agentbasedsimulation_b200.network.graph_abs import GraphSimulation, GRAPH_STAT_KEYS, default_money_bits
+    from covid19_agentbasedsimulation_b200.network import scenarios as sc
+    from oracle.graph_oracle import GraphOracle
+    kw = dict(sc.global_parameters)
+    kw.update(getattr(sc, scenario))
+    kw.pop("name")
+    kw.update(population_size=n, initial_infected_perc=0.03, length=300, height=300)
+    np.random.seed(5)
+    a = GraphSimulation(seed=99, **kw)
+    world, mode, sleep = a.build_world()
+    a.set_world(world, mode, sleep)
+    b = GraphSimulation(seed=99, **kw)
+    b.set_world(world, mode, sleep)
+    amp = [10.0, 10.0, 10.0, 0.0]
+    params = dict(population_size=n, total_wealth=kw["total_wealth"], contagion_distance=kw["contagion_distance"],
+                  contagion_rate=a.contagion_rate, critical_limit=kw["critical_limit"], amplitudes=amp,
+                  minimum_income=kw["minimum_income"], minimum_expense=kw["minimum_expense"],
+                  business_distance=kw["business_distance"], incubation_time=5, contagion_time=10, recovering_time=20,
+                  mode=mode, sleep=sleep, money_bits=default_money_bits(kw["total_wealth"]))
+    orc = GraphOracle(oracle_world(world, params), seed=99)
+    iters = 60
+    batched = a.run(iters)
+    for it in range(iters):
+        b.execute()
+        s = b.get_statistics('all')
+        o = orc.execute()
+        assert [float(s[k]) for k in GRAPH_STAT_KEYS] == batched[it].tolist() == [o[k] for k in GRAPH_STAT_KEYS], it
+    _compare_state(a, orc)
+    assert b.iteration == a.iteration == iters - 1
+
+
+def test_entities_are_materialised_like_the_reference_lists(native_lib):
+    from covid19_agentbasedsimulation_b200.network.graph_abs import GraphSimulation
+    from covid19_agentbasedsimulation_b200.network import scenarios as sc
+    kw = dict(sc.global_parameters)
+    kw.update(sc.scenario1)
+    kw.pop("name")
+    np.random.seed(1)
+    sim = GraphSimulation(seed=3, **kw)
+    sim.initialize()
+    sim.run(30)
+    assert len(sim.population) == 300 and len(sim.houses) >= 100 and len(sim.business) == 9
+    assert sum(len(b.employees) for b in sim.business) == sum(1 for p in sim.population if p.employer is not None)
+    assert sim.government.price == 1.0 and sim.healthcare is not None
+    assert set(sim.get_statistics('ecom')) == {"Q1", "Q2", "Q3", "Q4", "Q5", "Business", "Government"}
+    assert len(sim.get_positions()) == 300
