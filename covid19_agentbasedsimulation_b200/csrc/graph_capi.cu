@@ -142,7 +142,7 @@ extern "C" int cabs_graph_create(const cabs_graph_config *cfg, cabs_graph **out)
   return CABS_OK;
 }
 
-// host copies of the device-side bounds (oracle/graph_oracle.py states the same)
+// host copies of the device-side bounds (the CPU restatement of the tests states the same)
 static long long bound_lt(double p) {
   const double t = ceil(p * 4294967296.0 - 0.5);
   return t <= 0.0 ? 0ll : t >= 4294967296.0 ? 4294967296ll : (long long)t;

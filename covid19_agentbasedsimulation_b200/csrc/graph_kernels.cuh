@@ -18,7 +18,7 @@
 //   5 statistics  GraphSimulation.get_statistics (graph_abs.py:302-324) -> one row of the history
 //
 // Money that several threads add to is 64-bit fixed point (`money_bits` fractional bits, every flow rounded
-// to nearest-even once), so the sums do not depend on the order of the additions; oracle/graph_oracle.py
+// to nearest-even once), so the sums do not depend on the order of the additions; the CPU restatement the tests check against
 // does the same and the two agree bit for bit.  Draws: Philox4x32-10, counter (entity, iteration, stream, aux).
 #pragma once
 #include <limits.h>
@@ -37,7 +37,7 @@ constexpr int kStats = 14;
 enum : uint32_t { S_ = 0, I_ = 1, R_ = 2, D_ = 3 };
 enum : uint32_t { SEV_E_ = 0, SEV_A_ = 1, SEV_H_ = 2, SEV_G_ = 3 };
 enum : int { MODE_NONE = 0, MODE_LOCKDOWN = 1, MODE_CONDITIONAL = 2, MODE_VERTICAL = 3 };
-// draw streams: shared contract with oracle/graph_oracle.py
+// draw streams: shared contract with the CPU restatement the tests check against
 enum : uint32_t { ST_MOVE = 0, ST_UPDATE = 1, ST_HOSP_MOVE = 2, ST_DEATH_MOVE = 3, ST_CONTACT = 4, ST_GOV = 5,
                   ST_ACCOUNT = 6, ST_SHOP = 16 };
 constexpr uint32_t kGovId = 0xFFFFFFFFu, kBusinessId0 = 0xFFFF0000u;

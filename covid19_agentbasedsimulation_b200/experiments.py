@@ -23,6 +23,16 @@ def batch_experiment(experiments, iterations, file, simulation_type=Simulation, 
     verbose = kwargs.get('verbose', None)
     columns = None
     runs = []  # one [iterations_done, n_metrics] array per experiment
+    ensemble = getattr(simulation_type, 'run_ensemble', None)
+    if ensemble is not None and verbose != 'iterations' and experiments > 0:
+        # all experiments step concurrently on the device (one block per simulation), one copy back
+        try:
+            columns, table = ensemble(experiments, iterations, **kwargs)
+            runs = [table[k] for k in range(table.shape[0])]
+            experiments = 0
+        except Exception as ex:
+            print("Exception occurred in the ensemble run: {}".format(ex))
+            columns, runs = None, []
     for experiment in range(experiments):
         rows = []
         try:

@@ -392,6 +392,24 @@ class GraphSimulation(Simulation):
     def last_run_ms(self):
         return self._ghandle.last_run_ms()
 
+    @classmethod
+    def run_ensemble(cls, experiments, iterations, **kwargs):
+        """What batch_experiment (experiments.py:181-196) does with `experiments` simulations, as one launch.
+        Returns (statistics keys, float64 [experiments, iterations, 14])."""
+        from covid19_agentbasedsimulation_b200.network.ensemble import GraphEnsemble
+        kwargs = dict(kwargs)
+        kwargs.pop('verbose', None)
+        seed = kwargs.pop('seed', None)
+        sims = [cls(seed=None if seed is None else int(seed) + k, **kwargs) for k in range(int(experiments))]
+        ens = GraphEnsemble(sims, device=kwargs.get('device', 0),
+                            history_capacity=max(2048, min(int(iterations), 1 << 16)))
+        try:
+            ens.initialize()
+            table = ens.run(iterations)
+        finally:
+            ens.close()
+        return list(GRAPH_STAT_KEYS), table
+
 
 def _entity_property(index):
     def getter(self):

@@ -100,3 +100,41 @@ def test_entities_are_materialised_like_the_reference_lists(native_lib):
     assert sim.government.price == 1.0 and sim.healthcare is not None
     assert set(sim.get_statistics('ecom')) == {"Q1", "Q2", "Q3", "Q4", "Q5", "Business", "Government"}
     assert len(sim.get_positions()) == 300
+
+
+def test_ensemble_handle_equals_individual_runs_and_batch_experiment(native_lib, tmp_path):
+    from covid19_agentbasedsimulation_b200.network.graph_abs import GraphSimulation, GRAPH_STAT_KEYS
+    from covid19_agentbasedsimulation_b200.network.ensemble import GraphEnsemble, shard
+    from covid19_agentbasedsimulation_b200.network import scenarios as sc
+    from covid19_agentbasedsimulation_b200.experiments import batch_experiment
+    assert [list(shard(10, r, 4)) for r in range(4)] == [[0, 1, 2], [3, 4, 5], [6, 7], [8, 9]]
+    names = ("scenario1", "scenario2", "scenario3", "scenario4", "scenario6", "scenario8", "scenario10")
+    kws = []
+    for name in names:
+        kw = dict(sc.global_parameters)
+        kw.update(getattr(sc, name))
+        kw.pop("name")
+        kw.update(population_size=120, initial_infected_perc=0.05)
+        kws.append(kw)
+    np.random.seed(2)
+    sims = [GraphSimulation(seed=100 + k, **kw) for k, kw in enumerate(kws)]
+    worlds = [s.build_world() for s in sims]
+    ens = GraphEnsemble(sims)
+    ens.initialize(worlds)
+    table = ens.run(100)
+    assert table.shape == (7, 100, 14)
+    for k, kw in enumerate(kws):
+        one = GraphSimulation(seed=100 + k, **kw)
+        if "contagion_rate" in str(kw.get("callbacks", {})):
+            one.contagion_rate = 0.1
+        one.set_world(*worlds[k])
+        assert np.array_equal(one.run(100), table[k]), names[k]
+    assert not np.array_equal(table[0], table[1])
+    # batch_experiment drives the same ensemble path and keeps the reference's CSV schema (experiments.py:212)
+    kw = dict(kws[0])
+    np.random.seed(4)
+    df = batch_experiment(6, 50, str(tmp_path / "g.csv"), simulation_type=GraphSimulation, seed=7, **kw)
+    assert list(df.columns) == ['Iteration', 'Metric', 'Min', 'Avg', 'Std', 'Max']
+    assert len(df) == 50 * 14 and list(df['Metric'][:14]) == list(GRAPH_STAT_KEYS)
+    inf = df[df['Metric'] == 'Infected']
+    assert (inf['Min'] <= inf['Avg']).all() and (inf['Avg'] <= inf['Max']).all() and inf['Std'].max() > 0
