@@ -316,6 +316,17 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
 
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        # the GraphSimulation configs of BASELINE.json (configs[1], configs[4]-style), reported next to the headline
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import graph_bench
+            other = {"config2_graph_1k_lockdown": graph_bench.config2(),
+                     "config5_style_ensemble": graph_bench.ensemble(2000, 32, 120)}
+        except Exception as ex:  # the headline line must still be printed
+            other = {"error": repr(ex)}
+
     line = None
     if rank == 0:
         cpu = None
@@ -347,6 +358,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "final_stats": {"Susceptible": float(stats_last[0]), "Infected": float(stats_last[1])},
+            "other_configs": other,
         }
         print(json.dumps(line))
     if world > 1:
@@ -365,6 +377,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
     ap.add_argument("--ref-sample", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the GraphSimulation side measurements")
     ap.add_argument("--max-cells", type=int, default=0, help="cap on cell-list cells (0 = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

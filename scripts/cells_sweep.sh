@@ -1,7 +1,7 @@
 #!/bin/bash
 # effect of the cell edge (via the max_cells cap) on the per-kernel times of the bench workload
 for mc in ${SWEEP:-0 4000000 1000000}; do
-  python bench.py --steps 20 --warmup 5 --no-cpu-baseline --e2e-steps 3 --max-cells $mc > gpurun_out/sweep_$mc.json 2> gpurun_out/sweep_$mc.err || tail -3 gpurun_out/sweep_$mc.err
+  python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-other-configs --e2e-steps 3 --max-cells $mc > gpurun_out/sweep_$mc.json 2> gpurun_out/sweep_$mc.err || tail -3 gpurun_out/sweep_$mc.err
   python - $mc <<PY
 import json, sys
 d=json.load(open("gpurun_out/sweep_%s.json" % sys.argv[1]))

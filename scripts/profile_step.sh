@@ -2,7 +2,7 @@
 # ncu evidence for one round: launch list of a short bench run + one full capture of the step kernels.
 # usage: scripts/profile_step.sh <tag> [extra bench args]   (run under gpurun; outputs land in gpurun_out/)
 tag=${1:-r1}; shift
-args="--steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 3 $*"
+args="--steps 3 --warmup 3 --no-cpu-baseline --no-other-configs --e2e-steps 3 $*"
 set -x
 python bench.py $args > gpurun_out/plain_$tag.log 2>&1 || { tail -5 gpurun_out/plain_$tag.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$tag.csv python bench.py $args > gpurun_out/ncu_launch_$tag.log 2>&1
