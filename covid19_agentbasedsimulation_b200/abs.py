@@ -109,6 +109,9 @@ class Simulation(object):
         '''CUDA device ordinal'''
         self.placement = kwargs.get("placement", "reference")
         '''"reference": abs.py:97-114 consumed from np.random in the reference's order; "uniform": x,y ~ U{0..L}'''
+        self.schedule = kwargs.get("schedule", "synchronous")
+        '''"synchronous": agents infected in a step start transmitting in the next (one data-parallel pass);
+        "sequential": the reference's pair order with in-step chains (abs.py:261-265), exact, slower'''
         self.max_cells = kwargs.get("max_cells", 0)
         self.history_capacity = kwargs.get("history_capacity", 4096)
 
@@ -164,7 +167,7 @@ class Simulation(object):
         amp = amplitude_array(self.amplitudes)
         return (float(self.length), float(self.height), float(self.contagion_distance), float(self.contagion_rate),
                 float(self.critical_limit), tuple(amp.tolist()), float(self.minimum_income),
-                float(self.minimum_expense), int(self.population_size), float(self.total_wealth))
+                float(self.minimum_expense), int(self.population_size), float(self.total_wealth), self.schedule)
 
     def _push_params(self):
         """Send the attributes of abs.py:17-49 to the device if user code changed them (abs.py:267-271)."""
@@ -172,7 +175,7 @@ class Simulation(object):
         if t != self._pushed:
             p = _native.Params()
             (p.length, p.height, p.contagion_distance, p.contagion_rate, p.critical_limit, amp, p.minimum_income,
-             p.minimum_expense, pop, tw) = t
+             p.minimum_expense, pop, tw, _schedule) = t
             p.amplitudes[:] = amp
             p.basic_income[:] = [float(v) for v in basic_income]
             p.age_hospitalization_probs[:] = age_hospitalization_probs
@@ -181,7 +184,9 @@ class Simulation(object):
             p.population_size = max(1, pop)
             p.recovering_time = 20  # abs.py:225
             p.wealth_scale_bits = wealth_scale_bits(tw)
-            p.schedule = _native.SYNCHRONOUS
+            if self.schedule not in ("synchronous", "sequential"):
+                raise ValueError("schedule must be 'synchronous' or 'sequential'")
+            p.schedule = _native.SEQUENTIAL if self.schedule == "sequential" else _native.SYNCHRONOUS
             for h in self._targets():
                 h.set_params(p)
             self._pushed = t

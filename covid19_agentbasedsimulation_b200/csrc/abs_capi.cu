@@ -37,6 +37,9 @@ struct cabs_sim {
   bool slab_on = false;
   cabs_slab slab;
   unsigned *emig_list = nullptr, *imm_rank = nullptr;
+  // sequential schedule
+  unsigned long long *tinf = nullptr;
+  unsigned *newinf_list = nullptr;
   cudaStream_t own_stream = nullptr;
   Ctl *ctl = nullptr;
   StatRecord *history = nullptr;
@@ -112,7 +115,7 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
   cudaFree(sim->aux);
   cudaFree(sim->sqrt_tab);
   cudaFree(sim->cells[0]); cudaFree(sim->cells[1]); cudaFree(sim->tile_state); cudaFree(sim->inf_list);
-  cudaFree(sim->emig_list); cudaFree(sim->imm_rank);
+  cudaFree(sim->emig_list); cudaFree(sim->imm_rank); cudaFree(sim->tinf); cudaFree(sim->newinf_list);
   cudaFree(sim->ctl); cudaFree(sim->history);
   cudaFree(sim->stage); cudaFree(sim->stage_id); cudaFree(sim->pairs); cudaFree(sim->pair_count);
   for (cudaEvent_t e : sim->events) if (e) cudaEventDestroy(e);
@@ -198,7 +201,10 @@ extern "C" int cabs_set_params(cabs_sim *sim, const cabs_params *p) {
     return fail(sim, CABS_ERR_INVALID, "wealth_scale_bits must be in [0, 52]");
   if (p->recovering_time < 0 || p->recovering_time > 250)
     return fail(sim, CABS_ERR_INVALID, "recovering_time must be in [0, 250] (infected_time is stored in 8 bits)");
-  if (p->schedule != CABS_SYNCHRONOUS) return fail(sim, CABS_ERR_INVALID, "only CABS_SYNCHRONOUS is implemented");
+  if (p->schedule != CABS_SYNCHRONOUS && p->schedule != CABS_SEQUENTIAL)
+    return fail(sim, CABS_ERR_INVALID, "schedule must be CABS_SYNCHRONOUS or CABS_SEQUENTIAL");
+  if (p->schedule == CABS_SEQUENTIAL && sim->slab_on)
+    return fail(sim, CABS_ERR_INVALID, "the sequential schedule is defined on one device only (SURVEY.md 8e)");
   if (p->population_size == 0) return fail(sim, CABS_ERR_INVALID, "population_size must be > 0");
   for (int k = 0; k < 3; ++k)
     if (!(p->amplitudes[k] >= -5000.0 && p->amplitudes[k] <= 5000.0))
@@ -217,6 +223,10 @@ extern "C" int cabs_set_params(cabs_sim *sim, const cabs_params *p) {
   }
   b.pop_size = p->population_size;
   b.recovering_time = p->recovering_time; b.scale_bits = p->wealth_scale_bits; b.schedule = p->schedule;
+  if (p->schedule == CABS_SEQUENTIAL && !sim->tinf) {
+    CK(cudaMalloc(&sim->tinf, (sim->capacity + kPad) * sizeof(unsigned long long)));
+    CK(cudaMalloc(&sim->newinf_list, (sim->capacity + kPad) * sizeof(unsigned)));
+  }
   LAUNCH(k_set_params, 1, 32, sim->ctl, b);
   if (sim->n > 0) LAUNCH(k_replan, 1, 32, sim->ctl, 0);  // amplitudes / distance may have changed the margin
   CK(cudaGetLastError());
@@ -255,12 +265,27 @@ extern "C" int cabs_set_triggers(cabs_sim *sim, const cabs_trigger *t, int count
 template <bool kAdvance>
 static void enqueue_build(cabs_sim *sim) {
   const int c = sim->cur, o = c ^ 1, t = sim->tab;
+  const bool sequential = sim->have_params && sim->params.schedule == CABS_SEQUENTIAL;
   const int nb = agent_blocks(sim);
   LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl, sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list);
   LAUNCH(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
   LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", k_update_scatter<kAdvance>, nb, kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t],
-         sim->cells[t ^ 1], sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, nullptr, nullptr);
-  if (kAdvance) {
+         sim->cells[t ^ 1], sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, nullptr, nullptr,
+         (kAdvance && sequential) ? sim->tinf : nullptr);
+  if (kAdvance && sequential) {
+    // rounds of label-correcting relaxation until no infection time is lowered (one host round trip each)
+    for (int round = 0;; ++round) {
+      LAUNCH(k_contagion_sequential, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->tinf,
+             round == 0 ? sim->inf_list : sim->newinf_list, round == 0 ? 1 : 0, sim->newinf_list);
+      unsigned changed = 0;
+      if (cudaMemcpyAsync(&changed, &sim->ctl->seq_changed, sizeof changed, cudaMemcpyDeviceToHost, sim->stream) !=
+              cudaSuccess || cudaStreamSynchronize(sim->stream) != cudaSuccess)
+        break;
+      if (!changed) break;
+      cudaMemsetAsync(&sim->ctl->seq_changed, 0, sizeof(unsigned), sim->stream);
+    }
+    LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 1);
+  } else if (kAdvance) {
     LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, nullptr, nullptr, sim->history,
            nullptr, 1);
   } else {
@@ -301,7 +326,7 @@ extern "C" int cabs_set_slab(cabs_sim *sim, const cabs_slab *slab) {
       return fail(sim, CABS_ERR_INVALID, "cabs_set_slab: null exchange buffer");
   CK(cudaSetDevice(sim->device));
   CK(cudaStreamSynchronize(sim->stream));
-  cudaFree(sim->emig_list); cudaFree(sim->imm_rank);
+  cudaFree(sim->emig_list); cudaFree(sim->imm_rank); cudaFree(sim->tinf); cudaFree(sim->newinf_list);
   sim->emig_list = sim->imm_rank = nullptr;
   CK(cudaMalloc(&sim->emig_list, 2 * (size_t)slab->migrant_capacity * sizeof(unsigned)));
   CK(cudaMalloc(&sim->imm_rank, 2 * (size_t)slab->migrant_capacity * sizeof(unsigned)));
@@ -346,7 +371,7 @@ static int slab_phase(cabs_sim *sim, int phase) {
       LAUNCH(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
       LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", k_update_scatter<kAdvance>, nb,
                 kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t], sim->cells[t ^ 1],
-                sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, gs[0], gs[1]);
+                sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, gs[0], gs[1], nullptr);
       LAUNCH(k_scatter_immigrants, nbs, 256, sim->ctl, mr[0], mr[1], sim->cells[t], sim->imm_rank, sim->hot[o],
              sim->w[o], sim->inf_list, gs[0], gs[1]);
       break;

@@ -107,6 +107,8 @@ struct Ctl {
   int bb_xmin, bb_xmax, bb_ymin, bb_ymax;
   unsigned n_inf;          // entries of the Infected-slot list
   unsigned n_emig;         // agents that leave this slab in the running step
+  unsigned n_newinf;       // sequential schedule: entries of the newly-infected list
+  unsigned seq_changed;    // sequential schedule: infection times lowered in the last round
   unsigned scan_ticket;    // next tile of the scan
   unsigned done_ticket;    // blocks of k_contagion that have finished
   // ---- statistics of the previous step (what triggers and the critical-limit test read)
@@ -528,7 +530,8 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
                  const uint2 *__restrict__ aux, const unsigned *__restrict__ cell_start,
                  unsigned *__restrict__ stale_cells, uint4 *__restrict__ ohot, double *__restrict__ owealth,
                  unsigned *__restrict__ inf_list, const double *__restrict__ sqrt_tab,
-                 ExchangeHeader *__restrict__ ghost_left, ExchangeHeader *__restrict__ ghost_right) {
+                 ExchangeHeader *__restrict__ ghost_left, ExchangeHeader *__restrict__ ghost_right,
+                 unsigned long long *__restrict__ tinf) {
   __shared__ StepParams P;
   __shared__ BlockStats B;
   __shared__ long long s_q[5][kTile];  // per-thread Q1..Q5 partial sums (abs.py:309-312), no bank conflicts
@@ -618,6 +621,7 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
       bxmin = min(bxmin, nx); bxmax = max(bxmax, nx); bymin = min(bymin, ny); bymax = max(bymax, ny);
       ohot[slot] = make_uint4((uint32_t)nx, (uint32_t)ny, a, aid);
       owealth[slot] = w;
+      if (tinf) tinf[slot] = st == ST_I ? 0ull : ~0ull;   // sequential schedule: time of infection inside this step
     }
     // slots of the agents that can transmit in this step's contact phase (warp-aggregated append)
     const bool is_inf = valid && st == ST_I;
@@ -866,6 +870,64 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
 }
 
 // ------------------------------------------------------------------------------------------
+// Sequential schedule (abs.py:261-265 as written): the reference walks the pair list in lexicographic (i, j)
+// order while statuses mutate, so an agent infected by an earlier pair transmits along later ones (SURVEY.md
+// A.4).  With pair-keyed draws that is an earliest-arrival problem on a temporal graph in which the edge
+// (i, j) exists exactly at time rank(i, j):  T(a) = min{ rank(p) : p = (a, b) passes its draw, T(b) < rank(p) },
+// T = 0 for the agents Infected before the contact phase.  Earlier infection never blocks anyone, so
+// label-correcting relaxation with atomicMin converges to the exact answer; the host repeats rounds until a round
+// lowers no label.  Round 0 relaxes from the Infected list, later rounds from everyone infected in this step.
+__device__ __forceinline__ unsigned long long pair_rank(uint32_t a, uint32_t b) {
+  return (((unsigned long long)min(a, b) << 32) | (unsigned long long)max(a, b)) + 1ull;
+}
+
+__global__ void __launch_bounds__(256)
+k_contagion_sequential(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
+                       unsigned long long *__restrict__ tinf, const unsigned *__restrict__ sources, int first_round,
+                       unsigned *__restrict__ newinf_list) {
+  __shared__ StepParams P;
+  __shared__ unsigned s_count;
+  if (threadIdx.x == 0) {
+    load_params(P, ctl);
+    s_count = first_round ? ctl->n_inf : ctl->n_newinf;
+  }
+  __syncthreads();
+  if (P.T < 0) return;
+  const unsigned count = s_count;  // snapshot: agents appended during this round are picked up by the next one
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+    const unsigned s = sources[t];
+    const uint4 h = hot[s];
+    const unsigned long long ts = *reinterpret_cast<volatile unsigned long long *>(&tinf[s]);
+    const int xi = (int)h.x, yi = (int)h.y;
+    int clo, chi, rlo, rhi;
+    contact_cells(P, xi, yi, clo, chi, rlo, rhi);
+    for (int row = rlo; row <= rhi; ++row) {
+      const unsigned base = (unsigned)row * (unsigned)P.ncx;
+      const unsigned jb = cell_start[base + clo], je = cell_start[base + chi + 1];
+      for (unsigned j = jb; j < je; ++j) {
+        const uint4 c = hot[j];
+        if ((c.z & 3u) != ST_S || j == s) continue;   // Susceptible at the start of the phase (marked or not)
+        const long long dx = (int)c.x - xi, dy = (int)c.y - yi;
+        if (dx * dx + dy * dy > (long long)P.T) continue;
+        const unsigned long long rank = pair_rank(h.w, c.w);
+        if (rank <= ts) continue;                      // the pair was walked before the source was infected
+        const uint4 r = philox4x32_10(min(h.w, c.w), P.step, kStreamContact, max(h.w, c.w), P.k0, P.k1);
+        if ((long long)r.x > P.thr_rate) continue;     // contagion_test <= contagion_rate (abs.py:150-153)
+        const unsigned long long old = atomicMin(&tinf[j], rank);
+        if (rank < old) {
+          atomicAdd(&ctl->seq_changed, 1u);
+          if (old == ~0ull) {
+            atomicOr(reinterpret_cast<uint32_t *>(&hot[j]) + 2, kNewlyInfected);
+            atomicAdd(&ctl->newinf, 1ull);
+            newinf_list[atomicAdd(&ctl->n_newinf, 1u)] = j;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Test hook for the pair loop of abs.py:253-259: every (i, j), i < j, within contagion_distance.
 __global__ void __launch_bounds__(256)
 k_contact_pairs(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
@@ -946,6 +1008,8 @@ __device__ inline void reset_accumulators(Ctl *ctl) {
   ctl->bb_xmin = INT_MAX; ctl->bb_xmax = INT_MIN; ctl->bb_ymin = INT_MAX; ctl->bb_ymax = INT_MIN;
   ctl->n_inf = 0;
   ctl->n_emig = 0;
+  ctl->n_newinf = 0;
+  ctl->seq_changed = 0;
   ctl->scan_ticket = 0;
   ctl->done_ticket = 0;
 }

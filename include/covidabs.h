@@ -46,7 +46,8 @@ enum { CABS_EXPOSED = 0, CABS_ASYMPTOMATIC = 1, CABS_HOSPITALIZATION = 2, CABS_S
 /* contact schedule */
 enum {
   CABS_SYNCHRONOUS = 0, /* one neighbour scan: only agents infected before the contact phase transmit */
-  CABS_SEQUENTIAL = 1   /* abs.py:261-265 order: in-step chains along increasing (i,j) rank           */
+  CABS_SEQUENTIAL = 1   /* abs.py:261-265 order: in-step chains along increasing (i,j) rank; exact, by rounds
+                           of relaxation with one host round trip each (cabs_step waits); one device only     */
 };
 
 /* statistics slots, in the key order of abs.py:300-312 */

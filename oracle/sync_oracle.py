@@ -98,6 +98,10 @@ class SyncSimulation(object):
         self.minimum_expense = kwargs.get("minimum_expense", 1.0)
         self.total_wealth = kwargs.get("total_wealth", 10 ** 4)
         self.triggers = list(kwargs.get("triggers", []))
+        # "synchronous": only agents Infected before the contact phase transmit (one data-parallel pass);
+        # "sequential": the reference's own order -- pairs walked lexicographically, statuses mutating on the way,
+        # so an agent infected by an earlier pair transmits along later ones (abs.py:261-265)
+        self.schedule = kwargs.get("schedule", "synchronous")
         if wealth_scale_bits is None:
             wealth_scale_bits = default_wealth_scale_bits(self.total_wealth)
         self.wealth_scale_bits = int(wealth_scale_bits)
@@ -192,9 +196,23 @@ class SyncSimulation(object):
             a, b, si = a[enc], b[enc], si[enc]
             c0, _, _, _ = philox.pair_draws(self.seed, a.astype(np.uint64), b.astype(np.uint64), step)
             ok = philox.u01(c0) <= np.float64(self.contagion_rate)
-            target = np.where(si, a, b)[ok]
-            st = st.copy()
-            st[target] = I
+            if self.schedule == "sequential":
+                c_all, _, _, _ = philox.pair_draws(self.seed, pairs[:, 0].astype(np.uint64),
+                                                   pairs[:, 1].astype(np.uint64), step)
+                ok_all = philox.u01(c_all) <= np.float64(self.contagion_rate)
+                st = st.copy()
+                for k in range(len(pairs)):                      # lexicographic (i, j), abs.py:253-265
+                    i, j = pairs[k]
+                    if st[i] == S and st[j] == I:
+                        if ok_all[k]:
+                            st[i] = I
+                    elif st[j] == S and st[i] == I:
+                        if ok_all[k]:
+                            st[j] = I
+            else:
+                target = np.where(si, a, b)[ok]
+                st = st.copy()
+                st[target] = I
         self.status = st
         # ---- statistics + declarative triggers
         stats = self.get_statistics()
