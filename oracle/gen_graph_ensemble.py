@@ -1,6 +1,6 @@
 """Ensemble curves of the UNMODIFIED reference GraphSimulation under its own numpy stream (TEST INFRASTRUCTURE ONLY).
 
-    python oracle/gen_graph_ensemble.py      # writes tests/golden/graph_ensemble.json (a few minutes, all cores)
+    python oracle/gen_graph_ensemble.py      # writes tests/golden/ensemble_graph.json (a few minutes, all cores)
 
 For scenario families of run_batch.py, `seeds` runs of `iterations` hours each (np.random.seed(s), s = 0..seeds-1, the
 reference's native draw order); per iteration the mean and standard deviation across seeds of the 14 statistics
@@ -56,7 +56,7 @@ def main():
             out["cases"].append(dict(scenario=scenario, seeds=int(arr.shape[0]), iterations=iters, overrides=over,
                                      mean=arr.mean(axis=0).tolist(), std=arr.std(axis=0).tolist()))
             print(scenario, arr.shape, "final Infected mean", arr[:, -1, 8].mean())
-    with open(os.path.join(ROOT, "tests", "golden", "graph_ensemble.json"), "w") as f:
+    with open(os.path.join(ROOT, "tests", "golden", "ensemble_graph.json"), "w") as f:
         json.dump(out, f)
 
 

@@ -4,7 +4,7 @@
 The GPU draws are counter-based (Philox) and contacts are applied synchronously, so a stochastic run cannot match
 the reference's MT19937 trajectory; what must match is the distribution.  `tests/golden/simulation_ensemble.json`
 holds the per-iteration mean/std over 256 seeds (np.random.seed(0..255)) of the UNMODIFIED reference plus the
-per-seed rows at the middle and last iteration (oracle/gen_golden.py); `graph_ensemble.json` the same for
+per-seed rows at the middle and last iteration (oracle/gen_golden.py); `ensemble_graph.json` the same for
 GraphSimulation scenario families (oracle/gen_graph_ensemble.py).
 
 Tolerances, stated: a per-iteration two-sample z score (difference of the ensemble means over the combined standard
@@ -69,7 +69,7 @@ def test_graph_ensemble_matches_reference(native_lib):
     from covid19_agentbasedsimulation_b200.network.graph_abs import GraphSimulation
     from covid19_agentbasedsimulation_b200.network.ensemble import GraphEnsemble
     from covid19_agentbasedsimulation_b200.network import scenarios as sc
-    path = os.path.join(GOLDEN, "graph_ensemble.json")
+    path = os.path.join(GOLDEN, "ensemble_graph.json")
     if not os.path.exists(path):
         pytest.skip("graph ensemble fixture not generated")
     fix = json.load(open(path))
