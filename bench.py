@@ -206,7 +206,7 @@ def run_ours(args, rank, world, local_rank):
         sim = Simulation(**common)
         x_lo, x_hi = 0, side
     else:
-        sim = SlabSimulation(distributed=True, slab_devices=[local_rank], **common)
+        sim = SlabSimulation(distributed=True, slab_devices=[local_rank], transport=args.transport, **common)
         lo, hi = slab_bounds(side, world)[rank]
         x_lo, x_hi = max(lo, 0), min(hi - 1, side)
     # this rank's agents in pinned host memory (also the source of the end-to-end leg)
@@ -349,7 +349,7 @@ def run_ours(args, rank, world, local_rank):
                        "cache": "working set {:.0f} MB per GPU >> 126 MB L2 (inputs larger than L2)"
                        .format((56.0 * n + 8 * info["cells_x"] * info["cells_y"]) / 1e6),
                        "cell_edge": info["cell_edge"], "cells": info["cells_x"] * info["cells_y"],
-                       "multi_gpu": "x-slabs, torch.distributed NCCL" if world > 1 else "single device"},
+                       "multi_gpu": ("x-slabs, transport=" + args.transport) if world > 1 else "single device"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "agent-updates/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 12 * 8 + 7 * 8 + 4, "steps": e2e_steps,
@@ -362,6 +362,8 @@ def run_ours(args, rank, world, local_rank):
         }
         print(json.dumps(line))
     if world > 1:
+        if args.transport == "p2p":
+            sim.close()
         dist.destroy_process_group()
     return line
 
@@ -376,6 +378,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
     ap.add_argument("--ref-sample", type=int, default=500_000)
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "collective"],
+                    help="slab exchange at N > 1: NVLink peer stores + flags, or torch.distributed collectives")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the GraphSimulation side measurements")
     ap.add_argument("--max-cells", type=int, default=0, help="cap on cell-list cells (0 = library default)")

@@ -23,6 +23,8 @@ EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params",
             "cabs_upload", "cabs_download", "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_history",
             "cabs_contact_pairs", "cabs_get_info", "cabs_event_record", "cabs_event_elapsed_ms",
             "cabs_profile_enable", "cabs_profile_read", "cabs_set_slab", "cabs_slab_phase", "cabs_set_stream",
+            "cabs_slab_block_bytes", "cabs_set_slab_direct", "cabs_slab_step", "cabs_device_alloc", "cabs_device_free",
+            "cabs_ipc_export", "cabs_ipc_open", "cabs_ipc_close",
             "cabs_graph_create", "cabs_graph_destroy", "cabs_graph_last_error", "cabs_graph_upload", "cabs_graph_run",
             "cabs_graph_sync", "cabs_graph_stats", "cabs_graph_download", "cabs_graph_last_run_ms")
 
@@ -77,6 +79,14 @@ class Slab(C.Structure):
                 ("migrant_capacity", C.c_uint32), ("ghost_capacity", C.c_uint32),
                 ("migrant_send", C.c_void_p * 2), ("migrant_recv", C.c_void_p * 2),
                 ("ghost_send", C.c_void_p * 2), ("ghost_recv", C.c_void_p * 2), ("stats_rows", C.c_void_p)]
+
+
+MAX_RANKS = 16
+
+
+class SlabDirect(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("n_ranks", C.c_int32), ("x_lo", C.c_int32), ("x_hi", C.c_int32),
+                ("migrant_capacity", C.c_uint32), ("ghost_capacity", C.c_uint32), ("blocks", C.c_void_p * MAX_RANKS)]
 
 
 class KernelTime(C.Structure):
@@ -156,6 +166,15 @@ def load():
     lib.cabs_set_slab.argtypes = [P, C.POINTER(Slab)]
     lib.cabs_slab_phase.argtypes = [P, C.c_int, C.c_int]
     lib.cabs_set_stream.argtypes = [P, C.c_void_p]
+    lib.cabs_slab_block_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.cabs_slab_block_bytes.restype = C.c_size_t
+    lib.cabs_set_slab_direct.argtypes = [P, C.POINTER(SlabDirect)]
+    lib.cabs_slab_step.argtypes = [P, C.c_int]
+    lib.cabs_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(P)]
+    lib.cabs_device_free.argtypes = [C.c_int, P]
+    lib.cabs_ipc_export.argtypes = [C.c_int, P, C.c_char * 64]
+    lib.cabs_ipc_open.argtypes = [C.c_int, C.c_char * 64, C.POINTER(P)]
+    lib.cabs_ipc_close.argtypes = [C.c_int, P]
     lib.cabs_graph_create.argtypes = [C.POINTER(GraphConfig), C.POINTER(P)]
     lib.cabs_graph_destroy.argtypes = [P]
     lib.cabs_graph_destroy.restype = None
@@ -169,7 +188,8 @@ def load():
     lib.cabs_graph_last_run_ms.argtypes = [P, C.POINTER(C.c_double)]
     for name in EXPORTED:
         fn = getattr(lib, name)
-        if name not in ("cabs_destroy", "cabs_last_error", "cabs_graph_destroy", "cabs_graph_last_error"):
+        if name not in ("cabs_destroy", "cabs_last_error", "cabs_graph_destroy", "cabs_graph_last_error",
+                        "cabs_slab_block_bytes"):
             fn.restype = C.c_int
     _lib = lib
     return lib
@@ -257,6 +277,12 @@ class Handle(object):
 
     def slab_phase(self, phase, advance=True):
         self._check(self._lib.cabs_slab_phase(self._h, int(phase), 1 if advance else 0))
+
+    def set_slab_direct(self, slab):
+        self._check(self._lib.cabs_set_slab_direct(self._h, C.byref(slab)))
+
+    def slab_step(self, advance=True):
+        self._check(self._lib.cabs_slab_step(self._h, 1 if advance else 0))
 
     def set_stream(self, cuda_stream):
         self._check(self._lib.cabs_set_stream(self._h, C.c_void_p(int(cuda_stream) or None)))
@@ -403,3 +429,41 @@ class GraphHandle(object):
             if name != "reserved2":
                 world[name] = getattr(w, name)
         return world
+
+
+# ---- device memory shared between the processes of one box (exchange blocks of the direct slab transport)
+def _util_check(rc, what):
+    if rc != OK:
+        msg = load().cabs_last_error(None)
+        raise NativeError(rc, "{}: {}".format(what, msg.decode() if msg else "?"))
+
+
+def slab_block_bytes(n_ranks, migrant_capacity, ghost_capacity):
+    return int(load().cabs_slab_block_bytes(int(n_ranks), int(migrant_capacity), int(ghost_capacity)))
+
+
+def device_alloc(device, nbytes):
+    p = C.c_void_p()
+    _util_check(load().cabs_device_alloc(int(device), int(nbytes), C.byref(p)), "cabs_device_alloc")
+    return p.value
+
+
+def device_free(device, ptr):
+    _util_check(load().cabs_device_free(int(device), C.c_void_p(ptr)), "cabs_device_free")
+
+
+def ipc_export(device, ptr):
+    buf = (C.c_char * 64)()
+    _util_check(load().cabs_ipc_export(int(device), C.c_void_p(ptr), buf), "cabs_ipc_export")
+    return bytes(buf.raw)
+
+
+def ipc_open(device, handle):
+    buf = (C.c_char * 64).from_buffer_copy(handle)
+    p = C.c_void_p()
+    _util_check(load().cabs_ipc_open(int(device), buf, C.byref(p)), "cabs_ipc_open")
+    return p.value
+
+
+def ipc_close(device, ptr):
+    _util_check(load().cabs_ipc_close(int(device), C.c_void_p(ptr)), "cabs_ipc_close")

@@ -36,6 +36,10 @@ struct cabs_sim {
   // slab decomposition
   bool slab_on = false;
   cabs_slab slab;
+  bool direct = false;          // exchange through peer memory (cabs_set_slab_direct)
+  unsigned char *blocks[CABS_MAX_RANKS] = {};
+  unsigned char **dev_blocks = nullptr;
+  unsigned build_seq = 0;
   unsigned *emig_list = nullptr, *imm_rank = nullptr;
   // sequential schedule
   unsigned long long *tinf = nullptr;
@@ -116,6 +120,7 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
   cudaFree(sim->sqrt_tab);
   cudaFree(sim->cells[0]); cudaFree(sim->cells[1]); cudaFree(sim->tile_state); cudaFree(sim->inf_list);
   cudaFree(sim->emig_list); cudaFree(sim->imm_rank); cudaFree(sim->tinf); cudaFree(sim->newinf_list);
+  cudaFree(sim->dev_blocks);
   cudaFree(sim->ctl); cudaFree(sim->history);
   cudaFree(sim->stage); cudaFree(sim->stage_id); cudaFree(sim->pairs); cudaFree(sim->pair_count);
   for (cudaEvent_t e : sim->events) if (e) cudaEventDestroy(e);
@@ -286,8 +291,10 @@ static void enqueue_build(cabs_sim *sim) {
     }
     LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 1);
   } else if (kAdvance) {
+    SlabDirect none;
+    memset(&none, 0, sizeof none);
     LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, nullptr, nullptr, sim->history,
-           nullptr, 1);
+           nullptr, 1, none);
   } else {
     LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 0);
   }
@@ -327,6 +334,7 @@ extern "C" int cabs_set_slab(cabs_sim *sim, const cabs_slab *slab) {
   CK(cudaSetDevice(sim->device));
   CK(cudaStreamSynchronize(sim->stream));
   cudaFree(sim->emig_list); cudaFree(sim->imm_rank); cudaFree(sim->tinf); cudaFree(sim->newinf_list);
+  cudaFree(sim->dev_blocks);
   sim->emig_list = sim->imm_rank = nullptr;
   CK(cudaMalloc(&sim->emig_list, 2 * (size_t)slab->migrant_capacity * sizeof(unsigned)));
   CK(cudaMalloc(&sim->imm_rank, 2 * (size_t)slab->migrant_capacity * sizeof(unsigned)));
@@ -338,6 +346,7 @@ extern "C" int cabs_set_slab(cabs_sim *sim, const cabs_slab *slab) {
   }
   sim->slab = *slab;
   sim->slab_on = true;
+  sim->direct = false;
   LAUNCH(k_set_slab, 1, 32, sim->ctl, slab->rank, slab->n_ranks, slab->x_lo, slab->x_hi, slab->migrant_capacity,
          slab->ghost_capacity);
   if (sim->n > 0) LAUNCH(k_replan, 1, 32, sim->ctl, 0);
@@ -351,10 +360,34 @@ static int slab_phase(cabs_sim *sim, int phase) {
   const cabs_slab &sl = sim->slab;
   const int c = sim->cur, o = c ^ 1, t = sim->tab;
   const int nb = agent_blocks(sim), nbs = sim->num_sms;  // the exchange kernels see few records
-  ExchangeHeader *ms[2] = {(ExchangeHeader *)sl.migrant_send[0], (ExchangeHeader *)sl.migrant_send[1]};
-  ExchangeHeader *mr[2] = {(ExchangeHeader *)sl.migrant_recv[0], (ExchangeHeader *)sl.migrant_recv[1]};
-  ExchangeHeader *gs[2] = {(ExchangeHeader *)sl.ghost_send[0], (ExchangeHeader *)sl.ghost_send[1]};
-  ExchangeHeader *gr[2] = {(ExchangeHeader *)sl.ghost_recv[0], (ExchangeHeader *)sl.ghost_recv[1]};
+  ExchangeHeader *ms[2], *mr[2], *gs[2], *gr[2];
+  long long *rows;
+  SlabDirect D;
+  memset(&D, 0, sizeof D);
+  if (sim->direct) {
+    const BlockLayout L = block_layout(sl.n_ranks, sl.migrant_capacity, sl.ghost_capacity);
+    unsigned char *self = sim->blocks[sl.rank];
+    const unsigned seq = sim->build_seq + 1, par = seq & 1u;
+    for (int d = 0; d < 2; ++d) {
+      ms[d] = (ExchangeHeader *)(self + L.mig_send + d * L.mig_bytes);
+      gs[d] = (ExchangeHeader *)(self + L.ghost_send + d * L.ghost_bytes);
+      mr[d] = (ExchangeHeader *)(self + L.mig_recv + (d * 2 + par) * L.mig_bytes);
+      gr[d] = (ExchangeHeader *)(self + L.ghost_recv + (d * 2 + par) * L.ghost_bytes);
+    }
+    rows = (long long *)(self + L.rows) + (size_t)par * kMaxRanks * kSlabRow;
+    D.self = self;
+    D.left = sl.rank > 0 ? sim->blocks[sl.rank - 1] : nullptr;
+    D.right = sl.rank + 1 < sl.n_ranks ? sim->blocks[sl.rank + 1] : nullptr;
+    D.all = sim->dev_blocks;
+    D.seq = seq;
+    D.enabled = 1;
+  } else {
+    for (int d = 0; d < 2; ++d) {
+      ms[d] = (ExchangeHeader *)sl.migrant_send[d]; mr[d] = (ExchangeHeader *)sl.migrant_recv[d];
+      gs[d] = (ExchangeHeader *)sl.ghost_send[d]; gr[d] = (ExchangeHeader *)sl.ghost_recv[d];
+    }
+    rows = (long long *)sl.stats_rows;
+  }
   switch (phase) {
     case 0:
       if (!kAdvance) {
@@ -364,28 +397,29 @@ static int slab_phase(cabs_sim *sim, int phase) {
       LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl,
                 sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list);
       LAUNCH_AS("k_pack_emigrants", k_pack_emigrants<kAdvance>, nbs, 256, sim->ctl, sim->hot[c], sim->w[c], sim->aux,
-                sim->emig_list, ms[0], ms[1], sim->sqrt_tab);
+                sim->emig_list, ms[0], ms[1], sim->sqrt_tab, D);
       break;
     case 1:
-      LAUNCH(k_count_immigrants, nbs, 256, sim->ctl, mr[0], mr[1], sim->cells[t], sim->imm_rank);
+      LAUNCH(k_count_immigrants, nbs, 256, sim->ctl, mr[0], mr[1], sim->cells[t], sim->imm_rank, D);
       LAUNCH(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
       LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", k_update_scatter<kAdvance>, nb,
                 kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t], sim->cells[t ^ 1],
                 sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, gs[0], gs[1], nullptr);
       LAUNCH(k_scatter_immigrants, nbs, 256, sim->ctl, mr[0], mr[1], sim->cells[t], sim->imm_rank, sim->hot[o],
-             sim->w[o], sim->inf_list, gs[0], gs[1]);
+             sim->w[o], sim->inf_list, gs[0], gs[1], D);
       break;
     case 2:
       if (kAdvance) {
         LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, gr[0], gr[1], sim->history,
-               (long long *)sl.stats_rows, 2);
+               rows, 2, D);
       } else {
-        LAUNCH(k_slab_export, 1, 32, sim->ctl, (long long *)sl.stats_rows);
+        LAUNCH(k_slab_export, 1, 32, sim->ctl, rows, D);
       }
       break;
     case 3:
-      LAUNCH(k_slab_close, 1, 32, sim->ctl, (const long long *)sl.stats_rows, sim->cells[t], sim->history,
-             kAdvance ? 1 : 0, ms[0], ms[1], gs[0], gs[1]);
+      LAUNCH(k_slab_close, 1, 32, sim->ctl, (const long long *)rows, sim->cells[t], sim->history,
+             kAdvance ? 1 : 0, ms[0], ms[1], gs[0], gs[1], D);
+      sim->build_seq++;
       sim->cur = o;
       sim->tab = t ^ 1;
       if (kAdvance) sim->step++;
@@ -401,10 +435,114 @@ static int slab_phase(cabs_sim *sim, int phase) {
 
 extern "C" int cabs_slab_phase(cabs_sim *sim, int phase, int advance) {
   if (!sim) return fail(sim, CABS_ERR_INVALID, "cabs_slab_phase: null handle");
-  if (!sim->slab_on) return fail(sim, CABS_ERR_INVALID, "cabs_slab_phase: call cabs_set_slab first");
+  if (!sim->slab_on || sim->direct) return fail(sim, CABS_ERR_INVALID, "cabs_slab_phase: call cabs_set_slab first");
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_slab_phase: call cabs_set_params first");
   CK(cudaSetDevice(sim->device));
   return advance ? slab_phase<true>(sim, phase) : slab_phase<false>(sim, phase);
+}
+
+
+// ---- direct exchange over peer memory ---------------------------------------------------------------
+extern "C" size_t cabs_slab_block_bytes(uint32_t n_ranks, uint32_t migrant_capacity, uint32_t ghost_capacity) {
+  return block_layout(n_ranks, migrant_capacity, ghost_capacity).total;
+}
+
+static thread_local std::string g_util_error;
+static int util_fail(const char *what, cudaError_t e) {
+  g_util_error = std::string(what) + ": " + cudaGetErrorString(e);
+  g_create_error = g_util_error;
+  return CABS_ERR_CUDA;
+}
+
+extern "C" int cabs_device_alloc(int device, size_t bytes, void **ptr) {
+  if (!ptr || bytes == 0) return CABS_ERR_INVALID;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return util_fail("cudaSetDevice", e);
+  if ((e = cudaMalloc(ptr, bytes)) != cudaSuccess) return util_fail("cudaMalloc", e);
+  if ((e = cudaMemset(*ptr, 0, bytes)) != cudaSuccess) return util_fail("cudaMemset", e);
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return util_fail("cudaDeviceSynchronize", e);
+  return CABS_OK;
+}
+
+extern "C" int cabs_device_free(int device, void *ptr) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return util_fail("cudaSetDevice", e);
+  if ((e = cudaFree(ptr)) != cudaSuccess) return util_fail("cudaFree", e);
+  return CABS_OK;
+}
+
+extern "C" int cabs_ipc_export(int device, void *ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return util_fail("cudaSetDevice", e);
+  cudaIpcMemHandle_t h;
+  if ((e = cudaIpcGetMemHandle(&h, ptr)) != cudaSuccess) return util_fail("cudaIpcGetMemHandle", e);
+  memcpy(handle, &h, 64);
+  return CABS_OK;
+}
+
+extern "C" int cabs_ipc_open(int device, const unsigned char handle[64], void **ptr) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return util_fail("cudaSetDevice", e);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  if ((e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess)
+    return util_fail("cudaIpcOpenMemHandle", e);
+  return CABS_OK;
+}
+
+extern "C" int cabs_ipc_close(int device, void *ptr) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return util_fail("cudaSetDevice", e);
+  if ((e = cudaIpcCloseMemHandle(ptr)) != cudaSuccess) return util_fail("cudaIpcCloseMemHandle", e);
+  return CABS_OK;
+}
+
+extern "C" int cabs_set_slab_direct(cabs_sim *sim, const cabs_slab_direct *d) {
+  if (!sim || !d) return fail(sim, CABS_ERR_INVALID, "cabs_set_slab_direct: null argument");
+  if (d->n_ranks < 1 || d->n_ranks > CABS_MAX_RANKS || d->rank < 0 || d->rank >= d->n_ranks || d->x_lo >= d->x_hi)
+    return fail(sim, CABS_ERR_INVALID, "cabs_set_slab_direct: bad rank / bounds (at most 16 ranks)");
+  if (d->migrant_capacity == 0 || d->ghost_capacity == 0)
+    return fail(sim, CABS_ERR_INVALID, "cabs_set_slab_direct: capacities are required");
+  for (int r = 0; r < d->n_ranks; ++r)
+    if (!d->blocks[r]) return fail(sim, CABS_ERR_INVALID, "cabs_set_slab_direct: null exchange block");
+  if (sim->have_params && sim->params.schedule == CABS_SEQUENTIAL)
+    return fail(sim, CABS_ERR_INVALID, "the sequential schedule is defined on one device only");
+  CK(cudaSetDevice(sim->device));
+  CK(cudaStreamSynchronize(sim->stream));
+  cudaFree(sim->emig_list); cudaFree(sim->imm_rank); cudaFree(sim->dev_blocks);
+  sim->emig_list = sim->imm_rank = nullptr;
+  sim->dev_blocks = nullptr;
+  CK(cudaMalloc(&sim->emig_list, 2 * (size_t)d->migrant_capacity * sizeof(unsigned)));
+  CK(cudaMalloc(&sim->imm_rank, 2 * (size_t)d->migrant_capacity * sizeof(unsigned)));
+  CK(cudaMalloc(&sim->dev_blocks, CABS_MAX_RANKS * sizeof(unsigned char *)));
+  for (int r = 0; r < CABS_MAX_RANKS; ++r) sim->blocks[r] = r < d->n_ranks ? (unsigned char *)d->blocks[r] : nullptr;
+  CK(cudaMemcpyAsync(sim->dev_blocks, sim->blocks, CABS_MAX_RANKS * sizeof(unsigned char *), cudaMemcpyHostToDevice,
+                     sim->stream));
+  memset(&sim->slab, 0, sizeof sim->slab);
+  sim->slab.rank = d->rank; sim->slab.n_ranks = d->n_ranks; sim->slab.x_lo = d->x_lo; sim->slab.x_hi = d->x_hi;
+  sim->slab.migrant_capacity = d->migrant_capacity; sim->slab.ghost_capacity = d->ghost_capacity;
+  sim->slab_on = true;
+  sim->direct = true;
+  sim->build_seq = 0;
+  LAUNCH(k_set_slab, 1, 32, sim->ctl, d->rank, d->n_ranks, d->x_lo, d->x_hi, d->migrant_capacity, d->ghost_capacity);
+  if (sim->n > 0) LAUNCH(k_replan, 1, 32, sim->ctl, 0);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(sim->stream));
+  sim->cells_dirty = true;
+  return CABS_OK;
+}
+
+extern "C" int cabs_slab_step(cabs_sim *sim, int advance) {
+  if (!sim) return fail(sim, CABS_ERR_INVALID, "cabs_slab_step: null handle");
+  if (!sim->slab_on || !sim->direct) return fail(sim, CABS_ERR_INVALID, "cabs_slab_step: call cabs_set_slab_direct first");
+  if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_slab_step: call cabs_set_params first");
+  CK(cudaSetDevice(sim->device));
+  for (int phase = 0; phase < 4; ++phase) {
+    const int rc = advance ? slab_phase<true>(sim, phase) : slab_phase<false>(sim, phase);
+    if (rc != CABS_OK) return rc;
+  }
+  return CABS_OK;
 }
 
 // number of resident agents (changes on the device when agents migrate between slabs)

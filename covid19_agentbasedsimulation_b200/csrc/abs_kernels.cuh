@@ -107,6 +107,7 @@ struct Ctl {
   int bb_xmin, bb_xmax, bb_ymin, bb_ymax;
   unsigned n_inf;          // entries of the Infected-slot list
   unsigned n_emig;         // agents that leave this slab in the running step
+  unsigned pack_ticket, imm_ticket;  // blocks of k_pack_emigrants / k_scatter_immigrants that have finished
   unsigned n_newinf;       // sequential schedule: entries of the newly-infected list
   unsigned seq_changed;    // sequential schedule: infection times lowered in the last round
   unsigned scan_ticket;    // next tile of the scan
@@ -235,6 +236,61 @@ struct alignas(32) ExchangeHeader {
   unsigned pad[7];
 };
 constexpr int kSlabRow = 16;  // int64 values per rank in the statistics all-gather
+
+// Direct exchange over NVLink peer memory.  Every rank owns one "exchange block" (device memory that its
+// neighbours map through CUDA IPC); a producer kernel's last block copies what its rank packed straight into
+// the consumer's block with plain stores, fences at system scope and raises a flag that carries the build
+// sequence number; the consumer kernel's blocks spin on the flag in their own memory.  Receive buffers and
+// rows are double-buffered by the parity of the sequence number: a neighbour is never more than one build
+// ahead (it needs this rank's next message to go further), so two generations are enough.  No collective call,
+// no host involvement: a whole step is enqueued back to back.
+constexpr int kMaxRanks = 16;
+struct BlockLayout {
+  size_t flags, rows, mig_recv, ghost_recv, mig_send, ghost_send, total, mig_bytes, ghost_bytes;
+};
+__host__ __device__ inline BlockLayout block_layout(unsigned n_ranks, unsigned mig_cap, unsigned ghost_cap) {
+  BlockLayout L;
+  L.mig_bytes = sizeof(ExchangeHeader) + (size_t)mig_cap * sizeof(MigrantRecord);
+  L.ghost_bytes = sizeof(ExchangeHeader) + (size_t)ghost_cap * sizeof(uint4);
+  L.flags = 0;                                              // unsigned[8 + 2 * kMaxRanks]
+  L.rows = 256;                                             // [parity][rank][kSlabRow] int64
+  L.mig_recv = L.rows + 2 * (size_t)kMaxRanks * kSlabRow * sizeof(long long);   // [from dir][parity]
+  L.ghost_recv = L.mig_recv + 4 * L.mig_bytes;              // [from dir][parity]
+  L.mig_send = L.ghost_recv + 4 * L.ghost_bytes;            // [to dir]   (local staging)
+  L.ghost_send = L.mig_send + 2 * L.mig_bytes;              // [to dir]
+  L.total = L.ghost_send + 2 * L.ghost_bytes;
+  (void)n_ranks;
+  return L;
+}
+struct SlabDirect {
+  unsigned char *self, *left, *right;   // exchange blocks as mapped in this process; nullptr on an outer side
+  unsigned char *const *all;            // device array [n_ranks]: every rank's block (rows are broadcast)
+  unsigned seq;                         // sequence number of this build
+  int enabled;
+};
+enum { FLAG_MIG = 0, FLAG_GHOST = 4, FLAG_ROW = 8 };   // + from_dir * 2 + parity   /   + parity * kMaxRanks + rank
+
+__device__ __forceinline__ void wait_flag(const unsigned char *block, int index, unsigned seq) {
+  const volatile unsigned *f = reinterpret_cast<const volatile unsigned *>(block) + index;
+  while (*f != seq) __nanosleep(64);
+  __threadfence_system();
+}
+// Last block of a producer kernel (all its threads): copy `local` (header + records) into `remote`, then publish.
+__device__ __forceinline__ void push_buffer(const ExchangeHeader *local, unsigned char *remote_block, size_t remote_off,
+                                            unsigned rec_bytes, unsigned cap, int flag_index, unsigned seq) {
+  const unsigned count = min(__ldcg(&local->count), cap);
+  const uint4 *src = reinterpret_cast<const uint4 *>(local + 1);
+  uint4 *dst = reinterpret_cast<uint4 *>(remote_block + remote_off + sizeof(ExchangeHeader));
+  const size_t n16 = (size_t)count * rec_bytes / 16;
+  for (size_t k = threadIdx.x; k < n16; k += blockDim.x) dst[k] = __ldcg(src + k);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    reinterpret_cast<ExchangeHeader *>(remote_block + remote_off)->count = count;
+    __threadfence_system();
+    *(reinterpret_cast<volatile unsigned *>(remote_block) + flag_index) = seq;
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // Bulk asynchronous copies (TMA, cp.async.bulk) global -> shared, completion on an mbarrier.  The agent
@@ -684,8 +740,9 @@ __global__ void __launch_bounds__(256)
 k_pack_emigrants(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const double *__restrict__ wealth,
                  const uint2 *__restrict__ aux, const unsigned *__restrict__ emig_list,
                  ExchangeHeader *__restrict__ send_left, ExchangeHeader *__restrict__ send_right,
-                 const double *__restrict__ sqrt_tab) {
+                 const double *__restrict__ sqrt_tab, SlabDirect D) {
   __shared__ StepParams P;
+  __shared__ unsigned s_last;
   if (threadIdx.x == 0) load_params(P, ctl);
   __syncthreads();
   const unsigned count = min(ctl->n_emig, 2u * ctl->mig_cap);
@@ -713,6 +770,23 @@ k_pack_emigrants(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
       atomicOr(&ctl->err, kErrExchange);
     }
   }
+  if (D.enabled) {   // the last block hands both buffers to the neighbours
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&ctl->pack_ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
+      const unsigned par = D.seq & 1u;
+      // what I send to the left arrives there "from the right" (dir 1), and vice versa
+      if (D.left) push_buffer(send_left, D.left, L.mig_recv + (1 * 2 + par) * L.mig_bytes, sizeof(MigrantRecord),
+                              ctl->mig_cap, FLAG_MIG + 1 * 2 + par, D.seq);
+      __syncthreads();
+      if (D.right) push_buffer(send_right, D.right, L.mig_recv + (0 * 2 + par) * L.mig_bytes, sizeof(MigrantRecord),
+                               ctl->mig_cap, FLAG_MIG + 0 * 2 + par, D.seq);
+    }
+  }
 }
 
 // Slab exchange 1, receiver side, before the scan: count the immigrants in the histogram and keep
@@ -720,9 +794,16 @@ k_pack_emigrants(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
 __global__ void __launch_bounds__(256)
 k_count_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ recv_left,
                    const ExchangeHeader *__restrict__ recv_right, unsigned *__restrict__ cells,
-                   unsigned *__restrict__ imm_rank) {
+                   unsigned *__restrict__ imm_rank, SlabDirect D) {
   __shared__ StepParams P;
-  if (threadIdx.x == 0) load_params(P, ctl);
+  if (threadIdx.x == 0) {
+    load_params(P, ctl);
+    if (D.enabled) {   // the neighbours' migrants of this build have landed in my block
+      const unsigned par = D.seq & 1u;
+      if (D.left) wait_flag(D.self, FLAG_MIG + 0 * 2 + par, D.seq);
+      if (D.right) wait_flag(D.self, FLAG_MIG + 1 * 2 + par, D.seq);
+    }
+  }
   __syncthreads();
   const unsigned cap = ctl->mig_cap;
   const unsigned nl = min(recv_left->count, cap), nr = min(recv_right->count, cap);
@@ -750,15 +831,16 @@ k_scatter_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ r
                      const ExchangeHeader *__restrict__ recv_right, const unsigned *__restrict__ cell_start,
                      const unsigned *__restrict__ imm_rank, uint4 *__restrict__ ohot, double *__restrict__ owealth,
                      unsigned *__restrict__ inf_list, ExchangeHeader *__restrict__ ghost_left,
-                     ExchangeHeader *__restrict__ ghost_right) {
+                     ExchangeHeader *__restrict__ ghost_right, SlabDirect D) {
   __shared__ StepParams P;
+  __shared__ unsigned s_last;
   if (threadIdx.x == 0) load_params(P, ctl);
   __syncthreads();
-  if (P.overflow) return;
   const unsigned cap = ctl->mig_cap;
   const unsigned nl = min(recv_left->count, cap), nr = min(recv_right->count, cap);
   const double qscale = (double)(1ull << P.scale_bits);
-  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < nl + nr; t += gridDim.x * blockDim.x) {
+  const unsigned total = P.overflow ? 0u : nl + nr;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const MigrantRecord *src = t < nl ? reinterpret_cast<const MigrantRecord *>(recv_left + 1) + t
                                       : reinterpret_cast<const MigrantRecord *>(recv_right + 1) + (t - nl);
     const uint4 h = src->hot;
@@ -782,6 +864,22 @@ k_scatter_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ r
       send_ghost(ctl, P, h, ghost_left, ghost_right);
     }
   }
+  if (D.enabled) {   // pass B and this kernel have listed every ghost: the last block hands them over
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&ctl->imm_ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
+      const unsigned par = D.seq & 1u;
+      if (D.left) push_buffer(ghost_left, D.left, L.ghost_recv + (1 * 2 + par) * L.ghost_bytes, sizeof(uint4),
+                              ctl->ghost_cap, FLAG_GHOST + 1 * 2 + par, D.seq);
+      __syncthreads();
+      if (D.right) push_buffer(ghost_right, D.right, L.ghost_recv + (0 * 2 + par) * L.ghost_bytes, sizeof(uint4),
+                               ctl->ghost_cap, FLAG_GHOST + 0 * 2 + par, D.seq);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -797,7 +895,7 @@ __device__ __forceinline__ void contact_cells(const StepParams &P, int x, int y,
 }
 
 __device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats);
-__device__ void slab_export(Ctl *ctl, long long *rows);
+__device__ void slab_export(Ctl *ctl, long long *rows, SlabDirect D);
 
 // Pass C: the contact loop of abs.py:249-265 pushed from the agents that were Infected before this
 // contact phase to the Susceptible agents in reach; contact() = abs.py:141-154 with one draw per pair,
@@ -809,11 +907,16 @@ __global__ void __launch_bounds__(256)
 k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
             const unsigned *__restrict__ inf_list, const ExchangeHeader *__restrict__ ghosts_left,
             const ExchangeHeader *__restrict__ ghosts_right, StatRecord *__restrict__ history,
-            long long *__restrict__ rows, int finish) {
+            long long *__restrict__ rows, int finish, SlabDirect D) {
   __shared__ StepParams P;
   __shared__ unsigned s_new, s_local, s_left, s_right;
   if (threadIdx.x == 0) {
     load_params(P, ctl);
+    if (D.enabled) {   // the neighbours' ghosts of this build have landed in my block
+      const unsigned par = D.seq & 1u;
+      if (D.left) wait_flag(D.self, FLAG_GHOST + 0 * 2 + par, D.seq);
+      if (D.right) wait_flag(D.self, FLAG_GHOST + 1 * 2 + par, D.seq);
+    }
     s_new = 0;
     s_local = ctl->n_inf;
     s_left = ghosts_left ? min(ghosts_left->count, ctl->ghost_cap) : 0u;
@@ -863,7 +966,7 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
       if (ticket == gridDim.x - 1) {
         __threadfence();
         if (finish == 1) close_step(ctl, history, 1);
-        else slab_export(ctl, rows);
+        else slab_export(ctl, rows, D);
       }
     }
   }
@@ -1008,6 +1111,8 @@ __device__ inline void reset_accumulators(Ctl *ctl) {
   ctl->bb_xmin = INT_MAX; ctl->bb_xmax = INT_MIN; ctl->bb_ymin = INT_MAX; ctl->bb_ymax = INT_MIN;
   ctl->n_inf = 0;
   ctl->n_emig = 0;
+  ctl->pack_ticket = 0;
+  ctl->imm_ticket = 0;
   ctl->n_newinf = 0;
   ctl->seq_changed = 0;
   ctl->scan_ticket = 0;
@@ -1106,25 +1211,46 @@ __global__ void k_finalize(Ctl *ctl, StatRecord *history, int record_stats) {
 // Slab mode: a build ends with  k_slab_export -> all-gather of the rows -> k_slab_close  instead of the
 // in-kernel closing: statistics are summed and the y-range is joined over the slabs, so every device
 // takes the same trigger / critical-limit decisions and plans a grid that holds its future immigrants.
-__device__ void slab_export(Ctl *ctl, long long *rows) {
-  long long *r = rows + (size_t)ctl->rank * kSlabRow;
+__device__ void slab_export(Ctl *ctl, long long *rows, SlabDirect D) {
+  long long r[kSlabRow];
   for (int k = 0; k < 7; ++k) r[k] = (long long)ld_acc(&ctl->cnt[k]);
   for (int k = 0; k < 5; ++k) r[7 + k] = ld_acc(&ctl->q[k]);
   r[12] = (long long)ld_acc(&ctl->newinf);
   r[13] = ld_acc(&ctl->bb_ymin);
   r[14] = ld_acc(&ctl->bb_ymax);
   r[15] = (long long)atomicOr(&ctl->err, 0u);
+  if (!D.enabled) {
+    long long *dst = rows + (size_t)ctl->rank * kSlabRow;
+    for (int k = 0; k < kSlabRow; ++k) dst[k] = r[k];
+    return;
+  }
+  // broadcast this rank's row into every rank's block (its own included), then raise the flags
+  const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
+  const unsigned par = D.seq & 1u;
+  for (int g = 0; g < ctl->n_ranks; ++g) {
+    long long *dst = reinterpret_cast<long long *>(D.all[g] + L.rows) + ((size_t)par * kMaxRanks + ctl->rank) * kSlabRow;
+    for (int k = 0; k < kSlabRow; ++k) dst[k] = r[k];
+  }
+  __threadfence_system();
+  for (int g = 0; g < ctl->n_ranks; ++g)
+    *(reinterpret_cast<volatile unsigned *>(D.all[g]) + FLAG_ROW + par * kMaxRanks + ctl->rank) = D.seq;
 }
 
-__global__ void k_slab_export(Ctl *ctl, long long *rows) {
+__global__ void k_slab_export(Ctl *ctl, long long *rows, SlabDirect D) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  slab_export(ctl, rows);
+  slab_export(ctl, rows, D);
 }
 
 __global__ void k_slab_close(Ctl *ctl, const long long *rows, const unsigned *cell_start, StatRecord *history,
                              int record_stats, ExchangeHeader *s0, ExchangeHeader *s1, ExchangeHeader *s2,
-                             ExchangeHeader *s3) {
+                             ExchangeHeader *s3, SlabDirect D) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (D.enabled) {   // every rank's row of this build has landed in my block
+    const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
+    const unsigned par = D.seq & 1u;
+    for (int g = 0; g < ctl->n_ranks; ++g) wait_flag(D.self, FLAG_ROW + par * kMaxRanks + g, D.seq);
+    rows = reinterpret_cast<const long long *>(D.self + L.rows) + (size_t)par * kMaxRanks * kSlabRow;
+  }
   s0->count = 0; s1->count = 0; s2->count = 0; s3->count = 0;  // this slab's send buffers start the next build empty
   for (int k = 0; k < 7; ++k) ctl->cnt[k] = 0;
   for (int k = 0; k < 5; ++k) ctl->q[k] = 0;

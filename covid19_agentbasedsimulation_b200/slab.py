@@ -125,7 +125,10 @@ class DistComm(object):
     def gather_rows(self):
         import torch.distributed as dist
         mine = self.b.rows[self.rank].clone()
-        dist.all_gather([self.b.rows[g] for g in range(self.world)], mine)
+        if dist.get_backend() == "nccl":
+            dist.all_gather_into_tensor(self.b.rows.view(-1), mine)
+        else:   # gloo (CPU tests)
+            dist.all_gather([self.b.rows[g] for g in range(self.world)], mine)
 
 
 class SlabSimulation(Simulation):
@@ -149,7 +152,16 @@ class SlabSimulation(Simulation):
         self.migrant_capacity = kwargs.get("migrant_capacity", 0)
         self.ghost_capacity = kwargs.get("ghost_capacity", 0)
         self.capacity_factor = float(kwargs.get("capacity_factor", 1.25))
+        self.transport = kwargs.get("transport", "collective")
+        '''"collective": buffers move between the phases by torch.distributed send/recv + all_gather (or copies when
+        the slabs share a process); "p2p" (distributed only): the kernels write into the neighbours' memory over
+        NVLink peer mappings (CUDA IPC) and synchronise with flags -- no collective, one enqueue per step'''
+        if self.transport not in ("collective", "p2p"):
+            raise ValueError("transport must be 'collective' or 'p2p'")
+        if self.transport == "p2p" and not self.distributed:
+            raise ValueError("transport='p2p' needs one slab per process (distributed=True)")
         self._handles, self._buffers, self._comm = [], [], None
+        self._block, self._peer_blocks = None, []
 
     # ------------------------------------------------------------------ device side
     def _create(self, counts):
@@ -163,6 +175,9 @@ class SlabSimulation(Simulation):
         mig = int(self.migrant_capacity) or max(4096, min(biggest // 16, 1 << 17))
         gho = int(self.ghost_capacity) or mig
         self._handles, self._buffers = [], []
+        if self.transport == "p2p":
+            self._create_p2p(counts[0], mig, gho, bounds)
+            return
         for k, r in enumerate(self.my_ranks):
             dev = self.slab_devices[k]
             cap = int(max(1024, counts[k] * self.capacity_factor + 2 * mig))
@@ -184,10 +199,69 @@ class SlabSimulation(Simulation):
         else:
             self._comm = LocalComm(self._buffers)
 
+    def _create_p2p(self, count, mig, gho, bounds):
+        """One slab per process; exchange blocks mapped into the neighbours through CUDA IPC."""
+        import torch
+        import torch.distributed as dist
+        rank, dev = self.my_ranks[0], self.slab_devices[0]
+        # every rank must agree on the buffer sizes: take the largest request
+        sizes = [None] * self.n_slabs
+        dist.all_gather_object(sizes, (int(mig), int(gho)))
+        mig, gho = max(s[0] for s in sizes), max(s[1] for s in sizes)
+        cap = int(max(1024, count * self.capacity_factor + 2 * mig))
+        h = _native.Handle(capacity=cap, seed=self.seed, device=dev, max_cells=self.max_cells,
+                           history_capacity=self.history_capacity)
+        with torch.cuda.device(dev):
+            h.set_stream(torch.cuda.current_stream().cuda_stream)
+        self._release_p2p()
+        self._block = _native.device_alloc(dev, _native.slab_block_bytes(self.n_slabs, mig, gho))
+        handles = [None] * self.n_slabs
+        dist.all_gather_object(handles, _native.ipc_export(dev, self._block))
+        d = _native.SlabDirect()
+        d.rank, d.n_ranks, d.x_lo, d.x_hi = rank, self.n_slabs, bounds[rank][0], bounds[rank][1]
+        d.migrant_capacity, d.ghost_capacity = mig, gho
+        self._peer_blocks = []
+        for r in range(self.n_slabs):
+            if r == rank:
+                d.blocks[r] = self._block
+            else:
+                p = _native.ipc_open(dev, handles[r])
+                self._peer_blocks.append(p)
+                d.blocks[r] = p
+        self._handles, self._buffers = [h], []
+        self._handle = h
+        self._pushed = None
+        self._pushed_triggers = None
+        self._push_params()
+        h.set_slab_direct(d)
+        self._comm = None
+        dist.barrier()
+
+    def _release_p2p(self):
+        dev = self.slab_devices[0]
+        for p in self._peer_blocks:
+            _native.ipc_close(dev, p)
+        self._peer_blocks = []
+        if self._block is not None:
+            _native.device_free(dev, self._block)
+            self._block = None
+
+    def close(self):
+        for h in self._handles:
+            h.close()
+        self._handles = []
+        if self.transport == "p2p":
+            import torch.distributed as dist
+            dist.barrier()          # nobody unmaps a block a neighbour may still be writing to
+            self._release_p2p()
+
     def _targets(self):
         return self._handles
 
     def _build(self, advance):
+        if self.transport == "p2p":
+            self._handles[0].slab_step(advance)
+            return
         for phase in range(4):
             for h in self._handles:
                 h.slab_phase(phase, advance)
@@ -197,6 +271,11 @@ class SlabSimulation(Simulation):
                 self._comm.exchange("ghosts")
             elif phase == 2:
                 self._comm.gather_rows()
+        if self.distributed:
+            # collectives of consecutive builds are not queued behind each other: the conservative transport waits
+            # for the build (the p2p transport is the asynchronous one)
+            for h in self._handles:
+                h.sync()
 
     def set_population_arrays(self, x, y, status, age, stratum, wealth, severity=None, infected_time=None, ids=None,
                               population_size=None):

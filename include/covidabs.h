@@ -194,6 +194,28 @@ typedef struct cabs_slab {
 #define CABS_EXCHANGE_HEADER_BYTES 32
 int cabs_set_slab(cabs_sim *sim, const cabs_slab *slab);
 int cabs_slab_phase(cabs_sim *sim, int phase, int advance);
+
+/* Direct exchange: instead of handing buffers to the caller between the phases, the kernels write migrants,
+ * ghosts and statistics rows straight into the neighbours' memory over NVLink (peer mappings, e.g. CUDA IPC
+ * between the processes of one box) and synchronise with flags, so a whole build is enqueued by ONE call and no
+ * collective is launched.  Every rank owns one exchange block of cabs_slab_block_bytes() bytes of zeroed device
+ * memory (cabs_device_alloc) and passes the addresses at which it sees every rank's block. */
+#define CABS_MAX_RANKS 16
+typedef struct cabs_slab_direct {
+  int32_t rank, n_ranks;
+  int32_t x_lo, x_hi;
+  uint32_t migrant_capacity, ghost_capacity;
+  void *blocks[CABS_MAX_RANKS];        /* [r] = rank r's exchange block as mapped in this process */
+} cabs_slab_direct;
+size_t cabs_slab_block_bytes(uint32_t n_ranks, uint32_t migrant_capacity, uint32_t ghost_capacity);
+int cabs_set_slab_direct(cabs_sim *sim, const cabs_slab_direct *slab);
+int cabs_slab_step(cabs_sim *sim, int advance);   /* the four phases back to back; asynchronous */
+/* Device memory that can be shared between processes, and its CUDA IPC handle (64 bytes). */
+int cabs_device_alloc(int device, size_t bytes, void **ptr);
+int cabs_device_free(int device, void *ptr);
+int cabs_ipc_export(int device, void *ptr, unsigned char handle[64]);
+int cabs_ipc_open(int device, const unsigned char handle[64], void **ptr);
+int cabs_ipc_close(int device, void *ptr);
 /* Run on the caller's CUDA stream (e.g. the one its collectives are ordered on; NULL = CUDA's default stream)
  * instead of the handle's own. */
 int cabs_set_stream(cabs_sim *sim, void *cuda_stream);

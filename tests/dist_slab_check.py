@@ -14,6 +14,8 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(150, exit=True)   # a stuck rank reports where instead of hanging the test
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -24,7 +26,8 @@ def main():
     pop, tw = synthetic_population(n, side, side, seed=4, infected=0.05, immune=0.01)
     kw = dict(seed=21, population_size=n, length=side, height=side, total_wealth=tw, contagion_distance=1.0,
               contagion_rate=0.9, device=local)
-    sim = SlabSimulation(distributed=True, slab_devices=[local], **kw)
+    transport = os.environ.get("SLAB_TRANSPORT", "collective")
+    sim = SlabSimulation(distributed=True, slab_devices=[local], transport=transport, **kw)
     mine = owner_of(pop["x"], side, world) == rank
     ids = np.arange(n, dtype=np.uint32)
     sim.set_population_arrays(pop["x"][mine], pop["y"][mine], pop["status"][mine], pop["age"][mine],
@@ -47,7 +50,8 @@ def main():
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("DIST_SLAB_CHECK", "OK" if int(flag.item()) == 1 and sum(counts) == n else "FAIL", counts)
+        print("DIST_SLAB_CHECK", transport, "OK" if int(flag.item()) == 1 and sum(counts) == n else "FAIL", counts)
+    sim.close() if transport == "p2p" else None
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
 

@@ -85,8 +85,10 @@ def test_migrant_overflow_is_reported(native_lib):
         sim.get_statistics('all')
 
 
-def test_two_process_nccl_slabs_match_single_device(native_lib):
-    """One slab per process over NCCL (needs >= 2 GPUs; skipped on a one-GPU box)."""
+@pytest.mark.parametrize("transport", ["collective", "p2p"])
+def test_two_process_nccl_slabs_match_single_device(native_lib, transport):
+    """One slab per process (needs >= 2 GPUs; skipped on a one-GPU box): buffers exchanged by NCCL send/recv +
+    all_gather ("collective") or written straight into the neighbour's memory over NVLink ("p2p")."""
     import os
     import subprocess
     import sys
@@ -96,5 +98,7 @@ def test_two_process_nccl_slabs_match_single_device(native_lib):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dist_slab_check.py")]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=600)
-    assert res.returncode == 0 and "DIST_SLAB_CHECK OK" in res.stdout, res.stdout[-3000:]
+    env = dict(os.environ, SLAB_TRANSPORT=transport)
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=600,
+                         env=env)
+    assert res.returncode == 0 and "DIST_SLAB_CHECK {} OK".format(transport) in res.stdout, res.stdout[-3000:]
