@@ -746,6 +746,9 @@ k_pack_emigrants(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
   if (threadIdx.x == 0) load_params(P, ctl);
   __syncthreads();
   const unsigned count = min(ctl->n_emig, 2u * ctl->mig_cap);
+  const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
+  const size_t remote_mig = L.mig_recv, mig_bytes = L.mig_bytes;
+  const unsigned par = D.seq & 1u;
   for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
     const unsigned i = emig_list[t];
     const uint4 h = hot[i];
@@ -758,33 +761,42 @@ k_pack_emigrants(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
       apply_displacement(P, nx, ny, ix, iy, nx, ny);
       advance_agent(P, h.w, ix, iy, a, w, sqrt_tab);
     }
-    ExchangeHeader *dst = nx < P.slab_lo ? send_left : send_right;
+    const bool to_left = nx < P.slab_lo;
+    ExchangeHeader *dst = to_left ? send_left : send_right;   // the local header counts; records may go remote
     const unsigned k = atomicAdd(&dst->count, 1u);
     if (k < ctl->mig_cap) {
       MigrantRecord r;
       r.hot = make_uint4((uint32_t)nx, (uint32_t)ny, a, h.w);
       r.w = w;
       r.pad = 0;
-      reinterpret_cast<MigrantRecord *>(dst + 1)[k] = r;
+      MigrantRecord *out = reinterpret_cast<MigrantRecord *>(dst + 1);
+      unsigned char *peer = D.enabled ? (to_left ? D.left : D.right) : nullptr;
+      if (peer) {
+        // straight into the neighbour's receive buffer: what goes left arrives there "from the right" (dir 1)
+        out = reinterpret_cast<MigrantRecord *>(peer + remote_mig + ((to_left ? 1 : 0) * 2 + par) * mig_bytes +
+                                                sizeof(ExchangeHeader));
+      }
+      out[k] = r;
     } else {
       atomicOr(&ctl->err, kErrExchange);
     }
   }
-  if (D.enabled) {   // the last block hands both buffers to the neighbours
-    __threadfence();
+  if (D.enabled) {   // every block has fenced its remote stores; the last one publishes counts and flags
+    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(&ctl->pack_ticket, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (s_last) {
-      __threadfence();
-      const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
-      const unsigned par = D.seq & 1u;
-      // what I send to the left arrives there "from the right" (dir 1), and vice versa
-      if (D.left) push_buffer(send_left, D.left, L.mig_recv + (1 * 2 + par) * L.mig_bytes, sizeof(MigrantRecord),
-                              ctl->mig_cap, FLAG_MIG + 1 * 2 + par, D.seq);
-      __syncthreads();
-      if (D.right) push_buffer(send_right, D.right, L.mig_recv + (0 * 2 + par) * L.mig_bytes, sizeof(MigrantRecord),
-                               ctl->mig_cap, FLAG_MIG + 0 * 2 + par, D.seq);
+    if (s_last && threadIdx.x < 2) {
+      __threadfence_system();
+      const int to_left = threadIdx.x == 0;
+      unsigned char *peer = to_left ? D.left : D.right;
+      if (peer) {
+        const int from_dir = to_left ? 1 : 0;
+        const unsigned cnt = min(__ldcg(&(to_left ? send_left : send_right)->count), ctl->mig_cap);
+        reinterpret_cast<ExchangeHeader *>(peer + remote_mig + (from_dir * 2 + par) * mig_bytes)->count = cnt;
+        __threadfence_system();
+        *(reinterpret_cast<volatile unsigned *>(peer) + FLAG_MIG + from_dir * 2 + par) = D.seq;
+      }
     }
   }
 }
@@ -840,6 +852,16 @@ k_scatter_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ r
   const unsigned nl = min(recv_left->count, cap), nr = min(recv_right->count, cap);
   const double qscale = (double)(1ull << P.scale_bits);
   const unsigned total = P.overflow ? 0u : nl + nr;
+  __shared__ unsigned long long s_cnt[7];
+  __shared__ long long s_q[5];
+  __shared__ int s_bb[4];
+  if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x < 5) s_q[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    s_bb[0] = s_bb[2] = INT_MAX;
+    s_bb[1] = s_bb[3] = INT_MIN;
+  }
+  __syncthreads();
   for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const MigrantRecord *src = t < nl ? reinterpret_cast<const MigrantRecord *>(recv_left + 1) + t
                                       : reinterpret_cast<const MigrantRecord *>(recv_right + 1) + (t - nl);
@@ -848,21 +870,29 @@ k_scatter_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ r
     const int nx = (int)h.x, ny = (int)h.y;
     const uint32_t a = h.z, st = attr_status(a), sev = attr_severity(a);
     const unsigned slot = cell_start[cell_key(P, nx, ny, &ctl->err)] + imm_rank[t];
-    atomicAdd(&ctl->cnt[st], 1ull);
+    atomicAdd(&s_cnt[st], 1ull);                       // per block first, one set of global atomics at the end
     if (st != ST_D) {
-      if (sev != SEV_E) atomicAdd(&ctl->cnt[3 + sev], 1ull);
+      if (sev != SEV_E) atomicAdd(&s_cnt[3 + sev], 1ull);
       if (attr_age(a) >= 18u)
-        atomicAdd((unsigned long long *)&ctl->q[min(attr_stratum(a), 4u)],
+        atomicAdd((unsigned long long *)&s_q[min(attr_stratum(a), 4u)],
                   (unsigned long long)__double2ll_rn(__dmul_rn(w, qscale)));
     }
-    atomicMin(&ctl->bb_xmin, nx); atomicMax(&ctl->bb_xmax, nx);
-    atomicMin(&ctl->bb_ymin, ny); atomicMax(&ctl->bb_ymax, ny);
+    atomicMin(&s_bb[0], nx); atomicMax(&s_bb[1], nx);
+    atomicMin(&s_bb[2], ny); atomicMax(&s_bb[3], ny);
     ohot[slot] = h;
     owealth[slot] = w;
     if (st == ST_I) {
       inf_list[atomicAdd(&ctl->n_inf, 1u)] = slot;
       send_ghost(ctl, P, h, ghost_left, ghost_right);
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 7 && s_cnt[threadIdx.x]) atomicAdd(&ctl->cnt[threadIdx.x], s_cnt[threadIdx.x]);
+  if (threadIdx.x < 5 && s_q[threadIdx.x])
+    atomicAdd((unsigned long long *)&ctl->q[threadIdx.x], (unsigned long long)s_q[threadIdx.x]);
+  if (threadIdx.x == 0 && s_bb[0] <= s_bb[1]) {
+    atomicMin(&ctl->bb_xmin, s_bb[0]); atomicMax(&ctl->bb_xmax, s_bb[1]);
+    atomicMin(&ctl->bb_ymin, s_bb[2]); atomicMax(&ctl->bb_ymax, s_bb[3]);
   }
   if (D.enabled) {   // pass B and this kernel have listed every ghost: the last block hands them over
     __threadfence();

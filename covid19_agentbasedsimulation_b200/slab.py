@@ -175,6 +175,12 @@ class SlabSimulation(Simulation):
         mig = int(self.migrant_capacity) or max(4096, min(biggest // 16, 1 << 17))
         gho = int(self.ghost_capacity) or mig
         self._handles, self._buffers = [], []
+        if self.distributed:
+            # the exchange buffers have the same size on every rank (fixed-size messages): take the largest request
+            import torch.distributed as dist
+            sizes = [None] * self.n_slabs
+            dist.all_gather_object(sizes, (int(mig), int(gho)))
+            mig, gho = max(s[0] for s in sizes), max(s[1] for s in sizes)
         if self.transport == "p2p":
             self._create_p2p(counts[0], mig, gho, bounds)
             return
@@ -204,10 +210,6 @@ class SlabSimulation(Simulation):
         import torch
         import torch.distributed as dist
         rank, dev = self.my_ranks[0], self.slab_devices[0]
-        # every rank must agree on the buffer sizes: take the largest request
-        sizes = [None] * self.n_slabs
-        dist.all_gather_object(sizes, (int(mig), int(gho)))
-        mig, gho = max(s[0] for s in sizes), max(s[1] for s in sizes)
         cap = int(max(1024, count * self.capacity_factor + 2 * mig))
         h = _native.Handle(capacity=cap, seed=self.seed, device=dev, max_cells=self.max_cells,
                            history_capacity=self.history_capacity)
