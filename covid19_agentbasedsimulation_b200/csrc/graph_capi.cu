@@ -34,7 +34,8 @@ struct cabs_graph {
   int *bx = nullptr, *by = nullptr, *bstratum = nullptr, *bstocks = nullptr, *bsales = nullptr, *bnum = nullptr;
   double *bprice = nullptr;
   long long *bwealth = nullptr, *bfixed = nullptr, *bincomes = nullptr;
-  unsigned *cell_count = nullptr, *cell_items = nullptr, *contagious = nullptr;
+  unsigned *cell_count = nullptr, *contagious = nullptr;
+  int4 *cell_items = nullptr;
   double *history = nullptr, *initial_rows = nullptr;
   unsigned cell_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

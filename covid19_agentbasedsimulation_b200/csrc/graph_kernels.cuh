@@ -88,7 +88,7 @@ struct Sim {
   double prev_infected, prev_hosp_severe;   // memo of the previous executed hour (statistics fractions)
   // contact cell list scratch
   unsigned *cell_count;   // cell_cap + 1
-  unsigned *cell_items;   // n
+  int4 *cell_items;       // n: {x, y, person, -} of the Susceptible persons, grouped by cell
   unsigned *contagious;   // n
   int cell_cap;
   // output
@@ -222,10 +222,14 @@ __device__ __forceinline__ void fire(const Sim &S, Shared &sh, int b, uint32_t i
 }
 
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_graph_run(Sim *sims, int iterations) {
-  Sim &S = sims[blockIdx.x];
+__global__ void __launch_bounds__(kThreads, 2) k_graph_run(Sim *sims, int iterations) {
+  // the descriptor (pointers, parameters) is read by every thread all the time: keep a copy in shared memory
+  __shared__ Sim S;
   __shared__ Shared sh;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (unsigned k = tid; k < sizeof(Sim) / 4; k += kThreads)
+    reinterpret_cast<uint32_t *>(&S)[k] = reinterpret_cast<const uint32_t *>(&sims[blockIdx.x])[k];
+  __syncthreads();
   const int n = S.n, nh = S.nh, nb = S.nb;
   const double scale = S.scale;
 
@@ -630,13 +634,16 @@ __global__ void __launch_bounds__(kThreads) k_graph_run(Sim *sims, int iteration
       if (n > 0 && sh.bb[0] <= sh.bb[1]) {
         for (int c = tid; c <= ncells; c += kThreads) S.cell_count[c] = 0;
         __syncthreads();
+        // the cell list holds the possible targets only (Susceptible persons); the possible sources are listed
         for (int i = tid; i < n; i += kThreads) {
-          const int cx = ((S.px[i] - x0) >> eshift) + 1, cy = ((S.py[i] - y0) >> eshift) + 1;
-          atomicAdd(&S.cell_count[cy * ncx + cx], 1u);
           const uint32_t a = S.attr[i];
-          // sources: Infected persons whose infected_time can fall inside the window for some (low, up)
-          if (a_status(a) == I_ && (int)a_time(a) >= S.incubation - 1 && (int)a_time(a) <= S.contagion_time)
+          if (a_status(a) == S_) {
+            const int cx = ((S.px[i] - x0) >> eshift) + 1, cy = ((S.py[i] - y0) >> eshift) + 1;
+            atomicAdd(&S.cell_count[cy * ncx + cx], 1u);
+          } else if (a_status(a) == I_ && (int)a_time(a) >= S.incubation - 1 && (int)a_time(a) <= S.contagion_time) {
+            // Infected persons whose infected_time can fall inside the window for some (low, up)
             S.contagious[atomicAdd(&sh.n_contagious, 1u)] = i;
+          }
         }
         __syncthreads();
         // exclusive scan of cell_count[0..ncells] (chunked, running carry)
@@ -663,13 +670,17 @@ __global__ void __launch_bounds__(kThreads) k_graph_run(Sim *sims, int iteration
         }
         // fill: cell_count[c] is advanced to the end of cell c, i.e. becomes the start of cell c + 1
         for (int i = tid; i < n; i += kThreads) {
-          const int cx = ((S.px[i] - x0) >> eshift) + 1, cy = ((S.py[i] - y0) >> eshift) + 1;
-          S.cell_items[atomicAdd(&S.cell_count[cy * ncx + cx], 1u)] = i;
+          if (a_status(S.attr[i]) != S_) continue;
+          const int x = S.px[i], y = S.py[i];
+          const int cx = ((x - x0) >> eshift) + 1, cy = ((y - y0) >> eshift) + 1;
+          S.cell_items[atomicAdd(&S.cell_count[cy * ncx + cx], 1u)] = make_int4(x, y, i, 0);
         }
         __syncthreads();
-        // after the fill, items of cell c are [c == 0 ? 0 : cell_count[c - 1], cell_count[c])
+        // after the fill, items of cell c are [c == 0 ? 0 : cell_count[c - 1], cell_count[c]).  One warp per
+        // source, lanes over the candidates: persons pile up on single lattice points (homes, workplaces), so
+        // a source can have thousands of candidates while most have a handful.
         const unsigned nsrc = sh.n_contagious;
-        for (unsigned t = tid; t < nsrc; t += kThreads) {
+        for (unsigned t = wid; t < nsrc; t += kWarps) {
           const int j = (int)S.contagious[t];
           const int xj = S.px[j], yj = S.py[j], tj = (int)a_time(S.attr[j]);
           const int clo = max(((xj - S.reach - x0) >> eshift) + 1, 0), chi = min(((xj + S.reach - x0) >> eshift) + 1, ncx - 1);
@@ -677,12 +688,11 @@ __global__ void __launch_bounds__(kThreads) k_graph_run(Sim *sims, int iteration
           for (int r = rlo; r <= rhi; ++r) {
             const int c0 = r * ncx + clo, c1 = r * ncx + chi;
             const unsigned jb = c0 == 0 ? 0u : S.cell_count[c0 - 1], je = S.cell_count[c1];
-            for (unsigned k = jb; k < je; ++k) {
-              const int s = (int)S.cell_items[k];
-              const uint32_t as = S.attr[s];
-              if ((as & (3u | kNew)) != S_) continue;
-              const long long dx = S.px[s] - xj, dy = S.py[s] - yj;
+            for (unsigned k = jb + lane; k < je; k += 32) {
+              const int4 c = S.cell_items[k];
+              const long long dx = c.x - xj, dy = c.y - yj;
               if (dx * dx + dy * dy > (long long)S.T) continue;
+              const int s = c.z;
               const uint4 w = philox4x32_10((uint32_t)min(s, j), it, ST_CONTACT, (uint32_t)max(s, j), S.k0, S.k1);
               const int low = -1 + (int)(w.x >> 31), up = -1 + (int)(w.y >> 31);       // np.random.randint(-1, 1)
               if (tj >= S.incubation + low && tj <= S.contagion_time + up && (long long)w.z <= S.thr_rate)
@@ -749,11 +759,12 @@ __global__ void __launch_bounds__(kThreads) k_graph_run(Sim *sims, int iteration
     S.bstocks[tid] = sh.bstocks[tid]; S.bsales[tid] = sh.bsales[tid]; S.bnum[tid] = sh.bnum[tid];
   }
   if (tid == 0) {
-    S.gov_wealth = sh.gov_wealth; S.health_wealth = sh.health_wealth; S.health_expenses = sh.health_expenses;
-    S.next_hire_seq = sh.next_hire_seq;
-    S.iteration = it;
-    S.prev_infected = prev_infected;
-    S.prev_hosp_severe = prev_hs;
+    Sim &G = sims[blockIdx.x];
+    G.gov_wealth = sh.gov_wealth; G.health_wealth = sh.health_wealth; G.health_expenses = sh.health_expenses;
+    G.next_hire_seq = sh.next_hire_seq;
+    G.iteration = it;
+    G.prev_infected = prev_infected;
+    G.prev_hosp_severe = prev_hs;
   }
 }
 
