@@ -129,6 +129,7 @@ struct Shared {
   long long red[kWarps];
   long long acc[8];
   int wa[kWarps][kMaxBusiness], wm[kWarps][kMaxBusiness];   // per-warp max-plus totals
+  int ws[kWarps][kMaxBusiness];                              // stock before each warp of the current chunk
   unsigned present;          // businesses with an event in the current chunk
   int bb[4];
   unsigned n_contagious;
@@ -265,6 +266,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_graph_run(Sim *sims, int iterat
     const bool lock_all = S.mode == MODE_LOCKDOWN || (S.mode == MODE_CONDITIONAL && prev_infected > 0.05);
     const bool crit_active = prev_hs >= S.critical_limit;                        // network/agents.py:389-390
     const bool monthly = it > 1 && new_month;
+    int bus_reach = S.T_bus > 0 ? (int)__dsqrt_rn((double)S.T_bus) + 1 : 0;       // >= floor(sqrt(T_bus))
+    if (S.T_bus < 0) bus_reach = -1;                                                // nothing is in reach
     if (tid == 0) {
       sh.bb[0] = sh.bb[2] = INT_MAX; sh.bb[1] = sh.bb[3] = INT_MIN;
       sh.n_contagious = 0;
@@ -360,8 +363,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_graph_run(Sim *sims, int iterat
           uint4 q4 = make_uint4(0, 0, 0, 0);
           int have = -1;
           for (int b = 0; b < nb; ++b) {
-            const long long dx = sh.bx[b] - x, dy = sh.by[b] - y;
-            if (b == emp || dx * dx + dy * dy > (long long)S.T_bus) continue;
+            // cheap box test first: almost every (person, business) pair is far apart
+            const int ddx = sh.bx[b] - x, ddy = sh.by[b] - y;
+            if (b == emp || (unsigned)(ddx + bus_reach) > 2u * (unsigned)bus_reach ||
+                (unsigned)(ddy + bus_reach) > 2u * (unsigned)bus_reach)
+              continue;
+            const long long dx = ddx, dy = ddy;
+            if (dx * dx + dy * dy > (long long)S.T_bus) continue;
             if (have != (b >> 2)) {
               q4 = philox4x32_10(i, it, ST_SHOP + (b >> 2), 0u, S.k0, S.k1);
               have = b >> 2;
@@ -421,12 +429,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_graph_run(Sim *sims, int iterat
         }
       }
       __syncthreads();
+      // one thread per business carries the stock through the warps of the chunk: ws[w][b] = stock before warp w
+      if (tid < nb && ((present >> tid) & 1u)) {
+        int s0 = sh.bstocks[tid];
+        for (int w = 0; w < kWarps; ++w) {
+          sh.ws[w][tid] = s0;
+          s0 = max(s0 + sh.wa[w][tid], sh.wm[w][tid]);
+        }
+        sh.bstocks[tid] = s0;
+      }
+      __syncthreads();
       for (int b = 0; b < nb; ++b) {
         if (!((present >> b) & 1u)) continue;
         const unsigned nib = (unsigned)((ev >> (4 * b)) & 15ull);
-        // stock before this warp = carry through the earlier warps of the chunk
-        int s0 = sh.bstocks[b];
-        for (int w = 0; w < wid; ++w) s0 = max(s0 + sh.wa[w][b], sh.wm[w][b]);
+        const int s0 = sh.ws[wid][b];
         const int after = max(s0 + ea[b], em[b]);
         // exclusive prefix = inclusive prefix of the lane before
         const int pa = __shfl_up_sync(0xffffffffu, ea[b], 1), pm = __shfl_up_sync(0xffffffffu, em[b], 1);
@@ -440,12 +456,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_graph_run(Sim *sims, int iterat
           atom_add(&sh.bincomes[b], value);
           atomicAdd(&sh.bsales[b], taken);
         }
-      }
-      __syncthreads();
-      if (tid < nb && ((present >> tid) & 1u)) {
-        int s0 = sh.bstocks[tid];
-        for (int w = 0; w < kWarps; ++w) s0 = max(s0 + sh.wa[w][tid], sh.wm[w][tid]);
-        sh.bstocks[tid] = s0;
       }
       __syncthreads();
     }
