@@ -211,6 +211,8 @@ def run_ours(args, rank, world, local_rank):
         x_lo, x_hi = max(lo, 0), min(hi - 1, side)
     # this rank's agents in pinned host memory (also the source of the end-to-end leg)
     cols = make_population(n, x_lo, x_hi, side, seed=rank, id0=rank * n, total_wealth_per_agent=1e4 / 20)
+    if world == 1:
+        del cols["id"]       # ids are the list positions 0..n-1 (abs.py:15): nothing to send
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in cols.items()}
     ptrs = {k: t.data_ptr() for k, t in pinned.items()}
     h2d_bytes = sum(t.numel() * t.element_size() for t in pinned.values())
@@ -322,7 +324,8 @@ def run_ours(args, rank, world, local_rank):
         try:
             sys.path.insert(0, os.path.join(ROOT, "scripts"))
             import graph_bench
-            other = {"config2_graph_1k_lockdown": graph_bench.config2(),
+            other = {"config1_simulation_defaults": graph_bench.config1(),
+                     "config2_graph_1k_lockdown": graph_bench.config2(),
                      "config5_style_ensemble": graph_bench.ensemble(2000, 32, 120)}
         except Exception as ex:  # the headline line must still be printed
             other = {"error": repr(ex)}

@@ -20,6 +20,23 @@ def scenario_kwargs(s, **over):
     return kw
 
 
+def config1(iterations=2000):
+    """covid_abs Simulation, 'do nothing', reference defaults (N=20 on 10x10): the reference's own CPU-runnable case
+    (0.56 ms per iteration there).  Launch-bound on a GPU: 4 kernels per step."""
+    from covid19_agentbasedsimulation_b200.abs import Simulation
+    np.random.seed(0)
+    sim = Simulation(seed=1, history_capacity=4096)
+    sim.initialize()
+    sim.run(50)
+    h = sim._handle
+    h.event_record(0)
+    h.step(iterations)
+    h.event_record(1)
+    ms = h.event_elapsed_ms(0, 1)
+    return dict(config="Simulation() reference defaults, 20 agents, {} iterations enqueued at once".format(iterations),
+                ms=ms, us_per_iteration=1e3 * ms / iterations, agent_updates_per_s=20 * iterations / (ms * 1e-3))
+
+
 def config2(iterations=1440):
     """GraphSimulation 1k people, Lockdown scenario (run_batch.py:103-112), 1 440 hourly iterations."""
     np.random.seed(0)
@@ -62,7 +79,7 @@ def ensemble(n_persons=2000, seeds=64, iterations=240):
 
 
 if __name__ == "__main__":
-    out = dict(config2=config2(), ensemble_small=ensemble(2000, 32, 120))
+    out = dict(config1=config1(), config2=config2(), ensemble_small=ensemble(2000, 32, 120))
     if "--big" in sys.argv:
         out["ensemble_big"] = ensemble(20000, 64, 120)
     print(json.dumps(out))
