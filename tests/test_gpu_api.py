@@ -1,0 +1,119 @@
+"""Behaviour of the covid_abs-style host API on the GPU: triggers, attribute changes between steps, accessors,
+history ring, error paths (abs.py:57-95, 232-322)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _pop(n, side, seed, infected=0.05):
+    from oracle.sync_oracle import synthetic_population
+    return synthetic_population(n, side, side, seed=seed, infected=infected, immune=0.01)
+
+
+def _gpu(pop, tw, side, **kw):
+    from covid19_agentbasedsimulation_b200.abs import Simulation
+    sim = Simulation(population_size=len(pop["x"]), length=side, height=side, total_wealth=tw, **kw)
+    sim.set_population_arrays(pop["x"], pop["y"], pop["status"], pop["age"], pop["stratum"], pop["wealth"])
+    return sim
+
+
+def test_python_lambda_triggers_equal_declarative_ones(native_lib):
+    """The conditional lockdown of run_batch.py:628-643 written with lambdas (host, abs.py:267-271) and as device
+    triggers gives the same run."""
+    from covid19_agentbasedsimulation_b200.abs import Trigger
+    from covid19_agentbasedsimulation_b200.agents import Status
+    pop, tw = _pop(5000, 100, 2, infected=0.15)
+    low = {Status.Susceptible: 1.5, Status.Recovered_Immune: 1.5, Status.Infected: 1.5}
+    high = {Status.Susceptible: 5, Status.Recovered_Immune: 5, Status.Infected: 5}
+    a = _gpu(pop, tw, 100, seed=4, triggers_simulation=[Trigger('Infected', '>=', .2, 'amplitudes', low),
+                                                         Trigger('Infected', '<=', .05, 'amplitudes', high)])
+    b = _gpu(pop, tw, 100, seed=4)
+    # the reference's memo semantics: the lambda sees the statistics memoised after the previous step
+    memo = {"prev": b.get_statistics('all')}
+    b.append_trigger_simulation(lambda s: memo["prev"]['Infected'] >= .2, 'amplitudes', lambda x: low)
+    b.append_trigger_simulation(lambda s: memo["prev"]['Infected'] <= .05, 'amplitudes', lambda x: high)
+    rows_a = a.run(30)
+    for it in range(30):
+        b.execute()
+        cur = dict(b.get_statistics('all'))
+        assert [float(cur[k]) for k in cur] == rows_a[it].tolist(), it
+        memo["prev"] = cur
+    assert b.amplitudes in (low, high)
+
+
+def test_attribute_change_between_steps_reaches_the_device(native_lib):
+    from oracle.sync_oracle import SyncSimulation
+    pop, tw = _pop(4000, 90, 3)
+    sim = _gpu(pop, tw, 90, seed=6)
+    orc = SyncSimulation(seed=6, population_size=4000, length=90, height=90, total_wealth=tw)
+    orc.set_population(pop["x"], pop["y"], pop["status"], pop["age"], pop["stratum"], pop["wealth"])
+    for it in range(12):
+        if it == 4:
+            sim.contagion_rate, orc.contagion_rate = 0.2, 0.2
+        if it == 8:
+            sim.contagion_distance, orc.contagion_distance = 2.0, 2.0
+        sim.execute()
+        o = orc.execute()
+        g = sim.get_statistics('all')
+        assert [float(g[k]) for k in o] == [float(v) for v in o.values()], it
+    assert np.array_equal(sim.get_contact_pairs(), orc.last_pairs)
+
+
+def test_accessors_and_population_round_trip(native_lib):
+    from covid19_agentbasedsimulation_b200.abs import Simulation
+    from covid19_agentbasedsimulation_b200.agents import Status, Agent
+    np.random.seed(5)
+    sim = Simulation(seed=8)
+    sim.initialize()
+    sim.execute()
+    pop = sim.get_population()
+    assert len(pop) == 20 and all(isinstance(a, Agent) for a in pop)
+    assert sim.get_positions() == [[a.x, a.y] for a in pop]
+    assert sim.get_description() == [a.status.name for a in pop]
+    assert len(sim.get_description(complete=True)) == 20
+    assert set(sim.get_statistics('info')) == {"Susceptible", "Infected", "Recovered_Immune", "Death", "Asymptomatic",
+                                               "Hospitalization", "Severe"}
+    assert set(sim.get_statistics('ecom')) == {"Q1", "Q2", "Q3", "Q4", "Q5"}
+    before = sim.get_statistics('all')
+    clone = Simulation(seed=8)
+    clone.set_population(pop)                      # abs.py:65-69
+    assert clone.population_size == 20
+    after = clone.get_statistics('all')
+    assert [float(before[k]) for k in before] == [float(after[k]) for k in after]
+    assert sum(1 for a in clone.get_population() if a.status == Status.Infected) == \
+        sum(1 for a in pop if a.status == Status.Infected)
+
+
+def test_history_ring_and_error_paths(native_lib):
+    from covid19_agentbasedsimulation_b200 import _native
+    from covid19_agentbasedsimulation_b200.abs import Simulation
+    pop, tw = _pop(1000, 50, 1)
+    sim = _gpu(pop, tw, 50, seed=1, history_capacity=8)
+    rows = sim.run(8)
+    assert rows.shape == (8, 12)
+    long = sim.run(20)                              # longer than the ring: falls back to step-by-step reads
+    assert long.shape == (20, 12)
+    with pytest.raises(_native.NativeError) as e:
+        sim._handle.stats_history(0, 4)             # overwritten long ago
+    assert e.value.code == _native.ERR_CAPACITY
+    with pytest.raises(_native.NativeError):
+        sim._handle.stats_history(27, 5)            # not executed yet
+    # per-agent Python triggers cannot run on the device
+    sim.append_trigger_population(lambda a: True, 'wealth', lambda w: 0)
+    with pytest.raises(NotImplementedError):
+        sim.execute()
+    # coordinates beyond the supported box are reported, not silently wrapped
+    far = Simulation(seed=1, population_size=2, length=10, height=10)
+    far.set_population_arrays([0, 2 ** 29], [0, 0], [0, 1], [30, 30], [1, 1], [1.0, 1.0])
+    with pytest.raises(_native.NativeError) as e:
+        far.get_statistics('all')
+    assert e.value.code == _native.ERR_DOMAIN
+    # a bigger population than the handle was created for re-creates the handle
+    small = _gpu(*_pop(100, 20, 2), 20, seed=2)
+    big, tw2 = _pop(5000, 80, 3)
+    small.length = small.height = 80
+    small.set_population_arrays(big["x"], big["y"], big["status"], big["age"], big["stratum"], big["wealth"])
+    small.execute()
+    assert abs(sum(float(small.get_statistics('info')[k]) for k in ("Susceptible", "Infected", "Recovered_Immune",
+                                                                    "Death")) - 1.0) < 1e-12
