@@ -40,6 +40,9 @@ struct cabs_sim {
   unsigned char *blocks[CABS_MAX_RANKS] = {};
   unsigned char **dev_blocks = nullptr;
   unsigned build_seq = 0;
+  bool late_pending = false;    // direct mode: the global half of the last build's closing has not been enqueued
+  unsigned late_seq = 0;
+  int late_record = 0;
   unsigned *emig_list = nullptr, *imm_rank = nullptr;
   // sequential schedule
   unsigned long long *tinf = nullptr;
@@ -87,6 +90,8 @@ static void prof_mark(cabs_sim *sim, const char *name) {
       return CABS_ERR_CUDA;                                                                     \
     }                                                                                           \
   } while (0)
+
+static int flush_late_close(cabs_sim *sim);
 
 static int fail(cabs_sim *sim, int code, const char *msg) {
   if (sim) sim->err = msg;
@@ -215,6 +220,10 @@ extern "C" int cabs_set_params(cabs_sim *sim, const cabs_params *p) {
     if (!(p->amplitudes[k] >= -5000.0 && p->amplitudes[k] <= 5000.0))
       return fail(sim, CABS_ERR_INVALID, "amplitudes must be within +-5000 (displacements are stored in 16 bits)");
   CK(cudaSetDevice(sim->device));
+  {
+    const int rc = flush_late_close(sim);   // the critical-limit flag is recomputed from the current statistics
+    if (rc != CABS_OK) return rc;
+  }
   ParamBlock b;
   for (int k = 0; k < 4; ++k) b.amp[k] = (float)p->amplitudes[k];
   b.amp[3] = 0.f;
@@ -294,7 +303,7 @@ static void enqueue_build(cabs_sim *sim) {
     SlabDirect none;
     memset(&none, 0, sizeof none);
     LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, nullptr, nullptr, sim->history,
-           nullptr, 1, none);
+           nullptr, 1, none, nullptr);
   } else {
     LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 0);
   }
@@ -355,6 +364,20 @@ extern "C" int cabs_set_slab(cabs_sim *sim, const cabs_slab *slab) {
   return CABS_OK;
 }
 
+// Direct mode: enqueue the global half of the last build's closing (waits on the device for every rank's row).
+static int flush_late_close(cabs_sim *sim) {
+  if (!sim->late_pending) return CABS_OK;
+  SlabDirect D;
+  memset(&D, 0, sizeof D);
+  D.self = sim->blocks[sim->slab.rank];
+  D.seq = sim->late_seq;
+  D.enabled = 1;
+  LAUNCH(k_slab_close_global, 1, 32, sim->ctl, sim->history, sim->late_record, D);
+  sim->late_pending = false;
+  CK(cudaGetLastError());
+  return CABS_OK;
+}
+
 template <bool kAdvance>
 static int slab_phase(cabs_sim *sim, int phase) {
   const cabs_slab &sl = sim->slab;
@@ -396,6 +419,10 @@ static int slab_phase(cabs_sim *sim, int phase) {
       }
       LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl,
                 sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list);
+      {   // pass A needed nothing global; pass B and the emigrants' update need the critical-limit flag
+        const int rc = flush_late_close(sim);
+        if (rc != CABS_OK) return rc;
+      }
       LAUNCH_AS("k_pack_emigrants", k_pack_emigrants<kAdvance>, nbs, 256, sim->ctl, sim->hot[c], sim->w[c], sim->aux,
                 sim->emig_list, ms[0], ms[1], sim->sqrt_tab, D);
       break;
@@ -411,14 +438,27 @@ static int slab_phase(cabs_sim *sim, int phase) {
     case 2:
       if (kAdvance) {
         LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, gr[0], gr[1], sim->history,
-               rows, 2, D);
+               rows, sim->direct ? 3 : 2, D, (ExchangeHeader *)(sim->direct ? sim->blocks[sl.rank] : nullptr));
       } else {
         LAUNCH(k_slab_export, 1, 32, sim->ctl, rows, D);
       }
       break;
     case 3:
-      LAUNCH(k_slab_close, 1, 32, sim->ctl, (const long long *)rows, sim->cells[t], sim->history,
-             kAdvance ? 1 : 0, ms[0], ms[1], gs[0], gs[1], D);
+      if (sim->direct) {
+        // the local half ran inside the contact kernel (or runs here for a static build); the global half is
+        // enqueued behind the next build's pass A, or by whoever asks for statistics first
+        sim->late_pending = true;
+        sim->late_seq = D.seq;
+        sim->late_record = kAdvance ? 1 : 0;
+        if (!kAdvance) {   // a static build closes in order: the global y-range first, then the next grid
+          const int rc = flush_late_close(sim);
+          if (rc != CABS_OK) return rc;
+          LAUNCH(k_slab_close_local, 1, 32, sim->ctl, sim->cells[t], 0, ms[0], ms[1], gs[0], gs[1]);
+        }
+      } else {
+        LAUNCH(k_slab_close, 1, 32, sim->ctl, (const long long *)rows, sim->cells[t], sim->history,
+               kAdvance ? 1 : 0, ms[0], ms[1], gs[0], gs[1], D);
+      }
       sim->build_seq++;
       sim->cur = o;
       sim->tab = t ^ 1;
@@ -642,6 +682,10 @@ extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
 }
 
 static int check_device_error(cabs_sim *sim) {
+  {
+    const int rc = flush_late_close(sim);
+    if (rc != CABS_OK) return rc;
+  }
   unsigned err = 0;
   CK(cudaMemcpyAsync(&err, &sim->ctl->err, sizeof(unsigned), cudaMemcpyDeviceToHost, sim->stream));
   CK(cudaStreamSynchronize(sim->stream));
@@ -673,6 +717,10 @@ extern "C" int cabs_stats(cabs_sim *sim, double *values, int64_t *counts) {
   if (!sim || !values) return fail(sim, CABS_ERR_INVALID, "cabs_stats: null argument");
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_stats: call cabs_set_params first");
   CK(cudaSetDevice(sim->device));
+  {
+    const int rc = flush_late_close(sim);
+    if (rc != CABS_OK) return rc;
+  }
   StatRecord r;
   CK(cudaMemcpyAsync(&r, &sim->ctl->cur, sizeof r, cudaMemcpyDeviceToHost, sim->stream));
   const int rc = check_device_error(sim);  // synchronises
@@ -687,6 +735,10 @@ extern "C" int cabs_stats_history(cabs_sim *sim, uint64_t first_step, uint64_t c
   if (sim->step - first_step > sim->hist_cap)
     return fail(sim, CABS_ERR_CAPACITY, "cabs_stats_history: records already overwritten (history_capacity)");
   CK(cudaSetDevice(sim->device));
+  {
+    const int rc = flush_late_close(sim);
+    if (rc != CABS_OK) return rc;
+  }
   if (count == 0) return CABS_OK;
   std::vector<StatRecord> recs(count);
   uint64_t done = 0;

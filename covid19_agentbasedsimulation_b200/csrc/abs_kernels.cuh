@@ -108,6 +108,8 @@ struct Ctl {
   unsigned n_inf;          // entries of the Infected-slot list
   unsigned n_emig;         // agents that leave this slab in the running step
   unsigned pack_ticket, imm_ticket;  // blocks of k_pack_emigrants / k_scatter_immigrants that have finished
+  unsigned pending_step;   // direct slab mode: step whose global statistics the late closing will record
+  int glob_ymin, glob_ymax;  // direct slab mode: y-range of the whole population one build ago
   unsigned n_newinf;       // sequential schedule: entries of the newly-infected list
   unsigned seq_changed;    // sequential schedule: infection times lowered in the last round
   unsigned scan_ticket;    // next tile of the scan
@@ -926,6 +928,7 @@ __device__ __forceinline__ void contact_cells(const StepParams &P, int x, int y,
 
 __device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats);
 __device__ void slab_export(Ctl *ctl, long long *rows, SlabDirect D);
+__device__ void close_local(Ctl *ctl, const unsigned *cell_start, int record_stats);
 
 // Pass C: the contact loop of abs.py:249-265 pushed from the agents that were Infected before this
 // contact phase to the Susceptible agents in reach; contact() = abs.py:141-154 with one draw per pair,
@@ -937,7 +940,7 @@ __global__ void __launch_bounds__(256)
 k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
             const unsigned *__restrict__ inf_list, const ExchangeHeader *__restrict__ ghosts_left,
             const ExchangeHeader *__restrict__ ghosts_right, StatRecord *__restrict__ history,
-            long long *__restrict__ rows, int finish, SlabDirect D) {
+            long long *__restrict__ rows, int finish, SlabDirect D, ExchangeHeader *__restrict__ send_reset) {
   __shared__ StepParams P;
   __shared__ unsigned s_new, s_local, s_left, s_right;
   if (threadIdx.x == 0) {
@@ -995,8 +998,20 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
       const unsigned ticket = atomicAdd(&ctl->done_ticket, 1u);
       if (ticket == gridDim.x - 1) {
         __threadfence();
-        if (finish == 1) close_step(ctl, history, 1);
-        else slab_export(ctl, rows, D);
+        if (finish == 1) {
+          close_step(ctl, history, 1);
+        } else {
+          slab_export(ctl, rows, D);
+          if (finish == 3) {   // direct slab mode: the local half of the closing, nobody is waited for
+            const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
+            unsigned char *self = reinterpret_cast<unsigned char *>(send_reset);
+            for (int d = 0; d < 2; ++d) {
+              reinterpret_cast<ExchangeHeader *>(self + L.mig_send + d * L.mig_bytes)->count = 0;
+              reinterpret_cast<ExchangeHeader *>(self + L.ghost_send + d * L.ghost_bytes)->count = 0;
+            }
+            close_local(ctl, cell_start, 1);
+          }
+        }
       }
     }
   }
@@ -1271,6 +1286,106 @@ __global__ void k_slab_export(Ctl *ctl, long long *rows, SlabDirect D) {
   slab_export(ctl, rows, D);
 }
 
+// Direct slab mode splits the closing so that no rank waits for the others at the end of a step:
+//   close_local   right after the contact pass: triggers (they read the statistics of the step before, which are
+//                 already global), step counter, table flip, next grid, accumulator reset.  The next grid needs
+//                 the y-range of the whole population; the range of one build ago widened by one move is a
+//                 superset of it, and results do not depend on the grid.
+//   close_global  during the next build, after its pass A (which needs nothing global): waits for every rank's
+//                 row, sums the statistics of the step, records them, sets the critical-limit flag pass B reads.
+// Everything is identical to the one-device closing except for when it happens.
+__device__ void close_local(Ctl *ctl, const unsigned *cell_start, int record_stats) {
+  float amax = 0.f;
+  for (int k = 0; k < 3; ++k) amax = fmaxf(amax, fabsf(ctl->amp[k]));
+  const int widen = (int)(kMaxAbsNormal * amax) + 2;   // one move with the amplitudes of the step just done
+  ctl->overflow = 0;
+  if (record_stats) {
+    for (int t = 0; t < ctl->ntrig; ++t) {             // abs.py:267-271, on the memo of the previous step
+      const DevTrigger &tr = ctl->trig[t];
+      const double v = stat_value(ctl, ctl->prev, tr.metric);
+      const bool hit = tr.op == 0 ? v >= tr.threshold : tr.op == 1 ? v <= tr.threshold
+                     : tr.op == 2 ? v > tr.threshold : v < tr.threshold;
+      if (!hit) continue;
+      if (tr.attribute == 0) {
+        for (int k = 0; k < 4; ++k) ctl->amp[k] = (float)tr.value[k];
+      } else if (tr.attribute == 1) {
+        ctl->rate = tr.value[0];
+        ctl->thr_rate = prob_bound_le(tr.value[0]);
+      } else if (tr.attribute == 2) {
+        ctl->contagion_distance = tr.value[0];
+        ctl->T = threshold_T(tr.value[0]);
+      } else if (tr.attribute == 3) {
+        ctl->critical_limit = tr.value[0];
+      }
+    }
+    ctl->pending_step = ctl->step;
+    ctl->step += 1;
+  }
+  const unsigned n_next = cell_start[ctl->g.ncells];   // residents that stayed + immigrants
+  ctl->cells_used[ctl->cur_table] = ctl->g.ncells + 1;
+  ctl->cur_table ^= 1;
+  ctl->built = ctl->g;
+  int bx0 = ld_acc(&ctl->bb_xmin), bx1 = ld_acc(&ctl->bb_xmax);
+  int by0 = ld_acc(&ctl->bb_ymin), by1 = ld_acc(&ctl->bb_ymax);
+  if (ctl->glob_ymin <= ctl->glob_ymax) {
+    by0 = min(by0, ctl->glob_ymin - widen);
+    by1 = max(by1, ctl->glob_ymax + widen);
+  }
+  if (bx0 > bx1) bx0 = bx1 = ctl->slab_lo != INT_MIN ? ctl->slab_lo : ctl->slab_hi - 1;
+  ctl->last_bb[0] = bx0; ctl->last_bb[1] = bx1; ctl->last_bb[2] = by0; ctl->last_bb[3] = by1;
+  plan_grid(ctl, bx0, bx1, by0, by1, true);
+  reset_accumulators(ctl);
+  ctl->n = n_next;
+  __threadfence();
+}
+
+__device__ void close_global(Ctl *ctl, const long long *rows, StatRecord *history, int record_stats) {
+  StatRecord cur;
+  for (int k = 0; k < 7; ++k) cur.cnt[k] = 0;
+  for (int k = 0; k < 5; ++k) cur.q[k] = 0;
+  unsigned long long newinf = 0;
+  int ymin = INT_MAX, ymax = INT_MIN;
+  for (int g = 0; g < ctl->n_ranks; ++g) {
+    const long long *r = rows + (size_t)g * kSlabRow;
+    for (int k = 0; k < 7; ++k) cur.cnt[k] += (unsigned long long)r[k];
+    for (int k = 0; k < 5; ++k) cur.q[k] += r[7 + k];
+    newinf += (unsigned long long)r[12];
+    if (r[13] <= r[14]) {
+      ymin = min(ymin, (int)r[13]);
+      ymax = max(ymax, (int)r[14]);
+    }
+    ctl->err |= (unsigned)r[15];  // an exchange overflow anywhere invalidates the run everywhere
+  }
+  cur.cnt[ST_S] -= newinf;  // infections of the contact phase (abs.py:153)
+  cur.cnt[ST_I] += newinf;
+  cur.new_infections = newinf;
+  cur.n_resident = ctl->n;
+  cur.pad[0] = cur.pad[1] = 0;
+  if (record_stats) history[ctl->pending_step % ctl->hist_cap] = cur;
+  ctl->prev = cur;
+  ctl->cur = cur;
+  ctl->glob_ymin = ymin;
+  ctl->glob_ymax = ymax;
+  const double n = (double)ctl->pop_size;   // abs.py:215
+  ctl->crit_active = ((double)cur.cnt[6] / n + (double)cur.cnt[5] / n) >= ctl->critical_limit;
+}
+
+__global__ void k_slab_close_local(Ctl *ctl, const unsigned *cell_start, int record_stats, ExchangeHeader *s0,
+                                   ExchangeHeader *s1, ExchangeHeader *s2, ExchangeHeader *s3) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  s0->count = 0; s1->count = 0; s2->count = 0; s3->count = 0;
+  close_local(ctl, cell_start, record_stats);
+}
+
+__global__ void k_slab_close_global(Ctl *ctl, StatRecord *history, int record_stats, SlabDirect D) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
+  const unsigned par = D.seq & 1u;
+  for (int g = 0; g < ctl->n_ranks; ++g) wait_flag(D.self, FLAG_ROW + par * kMaxRanks + g, D.seq);
+  close_global(ctl, reinterpret_cast<const long long *>(D.self + L.rows) + (size_t)par * kMaxRanks * kSlabRow, history,
+               record_stats);
+}
+
 __global__ void k_slab_close(Ctl *ctl, const long long *rows, const unsigned *cell_start, StatRecord *history,
                              int record_stats, ExchangeHeader *s0, ExchangeHeader *s1, ExchangeHeader *s2,
                              ExchangeHeader *s3, SlabDirect D) {
@@ -1409,6 +1524,7 @@ __global__ void k_init_ctl(Ctl *ctl, unsigned k0, unsigned k1, unsigned max_cell
   ctl->n_ranks = 1; ctl->rank = 0;
   ctl->slab_lo = INT_MIN; ctl->slab_hi = INT_MAX;
   ctl->overflow = 0; ctl->mig_cap = 0; ctl->ghost_cap = 0;
+  ctl->pending_step = 0; ctl->glob_ymin = INT_MAX; ctl->glob_ymax = INT_MIN;
   reset_accumulators(ctl);
   plan_grid(ctl, 0, 0, 0, 0, false);
   ctl->built = ctl->g;
