@@ -437,8 +437,18 @@ static int slab_phase(cabs_sim *sim, int phase) {
       break;
     case 2:
       if (kAdvance) {
-        LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, gr[0], gr[1], sim->history,
-               rows, sim->direct ? 3 : 2, D, (ExchangeHeader *)(sim->direct ? sim->blocks[sl.rank] : nullptr));
+        if (sim->direct) {
+          // the local sources need nothing from the neighbours: their launch hides the wait for the ghosts
+          SlabDirect none;
+          memset(&none, 0, sizeof none);
+          LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, nullptr, nullptr,
+                 sim->history, rows, 0, none, nullptr);
+          LAUNCH_AS("k_contagion(ghosts)", k_contagion, nbs, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list,
+                    gr[0], gr[1], sim->history, rows, 8 | 3, D, (ExchangeHeader *)sim->blocks[sl.rank]);
+        } else {
+          LAUNCH(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, gr[0], gr[1], sim->history,
+                 rows, 2, D, nullptr);
+        }
       } else {
         LAUNCH(k_slab_export, 1, 32, sim->ctl, rows, D);
       }

@@ -905,11 +905,30 @@ k_scatter_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ r
       __threadfence();
       const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
       const unsigned par = D.seq & 1u;
-      if (D.left) push_buffer(ghost_left, D.left, L.ghost_recv + (1 * 2 + par) * L.ghost_bytes, sizeof(uint4),
-                              ctl->ghost_cap, FLAG_GHOST + 1 * 2 + par, D.seq);
+      // both directions at once: one round of stores, one system fence, then the two flags
+      const unsigned nl_g = D.left ? min(__ldcg(&ghost_left->count), ctl->ghost_cap) : 0u;
+      const unsigned nr_g = D.right ? min(__ldcg(&ghost_right->count), ctl->ghost_cap) : 0u;
+      uint4 *dl = D.left ? reinterpret_cast<uint4 *>(D.left + L.ghost_recv + (1 * 2 + par) * L.ghost_bytes +
+                                                     sizeof(ExchangeHeader)) : nullptr;
+      uint4 *dr = D.right ? reinterpret_cast<uint4 *>(D.right + L.ghost_recv + (0 * 2 + par) * L.ghost_bytes +
+                                                      sizeof(ExchangeHeader)) : nullptr;
+      const uint4 *sl = reinterpret_cast<const uint4 *>(ghost_left + 1), *sr = reinterpret_cast<const uint4 *>(ghost_right + 1);
+      for (unsigned k = threadIdx.x; k < nl_g + nr_g; k += blockDim.x) {
+        if (k < nl_g) dl[k] = __ldcg(sl + k);
+        else dr[k - nl_g] = __ldcg(sr + (k - nl_g));
+      }
+      __threadfence_system();
       __syncthreads();
-      if (D.right) push_buffer(ghost_right, D.right, L.ghost_recv + (0 * 2 + par) * L.ghost_bytes, sizeof(uint4),
-                               ctl->ghost_cap, FLAG_GHOST + 0 * 2 + par, D.seq);
+      if (threadIdx.x < 2) {
+        unsigned char *peer = threadIdx.x == 0 ? D.left : D.right;
+        if (peer) {
+          const int from_dir = threadIdx.x == 0 ? 1 : 0;
+          reinterpret_cast<ExchangeHeader *>(peer + L.ghost_recv + (from_dir * 2 + par) * L.ghost_bytes)->count =
+              threadIdx.x == 0 ? nl_g : nr_g;
+          __threadfence_system();
+          *(reinterpret_cast<volatile unsigned *>(peer) + FLAG_GHOST + from_dir * 2 + par) = D.seq;
+        }
+      }
     }
   }
 }
@@ -951,7 +970,7 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
       if (D.right) wait_flag(D.self, FLAG_GHOST + 1 * 2 + par, D.seq);
     }
     s_new = 0;
-    s_local = ctl->n_inf;
+    s_local = (finish & 8) ? 0u : ctl->n_inf;   // bit 8: ghost sources only (the local ones ran in their own launch)
     s_left = ghosts_left ? min(ghosts_left->count, ctl->ghost_cap) : 0u;
     s_right = ghosts_right ? min(ghosts_right->count, ctl->ghost_cap) : 0u;
   }
@@ -992,6 +1011,7 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
   __syncthreads();
   if (threadIdx.x == 0) {
     if (s_new) atomicAdd(&ctl->newinf, (unsigned long long)s_new);
+    finish &= 7;
     if (finish) {
       // the last block to get here has seen every other block's contribution
       __threadfence();
