@@ -58,6 +58,7 @@ struct cabs_sim {
   cabs_params params;
   bool have_params = false;
   bool cells_dirty = true;      // cell_start does not describe the current positions / distance
+  bool unsorted = false;        // the resident small-population kernel left the records out of cell order
   uint64_t n = 0, step = 0, launches = 0;
   cudaEvent_t events[CABS_NUM_EVENTS] = {};
   // per-kernel profiling: events[i] is recorded before launch i of the current batch, names[i] its kernel
@@ -318,6 +319,7 @@ static int rebuild_static(cabs_sim *sim) {
   enqueue_build<false>(sim);
   CK(cudaGetLastError());
   sim->cells_dirty = false;
+  sim->unsorted = false;
   return CABS_OK;
 }
 
@@ -681,6 +683,21 @@ extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_step: call cabs_set_params first");
   if (sim->slab_on) return fail(sim, CABS_ERR_INVALID, "cabs_step: a slab handle is stepped with cabs_slab_phase");
   CK(cudaSetDevice(sim->device));
+  if (sim->n > 0 && sim->n <= (uint64_t)kSmallMax && sim->params.schedule == CABS_SYNCHRONOUS && nsteps > 0) {
+    // the whole run in one launch of one resident block (small populations are launch-latency bound otherwise)
+    LAUNCH(k_small_run, 1, kSmallMax, sim->ctl, sim->hot[sim->cur], sim->w[sim->cur], sim->history, sim->sqrt_tab,
+           nsteps);
+    sim->step += nsteps;
+    sim->cells_dirty = true;   // the records are no longer in cell order; the pair hook rebuilds on demand
+    sim->unsorted = true;
+    if (sim->profiling) prof_mark(sim, nullptr);
+    CK(cudaGetLastError());
+    return CABS_OK;
+  }
+  if (sim->unsorted && sim->n > 0) {   // steps of the tiled path start from a cell-sorted population
+    const int rc = rebuild_static(sim);
+    if (rc != CABS_OK) return rc;
+  }
   for (int s = 0; s < nsteps; ++s) {
     enqueue_build<true>(sim);
     sim->step++;

@@ -1217,9 +1217,9 @@ __device__ __forceinline__ int ld_acc(const int *p) { return __ldcg(p); }
 // (experiments.py:193-196).  One thread.
 //   record_stats = 1 : after a real step
 //   record_stats = 0 : after upload / static rebuild (statistics of the initial state = "previous" stats)
-__device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats) {
+// Statistics half of the closing: the step's record, triggers on the memo of the step before, critical-limit flag.
+__device__ void close_stats(Ctl *ctl, StatRecord *history, int record_stats) {
   StatRecord cur;
-  ctl->overflow = 0;
   const unsigned long long newinf = ld_acc(&ctl->newinf);
   for (int k = 0; k < 7; ++k) cur.cnt[k] = ld_acc(&ctl->cnt[k]);
   cur.cnt[ST_S] -= newinf;  // infections of the contact phase (abs.py:153)
@@ -1256,6 +1256,11 @@ __device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats) {
   // abs.py:215: statistics['Severe'] + statistics['Hospitalization'] >= critical_limit
   const double n = (double)ctl->pop_size;
   ctl->crit_active = ((double)cur.cnt[6] / n + (double)cur.cnt[5] / n) >= ctl->critical_limit;
+}
+
+__device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats) {
+  ctl->overflow = 0;
+  close_stats(ctl, history, record_stats);
   // the table this build used stays valid (contact-pair hook) until the next build's pass B zeroes it
   ctl->cells_used[ctl->cur_table] = ctl->g.ncells + 1;
   ctl->cur_table ^= 1;
@@ -1442,6 +1447,96 @@ __global__ void k_slab_close(Ctl *ctl, const long long *rows, const unsigned *ce
   const unsigned n_next = cell_start[ctl->g.ncells];  // residents that stayed + immigrants
   close_step(ctl, history, record_stats);
   ctl->n = n_next;
+}
+
+// ------------------------------------------------------------------------------------------
+// Small populations (the reference's own sizes: 20 .. a few hundred agents, abs.py:17) are launch-latency bound
+// when every step is four kernels.  One block holds the whole population in registers / shared memory and
+// stays resident for a run of steps: move + update (the same device functions as passes A and B), contacts
+// by scanning the list of Infected agents (at these sizes a cell list costs more than it saves), closing.
+// Results are identical to the tiled path bit for bit: same draws, same arithmetic, integer statistics.
+constexpr int kSmallMax = 1024;
+
+__global__ void __launch_bounds__(kSmallMax)
+k_small_run(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, double *__restrict__ wealth,
+            StatRecord *__restrict__ history, const double *__restrict__ sqrt_tab, int nsteps) {
+  __shared__ StepParams P;
+  __shared__ int s_x[kSmallMax], s_y[kSmallMax];
+  __shared__ uint32_t s_id[kSmallMax];
+  __shared__ unsigned s_inf[kSmallMax];
+  __shared__ unsigned s_ninf, s_newinf;
+  __shared__ unsigned long long s_cnt[7];
+  __shared__ long long s_q[5];
+  const unsigned i = threadIdx.x, n = ctl->n;
+  const bool mine = i < n;
+  uint4 h = mine ? hot[i] : make_uint4(0, 0, 0, 0);
+  double w = mine ? wealth[i] : 0.0;
+  for (int s = 0; s < nsteps; ++s) {
+    if (i == 0) {
+      load_params(P, ctl);
+      s_ninf = 0;
+      s_newinf = 0;
+      for (int k = 0; k < 7; ++k) s_cnt[k] = 0;
+      for (int k = 0; k < 5; ++k) s_q[k] = 0;
+    }
+    __syncthreads();
+    uint32_t a = attr_normalize(h.z);
+    int nx = (int)h.x, ny = (int)h.y;
+    if (mine) {
+      // Simulation.move + Simulation.update (abs.py:156-230)
+      const uint4 r = philox4x32_10(h.w, P.step, kStreamAgent, 0u, P.k0, P.k1);
+      int ix, iy;
+      draw_displacement(P, a, r, ix, iy);
+      apply_displacement(P, nx, ny, ix, iy, nx, ny);
+      advance_agent(P, h.w, ix, iy, a, w, sqrt_tab);
+      // statistics (abs.py:300-312)
+      const uint32_t st = attr_status(a), sev = attr_severity(a);
+      atomicAdd(&s_cnt[st], 1ull);
+      if (st != ST_D) {
+        if (sev != SEV_E) atomicAdd(&s_cnt[3 + sev], 1ull);
+        if (attr_age(a) >= 18u)
+          atomicAdd((unsigned long long *)&s_q[min(attr_stratum(a), 4u)],
+                    (unsigned long long)__double2ll_rn(__dmul_rn(w, (double)(1ull << P.scale_bits))));
+      }
+      s_x[i] = nx;
+      s_y[i] = ny;
+      s_id[i] = h.w;
+      if (st == ST_I) s_inf[atomicAdd(&s_ninf, 1u)] = i;
+    }
+    __syncthreads();
+    // contact() (abs.py:141-154, 249-265): a Susceptible agent looks at every agent Infected before this phase
+    if (mine && attr_status(a) == ST_S && P.T >= 0) {
+      const unsigned ninf = s_ninf;
+      for (unsigned k = 0; k < ninf; ++k) {
+        const unsigned j = s_inf[k];
+        const long long dx = s_x[j] - nx, dy = s_y[j] - ny;
+        if (dx * dx + dy * dy > (long long)P.T) continue;
+        const uint32_t other = s_id[j];
+        const uint4 r = philox4x32_10(min(h.w, other), P.step, kStreamContact, max(h.w, other), P.k0, P.k1);
+        if ((long long)r.x <= P.thr_rate) {   // contagion_test <= contagion_rate (abs.py:150-153)
+          a |= kNewlyInfected;
+          atomicAdd(&s_newinf, 1u);
+          break;
+        }
+      }
+    }
+    h = make_uint4((uint32_t)nx, (uint32_t)ny, a, h.w);
+    __syncthreads();
+    if (i == 0) {
+      for (int k = 0; k < 7; ++k) ctl->cnt[k] = s_cnt[k];
+      for (int k = 0; k < 5; ++k) ctl->q[k] = s_q[k];
+      ctl->newinf = s_newinf;
+      close_stats(ctl, history, 1);
+      for (int k = 0; k < 7; ++k) ctl->cnt[k] = 0;
+      for (int k = 0; k < 5; ++k) ctl->q[k] = 0;
+      ctl->newinf = 0;
+    }
+    __syncthreads();
+  }
+  if (mine) {
+    hot[i] = h;
+    wealth[i] = w;
+  }
 }
 
 // Bounding box of the resident positions into ctl->bb_* (used once per upload).

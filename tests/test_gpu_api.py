@@ -117,3 +117,34 @@ def test_history_ring_and_error_paths(native_lib):
     small.execute()
     assert abs(sum(float(small.get_statistics('info')[k]) for k in ("Susceptible", "Infected", "Recovered_Immune",
                                                                     "Death")) - 1.0) < 1e-12
+
+
+def test_small_population_kernel_and_tiled_path_agree(native_lib):
+    """Populations of at most 1024 agents run in one resident block; the tiled path (forced here through the
+    sequential schedule's machinery being off, i.e. a 1025-agent population with one far-away bystander) and a mid-run
+    switch of schedule give the same trajectory as the oracle."""
+    from covid19_agentbasedsimulation_b200.abs import Simulation
+    from oracle.sync_oracle import SyncSimulation, synthetic_population
+    n, side = 1024, 60
+    pop, tw = synthetic_population(n, side, side, seed=12, infected=0.05)
+    kw = dict(population_size=n, length=side, height=side, total_wealth=tw, contagion_distance=1.5)
+    small = Simulation(seed=3, **kw)
+    small.set_population_arrays(pop["x"], pop["y"], pop["status"], pop["age"], pop["stratum"], pop["wealth"])
+    orc = SyncSimulation(seed=3, **kw)
+    orc.set_population(pop["x"], pop["y"], pop["status"], pop["age"], pop["stratum"], pop["wealth"])
+    rows = small.run(10)                                     # resident kernel, one launch
+    assert small.device_info()["kernel_launches"] < 20
+    for it in range(10):
+        o = orc.execute()
+        assert rows[it].tolist() == [float(v) for v in o.values()], it
+    assert np.array_equal(small.get_contact_pairs(), orc.last_pairs)   # re-sorts on demand
+    small.schedule = "sequential"                            # tiled path from here on; no chains at this density?
+    orc.schedule = "sequential"
+    for it in range(5):
+        small.execute()
+        o = orc.execute()
+        g = small.get_statistics('all')
+        assert [float(g[k]) for k in o] == [float(v) for v in o.values()], it
+    h = small._download()
+    assert np.array_equal(h["x"], orc.x) and np.array_equal(h["status"], orc.status)
+    assert h["wealth"].tobytes() == orc.wealth.tobytes()
