@@ -266,6 +266,8 @@ class GraphSimulation(Simulation):
     def set_world(self, world, mode=_native.GRAPH_MODE_NONE, sleep=False, handle=None, index=0):
         """Upload a world given as columns (keys of cabs_graph_world).  `handle`/`index`: slot of a shared handle."""
         self._take_seed()
+        for k, v in lower_callbacks(self.callbacks)[3].items():   # on_initialize overrides (graph_abs.py:94), idempotent
+            setattr(self, k, v)
         n, nh, nb = len(world["px"]), len(world["hx"]), len(world["bx"])
         if handle is None:
             if self._ghandle is not None:

@@ -125,9 +125,8 @@ def test_ensemble_handle_equals_individual_runs_and_batch_experiment(native_lib,
     assert table.shape == (7, 100, 14)
     for k, kw in enumerate(kws):
         one = GraphSimulation(seed=100 + k, **kw)
-        if "contagion_rate" in str(kw.get("callbacks", {})):
-            one.contagion_rate = 0.1
-        one.set_world(*worlds[k])
+        one.set_world(*worlds[k])                  # on_initialize overrides (masks: contagion_rate) apply here too
+        assert one.contagion_rate == (0.1 if names[k] in ("scenario8", "scenario10") else 0.9)
         assert np.array_equal(one.run(100), table[k]), names[k]
     assert not np.array_equal(table[0], table[1])
     # batch_experiment drives the same ensemble path and keeps the reference's CSV schema (experiments.py:212)
