@@ -45,6 +45,13 @@ CASES = [  # name, scenario, np seed, draw seed, iterations, overrides
     ("graph_masks", "none", 8, 82, 100, dict(population_size=90, initial_infected_perc=0.1, contagion_distance=.05,
                                              contagion_rate=.1)),
     ("graph_month", "none", 9, 83, 760, dict(population_size=60, initial_infected_perc=0.05)),
+    # many homeless and unemployed persons (own-wealth flows, government payments at the monthly accounting)
+    ("graph_homeless", "none", 10, 84, 760, dict(population_size=60, initial_infected_perc=0.05, homeless_rate=0.6,
+                                                 unemployment_rate=0.5)),
+    # few businesses (the other branch of graph_abs.py:138-143), per-status amplitudes, short infectious window
+    ("graph_fewbusiness", "conditional_lockdown", 11, 85, 200,
+     dict(population_size=80, initial_infected_perc=0.08, total_business=4, incubation_time=2, contagion_time=6,
+          recovering_time=9, business_distance=60)),
 ]
 
 
@@ -66,7 +73,10 @@ def jsonable(o):
 
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
+    only = sys.argv[1:]
     for name, scenario, np_seed, seed, iters, over in CASES:
+        if only and name not in only:
+            continue
         sim, iso = reference_simulation(MODS, scenario, np_seed, **over)
         world = world_from_reference(sim, mode=MODES[scenario], sleep=True, isolated_ids=iso)
         rows = []
@@ -76,7 +86,7 @@ def main():
                 st = sim.get_statistics('all')
                 rows.append([float(st[k]) for k in GRAPH_STAT_KEYS])
         pop = sim.population
-        fix = dict(name=name, scenario=scenario, np_seed=np_seed, seed=seed, iterations=iters, world=world,
+        fix = dict(name=name, scenario=scenario, np_seed=np_seed, seed=seed, iterations=iters, overrides=over, world=world,
                    stat_keys=list(GRAPH_STAT_KEYS), rows=rows,
                    final=dict(px=[int(a.x) for a in pop], py=[int(a.y) for a in pop],
                               status=[STC[a.status.value] for a in pop],

@@ -24,9 +24,7 @@ def _scenario_kwargs(fix):
     else:
         kw.update(getattr(sc, SCEN[fix["scenario"]]))
     kw.pop("name")
-    n_inf = int(np.sum(np.asarray(fix["world"]["infected_time"]) == 5))
-    kw.update(population_size=p["population_size"], contagion_distance=p["contagion_distance"],
-              contagion_rate=p["contagion_rate"], initial_infected_perc=(n_inf + 0.5) / p["population_size"])
+    kw.update(fix["overrides"])
     return kw
 
 
