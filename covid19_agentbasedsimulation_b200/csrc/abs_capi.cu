@@ -718,6 +718,8 @@ static int check_device_error(cabs_sim *sim) {
   CK(cudaStreamSynchronize(sim->stream));
   if (err & kErrDomain) return fail(sim, CABS_ERR_DOMAIN, "population bounding box exceeds the supported 2^28 lattice units");
   if (err & kErrOutOfGrid) return fail(sim, CABS_ERR_DOMAIN, "internal: an agent left the planned cell grid");
+  if (err & kErrPeerTimeout)
+    return fail(sim, CABS_ERR_CUDA, "slab exchange: a neighbour's message did not arrive within 30 s (peer lost or out of step)");
   if (err & kErrExchange)
     return fail(sim, CABS_ERR_CAPACITY, "slab exchange overflow: more migrants / ghosts / residents than the buffers hold");
   return CABS_OK;

@@ -272,9 +272,18 @@ struct SlabDirect {
 };
 enum { FLAG_MIG = 0, FLAG_GHOST = 4, FLAG_ROW = 8 };   // + from_dir * 2 + parity   /   + parity * kMaxRanks + rank
 
-__device__ __forceinline__ void wait_flag(const unsigned char *block, int index, unsigned seq) {
+constexpr uint32_t kErrPeerTimeout = 16u;   // a neighbour's message did not arrive (its process died or fell out of step)
+// `err`: sticky error word; a wait gives up after ~30 s so that a lost peer ends in an error, not in a hung GPU
+__device__ __forceinline__ void wait_flag(const unsigned char *block, int index, unsigned seq, unsigned *err = nullptr) {
   const volatile unsigned *f = reinterpret_cast<const volatile unsigned *>(block) + index;
-  while (*f != seq) __nanosleep(64);
+  const long long t0 = clock64();
+  while (*f != seq) {
+    __nanosleep(64);
+    if (clock64() - t0 > 60000000000ll) {
+      if (err) atomicOr(err, kErrPeerTimeout);
+      break;
+    }
+  }
   __threadfence_system();
 }
 // Last block of a producer kernel (all its threads): copy `local` (header + records) into `remote`, then publish.
@@ -814,8 +823,8 @@ k_count_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ rec
     load_params(P, ctl);
     if (D.enabled) {   // the neighbours' migrants of this build have landed in my block
       const unsigned par = D.seq & 1u;
-      if (D.left) wait_flag(D.self, FLAG_MIG + 0 * 2 + par, D.seq);
-      if (D.right) wait_flag(D.self, FLAG_MIG + 1 * 2 + par, D.seq);
+      if (D.left) wait_flag(D.self, FLAG_MIG + 0 * 2 + par, D.seq, &ctl->err);
+      if (D.right) wait_flag(D.self, FLAG_MIG + 1 * 2 + par, D.seq, &ctl->err);
     }
   }
   __syncthreads();
@@ -966,8 +975,8 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
     load_params(P, ctl);
     if (D.enabled) {   // the neighbours' ghosts of this build have landed in my block
       const unsigned par = D.seq & 1u;
-      if (D.left) wait_flag(D.self, FLAG_GHOST + 0 * 2 + par, D.seq);
-      if (D.right) wait_flag(D.self, FLAG_GHOST + 1 * 2 + par, D.seq);
+      if (D.left) wait_flag(D.self, FLAG_GHOST + 0 * 2 + par, D.seq, &ctl->err);
+      if (D.right) wait_flag(D.self, FLAG_GHOST + 1 * 2 + par, D.seq, &ctl->err);
     }
     s_new = 0;
     s_local = (finish & 8) ? 0u : ctl->n_inf;   // bit 8: ghost sources only (the local ones ran in their own launch)
@@ -1406,7 +1415,7 @@ __global__ void k_slab_close_global(Ctl *ctl, StatRecord *history, int record_st
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
   const unsigned par = D.seq & 1u;
-  for (int g = 0; g < ctl->n_ranks; ++g) wait_flag(D.self, FLAG_ROW + par * kMaxRanks + g, D.seq);
+  for (int g = 0; g < ctl->n_ranks; ++g) wait_flag(D.self, FLAG_ROW + par * kMaxRanks + g, D.seq, &ctl->err);
   close_global(ctl, reinterpret_cast<const long long *>(D.self + L.rows) + (size_t)par * kMaxRanks * kSlabRow, history,
                record_stats);
 }
@@ -1418,7 +1427,7 @@ __global__ void k_slab_close(Ctl *ctl, const long long *rows, const unsigned *ce
   if (D.enabled) {   // every rank's row of this build has landed in my block
     const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
     const unsigned par = D.seq & 1u;
-    for (int g = 0; g < ctl->n_ranks; ++g) wait_flag(D.self, FLAG_ROW + par * kMaxRanks + g, D.seq);
+    for (int g = 0; g < ctl->n_ranks; ++g) wait_flag(D.self, FLAG_ROW + par * kMaxRanks + g, D.seq, &ctl->err);
     rows = reinterpret_cast<const long long *>(D.self + L.rows) + (size_t)par * kMaxRanks * kSlabRow;
   }
   s0->count = 0; s1->count = 0; s2->count = 0; s3->count = 0;  // this slab's send buffers start the next build empty
