@@ -1,0 +1,92 @@
+"""Properties at BASELINE.json's full single-GPU size (10^7 agents, config 3) that need no oracle:
+
+* the result does not depend on the cell grid: two runs of the same population with different cell edges (different
+  physical orders, different scatter patterns) give bit-identical statistics and, sorted by id, identical populations;
+* the four status counts sum to the population every step; the contact-pair hook returns unique ordered pairs whose
+  members really are within the distance;
+* one slab and three slabs agree bit for bit at 3*10^6 agents.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _population(n, side, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, side + 1, size=n, dtype=np.int32)
+    y = rng.integers(0, side + 1, size=n, dtype=np.int32)
+    age = (rng.beta(2, 5, size=n) * 100).astype(np.uint8)
+    stratum = rng.integers(0, 5, size=n, dtype=np.uint8)
+    status = np.zeros(n, dtype=np.uint8)
+    status[:n // 50] = 1
+    status[n // 50:n // 25] = 2
+    wealth = rng.random(n) * 1000.0
+    return x, y, status, age, stratum, wealth
+
+
+def test_grid_independence_at_ten_million_agents(native_lib):
+    from covid19_agentbasedsimulation_b200.abs import Simulation
+    n, side = 10_000_000, 7071
+    x, y, status, age, stratum, wealth = _population(n, side, 1)
+    runs = []
+    for max_cells in (0, 6_000_000):            # default (edge 8) and a finer grid (edge 4)
+        sim = Simulation(seed=5, population_size=n, length=side, height=side, total_wealth=5e9, max_cells=max_cells,
+                         contagion_distance=1.0, contagion_rate=0.9)
+        sim.set_population_arrays(x, y, status, age, stratum, wealth)
+        rows = sim.run(6)
+        info = sim.device_info()
+        runs.append((rows, sim._download(), info["cell_edge"]))
+        assert np.allclose(rows[:, :4].sum(axis=1), 1.0, atol=1e-12)          # S + I + R + D = N
+        del sim
+    assert runs[0][2] != runs[1][2]
+    assert np.array_equal(runs[0][0], runs[1][0])
+    for k in ("x", "y", "status", "severity", "infected_time"):
+        assert np.array_equal(runs[0][1][k], runs[1][1][k]), k
+    assert runs[0][1]["wealth"].tobytes() == runs[1][1]["wealth"].tobytes()
+    assert runs[0][0][-1, 1] > runs[0][0][0, 1]                                # the epidemic does grow
+
+
+def test_contact_pairs_are_sound_at_full_size(native_lib):
+    from covid19_agentbasedsimulation_b200.abs import Simulation
+    n, side = 10_000_000, 7071
+    x, y, status, age, stratum, wealth = _population(n, side, 2)
+    sim = Simulation(seed=1, population_size=n, length=side, height=side, total_wealth=5e9, contagion_distance=1.0)
+    sim.set_population_arrays(x, y, status, age, stratum, wealth)
+    pairs = sim.get_contact_pairs()
+    assert len(pairs) > n // 4                                                 # about 0.5 contacts per agent at this density
+    assert np.all(pairs[:, 0] < pairs[:, 1])
+    key = pairs[:, 0].astype(np.int64) * n + pairs[:, 1]
+    assert len(np.unique(key)) == len(key)
+    dx = x[pairs[:, 0]].astype(np.int64) - x[pairs[:, 1]]
+    dy = y[pairs[:, 0]].astype(np.int64) - y[pairs[:, 1]]
+    assert np.all(dx * dx + dy * dy <= 1)
+    # completeness on a window small enough for brute force
+    sel = np.nonzero((x < 120) & (y < 120))[0]
+    bx, by = x[sel].astype(np.int64), y[sel].astype(np.int64)
+    d2 = (bx[:, None] - bx[None, :]) ** 2 + (by[:, None] - by[None, :]) ** 2
+    ii, jj = np.nonzero(np.triu(d2 <= 1, k=1))
+    want = set(zip(sel[ii].tolist(), sel[jj].tolist()))
+    inside = np.isin(pairs[:, 0], sel) & np.isin(pairs[:, 1], sel)
+    got = set(map(tuple, pairs[inside].tolist()))
+    assert got == {(min(a, b), max(a, b)) for a, b in want}
+
+
+def test_slab_invariance_at_three_million_agents(native_lib):
+    from covid19_agentbasedsimulation_b200.abs import Simulation
+    from covid19_agentbasedsimulation_b200.slab import SlabSimulation
+    n, side = 3_000_000, 3873
+    x, y, status, age, stratum, wealth = _population(n, side, 3)
+    kw = dict(seed=9, population_size=n, length=side, height=side, total_wealth=1.5e9, contagion_distance=1.0,
+              contagion_rate=0.9)
+    one = Simulation(**kw)
+    one.set_population_arrays(x, y, status, age, stratum, wealth)
+    a = one.run(5)
+    many = SlabSimulation(slabs=3, **kw)
+    many.set_population_arrays(x, y, status, age, stratum, wealth)
+    b = many.run(5)
+    assert np.array_equal(a, b)
+    pa, pb = one._download(), many._download()
+    for k in ("x", "y", "status", "infected_time"):
+        assert np.array_equal(pa[k], pb[k]), k
+    assert pa["wealth"].tobytes() == pb["wealth"].tobytes()
