@@ -67,53 +67,37 @@ def wealth_scale_bits(total_wealth):
     return max(0, min(40, s))
 
 
+# constructor keyword -> default (abs.py:17-49); values the reference's scenario dictionaries may pass
+_REFERENCE_KWARGS = (
+    ("population_size", 20),          # number of agents
+    ("length", 10), ("height", 10),   # extent of the shared environment
+    ("initial_infected_perc", 0.05), ("initial_immune_perc", 0.05),
+    ("contagion_distance", 1.),       # contact = distance at most this
+    ("contagion_rate", 0.9),          # probability of contagion per contact
+    ("critical_limit", 0.6),          # fraction of the population the health system can treat
+    ("minimum_income", 1.0), ("minimum_expense", 1.0),   # daily units of the poorest quintile
+    ("total_wealth", 10 ** 4),
+)
+# keyword -> default of what this implementation adds (nothing the reference passes is reinterpreted)
+_EXTRA_KWARGS = (
+    ("seed", None),                   # Philox seed; None = drawn from np.random at initialize(), so np.random.seed() governs
+    ("device", 0),                    # CUDA device ordinal
+    ("placement", "reference"),       # "reference": abs.py:97-114 from np.random in the reference's order; "uniform": x, y ~ U{0..L}
+    ("schedule", "synchronous"),      # or "sequential": the reference's pair order with in-step chains (abs.py:261-265), exact, slower
+    ("max_cells", 0), ("history_capacity", 4096),
+)
+
+
 class Simulation(object):
     def __init__(self, **kwargs):
-        self.population_size = kwargs.get("population_size", 20)
-        '''The number of agents'''
-        self.length = kwargs.get("length", 10)
-        '''The length of the shared environment'''
-        self.height = kwargs.get("height", 10)
-        '''The height of the shared environment'''
-        self.initial_infected_perc = kwargs.get("initial_infected_perc", 0.05)
-        '''The initial percent of population which starts the simulation with the status Infected'''
-        self.initial_immune_perc = kwargs.get("initial_immune_perc", 0.05)
-        '''The initial percent of population which starts the simulation with the status Immune'''
-        self.contagion_distance = kwargs.get("contagion_distance", 1.)
-        '''The minimal distance considered as contact (or exposition)'''
-        self.contagion_rate = kwargs.get("contagion_rate", 0.9)
-        '''The probability of contagion given two agents were in contact'''
-        self.critical_limit = kwargs.get("critical_limit", 0.6)
-        '''The percent of population which the Health System can afford'''
-        self.amplitudes = kwargs.get('amplitudes',
-                                     {Status.Susceptible: 5,
-                                      Status.Recovered_Immune: 5,
-                                      Status.Infected: 5})
-        '''A dictionary with the average mobility of agents inside the shared environment for each status'''
-        self.minimum_income = kwargs.get("minimum_income", 1.0)
-        '''The base (or minimum) daily income, related to the most poor wealth quintile'''
-        self.minimum_expense = kwargs.get("minimum_expense", 1.0)
-        '''The base (or minimum) daily expense, related to the most poor wealth quintile'''
-        self.statistics = None
-        '''A dictionary with the population statistics for the current iteration'''
-        self.triggers_simulation = kwargs.get("triggers_simulation", [])
-        "A dictionary with conditional changes in the Simulation attributes"
-        self.triggers_population = kwargs.get("triggers_population", [])
-        "A dictionary with conditional changes in the Agent attributes"
-        self.total_wealth = kwargs.get("total_wealth", 10 ** 4)
-
-        # ---- new, optional (SURVEY.md 8b): nothing the reference passes is reinterpreted
-        self.seed = kwargs.get("seed", None)
-        '''Philox seed; None = drawn from np.random at initialize(), so np.random.seed() governs the run'''
-        self.device = kwargs.get("device", 0)
-        '''CUDA device ordinal'''
-        self.placement = kwargs.get("placement", "reference")
-        '''"reference": abs.py:97-114 consumed from np.random in the reference's order; "uniform": x,y ~ U{0..L}'''
-        self.schedule = kwargs.get("schedule", "synchronous")
-        '''"synchronous": agents infected in a step start transmitting in the next (one data-parallel pass);
-        "sequential": the reference's pair order with in-step chains (abs.py:261-265), exact, slower'''
-        self.max_cells = kwargs.get("max_cells", 0)
-        self.history_capacity = kwargs.get("history_capacity", 4096)
+        for name, default in _REFERENCE_KWARGS + _EXTRA_KWARGS:
+            setattr(self, name, kwargs.get(name, default))
+        # mobility (standard deviation of a move) by status; Death never moves
+        self.amplitudes = kwargs.get('amplitudes', {st: 5 for st in (Status.Susceptible, Status.Recovered_Immune,
+                                                                     Status.Infected)})
+        self.triggers_simulation = kwargs.get("triggers_simulation", [])   # conditional rewrites of simulation attributes
+        self.triggers_population = kwargs.get("triggers_population", [])   # conditional rewrites of agent attributes
+        self.statistics = None        # memo of get_statistics(), dropped at the end of execute()
 
         self._handle = None
         self._pushed = None          # last parameter tuple sent to the device

@@ -1,67 +1,48 @@
 """Agent record and its enumerations -- host-side mirror of covid_abs/agents.py.
 
-Same names, values and declaration order as the reference (agents.py:9-37): the declaration order of
-`Status` defines the key order of `get_statistics` (abs.py:300-302).  On the device the population is
-held as structure of arrays; `Agent` objects are materialised lazily by `Simulation.get_population`.
+Names, values and declaration order are the reference's (agents.py:9-37): scenario dictionaries are keyed by
+`Status` members, statistics keys are the member names, and the declaration order of `Status` is the key order of
+`get_statistics` (abs.py:300-302).  On the device a population is structure of arrays; `Agent` objects are only
+materialised on request (`Simulation.get_population`).
 """
 from enum import Enum
 import uuid
 
+# member name -> one-letter value, in the reference's declaration order
+Status = Enum('Status', [('Susceptible', 's'), ('Infected', 'i'), ('Recovered_Immune', 'c'), ('Death', 'm')])
+Status.__doc__ = "Health status of an agent, SIR plus death (agents.py:9-16)."
+InfectionSeverity = Enum('InfectionSeverity', [('Exposed', 'e'), ('Asymptomatic', 'a'), ('Hospitalization', 'h'),
+                                               ('Severe', 'g')])
+InfectionSeverity.__doc__ = "Severity of an infection (agents.py:19-26)."
+AgentType = Enum('AgentType', [('Person', 'p'), ('Business', 'b'), ('House', 'h'), ('Government', 'g'),
+                               ('Healthcare', 'c')])
+AgentType.__doc__ = "Kind of node in the routine model (agents.py:29-37)."
 
-class Status(Enum):
-    """Agent status, following the SIR model (agents.py:9-16)."""
-    Susceptible = 's'
-    Infected = 'i'
-    Recovered_Immune = 'c'
-    Death = 'm'
+# device encodings (include/covidabs.h): position in the declaration order
+STATUS_LIST = list(Status)
+STATUS_CODE = {member: code for code, member in enumerate(STATUS_LIST)}
+SEVERITY_LIST = list(InfectionSeverity)
+SEVERITY_CODE = {member: code for code, member in enumerate(SEVERITY_LIST)}
 
-
-class InfectionSeverity(Enum):
-    """Severity of the Infected agents (agents.py:19-26)."""
-    Exposed = 'e'
-    Asymptomatic = 'a'
-    Hospitalization = 'h'
-    Severe = 'g'
-
-
-class AgentType(Enum):
-    """Type of the agent / node of the graph (agents.py:29-37)."""
-    Person = 'p'
-    Business = 'b'
-    House = 'h'
-    Government = 'g'
-    Healthcare = 'c'
-
-
-# device encodings (include/covidabs.h)
-STATUS_LIST = [Status.Susceptible, Status.Infected, Status.Recovered_Immune, Status.Death]
-STATUS_CODE = {s: i for i, s in enumerate(STATUS_LIST)}
-SEVERITY_LIST = [InfectionSeverity.Exposed, InfectionSeverity.Asymptomatic, InfectionSeverity.Hospitalization,
-                 InfectionSeverity.Severe]
-SEVERITY_CODE = {s: i for i, s in enumerate(SEVERITY_LIST)}
+# attribute -> default of an Agent (agents.py:44-64)
+_AGENT_FIELDS = (('x', 0), ('y', 0), ('status', Status.Susceptible), ('infected_status', InfectionSeverity.Asymptomatic),
+                 ('infected_time', 0), ('age', 0), ('social_stratum', 0), ('wealth', 0.0), ('environment', None))
 
 
 class Agent(object):
-    """Container of an agent's attributes (agents.py:40-64)."""
+    """Attribute bag of one agent (agents.py:40-64).  `id` defaults to a random 128-bit integer like the reference's;
+    agents materialised from the device carry their index in the population list instead."""
 
     def __init__(self, **kwargs):
-        self.id = kwargs.get('id', int(uuid.uuid4()))
-        self.x = kwargs.get('x', 0)
-        self.y = kwargs.get('y', 0)
-        self.status = kwargs.get('status', Status.Susceptible)
-        self.infected_status = kwargs.get('infected_status', InfectionSeverity.Asymptomatic)
-        self.infected_time = kwargs.get('infected_time', 0)
-        self.age = kwargs.get('age', 0)
-        self.social_stratum = kwargs.get('social_stratum', 0)
-        self.wealth = kwargs.get('wealth', 0.0)
+        self.id = kwargs['id'] if 'id' in kwargs else int(uuid.uuid4())
+        for name, default in _AGENT_FIELDS:
+            setattr(self, name, kwargs.get(name, default))
         self.type = AgentType.Person
-        self.environment = kwargs.get('environment', None)
 
     def get_description(self):
-        """Simplified description of the health status (agents.py:66-75)."""
-        if self.status == Status.Infected:
-            return "{}({})".format(self.status.name, self.infected_status.name)
-        return self.status.name
+        """Status name, with the severity appended for the Infected (agents.py:66-75)."""
+        name = self.status.name
+        return "{}({})".format(name, self.infected_status.name) if self.status == Status.Infected else name
 
     def __str__(self):
         return str(self.status.name)

@@ -10,16 +10,9 @@ from covid19_agentbasedsimulation_b200.abs import Simulation
 
 
 def batch_experiment(experiments, iterations, file, simulation_type=Simulation, **kwargs):
-    """
-    Execute several simulations with the same parameters and store the average statistics by iteration
-
-    :param experiments: number of simulations to be performed
-    :param iterations: number of iterations on each simulation
-    :param file: filename to store the consolidated statistics
-    :param simulation_type: Simulation or any class with initialize/execute/get_statistics
-    :param kwargs: the parameters of the simulation
-    :return: a Pandas Dataframe with the consolidated statistics by iteration
-    """
+    """`experiments` independent runs of `simulation_type(**kwargs)`, `iterations` steps each; per iteration and
+    metric the minimum, mean, population standard deviation and maximum over the runs are written to `file` as CSV and
+    returned as a DataFrame (experiments.py:167-216).  `verbose='experiments'|'iterations'` prints progress."""
     verbose = kwargs.get('verbose', None)
     columns = None
     runs = []  # one [iterations_done, n_metrics] array per experiment

@@ -69,33 +69,27 @@ def lower_callbacks(callbacks):
     return mode, sleep, rate, overrides
 
 
+# constructor keyword -> default of what GraphSimulation adds to Simulation (graph_abs.py:15-32)
+_GRAPH_KWARGS = (
+    ("total_population", 0), ("total_business", 10), ("business_distance", 10),
+    ("homeless_rate", 0.01), ("unemployment_rate", 0.09), ("homemates_avg", 3), ("homemates_std", 1),
+    ("public_gdp_share", 0.1), ("business_gdp_share", 0.5),
+    ("incubation_time", 5), ("contagion_time", 10), ("recovering_time", 20),
+    ("money_bits", None),             # new, optional: fractional bits of the fixed-point accounts
+)
+
+
 class GraphSimulation(Simulation):
     def __init__(self, **kwargs):
         super(GraphSimulation, self).__init__(**kwargs)
-        self.total_population = kwargs.get('total_population', 0)
-        self.total_business = kwargs.get('total_business', 10)
-        self.business_distance = kwargs.get('business_distance', 10)
-        self.government = None
-        self.business = []
-        self.houses = []
-        self.healthcare = None
-        self.homeless_rate = kwargs.get("homeless_rate", 0.01)
-        self.unemployment_rate = kwargs.get("unemployment_rate", 0.09)
-        self.homemates_avg = kwargs.get("homemates_avg", 3)
-        self.homemates_std = kwargs.get("homemates_std", 1)
-        self.iteration = -1
+        for name, default in _GRAPH_KWARGS:
+            setattr(self, name, kwargs.get(name, default))
         self.callbacks = kwargs.get('callbacks', {})
-        self.public_gdp_share = kwargs.get('public_gdp_share', 0.1)
-        self.business_gdp_share = kwargs.get('business_gdp_share', 0.5)
-        self.incubation_time = kwargs.get('incubation_time', 5)
-        self.contagion_time = kwargs.get('contagion_time', 10)
-        self.recovering_time = kwargs.get('recovering_time', 20)
-        # new, optional
-        self.money_bits = kwargs.get('money_bits', None)
+        self.iteration = -1           # the first execute() is iteration 0 (graph_abs.py:25,192)
         self._ghandle = None
-        self._gsim = 0              # index of this simulation inside the handle (ensembles share one handle)
-        self._world = None          # host copy of the current world (dict of columns), refreshed lazily
-        self._stats_iteration = None
+        self._gsim = 0                # index of this simulation inside the handle (ensembles share one handle)
+        self._world = None            # host copy of the current world (dict of columns), refreshed lazily
+        self._entities = None         # (persons, houses, businesses, government, healthcare) materialised on request
 
     def register_callback(self, event, action):
         self.callbacks[event] = action

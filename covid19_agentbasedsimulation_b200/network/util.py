@@ -1,49 +1,58 @@
-"""Iteration -> clock predicates of the routine model -- mirror of covid_abs/network/util.py:3-63.
+"""Clock of the routine model: which hour, day and month an iteration falls in.
 
-One iteration is one hour; iteration 0 is hour 0 of day 1 of the week (a non-working day) and of the month.
-The device evaluates the same predicates inside the step kernel (csrc/graph_kernels.cuh).
+Same function names and results as covid_abs/network/util.py:3-63 (one iteration = one hour).  Quirks that shape
+results and are therefore kept: iteration 0 is hour 0 of day 1 of the week, days 1 and 7 are the non-working ones,
+so a run starts on a day off; hour 16 of a working day matches none of bed/work/lunch/free, so nobody moves then;
+hour 12 is both work time and lunch time and lunch wins in the step (graph_abs.py:213-220).  The device evaluates
+the same table inside the step kernel (csrc/graph_kernels.cuh).
 """
+HOURS_PER_DAY, DAYS_PER_WEEK, DAYS_PER_MONTH = 24, 7, 30
+_WINDOWS = {'bed': (0, 8), 'work': (8, 16), 'free': (17, 24)}   # [start, end) hours of the day
+
+
+def _hour(iteration):
+    return iteration % HOURS_PER_DAY
 
 
 def number_of_days(iteration):
-    return iteration // 24
+    return iteration // HOURS_PER_DAY
 
 
 def check_time(iteration, start, end):
-    return start <= iteration % 24 < end
+    return start <= _hour(iteration) < end
 
 
 def new_day(iteration):
-    return iteration % 24 == 0
+    return _hour(iteration) == 0
 
 
 def day_of_week(iteration):
-    return (iteration // 24) % 7 + 1
+    return number_of_days(iteration) % DAYS_PER_WEEK + 1
 
 
 def work_day(iteration):
-    return day_of_week(iteration) not in [1, 7]
+    return 1 < day_of_week(iteration) < DAYS_PER_WEEK
 
 
 def day_of_month(iteration):
-    return (iteration // 24) % 30 + 1
+    return number_of_days(iteration) % DAYS_PER_MONTH + 1
 
 
 def new_month(iteration):
-    return day_of_month(iteration) == 1 and iteration % 24 == 0
+    return new_day(iteration) and day_of_month(iteration) == 1
 
 
 def bed_time(iteration):
-    return check_time(iteration, 0, 8)
+    return check_time(iteration, *_WINDOWS['bed'])
 
 
 def work_time(iteration):
-    return check_time(iteration, 8, 16)
+    return check_time(iteration, *_WINDOWS['work'])
 
 
 def lunch_time(iteration):
-    return iteration % 24 == 12
+    return _hour(iteration) == 12
 
 
 def free_time(iteration):
-    return check_time(iteration, 17, 24)
+    return check_time(iteration, *_WINDOWS['free'])
