@@ -184,8 +184,8 @@ __device__ __forceinline__ void load_params(StepParams &P, const Ctl *ctl, bool 
   P.k0 = ctl->k0; P.k1 = ctl->k1; P.step = ctl->step; P.n = ctl->n;
 }
 
-// Simulation.move (abs.py:156-189): displacement of this step.  `w` = stream-0 words.
-__device__ __forceinline__ void draw_displacement(const StepParams &P, uint32_t attr, const uint4 &w, int &ix,
+// Simulation.move (abs.py:156-189): displacement of this step.  `w` = the two words of the move stream.
+__device__ __forceinline__ void draw_displacement(const StepParams &P, uint32_t attr, const uint2 &w, int &ix,
                                                   int &iy) {
   const uint32_t st = attr_status(attr), sev = attr_severity(attr);
   const bool mobile = !(st == ST_D || (st == ST_I && (sev == SEV_H || sev == SEV_G)));  // abs.py:164-167
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const
     uint32_t d = 0;
     if (kAdvance) {
       const uint32_t a = attr_normalize(h.z);
-      const uint4 w = philox4x32_10(h.w, P.step, kStreamAgent, 0u, P.k0, P.k1);
+      const uint2 w = agent_draw(h.w, P.step, kStreamMove, P.k0, P.k1);
       int ix, iy;
       draw_displacement(P, a, w, ix, iy);
       apply_displacement(P, nx, ny, ix, iy, nx, ny);
@@ -524,13 +524,13 @@ __device__ __forceinline__ void advance_agent(const StepParams &P, uint32_t aid,
   uint32_t st = attr_status(a), sev = attr_severity(a), time = attr_time(a);
   const uint32_t stratum = attr_stratum(a), age = attr_age(a);
   const bool mobile = !(st == ST_D || (st == ST_I && (sev == SEV_H || sev == SEV_G)));  // abs.py:164-167
-  const uint4 r0 = philox4x32_10(aid, P.step, kStreamAgent, 0u, P.k0, P.k1);
+  const uint2 r0 = agent_draw(aid, P.step, kStreamEconomy, P.k0, P.k1);
   const double bi = P.bi[min(stratum, 4u)];
   if (mobile) {
     // abs.py:187-189: wealth += sqrt(ix^2+iy^2) * rand * minimum_expense * basic_income[stratum]
     const int d2 = ix * ix + iy * iy;
     const double dist = d2 < kSqrtTable ? __ldg(&sqrt_tab[d2]) : __dsqrt_rn((double)d2);
-    const double inc = __dmul_rn(__dmul_rn(__dmul_rn(dist, u01(r0.z)), P.min_expense), bi);
+    const double inc = __dmul_rn(__dmul_rn(__dmul_rn(dist, u01(r0.x)), P.min_expense), bi);
     w = __dadd_rn(w, inc);
   }
   // abs.py:191-230
@@ -539,7 +539,7 @@ __device__ __forceinline__ void advance_agent(const StepParams &P, uint32_t aid,
     if (st == ST_I) {
       time += 1;
       const uint32_t idx = min(age > 10u ? age / 10u - 1u : 0u, 8u);  // abs.py:204
-      const long long w_sub = (long long)r0.w;
+      const long long w_sub = (long long)r0.y;
       if (sev == SEV_A) {
         if (w_sub < P.thr_hosp[idx]) sev = SEV_H;  // age_hospitalization_probs[idx] > u (abs.py:209)
       } else if (sev == SEV_H) {
@@ -551,7 +551,7 @@ __device__ __forceinline__ void advance_agent(const StepParams &P, uint32_t aid,
           }
         }
       }
-      const uint4 r1 = philox4x32_10(aid, P.step, kStreamAgent2, 0u, P.k0, P.k1);
+      const uint2 r1 = agent_draw(aid, P.step, kStreamDeath, P.k0, P.k1);
       if ((long long)r1.x < P.thr_death[idx]) {    // age_death_probs[idx] > u (abs.py:219-223)
         st = ST_D;
         sev = SEV_A;
@@ -1493,7 +1493,7 @@ k_small_run(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, double *__restrict__
     int nx = (int)h.x, ny = (int)h.y;
     if (mine) {
       // Simulation.move + Simulation.update (abs.py:156-230)
-      const uint4 r = philox4x32_10(h.w, P.step, kStreamAgent, 0u, P.k0, P.k1);
+      const uint2 r = agent_draw(h.w, P.step, kStreamMove, P.k0, P.k1);
       int ix, iy;
       draw_displacement(P, a, r, ix, iy);
       apply_displacement(P, nx, ny, ix, iy, nx, ny);

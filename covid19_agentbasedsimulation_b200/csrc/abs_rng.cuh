@@ -18,9 +18,15 @@ constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
 constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 
-constexpr uint32_t kStreamAgent = 0;    // w0,w1: move normals, w2: income uniform, w3: severity test
-constexpr uint32_t kStreamAgent2 = 1;   // w0: death test
-constexpr uint32_t kStreamContact = 2;  // ctr = (lower id, step, 2, higher id); w0: contagion test
+// Per-agent draws need two words at a time, so they use the two-word variant (Philox2x32-10: half the multiplies
+// of 4x32 per call); the counter is (agent id, step ^ seed_hi) and the key is seed_lo mixed with the stream:
+constexpr uint32_t kStreamMove = 0;     // r0, r1: the two move normals            (abs.py:174-175)
+constexpr uint32_t kStreamEconomy = 1;  // r0: income uniform, r1: severity test   (abs.py:188, 206)
+constexpr uint32_t kStreamDeath = 2;    // r0: death test                          (abs.py:219)
+// Pair draws stay on Philox4x32-10: ctr = (lower id, step, 2, higher id), key = seed; w0: contagion test (abs.py:150)
+constexpr uint32_t kStreamContact = 2;
+constexpr uint32_t kPhilox2M = 0xD256D193u;
+constexpr uint32_t kStreamMix = 0x85EBCA6Bu;   // odd, unrelated to the round-key increment
 
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                                uint32_t k1) {
@@ -36,6 +42,21 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     k1 += kPhiloxW1;
   }
   return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi = __umulhi(kPhilox2M, c0), lo = kPhilox2M * c0;
+    c0 = hi ^ k ^ c1;
+    c1 = lo;
+    k += kPhiloxW0;
+  }
+  return make_uint2(c0, c1);
+}
+// the two words of (agent, step, stream) under seed = (k0, k1)
+__device__ __forceinline__ uint2 agent_draw(uint32_t id, uint32_t step, uint32_t stream, uint32_t k0, uint32_t k1) {
+  return philox2x32_10(id, step ^ k1, k0 ^ (stream * kStreamMix));
 }
 
 // 32 random bits -> double in (0,1): (w + 0.5) * 2^-32 (exact in binary64).

@@ -8,12 +8,12 @@ consumed in parallel, so stochastic parity with the reference is statistical;
 bit parity is between this file and the CUDA kernels.
 
 Counter / key layout (shared contract with csrc/abs_rng.cuh):
-    key = (seed & 0xffffffff, seed >> 32)
-    ctr = (c0, step, stream, c3)
-      stream 0, c0 = agent id, c3 = 0: w0,w1 -> the two move normals, w2 -> income
-                                       uniform, w3 -> severity-test uniform
-      stream 1, c0 = agent id, c3 = 0: w0 -> death-test uniform
-      stream 2, c0 = lower id, c3 = higher id of a contact pair: w0 -> contagion test
+    (k0, k1) = (seed & 0xffffffff, seed >> 32)
+    per-agent draws: Philox2x32-10, ctr = (agent id, step ^ k1), key = k0 ^ (stream * 0x85EBCA6B)
+      stream 0: r0, r1 -> the two move normals
+      stream 1: r0 -> income uniform, r1 -> severity-test uniform
+      stream 2: r0 -> death-test uniform
+    pair draws: Philox4x32-10, ctr = (lower id, step, 2, higher id), key = (k0, k1): w0 -> contagion test
 
 Every floating-point operation below is a single IEEE-754 correctly rounded
 add / mul / div / sqrt (no fused multiply-add), so the same sequence of
@@ -27,9 +27,12 @@ W0 = 0x9E3779B9
 W1 = 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
 
-STREAM_AGENT = 0
-STREAM_AGENT2 = 1
+STREAM_MOVE = 0
+STREAM_ECONOMY = 1
+STREAM_DEATH = 2
 STREAM_CONTACT = 2
+M2 = np.uint64(0xD256D193)
+STREAM_MIX = 0x85EBCA6B
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -46,6 +49,18 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
         k0 = (k0 + W0) & 0xFFFFFFFF
         k1 = (k1 + W1) & 0xFFFFFFFF
     return (c0.astype(np.uint32), c1.astype(np.uint32), c2.astype(np.uint32), c3.astype(np.uint32))
+
+
+def philox2x32_10(c0, c1, k):
+    """Vectorised Philox2x32-10 (Random123 `philox2x32_R(10, ...)`).  Returns two uint32 arrays."""
+    c0, c1 = [np.asarray(c, dtype=np.uint64) & MASK for c in np.broadcast_arrays(c0, c1)]
+    k = int(k) & 0xFFFFFFFF
+    for _ in range(10):
+        prod = M2 * c0
+        hi, lo = prod >> np.uint64(32), prod & MASK
+        c0, c1 = (hi ^ np.uint64(k) ^ c1), lo
+        k = (k + W0) & 0xFFFFFFFF
+    return c0.astype(np.uint32), c1.astype(np.uint32)
 
 
 def split_seed(seed):
@@ -125,9 +140,10 @@ def normal_pair(w0, w1):
     return z0, z1
 
 
-def agent_draws(seed, ids, step, stream=STREAM_AGENT):
+def agent_draws(seed, ids, step, stream=STREAM_MOVE):
+    """The two words of (agent, step, stream)."""
     k0, k1 = split_seed(seed)
-    return philox4x32_10(ids, step, stream, 0, k0, k1)
+    return philox2x32_10(ids, (int(step) ^ k1) & 0xFFFFFFFF, k0 ^ ((stream * STREAM_MIX) & 0xFFFFFFFF))
 
 
 def pair_draws(seed, lo_ids, hi_ids, step):

@@ -4,11 +4,11 @@ Same idea as oracle/graph_shim.py: while the reference's `execute()` runs, `np.r
 replaced by functions that look at the calling frame (move / update of which agent, contact of which pair) and
 return the draw the counter-based map of oracle/philox.py assigns to that site:
 
-    move    abs.py:174-175  np.random.randn(1) x2 -> the Box-Muller pair of stream 0 words 0,1 (float32, so that the
-                            product with the amplitude is the binary32 product the device computes)
-            abs.py:188      np.random.rand(1)     -> u01(stream 0 word 2)
-    update  abs.py:206,219  np.random.random() x2 -> u01(stream 0 word 3), u01(stream 1 word 0)
-    contact abs.py:150      np.random.random()    -> u01(stream 2 word 0 of the unordered pair)
+    move    abs.py:174-175  np.random.randn(1) x2 -> the Box-Muller pair of the move stream's two words (float32, so
+                            that the product with the amplitude is the binary32 product the device computes)
+            abs.py:188      np.random.rand(1)     -> u01(economy stream word 0)
+    update  abs.py:206,219  np.random.random() x2 -> u01(economy stream word 1), u01(death stream word 0)
+    contact abs.py:150      np.random.random()    -> u01(pair stream word 0 of the unordered pair)
 
 With it the reference -- its own sequential loop, including in-step infection chains -- must produce the trajectory
 of `SyncSimulation(schedule="sequential")`, and the GPU's sequential schedule must equal both.
@@ -48,7 +48,7 @@ class KeyedSimulationRandom(object):
         f = sys._getframe(1)
         assert f.f_code.co_name == "move"
         a = self._agent(f)
-        w = philox.agent_draws(self.seed, a, self.step, philox.STREAM_AGENT)
+        w = philox.agent_draws(self.seed, a, self.step, philox.STREAM_MOVE)
         z = philox.normal_pair(w[0], w[1])
         k = self.calls.get(("n", a), 0)
         self.calls[("n", a)] = k + 1
@@ -57,8 +57,8 @@ class KeyedSimulationRandom(object):
     def rand(self, n):
         f = sys._getframe(1)
         assert f.f_code.co_name == "move"
-        w = philox.agent_draws(self.seed, self._agent(f), self.step, philox.STREAM_AGENT)
-        return np.array([philox.u01(w[2])], dtype=np.float64)
+        w = philox.agent_draws(self.seed, self._agent(f), self.step, philox.STREAM_ECONOMY)
+        return np.array([philox.u01(w[0])], dtype=np.float64)
 
     def random(self):
         f = sys._getframe(1)
@@ -68,8 +68,8 @@ class KeyedSimulationRandom(object):
             k = self.calls.get(("u", a), 0)
             self.calls[("u", a)] = k + 1
             if k == 0:
-                return float(philox.u01(philox.agent_draws(self.seed, a, self.step, philox.STREAM_AGENT)[3]))
-            return float(philox.u01(philox.agent_draws(self.seed, a, self.step, philox.STREAM_AGENT2)[0]))
+                return float(philox.u01(philox.agent_draws(self.seed, a, self.step, philox.STREAM_ECONOMY)[1]))
+            return float(philox.u01(philox.agent_draws(self.seed, a, self.step, philox.STREAM_DEATH)[0]))
         if name == "contact":
             a, b = self.index[id(f.f_locals["agent1"])], self.index[id(f.f_locals["agent2"])]
             lo, hi = min(a, b), max(a, b)

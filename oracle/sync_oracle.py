@@ -133,8 +133,9 @@ class SyncSimulation(object):
         n = self.population_size
         ids = np.arange(n, dtype=np.uint64)
         step = self.step_index
-        w0, w1, w2, w3 = philox.agent_draws(self.seed, ids, step, philox.STREAM_AGENT)
-        v0, _, _, _ = philox.agent_draws(self.seed, ids, step, philox.STREAM_AGENT2)
+        w0, w1 = philox.agent_draws(self.seed, ids, step, philox.STREAM_MOVE)
+        w2, w3 = philox.agent_draws(self.seed, ids, step, philox.STREAM_ECONOMY)
+        v0, _ = philox.agent_draws(self.seed, ids, step, philox.STREAM_DEATH)
         st, sev = self.status, self.severity
         dead = st == D
         inf = st == I

@@ -1,4 +1,5 @@
-"""Known-answer tests of the oracle's Philox4x32-10 (Random123 kat_vectors) and of the draw transforms."""
+"""Known-answer tests of the oracle's Philox4x32-10 / Philox2x32-10 (Random123 kat_vectors) and of the draw
+transforms."""
 import numpy as np
 
 from oracle import philox
@@ -14,12 +15,26 @@ def test_random123_kat_vectors():
         assert tuple(int(v) for v in got) == out
 
 
-def test_vectorised_matches_scalar():
+def test_random123_kat_vectors_2x32():
+    kat = [((0, 0), 0, (0xff1dae59, 0x6cd10df2)),
+           ((0xffffffff, 0xffffffff), 0xffffffff, (0x2c3f628b, 0xab4fd7ad)),
+           ((0x243f6a88, 0x85a308d3), 0x13198a2e, (0xdd7ce038, 0xf62a4c12))]
+    for ctr, key, out in kat:
+        got = philox.philox2x32_10(*ctr, key)
+        assert tuple(int(v) for v in got) == out
+
+
+def test_agent_draw_layout_and_vectorisation():
+    """ctr = (agent id, step ^ seed_hi), key = seed_lo ^ (stream * 0x85EBCA6B); streams are unrelated words."""
     ids = np.arange(100, dtype=np.uint64)
-    w = philox.agent_draws(0x123456789ABCDEF, ids, 7, 0)
-    for k in (0, 13, 99):
-        s = philox.philox4x32_10(k, 7, 0, 0, 0x89ABCDEF, 0x1234567)
-        assert [int(a[k]) for a in w] == [int(v) for v in s]
+    seed = 0x123456789ABCDEF
+    for stream in (0, 1, 2):
+        w = philox.agent_draws(seed, ids, 7, stream)
+        for k in (0, 13, 99):
+            s = philox.philox2x32_10(k, 7 ^ 0x1234567, 0x89ABCDEF ^ ((stream * 0x85EBCA6B) & 0xFFFFFFFF))
+            assert [int(a[k]) for a in w] == [int(v) for v in s]
+    a, b = philox.agent_draws(seed, ids, 7, 0), philox.agent_draws(seed, ids, 7, 1)
+    assert not np.array_equal(a[0], b[0]) and not np.array_equal(a[0], philox.agent_draws(seed, ids, 8, 0)[0])
 
 
 def test_u01_open_interval_and_exact():
