@@ -59,6 +59,10 @@ struct cabs_sim {
   bool have_params = false;
   bool cells_dirty = true;      // cell_start does not describe the current positions / distance
   bool unsorted = false;        // the resident small-population kernel left the records out of cell order
+  // two consecutive steps (one ping + one pong of the record / table copies) captured as a CUDA graph: a run of
+  // steps is replayed without per-kernel launch gaps.  Valid while `cur == graph_cur`, `tab == graph_tab`.
+  cudaGraphExec_t step_graph = nullptr;
+  int graph_cur = -1, graph_tab = -1;
   uint64_t n = 0, step = 0, launches = 0;
   cudaEvent_t events[CABS_NUM_EVENTS] = {};
   // per-kernel profiling: events[i] is recorded before launch i of the current batch, names[i] its kernel
@@ -129,6 +133,7 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
   cudaFree(sim->dev_blocks);
   cudaFree(sim->ctl); cudaFree(sim->history);
   cudaFree(sim->stage); cudaFree(sim->stage_id); cudaFree(sim->pairs); cudaFree(sim->pair_count);
+  if (sim->step_graph) cudaGraphExecDestroy(sim->step_graph);
   for (cudaEvent_t e : sim->events) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
   if (sim->stream) cudaStreamDestroy(sim->stream);
@@ -698,7 +703,38 @@ extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
     const int rc = rebuild_static(sim);
     if (rc != CABS_OK) return rc;
   }
-  for (int s = 0; s < nsteps; ++s) {
+  int s = 0;
+  const bool sequential = sim->params.schedule == CABS_SEQUENTIAL;
+  if (!sim->profiling && !sequential && nsteps >= 4) {
+    // pairs of steps through the captured graph (the kernels take every changing quantity from Ctl, so the same
+    // eight launches are valid for any pair of steps that starts from the same ping/pong phase)
+    if (sim->step_graph && (sim->graph_cur != sim->cur || sim->graph_tab != sim->tab)) {
+      cudaGraphExecDestroy(sim->step_graph);
+      sim->step_graph = nullptr;
+    }
+    if (!sim->step_graph) {
+      cudaGraph_t graph = nullptr;
+      const int cur0 = sim->cur, tab0 = sim->tab;
+      const uint64_t launches0 = sim->launches;
+      CK(cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal));
+      enqueue_build<true>(sim);
+      enqueue_build<true>(sim);
+      CK(cudaStreamEndCapture(sim->stream, &graph));
+      sim->cur = cur0;              // capturing enqueued nothing: restore the host-side phase
+      sim->tab = tab0;
+      sim->launches = launches0;
+      CK(cudaGraphInstantiate(&sim->step_graph, graph, 0));
+      CK(cudaGraphDestroy(graph));
+      sim->graph_cur = cur0;
+      sim->graph_tab = tab0;
+    }
+    for (; s + 2 <= nsteps; s += 2) {
+      CK(cudaGraphLaunch(sim->step_graph, sim->stream));
+      sim->launches += 8;
+      sim->step += 2;
+    }
+  }
+  for (; s < nsteps; ++s) {
     enqueue_build<true>(sim);
     sim->step++;
   }
