@@ -237,12 +237,15 @@ def run_ours(args, rank, world, local_rank):
             sim._build(advance=False)
 
         def step(k):
-            for _ in range(k):
-                sim._build(advance=True)
+            if args.transport == "p2p":
+                h.slab_run(k)
+            else:
+                for _ in range(k):
+                    sim._build(advance=True)
 
     def timed(fn):
         """Device time of fn() on the stream the library runs on, ms."""
-        if world == 1:
+        if world == 1 or args.transport == "p2p":   # the library's own stream
             h.event_record(0)
             fn()
             h.event_record(1)

@@ -23,7 +23,7 @@ EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params",
             "cabs_upload", "cabs_download", "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_history",
             "cabs_contact_pairs", "cabs_get_info", "cabs_event_record", "cabs_event_elapsed_ms",
             "cabs_profile_enable", "cabs_profile_read", "cabs_set_slab", "cabs_slab_phase", "cabs_set_stream",
-            "cabs_slab_block_bytes", "cabs_set_slab_direct", "cabs_slab_step", "cabs_device_alloc", "cabs_device_free",
+            "cabs_slab_block_bytes", "cabs_set_slab_direct", "cabs_slab_step", "cabs_slab_run", "cabs_device_alloc", "cabs_device_free",
             "cabs_ipc_export", "cabs_ipc_open", "cabs_ipc_close",
             "cabs_graph_create", "cabs_graph_destroy", "cabs_graph_last_error", "cabs_graph_upload", "cabs_graph_run",
             "cabs_graph_sync", "cabs_graph_stats", "cabs_graph_download", "cabs_graph_last_run_ms")
@@ -170,6 +170,7 @@ def load():
     lib.cabs_slab_block_bytes.restype = C.c_size_t
     lib.cabs_set_slab_direct.argtypes = [P, C.POINTER(SlabDirect)]
     lib.cabs_slab_step.argtypes = [P, C.c_int]
+    lib.cabs_slab_run.argtypes = [P, C.c_int]
     lib.cabs_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(P)]
     lib.cabs_device_free.argtypes = [C.c_int, P]
     lib.cabs_ipc_export.argtypes = [C.c_int, P, C.c_char * 64]
@@ -283,6 +284,9 @@ class Handle(object):
 
     def slab_step(self, advance=True):
         self._check(self._lib.cabs_slab_step(self._h, 1 if advance else 0))
+
+    def slab_run(self, nsteps):
+        self._check(self._lib.cabs_slab_run(self._h, int(nsteps)))
 
     def set_stream(self, cuda_stream):
         self._check(self._lib.cabs_set_stream(self._h, C.c_void_p(int(cuda_stream) or None)))

@@ -41,8 +41,12 @@ struct cabs_sim {
   unsigned char **dev_blocks = nullptr;
   unsigned build_seq = 0;
   bool late_pending = false;    // direct mode: the global half of the last build's closing has not been enqueued
-  unsigned late_seq = 0;
+  unsigned late_offset = 0;     // its sequence number relative to Ctl::build_seq (0 once the local half has run)
   int late_record = 0;
+  cudaGraphExec_t slab_graph = nullptr;   // two consecutive builds of the direct mode (see step_graph)
+  uint64_t slab_graph_launches = 0;
+  int slab_graph_cur = -1, slab_graph_tab = -1;
+  unsigned slab_graph_parity = 0;
   unsigned *emig_list = nullptr, *imm_rank = nullptr;
   // sequential schedule
   unsigned long long *tinf = nullptr;
@@ -134,6 +138,7 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
   cudaFree(sim->ctl); cudaFree(sim->history);
   cudaFree(sim->stage); cudaFree(sim->stage_id); cudaFree(sim->pairs); cudaFree(sim->pair_count);
   if (sim->step_graph) cudaGraphExecDestroy(sim->step_graph);
+  if (sim->slab_graph) cudaGraphExecDestroy(sim->slab_graph);
   for (cudaEvent_t e : sim->events) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
   if (sim->stream) cudaStreamDestroy(sim->stream);
@@ -377,7 +382,7 @@ static int flush_late_close(cabs_sim *sim) {
   SlabDirect D;
   memset(&D, 0, sizeof D);
   D.self = sim->blocks[sim->slab.rank];
-  D.seq = sim->late_seq;
+  D.seq = sim->late_offset;
   D.enabled = 1;
   LAUNCH(k_slab_close_global, 1, 32, sim->ctl, sim->history, sim->late_record, D);
   sim->late_pending = false;
@@ -409,7 +414,7 @@ static int slab_phase(cabs_sim *sim, int phase) {
     D.left = sl.rank > 0 ? sim->blocks[sl.rank - 1] : nullptr;
     D.right = sl.rank + 1 < sl.n_ranks ? sim->blocks[sl.rank + 1] : nullptr;
     D.all = sim->dev_blocks;
-    D.seq = seq;
+    D.seq = 1;   // relative to Ctl::build_seq: the build in flight
     D.enabled = 1;
   } else {
     for (int d = 0; d < 2; ++d) {
@@ -465,7 +470,7 @@ static int slab_phase(cabs_sim *sim, int phase) {
         // the local half ran inside the contact kernel (or runs here for a static build); the global half is
         // enqueued behind the next build's pass A, or by whoever asks for statistics first
         sim->late_pending = true;
-        sim->late_seq = D.seq;
+        sim->late_offset = kAdvance ? 0u : 1u;   // a step has closed locally (build_seq advanced) when its global half runs
         sim->late_record = kAdvance ? 1 : 0;
         if (!kAdvance) {   // a static build closes in order: the global y-range first, then the next grid
           const int rc = flush_late_close(sim);
@@ -597,6 +602,60 @@ extern "C" int cabs_slab_step(cabs_sim *sim, int advance) {
   CK(cudaSetDevice(sim->device));
   for (int phase = 0; phase < 4; ++phase) {
     const int rc = advance ? slab_phase<true>(sim, phase) : slab_phase<false>(sim, phase);
+    if (rc != CABS_OK) return rc;
+  }
+  return CABS_OK;
+}
+
+// `nsteps` steps of the direct mode.  Pairs of steps replay a captured CUDA graph: every launch argument is the same
+// for any two builds that start from the same ping/pong phase and flag parity (the sequence number itself lives in Ctl).
+extern "C" int cabs_slab_run(cabs_sim *sim, int nsteps) {
+  if (!sim || nsteps < 0) return fail(sim, CABS_ERR_INVALID, "cabs_slab_run: bad argument");
+  if (!sim->slab_on || !sim->direct) return fail(sim, CABS_ERR_INVALID, "cabs_slab_run: call cabs_set_slab_direct first");
+  if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_slab_run: call cabs_set_params first");
+  CK(cudaSetDevice(sim->device));
+  int s = 0;
+  // steady state only: the previous build was a step whose global closing is still pending
+  if (!sim->profiling && nsteps >= 5) {
+    for (; s < 1; ++s) {
+      const int rc = cabs_slab_step(sim, 1);
+      if (rc != CABS_OK) return rc;
+    }
+    const unsigned parity = (sim->build_seq + 1) & 1u;
+    if (sim->slab_graph && (sim->slab_graph_cur != sim->cur || sim->slab_graph_tab != sim->tab ||
+                            sim->slab_graph_parity != parity)) {
+      cudaGraphExecDestroy(sim->slab_graph);
+      sim->slab_graph = nullptr;
+    }
+    if (!sim->slab_graph && sim->late_pending && sim->late_record == 1 && sim->late_offset == 0) {
+      cudaGraph_t graph = nullptr;
+      const int cur0 = sim->cur, tab0 = sim->tab;
+      const uint64_t launches0 = sim->launches, step0 = sim->step;
+      const unsigned seq0 = sim->build_seq;
+      CK(cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = cabs_slab_step(sim, 1);
+      if (rc == CABS_OK) rc = cabs_slab_step(sim, 1);
+      cudaError_t ce = cudaStreamEndCapture(sim->stream, &graph);
+      sim->slab_graph_launches = sim->launches - launches0;
+      sim->cur = cur0; sim->tab = tab0; sim->launches = launches0; sim->step = step0; sim->build_seq = seq0;
+      sim->late_pending = true; sim->late_offset = 0; sim->late_record = 1;
+      if (rc != CABS_OK) return rc;
+      if (ce != cudaSuccess) { sim->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return CABS_ERR_CUDA; }
+      CK(cudaGraphInstantiate(&sim->slab_graph, graph, 0));
+      CK(cudaGraphDestroy(graph));
+      sim->slab_graph_cur = cur0; sim->slab_graph_tab = tab0; sim->slab_graph_parity = parity;
+    }
+    if (sim->slab_graph) {
+      for (; s + 2 <= nsteps; s += 2) {
+        CK(cudaGraphLaunch(sim->slab_graph, sim->stream));
+        sim->launches += sim->slab_graph_launches;
+        sim->step += 2;
+        sim->build_seq += 2;
+      }
+    }
+  }
+  for (; s < nsteps; ++s) {
+    const int rc = cabs_slab_step(sim, 1);
     if (rc != CABS_OK) return rc;
   }
   return CABS_OK;

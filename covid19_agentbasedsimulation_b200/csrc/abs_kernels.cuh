@@ -108,6 +108,7 @@ struct Ctl {
   unsigned n_inf;          // entries of the Infected-slot list
   unsigned n_emig;         // agents that leave this slab in the running step
   unsigned pack_ticket, imm_ticket;  // blocks of k_pack_emigrants / k_scatter_immigrants that have finished
+  unsigned build_seq;      // direct slab mode: builds completed; exchange flags carry build_seq + 1 of the build in flight
   unsigned pending_step;   // direct slab mode: step whose global statistics the late closing will record
   int glob_ymin, glob_ymax;  // direct slab mode: y-range of the whole population one build ago
   unsigned n_newinf;       // sequential schedule: entries of the newly-infected list
@@ -267,7 +268,8 @@ __host__ __device__ inline BlockLayout block_layout(unsigned n_ranks, unsigned m
 struct SlabDirect {
   unsigned char *self, *left, *right;   // exchange blocks as mapped in this process; nullptr on an outer side
   unsigned char *const *all;            // device array [n_ranks]: every rank's block (rows are broadcast)
-  unsigned seq;                         // sequence number of this build
+  unsigned seq;                         // sequence number of the build, RELATIVE to Ctl::build_seq (1 = the build in
+                                        // flight), so that the same launch arguments serve every build (CUDA graphs)
   int enabled;
 };
 enum { FLAG_MIG = 0, FLAG_GHOST = 4, FLAG_ROW = 8 };   // + from_dir * 2 + parity   /   + parity * kMaxRanks + rank
@@ -759,7 +761,8 @@ k_pack_emigrants(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
   const unsigned count = min(ctl->n_emig, 2u * ctl->mig_cap);
   const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
   const size_t remote_mig = L.mig_recv, mig_bytes = L.mig_bytes;
-  const unsigned par = D.seq & 1u;
+  const unsigned dseq = ctl->build_seq + D.seq;
+  const unsigned par = dseq & 1u;
   for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
     const unsigned i = emig_list[t];
     const uint4 h = hot[i];
@@ -806,7 +809,7 @@ k_pack_emigrants(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
         const unsigned cnt = min(__ldcg(&(to_left ? send_left : send_right)->count), ctl->mig_cap);
         reinterpret_cast<ExchangeHeader *>(peer + remote_mig + (from_dir * 2 + par) * mig_bytes)->count = cnt;
         __threadfence_system();
-        *(reinterpret_cast<volatile unsigned *>(peer) + FLAG_MIG + from_dir * 2 + par) = D.seq;
+        *(reinterpret_cast<volatile unsigned *>(peer) + FLAG_MIG + from_dir * 2 + par) = dseq;
       }
     }
   }
@@ -822,9 +825,10 @@ k_count_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ rec
   if (threadIdx.x == 0) {
     load_params(P, ctl);
     if (D.enabled) {   // the neighbours' migrants of this build have landed in my block
-      const unsigned par = D.seq & 1u;
-      if (D.left) wait_flag(D.self, FLAG_MIG + 0 * 2 + par, D.seq, &ctl->err);
-      if (D.right) wait_flag(D.self, FLAG_MIG + 1 * 2 + par, D.seq, &ctl->err);
+      const unsigned dseq = ctl->build_seq + D.seq;
+      const unsigned par = dseq & 1u;
+      if (D.left) wait_flag(D.self, FLAG_MIG + 0 * 2 + par, dseq, &ctl->err);
+      if (D.right) wait_flag(D.self, FLAG_MIG + 1 * 2 + par, dseq, &ctl->err);
     }
   }
   __syncthreads();
@@ -913,7 +917,8 @@ k_scatter_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ r
     if (s_last) {
       __threadfence();
       const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
-      const unsigned par = D.seq & 1u;
+      const unsigned dseq = ctl->build_seq + D.seq;
+      const unsigned par = dseq & 1u;
       // both directions at once: one round of stores, one system fence, then the two flags
       const unsigned nl_g = D.left ? min(__ldcg(&ghost_left->count), ctl->ghost_cap) : 0u;
       const unsigned nr_g = D.right ? min(__ldcg(&ghost_right->count), ctl->ghost_cap) : 0u;
@@ -935,7 +940,7 @@ k_scatter_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ r
           reinterpret_cast<ExchangeHeader *>(peer + L.ghost_recv + (from_dir * 2 + par) * L.ghost_bytes)->count =
               threadIdx.x == 0 ? nl_g : nr_g;
           __threadfence_system();
-          *(reinterpret_cast<volatile unsigned *>(peer) + FLAG_GHOST + from_dir * 2 + par) = D.seq;
+          *(reinterpret_cast<volatile unsigned *>(peer) + FLAG_GHOST + from_dir * 2 + par) = dseq;
         }
       }
     }
@@ -974,9 +979,10 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
   if (threadIdx.x == 0) {
     load_params(P, ctl);
     if (D.enabled) {   // the neighbours' ghosts of this build have landed in my block
-      const unsigned par = D.seq & 1u;
-      if (D.left) wait_flag(D.self, FLAG_GHOST + 0 * 2 + par, D.seq, &ctl->err);
-      if (D.right) wait_flag(D.self, FLAG_GHOST + 1 * 2 + par, D.seq, &ctl->err);
+      const unsigned dseq = ctl->build_seq + D.seq;
+      const unsigned par = dseq & 1u;
+      if (D.left) wait_flag(D.self, FLAG_GHOST + 0 * 2 + par, dseq, &ctl->err);
+      if (D.right) wait_flag(D.self, FLAG_GHOST + 1 * 2 + par, dseq, &ctl->err);
     }
     s_new = 0;
     s_local = (finish & 8) ? 0u : ctl->n_inf;   // bit 8: ghost sources only (the local ones ran in their own launch)
@@ -1305,14 +1311,15 @@ __device__ void slab_export(Ctl *ctl, long long *rows, SlabDirect D) {
   }
   // broadcast this rank's row into every rank's block (its own included), then raise the flags
   const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
-  const unsigned par = D.seq & 1u;
+  const unsigned dseq = ctl->build_seq + D.seq;
+  const unsigned par = dseq & 1u;
   for (int g = 0; g < ctl->n_ranks; ++g) {
     long long *dst = reinterpret_cast<long long *>(D.all[g] + L.rows) + ((size_t)par * kMaxRanks + ctl->rank) * kSlabRow;
     for (int k = 0; k < kSlabRow; ++k) dst[k] = r[k];
   }
   __threadfence_system();
   for (int g = 0; g < ctl->n_ranks; ++g)
-    *(reinterpret_cast<volatile unsigned *>(D.all[g]) + FLAG_ROW + par * kMaxRanks + ctl->rank) = D.seq;
+    *(reinterpret_cast<volatile unsigned *>(D.all[g]) + FLAG_ROW + par * kMaxRanks + ctl->rank) = dseq;
 }
 
 __global__ void k_slab_export(Ctl *ctl, long long *rows, SlabDirect D) {
@@ -1370,6 +1377,7 @@ __device__ void close_local(Ctl *ctl, const unsigned *cell_start, int record_sta
   plan_grid(ctl, bx0, bx1, by0, by1, true);
   reset_accumulators(ctl);
   ctl->n = n_next;
+  ctl->build_seq += 1;
   __threadfence();
 }
 
@@ -1414,8 +1422,9 @@ __global__ void k_slab_close_local(Ctl *ctl, const unsigned *cell_start, int rec
 __global__ void k_slab_close_global(Ctl *ctl, StatRecord *history, int record_stats, SlabDirect D) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
-  const unsigned par = D.seq & 1u;
-  for (int g = 0; g < ctl->n_ranks; ++g) wait_flag(D.self, FLAG_ROW + par * kMaxRanks + g, D.seq, &ctl->err);
+  const unsigned dseq = ctl->build_seq + D.seq;   // D.seq = 0: the build that has just been closed locally
+  const unsigned par = dseq & 1u;
+  for (int g = 0; g < ctl->n_ranks; ++g) wait_flag(D.self, FLAG_ROW + par * kMaxRanks + g, dseq, &ctl->err);
   close_global(ctl, reinterpret_cast<const long long *>(D.self + L.rows) + (size_t)par * kMaxRanks * kSlabRow, history,
                record_stats);
 }
@@ -1426,8 +1435,9 @@ __global__ void k_slab_close(Ctl *ctl, const long long *rows, const unsigned *ce
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (D.enabled) {   // every rank's row of this build has landed in my block
     const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
-    const unsigned par = D.seq & 1u;
-    for (int g = 0; g < ctl->n_ranks; ++g) wait_flag(D.self, FLAG_ROW + par * kMaxRanks + g, D.seq, &ctl->err);
+    const unsigned dseq = ctl->build_seq + D.seq;
+    const unsigned par = dseq & 1u;
+    for (int g = 0; g < ctl->n_ranks; ++g) wait_flag(D.self, FLAG_ROW + par * kMaxRanks + g, dseq, &ctl->err);
     rows = reinterpret_cast<const long long *>(D.self + L.rows) + (size_t)par * kMaxRanks * kSlabRow;
   }
   s0->count = 0; s1->count = 0; s2->count = 0; s3->count = 0;  // this slab's send buffers start the next build empty
@@ -1635,6 +1645,7 @@ __global__ void k_set_slab(Ctl *ctl, int rank, int n_ranks, int lo, int hi, unsi
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ctl->rank = rank; ctl->n_ranks = n_ranks; ctl->slab_lo = lo; ctl->slab_hi = hi;
   ctl->mig_cap = mig_cap; ctl->ghost_cap = ghost_cap;
+  ctl->build_seq = 0;
 }
 
 __global__ void k_init_ctl(Ctl *ctl, unsigned k0, unsigned k1, unsigned max_cells, unsigned hist_cap,

@@ -213,8 +213,8 @@ class SlabSimulation(Simulation):
         cap = int(max(1024, count * self.capacity_factor + 2 * mig))
         h = _native.Handle(capacity=cap, seed=self.seed, device=dev, max_cells=self.max_cells,
                            history_capacity=self.history_capacity)
-        with torch.cuda.device(dev):
-            h.set_stream(torch.cuda.current_stream().cuda_stream)
+        # the handle keeps its own stream: nothing of torch's is ordered against the step in this transport, and
+        # pairs of steps are replayed as a captured CUDA graph (the legacy default stream cannot be captured)
         self._release_p2p()
         self._block = _native.device_alloc(dev, _native.slab_block_bytes(self.n_slabs, mig, gho))
         handles = [None] * self.n_slabs
@@ -339,8 +339,11 @@ class SlabSimulation(Simulation):
             return super(SlabSimulation, self).run(iterations)
         self._push_params()
         first = self._iteration
-        for _ in range(iterations):
-            self._build(advance=True)
+        if self.transport == "p2p":
+            self._handles[0].slab_run(iterations)     # pairs of steps replay a captured CUDA graph
+        else:
+            for _ in range(iterations):
+                self._build(advance=True)
         self._iteration += iterations
         self._invalidate_host()
         self.statistics = None

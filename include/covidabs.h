@@ -210,6 +210,7 @@ typedef struct cabs_slab_direct {
 size_t cabs_slab_block_bytes(uint32_t n_ranks, uint32_t migrant_capacity, uint32_t ghost_capacity);
 int cabs_set_slab_direct(cabs_sim *sim, const cabs_slab_direct *slab);
 int cabs_slab_step(cabs_sim *sim, int advance);   /* the four phases back to back; asynchronous */
+int cabs_slab_run(cabs_sim *sim, int nsteps);     /* nsteps steps; pairs of steps replay a captured CUDA graph */
 /* Device memory that can be shared between processes, and its CUDA IPC handle (64 bytes). */
 int cabs_device_alloc(int device, size_t bytes, void **ptr);
 int cabs_device_free(int device, void *ptr);
