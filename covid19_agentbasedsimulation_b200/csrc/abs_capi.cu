@@ -22,6 +22,7 @@ struct cabs_sim {
   int num_sms = 148;
   uint64_t capacity = 0;
   unsigned max_cells = 0;
+  unsigned coarse_cells = 0;
   unsigned hist_cap = 0;
   // ping/pong population: 16-byte hot records {x, y, attr, id} + wealth; per-step displacement
   uint4 *hot[2] = {nullptr, nullptr};
@@ -159,15 +160,26 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   sim->own_stream = sim->stream;
   sim->capacity = cfg->capacity ? cfg->capacity : 1;
   if (sim->capacity >= (1ull << 31)) return fail(sim, CABS_ERR_CAPACITY, "capacity must be < 2^31 agents per device");
-  uint64_t mc = cfg->max_cells;
+  // Two budgets for the cell table.  While few agents can transmit (or few can be infected) the contact pass is
+  // cheap whatever the cell size, and a coarse grid (one cell per 8..32 agents) keeps the table small for the
+  // scan and the scatter.  In a dense epidemic the contact pass visits every candidate of every source, so the
+  // closing of a step switches to the fine budget (about one cell per agent).  Results do not depend on the grid.
+  uint64_t mc = cfg->max_cells, coarse = 0;
   if (mc == 0) {
-    mc = sim->capacity / 8;  // about one cell per 8..32 agents: the table stays a small fraction of the records
-    if (mc < 4096) mc = 4096;
+    mc = sim->capacity + sim->capacity / 2;
     if (mc > (1ull << 24)) mc = 1ull << 24;
+    coarse = sim->capacity / 8;
+  } else {
+    coarse = mc;             // an explicit cap is used as is, in both regimes
   }
+  if (mc < 4096 && cfg->max_cells == 0) mc = 4096;
   if (mc < 64) mc = 64;
   if (mc > (1ull << 30)) mc = 1ull << 30;
+  if (coarse < 4096 && cfg->max_cells == 0) coarse = 4096;
+  if (coarse < 64) coarse = 64;
+  if (coarse > mc) coarse = mc;
   sim->max_cells = (unsigned)mc;
+  sim->coarse_cells = (unsigned)coarse;
   sim->hist_cap = cfg->history_capacity ? cfg->history_capacity : 4096;
   const size_t cap = sim->capacity;
   const size_t capp = cap + kPad;  // the agent passes load whole tiles
@@ -194,7 +206,7 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   CK(cudaMemsetAsync(sim->ctl, 0, sizeof(Ctl), sim->stream));
   CK(cudaMemsetAsync(sim->history, 0, (size_t)sim->hist_cap * sizeof(StatRecord), sim->stream));
   LAUNCH(k_init_ctl, 1, 256, sim->ctl, (unsigned)(cfg->seed & 0xFFFFFFFFu), (unsigned)(cfg->seed >> 32),
-         sim->max_cells, sim->hist_cap, (unsigned)sim->capacity, sim->sqrt_tab);
+         sim->max_cells, sim->coarse_cells, sim->hist_cap, (unsigned)sim->capacity, sim->sqrt_tab);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(sim->stream));
   return CABS_OK;

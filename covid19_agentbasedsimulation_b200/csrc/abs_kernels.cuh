@@ -70,7 +70,10 @@ struct Ctl {
   //      the previous step's closing; `built` is the one the current cell table was built with
   Grid g, built;
   int last_bb[4];     // bounding box of the current positions (xmin, xmax, ymin, ymax)
-  unsigned max_cells;
+  unsigned max_cells;      // entries the cell tables hold (fine budget)
+  unsigned coarse_cells;   // budget while the epidemic is sparse
+  unsigned cell_budget;    // the one in force for the next grid (chosen when a step closes)
+  int pull_mode;           // contact pass direction for the next step: 0 push from the Infected list, 1 pull by the Susceptible
   unsigned cells_used[2];  // entries of each cell table that may be non-zero
   int cur_table;           // table the build in flight / the last build uses
   // ---- simulation attributes (abs.py:17-49); triggers rewrite them on the device
@@ -156,7 +159,7 @@ struct StepParams {
   long long thr_rate;
   int T, reach, recovering_time, scale_bits, crit_active;
   int len_i, hei_i;  // x >= length  <=>  x >= ceil(length) for integer x (abs.py:177,182)
-  int slab_lo, slab_hi, overflow;
+  int slab_lo, slab_hi, overflow, pull;
   unsigned k0, k1, step, n;
 };
 
@@ -181,7 +184,7 @@ __device__ __forceinline__ void load_params(StepParams &P, const Ctl *ctl, bool 
   P.reach = reach;
   P.recovering_time = ctl->recovering_time; P.scale_bits = ctl->scale_bits;
   P.crit_active = ctl->crit_active;
-  P.slab_lo = ctl->slab_lo; P.slab_hi = ctl->slab_hi; P.overflow = ctl->overflow;
+  P.slab_lo = ctl->slab_lo; P.slab_hi = ctl->slab_hi; P.overflow = ctl->overflow; P.pull = ctl->pull_mode;
   P.k0 = ctl->k0; P.k1 = ctl->k1; P.step = ctl->step; P.n = ctl->n;
 }
 
@@ -694,15 +697,13 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     }
     // slots of the agents that can transmit in this step's contact phase (warp-aggregated append)
     const bool is_inf = valid && st == ST_I;
-    const unsigned m_inf = __ballot_sync(0xffffffffu, is_inf);
+    if (is_inf && ghost_left) send_ghost(ctl, P, make_uint4((uint32_t)nx, (uint32_t)ny, a, aid), ghost_left, ghost_right);
+    const unsigned m_inf = P.pull ? 0u : __ballot_sync(0xffffffffu, is_inf);   // pull mode needs no source list
     if (m_inf) {
       unsigned base = 0;
       if (lane == 0) base = atomicAdd(&ctl->n_inf, (unsigned)__popc(m_inf));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (is_inf) {
-        inf_list[base + __popc(m_inf & ((1u << lane) - 1u))] = slot;
-        send_ghost(ctl, P, make_uint4((uint32_t)nx, (uint32_t)ny, a, aid), ghost_left, ghost_right);
-      }
+      if (is_inf) inf_list[base + __popc(m_inf & ((1u << lane) - 1u))] = slot;
     }
   }
   // block reduction: per-warp shared atomics, then one set of global atomics per block
@@ -897,7 +898,7 @@ k_scatter_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ r
     ohot[slot] = h;
     owealth[slot] = w;
     if (st == ST_I) {
-      inf_list[atomicAdd(&ctl->n_inf, 1u)] = slot;
+      if (!P.pull) inf_list[atomicAdd(&ctl->n_inf, 1u)] = slot;
       send_ghost(ctl, P, h, ghost_left, ghost_right);
     }
   }
@@ -985,7 +986,8 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
       if (D.right) wait_flag(D.self, FLAG_GHOST + 1 * 2 + par, dseq, &ctl->err);
     }
     s_new = 0;
-    s_local = (finish & 8) ? 0u : ctl->n_inf;   // bit 8: ghost sources only (the local ones ran in their own launch)
+    s_local = (finish & 8) ? 0u : ctl->n_inf;   // bit 8: ghost sources only (the local ones ran in their own launch);
+                                                // in pull mode pass B listed nobody, so this is 0
     s_left = ghosts_left ? min(ghosts_left->count, ctl->ghost_cap) : 0u;
     s_right = ghosts_right ? min(ghosts_right->count, ctl->ghost_cap) : 0u;
   }
@@ -993,6 +995,42 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
   unsigned newinf = 0;
   const unsigned stride = gridDim.x * blockDim.x;
   const unsigned total = s_local + s_left + s_right;
+  if (P.T >= 0 && P.pull && !(finish & 8) && *(const volatile unsigned long long *)&ctl->cnt[ST_S] > 0) {
+    // pull: every Susceptible agent (in cell order: neighbouring threads share cells) looks for an agent that was
+    // Infected before this phase and stops at the first contact that transmits
+    // residents after this step's migration (slab mode): the end of the last cell, not the count the step began with
+    const unsigned n_now = cell_start[ctl->g.ncells];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_now; i += stride) {
+      const uint4 h = hot[i];
+      if ((h.z & (3u | kNewlyInfected)) != ST_S) continue;
+      const int xi = (int)h.x, yi = (int)h.y;
+      int clo, chi, rlo, rhi;
+      contact_cells(P, xi, yi, clo, chi, rlo, rhi);
+      bool hit = false;
+      for (int row = rlo; row <= rhi && !hit; ++row) {
+        const unsigned base = (unsigned)row * (unsigned)P.ncx;
+        const unsigned jb = cell_start[base + clo], je = cell_start[base + chi + 1];
+        for (unsigned j = jb; j < je; ++j) {
+          const uint2 cp = *reinterpret_cast<const uint2 *>(&hot[j]);
+          const int ddx = (int)cp.x - xi, ddy = (int)cp.y - yi;
+          if ((unsigned)(ddx + P.reach) > 2u * (unsigned)P.reach || (unsigned)(ddy + P.reach) > 2u * (unsigned)P.reach)
+            continue;
+          if (ddx * ddx + ddy * ddy > P.T) continue;
+          const uint2 cq = *(reinterpret_cast<const uint2 *>(&hot[j]) + 1);
+          if ((cq.x & 3u) != ST_I) continue;   // newly infected agents still read Susceptible: they do not transmit yet
+          const uint4 r = philox4x32_10(min(h.w, cq.y), P.step, kStreamContact, max(h.w, cq.y), P.k0, P.k1);
+          if ((long long)r.x <= P.thr_rate) {   // contagion_test <= contagion_rate (abs.py:150-153)
+            hit = true;
+            break;
+          }
+        }
+      }
+      if (hit) {   // a ghost source of the same launch may have marked this agent too: count it once
+        const uint32_t old = atomicOr(reinterpret_cast<uint32_t *>(&hot[i]) + 2, kNewlyInfected);
+        if (!(old & kNewlyInfected)) ++newinf;
+      }
+    }
+  }
   if (P.T >= 0) {
     for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
       uint4 h;
@@ -1006,10 +1044,15 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
         const unsigned base = (unsigned)row * (unsigned)P.ncx;
         const unsigned jb = cell_start[base + clo], je = cell_start[base + chi + 1];
         for (unsigned j = jb; j < je; ++j) {
-          const uint4 c = hot[j];
+          // positions first (8 of the 16 bytes): almost every candidate of a coarse cell is out of reach
+          const uint2 cp = *reinterpret_cast<const uint2 *>(&hot[j]);
+          const int ddx = (int)cp.x - xi, ddy = (int)cp.y - yi;
+          if ((unsigned)(ddx + P.reach) > 2u * (unsigned)P.reach || (unsigned)(ddy + P.reach) > 2u * (unsigned)P.reach)
+            continue;
+          if (ddx * ddx + ddy * ddy > P.T) continue;     // |ddx|, |ddy| <= reach <= 16000: no overflow
+          const uint2 cq = *(reinterpret_cast<const uint2 *>(&hot[j]) + 1);
+          const uint4 c = make_uint4(cp.x, cp.y, cq.x, cq.y);
           if ((c.z & (3u | kNewlyInfected)) != ST_S) continue;  // only a still Susceptible agent can be infected
-          const long long dx = (int)c.x - xi, dy = (int)c.y - yi;
-          if (dx * dx + dy * dy > (long long)P.T) continue;
           const uint4 r = philox4x32_10(min(h.w, c.w), P.step, kStreamContact, max(h.w, c.w), P.k0, P.k1);
           if ((long long)r.x <= P.thr_rate) {  // contagion_test <= contagion_rate (abs.py:150-153)
             // status bits stay Susceptible during this pass (see attr_normalize)
@@ -1171,10 +1214,10 @@ __device__ inline void plan_grid(Ctl *ctl, int xmin, int xmax, int ymin, int yma
   // (1<<eshift)^2 >= T  =>  1<<eshift >= sqrt(T) >= any |dx| of a contact
   for (;;) {
     const long long ncx = ((x1 - x0) >> eshift) + 3, ncy = ((y1 - y0) >> eshift) + 3;
-    if (ncx * ncy <= (long long)ctl->max_cells || eshift >= 28) {
+    if (ncx * ncy <= (long long)ctl->cell_budget || eshift >= 28) {
       ctl->g.ncx = (int)ncx;
       ctl->g.ncy = (int)ncy;
-      ctl->g.ncells = (unsigned)min(ncx * ncy, (long long)ctl->max_cells);
+      ctl->g.ncells = (unsigned)min(ncx * ncy, (long long)ctl->cell_budget);
       break;
     }
     ++eshift;
@@ -1232,6 +1275,19 @@ __device__ __forceinline__ int ld_acc(const int *p) { return __ldcg(p); }
 // (experiments.py:193-196).  One thread.
 //   record_stats = 1 : after a real step
 //   record_stats = 0 : after upload / static rebuild (statistics of the initial state = "previous" stats)
+// Dense epidemic = many agents that can transmit AND many that can be infected: the contact pass then pays for every
+// candidate in the cells it visits, and a fine grid is worth its larger table.
+// Direction of the contact pass: whoever is rarer does the scanning.  While the Infected are few, their list is
+// pushed to the Susceptible in reach; once they outnumber the Susceptible four to one, every Susceptible agent looks
+// for an Infected one instead (and stops at the first success) -- in a saturated epidemic almost nobody scans.  Both
+// directions evaluate the same pair draws, so the result is the same bit for bit; the choice uses the counts of the
+// step just closed and only affects speed.
+__device__ inline void choose_cell_budget(Ctl *ctl, const StatRecord &cur) {
+  const unsigned long long lesser = min(cur.cnt[ST_S], cur.cnt[ST_I]);
+  ctl->cell_budget = (lesser * 16ull > ctl->pop_size && ctl->T >= 0) ? ctl->max_cells : ctl->coarse_cells;
+  ctl->pull_mode = (ctl->schedule == 0 && cur.cnt[ST_I] > 4ull * cur.cnt[ST_S]) ? 1 : 0;
+}
+
 // Statistics half of the closing: the step's record, triggers on the memo of the step before, critical-limit flag.
 __device__ void close_stats(Ctl *ctl, StatRecord *history, int record_stats) {
   StatRecord cur;
@@ -1271,6 +1327,7 @@ __device__ void close_stats(Ctl *ctl, StatRecord *history, int record_stats) {
   // abs.py:215: statistics['Severe'] + statistics['Hospitalization'] >= critical_limit
   const double n = (double)ctl->pop_size;
   ctl->crit_active = ((double)cur.cnt[6] / n + (double)cur.cnt[5] / n) >= ctl->critical_limit;
+  choose_cell_budget(ctl, cur);
 }
 
 __device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats) {
@@ -1410,6 +1467,7 @@ __device__ void close_global(Ctl *ctl, const long long *rows, StatRecord *histor
   ctl->glob_ymax = ymax;
   const double n = (double)ctl->pop_size;   // abs.py:215
   ctl->crit_active = ((double)cur.cnt[6] / n + (double)cur.cnt[5] / n) >= ctl->critical_limit;
+  choose_cell_budget(ctl, cur);
 }
 
 __global__ void k_slab_close_local(Ctl *ctl, const unsigned *cell_start, int record_stats, ExchangeHeader *s0,
@@ -1648,11 +1706,12 @@ __global__ void k_set_slab(Ctl *ctl, int rank, int n_ranks, int lo, int hi, unsi
   ctl->build_seq = 0;
 }
 
-__global__ void k_init_ctl(Ctl *ctl, unsigned k0, unsigned k1, unsigned max_cells, unsigned hist_cap,
-                           unsigned capacity, double *sqrt_tab) {
+__global__ void k_init_ctl(Ctl *ctl, unsigned k0, unsigned k1, unsigned max_cells, unsigned coarse_cells,
+                           unsigned hist_cap, unsigned capacity, double *sqrt_tab) {
   for (int d2 = threadIdx.x; d2 < kSqrtTable; d2 += blockDim.x) sqrt_tab[d2] = __dsqrt_rn((double)d2);
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ctl->k0 = k0; ctl->k1 = k1; ctl->max_cells = max_cells; ctl->hist_cap = hist_cap; ctl->capacity = capacity;
+  ctl->coarse_cells = coarse_cells; ctl->cell_budget = coarse_cells; ctl->pull_mode = 0;
   ctl->step = 0; ctl->n = 0; ctl->err = 0; ctl->ntrig = 0; ctl->pop_size = 1; ctl->T = -1;
   ctl->cells_used[0] = ctl->cells_used[1] = 0;
   ctl->cur_table = 0;

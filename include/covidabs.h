@@ -65,7 +65,7 @@ typedef struct cabs_config {
   uint32_t abi_version;      /* CABS_ABI_VERSION                                                  */
   int32_t device;            /* CUDA device ordinal                                               */
   uint64_t capacity;         /* max agents resident on this device                                */
-  uint64_t max_cells;        /* cap on cell-list cells (0 = auto: min(2^24, max(4096, capacity/8))) */
+  uint64_t max_cells;        /* cap on cell-list cells (0 = auto: capacity/8 while the epidemic is sparse, 1.5*capacity when dense; explicit = fixed) */
   uint64_t seed;             /* Philox key; draws are keyed (seed, agent id, step)                */
   uint32_t history_capacity; /* per-step statistics records kept on the device (ring)             */
   uint32_t flags;            /* reserved, 0                                                       */

@@ -198,3 +198,31 @@ def test_piled_up_population(native_lib):
         assert_same_state(gpu, orc, "it %d" % it)
         assert_same_stats(gpu.get_statistics('all'), ostats)
     np.testing.assert_array_equal(gpu.get_contact_pairs(), orc.last_pairs)
+
+
+def test_saturating_epidemic_switches_direction_and_grid(native_lib):
+    """Unmasked epidemic from 5 % to saturation: the contact pass switches from pushing the Infected list to pulling
+    by the Susceptible (and the cell table from the coarse to the fine budget and back) on the way; every step must
+    still equal the oracle, for one handle and for three slabs."""
+    from covid19_agentbasedsimulation_b200.abs import Simulation
+    from covid19_agentbasedsimulation_b200.slab import SlabSimulation
+    n, side = 30000, 300
+    pop, tw = synthetic_population(n, side, side, seed=3, infected=0.05)
+    kw = dict(seed=11, population_size=n, length=side, height=side, total_wealth=tw, contagion_distance=1.0,
+              contagion_rate=0.9)
+    one = Simulation(**kw)
+    one.set_population_arrays(pop["x"], pop["y"], pop["status"], pop["age"], pop["stratum"], pop["wealth"])
+    many = SlabSimulation(slabs=3, **kw)
+    many.set_population_arrays(pop["x"], pop["y"], pop["status"], pop["age"], pop["stratum"], pop["wealth"])
+    orc = SyncSimulation(**kw)
+    orc.set_population(pop["x"], pop["y"], pop["status"], pop["age"], pop["stratum"], pop["wealth"])
+    edges = set()
+    for it in range(16):
+        one.execute()
+        many.execute()
+        o = [float(v) for v in orc.execute().values()]
+        a, b = one.get_statistics('all'), many.get_statistics('all')
+        assert [float(a[k]) for k in a] == o and [float(b[k]) for k in b] == o, it
+        edges.add(one.device_info()["cell_edge"])
+    assert o[1] > 0.9 and len(edges) >= 2          # saturated, and both cell budgets were used
+    assert np.array_equal(one._download()["status"], orc.status)
