@@ -304,11 +304,13 @@ static void enqueue_build(cabs_sim *sim) {
   const int c = sim->cur, o = c ^ 1, t = sim->tab;
   const bool sequential = sim->have_params && sim->params.schedule == CABS_SEQUENTIAL;
   const int nb = agent_blocks(sim);
+  SlabDirect no_direct;
+  memset(&no_direct, 0, sizeof no_direct);
   LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl, sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list);
   LAUNCH(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
   LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", k_update_scatter<kAdvance>, nb, kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t],
          sim->cells[t ^ 1], sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, nullptr, nullptr,
-         (kAdvance && sequential) ? sim->tinf : nullptr);
+         (kAdvance && sequential) ? sim->tinf : nullptr, nullptr, nullptr, nullptr, no_direct);
   if (kAdvance && sequential) {
     // rounds of label-correcting relaxation until no infection time is lowered (one host round trip each)
     for (int round = 0;; ++round) {
@@ -455,9 +457,8 @@ static int slab_phase(cabs_sim *sim, int phase) {
       LAUNCH(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
       LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", k_update_scatter<kAdvance>, nb,
                 kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t], sim->cells[t ^ 1],
-                sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, gs[0], gs[1], nullptr);
-      LAUNCH(k_scatter_immigrants, nbs, 256, sim->ctl, mr[0], mr[1], sim->cells[t], sim->imm_rank, sim->hot[o],
-             sim->w[o], sim->inf_list, gs[0], gs[1], D);
+                sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, gs[0], gs[1], nullptr, mr[0], mr[1],
+                sim->imm_rank, D);   // the immigrants take their slots inside pass B; its last block pushes the ghosts
       break;
     case 2:
       if (kAdvance) {

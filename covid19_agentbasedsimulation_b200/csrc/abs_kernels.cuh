@@ -323,6 +323,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// orders this thread's generic-proxy accesses to shared memory before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void mbar_fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
   asm volatile(
       "{\n"
@@ -603,9 +605,11 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
                  unsigned *__restrict__ stale_cells, uint4 *__restrict__ ohot, double *__restrict__ owealth,
                  unsigned *__restrict__ inf_list, const double *__restrict__ sqrt_tab,
                  ExchangeHeader *__restrict__ ghost_left, ExchangeHeader *__restrict__ ghost_right,
-                 unsigned long long *__restrict__ tinf) {
+                 unsigned long long *__restrict__ tinf, const ExchangeHeader *__restrict__ recv_left,
+                 const ExchangeHeader *__restrict__ recv_right, const unsigned *__restrict__ imm_rank, SlabDirect D) {
   __shared__ StepParams P;
   __shared__ BlockStats B;
+  __shared__ unsigned s_last;
   __shared__ long long s_q[5][kTile];  // per-thread Q1..Q5 partial sums (abs.py:309-312), no bank conflicts
   __shared__ unsigned s_stale;
   __shared__ StageB s_in[kStagesB];
@@ -666,6 +670,10 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     const uint4 h = s_in[s].hot[threadIdx.x];
     double w = s_in[s].w[threadIdx.x];
     const uint2 ax = s_in[s].aux[threadIdx.x];
+    // The stage is refilled by the bulk-copy engine (async proxy) once every warp has released it, but the reads above
+    // went through the generic proxy: without this fence the refill may overtake reads still queued in the shared-memory
+    // pipe (seen as scrambled records once a block wraps the ring, i.e. above 4 tiles per block).
+    mbar_fence_async_shared();
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[s]);  // this warp is done with the stage
     const unsigned i = tile * kTile + threadIdx.x;
@@ -706,6 +714,35 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
       if (is_inf) inf_list[base + __popc(m_inf & ((1u << lane) - 1u))] = slot;
     }
   }
+  // Slab mode: the agents that moved in from the neighbour slabs take their slots here too (they were counted in the
+  // histogram before the scan): statistics, Infected list and ghosts exactly as for the residents -- every agent is
+  // accounted once, by the device that owns it after the move.  A handful of records per block, hidden behind the tiles.
+  if (!producer && recv_left) {
+    const unsigned cap = ctl->mig_cap;
+    const unsigned nl = min(recv_left->count, cap), nr = min(recv_right->count, cap);
+    const unsigned total = P.overflow ? 0u : nl + nr;
+    for (unsigned t = blockIdx.x * kTile + threadIdx.x; t < total; t += gridDim.x * kTile) {
+      const MigrantRecord *src = t < nl ? reinterpret_cast<const MigrantRecord *>(recv_left + 1) + t
+                                        : reinterpret_cast<const MigrantRecord *>(recv_right + 1) + (t - nl);
+      const uint4 h = src->hot;
+      const double w = src->w;
+      const int nx = (int)h.x, ny = (int)h.y;
+      const uint32_t a = h.z, st = attr_status(a), sev = attr_severity(a);
+      const unsigned slot = cell_start[cell_key(P, nx, ny, &ctl->err)] + imm_rank[t];
+      c_st += 1ull << (16 * st);
+      if (st != ST_D) {
+        c_sev += (sev != SEV_E) ? (1ull << (16 * (sev - 1))) : 0ull;
+        if (attr_age(a) >= 18u) s_q[min(attr_stratum(a), 4u)][threadIdx.x] += __double2ll_rn(__dmul_rn(w, qscale));
+      }
+      bxmin = min(bxmin, nx); bxmax = max(bxmax, nx); bymin = min(bymin, ny); bymax = max(bymax, ny);
+      ohot[slot] = h;
+      owealth[slot] = w;
+      if (st == ST_I) {
+        if (!P.pull) inf_list[atomicAdd(&ctl->n_inf, 1u)] = slot;
+        send_ghost(ctl, P, h, ghost_left, ghost_right);
+      }
+    }
+  }
   // block reduction: per-warp shared atomics, then one set of global atomics per block
   if (!producer) {
     unsigned long long cnt[7];
@@ -742,6 +779,42 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     if (B.bb[0] <= B.bb[1]) {
       atomicMin(&ctl->bb_xmin, B.bb[0]); atomicMax(&ctl->bb_xmax, B.bb[1]);
       atomicMin(&ctl->bb_ymin, B.bb[2]); atomicMax(&ctl->bb_ymax, B.bb[3]);
+    }
+  }
+  if (D.enabled) {   // direct slab mode: every ghost is listed once all blocks are done; the last one hands them over
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&ctl->imm_ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
+      const unsigned dseq = ctl->build_seq + D.seq;
+      const unsigned par = dseq & 1u;
+      // both directions at once: one round of stores, one system fence, then the two flags
+      const unsigned nl_g = D.left ? min(__ldcg(&ghost_left->count), ctl->ghost_cap) : 0u;
+      const unsigned nr_g = D.right ? min(__ldcg(&ghost_right->count), ctl->ghost_cap) : 0u;
+      uint4 *dl = D.left ? reinterpret_cast<uint4 *>(D.left + L.ghost_recv + (1 * 2 + par) * L.ghost_bytes +
+                                                     sizeof(ExchangeHeader)) : nullptr;
+      uint4 *dr = D.right ? reinterpret_cast<uint4 *>(D.right + L.ghost_recv + (0 * 2 + par) * L.ghost_bytes +
+                                                      sizeof(ExchangeHeader)) : nullptr;
+      const uint4 *sl = reinterpret_cast<const uint4 *>(ghost_left + 1), *sr = reinterpret_cast<const uint4 *>(ghost_right + 1);
+      for (unsigned k = threadIdx.x; k < nl_g + nr_g; k += blockDim.x) {
+        if (k < nl_g) dl[k] = __ldcg(sl + k);
+        else dr[k - nl_g] = __ldcg(sr + (k - nl_g));
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x < 2) {
+        unsigned char *peer = threadIdx.x == 0 ? D.left : D.right;
+        if (peer) {
+          const int from_dir = threadIdx.x == 0 ? 1 : 0;
+          reinterpret_cast<ExchangeHeader *>(peer + L.ghost_recv + (from_dir * 2 + par) * L.ghost_bytes)->count =
+              threadIdx.x == 0 ? nl_g : nr_g;
+          __threadfence_system();
+          *(reinterpret_cast<volatile unsigned *>(peer) + FLAG_GHOST + from_dir * 2 + par) = dseq;
+        }
+      }
     }
   }
 }
@@ -848,103 +921,6 @@ k_count_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ rec
                                       : reinterpret_cast<const MigrantRecord *>(recv_right + 1) + (t - nl);
     const uint4 h = src->hot;
     imm_rank[t] = atomicAdd(&cells[cell_key(P, (int)h.x, (int)h.y, &ctl->err)], 1u);
-  }
-}
-
-// Slab exchange 1, receiver side, after the scan: the immigrants take their slots; statistics, Infected
-// list and ghosts exactly as pass B does for the residents (every agent is counted once, by the device
-// that owns it after the move).
-__global__ void __launch_bounds__(256)
-k_scatter_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ recv_left,
-                     const ExchangeHeader *__restrict__ recv_right, const unsigned *__restrict__ cell_start,
-                     const unsigned *__restrict__ imm_rank, uint4 *__restrict__ ohot, double *__restrict__ owealth,
-                     unsigned *__restrict__ inf_list, ExchangeHeader *__restrict__ ghost_left,
-                     ExchangeHeader *__restrict__ ghost_right, SlabDirect D) {
-  __shared__ StepParams P;
-  __shared__ unsigned s_last;
-  if (threadIdx.x == 0) load_params(P, ctl);
-  __syncthreads();
-  const unsigned cap = ctl->mig_cap;
-  const unsigned nl = min(recv_left->count, cap), nr = min(recv_right->count, cap);
-  const double qscale = (double)(1ull << P.scale_bits);
-  const unsigned total = P.overflow ? 0u : nl + nr;
-  __shared__ unsigned long long s_cnt[7];
-  __shared__ long long s_q[5];
-  __shared__ int s_bb[4];
-  if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0;
-  if (threadIdx.x < 5) s_q[threadIdx.x] = 0;
-  if (threadIdx.x == 0) {
-    s_bb[0] = s_bb[2] = INT_MAX;
-    s_bb[1] = s_bb[3] = INT_MIN;
-  }
-  __syncthreads();
-  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    const MigrantRecord *src = t < nl ? reinterpret_cast<const MigrantRecord *>(recv_left + 1) + t
-                                      : reinterpret_cast<const MigrantRecord *>(recv_right + 1) + (t - nl);
-    const uint4 h = src->hot;
-    const double w = src->w;
-    const int nx = (int)h.x, ny = (int)h.y;
-    const uint32_t a = h.z, st = attr_status(a), sev = attr_severity(a);
-    const unsigned slot = cell_start[cell_key(P, nx, ny, &ctl->err)] + imm_rank[t];
-    atomicAdd(&s_cnt[st], 1ull);                       // per block first, one set of global atomics at the end
-    if (st != ST_D) {
-      if (sev != SEV_E) atomicAdd(&s_cnt[3 + sev], 1ull);
-      if (attr_age(a) >= 18u)
-        atomicAdd((unsigned long long *)&s_q[min(attr_stratum(a), 4u)],
-                  (unsigned long long)__double2ll_rn(__dmul_rn(w, qscale)));
-    }
-    atomicMin(&s_bb[0], nx); atomicMax(&s_bb[1], nx);
-    atomicMin(&s_bb[2], ny); atomicMax(&s_bb[3], ny);
-    ohot[slot] = h;
-    owealth[slot] = w;
-    if (st == ST_I) {
-      if (!P.pull) inf_list[atomicAdd(&ctl->n_inf, 1u)] = slot;
-      send_ghost(ctl, P, h, ghost_left, ghost_right);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < 7 && s_cnt[threadIdx.x]) atomicAdd(&ctl->cnt[threadIdx.x], s_cnt[threadIdx.x]);
-  if (threadIdx.x < 5 && s_q[threadIdx.x])
-    atomicAdd((unsigned long long *)&ctl->q[threadIdx.x], (unsigned long long)s_q[threadIdx.x]);
-  if (threadIdx.x == 0 && s_bb[0] <= s_bb[1]) {
-    atomicMin(&ctl->bb_xmin, s_bb[0]); atomicMax(&ctl->bb_xmax, s_bb[1]);
-    atomicMin(&ctl->bb_ymin, s_bb[2]); atomicMax(&ctl->bb_ymax, s_bb[3]);
-  }
-  if (D.enabled) {   // pass B and this kernel have listed every ghost: the last block hands them over
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&ctl->imm_ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
-      const unsigned dseq = ctl->build_seq + D.seq;
-      const unsigned par = dseq & 1u;
-      // both directions at once: one round of stores, one system fence, then the two flags
-      const unsigned nl_g = D.left ? min(__ldcg(&ghost_left->count), ctl->ghost_cap) : 0u;
-      const unsigned nr_g = D.right ? min(__ldcg(&ghost_right->count), ctl->ghost_cap) : 0u;
-      uint4 *dl = D.left ? reinterpret_cast<uint4 *>(D.left + L.ghost_recv + (1 * 2 + par) * L.ghost_bytes +
-                                                     sizeof(ExchangeHeader)) : nullptr;
-      uint4 *dr = D.right ? reinterpret_cast<uint4 *>(D.right + L.ghost_recv + (0 * 2 + par) * L.ghost_bytes +
-                                                      sizeof(ExchangeHeader)) : nullptr;
-      const uint4 *sl = reinterpret_cast<const uint4 *>(ghost_left + 1), *sr = reinterpret_cast<const uint4 *>(ghost_right + 1);
-      for (unsigned k = threadIdx.x; k < nl_g + nr_g; k += blockDim.x) {
-        if (k < nl_g) dl[k] = __ldcg(sl + k);
-        else dr[k - nl_g] = __ldcg(sr + (k - nl_g));
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x < 2) {
-        unsigned char *peer = threadIdx.x == 0 ? D.left : D.right;
-        if (peer) {
-          const int from_dir = threadIdx.x == 0 ? 1 : 0;
-          reinterpret_cast<ExchangeHeader *>(peer + L.ghost_recv + (from_dir * 2 + par) * L.ghost_bytes)->count =
-              threadIdx.x == 0 ? nl_g : nr_g;
-          __threadfence_system();
-          *(reinterpret_cast<volatile unsigned *>(peer) + FLAG_GHOST + from_dir * 2 + par) = dseq;
-        }
-      }
-    }
   }
 }
 

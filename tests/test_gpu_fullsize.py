@@ -90,3 +90,30 @@ def test_slab_invariance_at_three_million_agents(native_lib):
     for k in ("x", "y", "status", "infected_time"):
         assert np.array_equal(pa[k], pb[k]), k
     assert pa["wealth"].tobytes() == pb["wealth"].tobytes()
+
+
+def test_three_million_agents_match_the_cpu_restatement(native_lib):
+    """Above 4 tiles per block the staging ring of pass B wraps (148*8 blocks x 4 stages x 256 agents = 1.2e6): the sizes
+    of the other parity tests never get there.  3e6 agents, two steps (the second runs on the output of a wrapped pass),
+    statistics rows and every agent's state bit for bit against the CPU restatement."""
+    from covid19_agentbasedsimulation_b200.abs import Simulation
+    from oracle.sync_oracle import SyncSimulation
+    n, side, steps = 3_000_000, 3873, 2
+    x, y, status, age, stratum, wealth = _population(n, side, 4)
+    kw = dict(seed=5, population_size=n, length=side, height=side, total_wealth=1.5e9, contagion_distance=1.0,
+              contagion_rate=0.9)
+    cpu = SyncSimulation(**kw)
+    cpu.set_population(x, y, status, age, stratum, wealth)
+    sim = Simulation(**kw)
+    sim.set_population_arrays(x, y, status, age, stratum, wealth)
+    rows = sim.run(steps)
+    for it in range(steps):
+        cpu.execute(need_pairs=False)
+        st = cpu.get_statistics()
+        assert np.array_equal(rows[it], np.array([st[k] for k in st])), it
+    h = sim._download()
+    order = np.argsort(h["id"], kind="stable")
+    assert np.array_equal(h["id"][order], np.arange(n, dtype=h["id"].dtype))
+    for k in ("x", "y", "status", "severity", "infected_time"):
+        assert np.array_equal(h[k][order].astype(np.int64), np.asarray(getattr(cpu, k), dtype=np.int64)), k
+    assert h["wealth"][order].tobytes() == np.asarray(cpu.wealth, dtype=np.float64).tobytes()
