@@ -110,7 +110,7 @@ struct Ctl {
   int bb_xmin, bb_xmax, bb_ymin, bb_ymax;
   unsigned n_inf;          // entries of the Infected-slot list
   unsigned n_emig;         // agents that leave this slab in the running step
-  unsigned pack_ticket, imm_ticket;  // blocks of k_pack_emigrants / k_scatter_immigrants that have finished
+  unsigned pack_ticket, imm_ticket;  // blocks of k_pack_emigrants / of pass B (slab mode) that have finished
   unsigned build_seq;      // direct slab mode: builds completed; exchange flags carry build_seq + 1 of the build in flight
   unsigned pending_step;   // direct slab mode: step whose global statistics the late closing will record
   int glob_ymin, glob_ymax;  // direct slab mode: y-range of the whole population one build ago
