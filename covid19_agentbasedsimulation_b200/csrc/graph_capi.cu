@@ -325,13 +325,49 @@ extern "C" int cabs_graph_stats(cabs_graph *g, uint32_t sim, int64_t first, uint
     return gfail(g, CABS_ERR_INVALID, "cabs_graph_stats: iterations not executed yet");
   if (last - first >= (int64_t)cur.hist_cap)
     return gfail(g, CABS_ERR_CAPACITY, "cabs_graph_stats: rows already overwritten (history_capacity)");
-  for (uint32_t k = 0; k < count; ++k) {
-    const int64_t it = first + k;
-    const double *src = it < 0 ? g->initial_rows + (size_t)sim * kStats
-                               : cur.history + (size_t)(it % cur.hist_cap) * kStats;
-    GCK(cudaMemcpyAsync(rows + (size_t)k * kStats, src, kStats * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  // the rows of a run are contiguous in the ring except where it wraps: at most three copies
+  uint32_t k = 0;
+  if (count && first < 0) {
+    GCK(cudaMemcpyAsync(rows, g->initial_rows + (size_t)sim * kStats, kStats * sizeof(double), cudaMemcpyDeviceToHost,
+                        g->stream));
+    k = 1;
+  }
+  while (k < count) {
+    const int64_t slot = (first + k) % cur.hist_cap;
+    const uint32_t run = (uint32_t)std::min<int64_t>(count - k, cur.hist_cap - slot);
+    GCK(cudaMemcpyAsync(rows + (size_t)k * kStats, cur.history + (size_t)slot * kStats,
+                        (size_t)run * kStats * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    k += run;
   }
   GCK(cudaStreamSynchronize(g->stream));
+  return CABS_OK;
+}
+
+extern "C" int cabs_graph_aggregate(cabs_graph *g, int64_t first, uint32_t count, double *out) {
+  if (!g || (count && !out)) return gfail(g, CABS_ERR_INVALID, "cabs_graph_aggregate: null argument");
+  for (uint32_t s = 0; s < g->cfg.n_sims; ++s)
+    if (!g->uploaded[s]) return gfail(g, CABS_ERR_INVALID, "cabs_graph_aggregate: every simulation of the handle must be uploaded");
+  if (count == 0) return CABS_OK;
+  GCK(cudaSetDevice(g->device));
+  Sim cur;
+  GCK(cudaMemcpyAsync(&cur, g->sims, sizeof(Sim), cudaMemcpyDeviceToHost, g->stream));
+  GCK(cudaStreamSynchronize(g->stream));
+  const int64_t last = cur.iteration;  // every simulation of a handle is at the same iteration
+  if (first < -1 || first + (int64_t)count - 1 > last)
+    return gfail(g, CABS_ERR_INVALID, "cabs_graph_aggregate: iterations not executed yet");
+  if (last - first >= (int64_t)cur.hist_cap)
+    return gfail(g, CABS_ERR_CAPACITY, "cabs_graph_aggregate: rows already overwritten (history_capacity)");
+  double *dev = nullptr;
+  const size_t bytes = (size_t)count * kStats * 4 * sizeof(double);
+  GCK(cudaMalloc(&dev, bytes));
+  k_graph_aggregate<<<count, kStats * 32, 0, g->stream>>>(g->history, g->initial_rows, (int)g->cfg.n_sims, cur.hist_cap,
+                                                          (long long)first, dev);
+  g->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, g->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+  cudaFree(dev);
+  GCK(e);
   return CABS_OK;
 }
 

@@ -816,5 +816,47 @@ __global__ void __launch_bounds__(kThreads) k_graph_initial_stats(Sim *sims, dou
   }
 }
 
+// What batch_experiment does with the rows of its experiments (experiments.py:200-208): per iteration and metric
+// the minimum, mean, population standard deviation (ddof = 0) and maximum over the simulations of the handle.
+// One block per iteration, one warp per metric; lanes stride over the simulations and combine in a fixed
+// butterfly, so the result does not depend on scheduling.  out[iteration][metric] = {min, avg, std, max}.
+__global__ void __launch_bounds__(kStats * 32)
+k_graph_aggregate(const double *__restrict__ history, const double *__restrict__ initial_rows, int n_sims, int hist_cap,
+                  long long first, double *__restrict__ out) {
+  const long long it = first + blockIdx.x;
+  const int m = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t row = it < 0 ? 0 : (size_t)(it % hist_cap) * kStats;
+  const double *base = it < 0 ? initial_rows : history + row;
+  const size_t stride = it < 0 ? (size_t)kStats : (size_t)hist_cap * kStats;
+  double mn = INFINITY, mx = -INFINITY, sum = 0.0;
+  for (int s = lane; s < n_sims; s += 32) {
+    const double v = base[(size_t)s * stride + m];
+    mn = fmin(mn, v);
+    mx = fmax(mx, v);
+    sum = __dadd_rn(sum, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+  }
+  const double mean = __ddiv_rn(sum, (double)n_sims);
+  double ss = 0.0;
+  for (int s = lane; s < n_sims; s += 32) {
+    const double d = __dsub_rn(base[(size_t)s * stride + m], mean);
+    ss = __dadd_rn(ss, __dmul_rn(d, d));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss = __dadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
+  if (lane == 0) {
+    double *o4 = out + ((size_t)blockIdx.x * kStats + m) * 4;
+    o4[0] = mn;
+    o4[1] = mean;
+    o4[2] = __dsqrt_rn(__ddiv_rn(ss, (double)n_sims));
+    o4[3] = mx;
+  }
+}
+
 }  // namespace graph
 }  // namespace cabs

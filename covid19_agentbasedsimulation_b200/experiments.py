@@ -16,6 +16,18 @@ def batch_experiment(experiments, iterations, file, simulation_type=Simulation, 
     verbose = kwargs.get('verbose', None)
     columns = None
     runs = []  # one [iterations_done, n_metrics] array per experiment
+    aggregated = getattr(simulation_type, 'run_ensemble_aggregated', None)
+    if aggregated is not None and verbose != 'iterations' and experiments > 0:
+        # all experiments step concurrently on the device and the table below is reduced there too
+        try:
+            columns, agg = aggregated(experiments, iterations, **kwargs)
+            rows2 = [[it, col] + [float(v) for v in agg[it, k]] for it in range(iterations)
+                     for k, col in enumerate(columns)]
+            df2 = pd.DataFrame(rows2, columns=['Iteration', 'Metric', 'Min', 'Avg', 'Std', 'Max'])
+            df2.to_csv(file, index=False)
+            return df2
+        except Exception as ex:
+            print("Exception occurred in the aggregated ensemble run: {}".format(ex))
     ensemble = getattr(simulation_type, 'run_ensemble', None)
     if ensemble is not None and verbose != 'iterations' and experiments > 0:
         # all experiments step concurrently on the device (one block per simulation), one copy back

@@ -73,6 +73,27 @@ class GraphEnsemble(object):
             done += chunk
         return out
 
+    def run_aggregated(self, iterations):
+        """`iterations` hours of every simulation, then what batch_experiment computes from their rows
+        (experiments.py:200-208), reduced on the device: float64 [iterations, 14, 4] = Min, Avg, Std (ddof=0), Max.
+        Only the aggregate crosses the bus (config 5: 0.6 MB instead of the 1.1 GB of per-simulation rows)."""
+        iterations = int(iterations)
+        out = np.empty((iterations, _native.GRAPH_NUM_STATS, 4))
+        done = 0
+        while done < iterations:
+            chunk = min(self.history_capacity, iterations - done)
+            first = self.iteration + 1
+            self.handle.run(chunk)
+            self.iteration += chunk
+            out[done:done + chunk] = self.handle.aggregate(first, chunk)
+            done += chunk
+        for sim in self.sims:
+            sim.iteration = self.iteration
+            sim._world = None
+            sim._entities = None
+            sim.statistics = None
+        return out
+
     def last_run_ms(self):
         return self.handle.last_run_ms()
 

@@ -406,6 +406,24 @@ class GraphSimulation(Simulation):
             ens.close()
         return list(GRAPH_STAT_KEYS), table
 
+    @classmethod
+    def run_ensemble_aggregated(cls, experiments, iterations, **kwargs):
+        """run_ensemble followed by the Min/Avg/Std/Max loop of batch_experiment (experiments.py:200-208) on the device.
+        Returns (statistics keys, float64 [iterations, 14, 4])."""
+        from covid19_agentbasedsimulation_b200.network.ensemble import GraphEnsemble
+        kwargs = dict(kwargs)
+        kwargs.pop('verbose', None)
+        seed = kwargs.pop('seed', None)
+        sims = [cls(seed=None if seed is None else int(seed) + k, **kwargs) for k in range(int(experiments))]
+        ens = GraphEnsemble(sims, device=kwargs.get('device', 0),
+                            history_capacity=max(2048, min(int(iterations), 1 << 16)))
+        try:
+            ens.initialize()
+            agg = ens.run_aggregated(iterations)
+        finally:
+            ens.close()
+        return list(GRAPH_STAT_KEYS), agg
+
 
 def _entity_property(index):
     def getter(self):

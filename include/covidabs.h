@@ -314,6 +314,10 @@ int cabs_graph_sync(cabs_graph *g);
 /* Replaces get_statistics(kind='all') (graph_abs.py:302-324): rows after iterations
  * [first_iteration, first_iteration + count); first_iteration = -1 is the initial state. */
 int cabs_graph_stats(cabs_graph *g, uint32_t sim, int64_t first_iteration, uint32_t count, double *rows);
+/* Replaces the aggregation loop of batch_experiment (covid_abs/experiments.py:200-208) over the simulations of the
+ * handle (its "experiments"): out[count][CABS_GRAPH_NUM_STATS][4] = Min, Avg, Std (ddof = 0), Max of every metric
+ * after iterations [first_iteration, first_iteration + count), reduced on the device. */
+int cabs_graph_aggregate(cabs_graph *g, int64_t first_iteration, uint32_t count, double *out);
 /* Current state of simulation `sim` (caller-allocated arrays of at least the uploaded sizes). */
 int cabs_graph_download(cabs_graph *g, uint32_t sim, cabs_graph_world *world);
 /* Device time of the last cabs_graph_run (CUDA events on the handle's stream); waits for it. */

@@ -137,3 +137,40 @@ def test_ensemble_handle_equals_individual_runs_and_batch_experiment(native_lib,
     assert len(df) == 50 * 14 and list(df['Metric'][:14]) == list(GRAPH_STAT_KEYS)
     inf = df[df['Metric'] == 'Infected']
     assert (inf['Min'] <= inf['Avg']).all() and (inf['Avg'] <= inf['Max']).all() and inf['Std'].max() > 0
+
+
+def test_device_aggregate_equals_numpy_over_the_rows(native_lib):
+    """cabs_graph_aggregate = the Min/Avg/Std/Max loop of batch_experiment (experiments.py:200-208) over the handle's
+    simulations.  Min and Max are exact; Avg and Std are float64 reductions in a different (fixed) order than numpy's
+    pairwise sum: tolerance 1e-13 relative for Avg, 1e-10 for Std (a sum of squared differences)."""
+    from covid19_agentbasedsimulation_b200.network.graph_abs import GraphSimulation
+    from covid19_agentbasedsimulation_b200.network.ensemble import GraphEnsemble
+    from covid19_agentbasedsimulation_b200.network import scenarios as sc
+    kw = dict(sc.global_parameters)
+    kw.update(sc.scenario2)
+    kw.pop("name")
+    kw.update(population_size=90, initial_infected_perc=0.05)
+    n_sims, iterations = 37, 60          # 37: lanes with one and with two simulations each
+    np.random.seed(11)
+    world = GraphSimulation(seed=0, **kw).build_world()
+    tables = []
+    for cap in (2048, 16):               # 16: the history ring wraps, the run proceeds in chunks
+        ens = GraphEnsemble([GraphSimulation(seed=500 + k, **kw) for k in range(n_sims)], history_capacity=cap)
+        ens.initialize(world)
+        if cap == 2048:
+            table = ens.run(iterations)
+            agg = ens.handle.aggregate(0, iterations)
+            first = ens.handle.aggregate(-1, 3)       # starts at the initial state
+            init = np.stack([ens.handle.stats(k, -1, 1)[0] for k in range(n_sims)])
+        else:
+            agg = ens.run_aggregated(iterations)
+        tables.append(agg)
+        ens.close()
+    assert np.array_equal(tables[0], tables[1])
+    agg = tables[0]
+    assert agg.shape == (iterations, 14, 4)
+    assert np.array_equal(agg[:, :, 0], table.min(axis=0)) and np.array_equal(agg[:, :, 3], table.max(axis=0))
+    assert np.allclose(agg[:, :, 1], table.mean(axis=0), rtol=1e-13, atol=1e-300)
+    assert np.allclose(agg[:, :, 2], table.std(axis=0), rtol=1e-10, atol=1e-15)
+    assert agg[:, 8, 2].max() > 0                      # the seeds do differ (Infected)
+    assert np.array_equal(first[0, :, 0], init.min(axis=0)) and np.array_equal(first[1:], agg[:2])

@@ -46,6 +46,37 @@ def test_batch_experiment_schema_and_aggregation(tmp_path):
     assert back.shape == df.shape
 
 
+class FakeAggregating(FakeSim):
+    """A simulation type that offers the device-side reduction hook (network/graph_abs.py::run_ensemble_aggregated)."""
+    broken = False
+
+    @classmethod
+    def run_ensemble_aggregated(cls, experiments, iterations, **kw):
+        if cls.broken:
+            raise RuntimeError("no device")
+        t = np.arange(1, iterations + 1, dtype=np.float64)
+        agg = np.empty((iterations, 2, 4))
+        agg[:, 0] = np.stack([t + 1, t + 2.5, np.full_like(t, 0.5), t + 4], axis=1)
+        agg[:, 1] = np.stack([2 * t, 2 * t, np.zeros_like(t), 2 * t], axis=1)
+        return ["A", "B"], agg
+
+
+def test_batch_experiment_takes_the_device_aggregate_when_offered(tmp_path, capsys):
+    FakeAggregating.broken = False
+    df = batch_experiment(4, 3, str(tmp_path / "a.csv"), simulation_type=FakeAggregating)
+    assert list(df.columns) == ['Iteration', 'Metric', 'Min', 'Avg', 'Std', 'Max']
+    assert df["Metric"].tolist() == ["A", "B"] * 3 and df["Iteration"].tolist() == [0, 0, 1, 1, 2, 2]
+    assert df.iloc[2].tolist() == [1, "A", 3.0, 4.5, 0.5, 6.0]
+    assert pd.read_csv(tmp_path / "a.csv").shape == df.shape
+    # a failing device path falls back to one experiment after the other (the reference's own loop)
+    FakeAggregating.broken = True
+    FakeSim.calls = 0
+    df = batch_experiment(4, 3, str(tmp_path / "b.csv"), simulation_type=FakeAggregating)
+    assert "aggregated ensemble run" in capsys.readouterr().out
+    row = df[(df.Iteration == 0) & (df.Metric == "A")].iloc[0]
+    assert row.Min == 2.0 and row.Max == 5.0
+
+
 def test_batch_experiment_swallows_failed_experiments(tmp_path, capsys):
     FakeSim.calls = 0
     df = batch_experiment(4, 4, str(tmp_path / "o.csv"), simulation_type=FakeSim, fail_at=3)
