@@ -21,7 +21,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_DOMAIN, ERR_NOGPU = 0, -1, -2, -3, 
 # every symbol include/covidabs.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params", "cabs_set_triggers",
             "cabs_upload", "cabs_download", "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_history",
-            "cabs_contact_pairs", "cabs_get_info", "cabs_event_record", "cabs_event_elapsed_ms",
+            "cabs_contact_pairs", "cabs_cross_contact", "cabs_get_info", "cabs_event_record", "cabs_event_elapsed_ms",
             "cabs_profile_enable", "cabs_profile_read", "cabs_set_slab", "cabs_slab_phase", "cabs_set_stream",
             "cabs_slab_block_bytes", "cabs_set_slab_direct", "cabs_slab_step", "cabs_slab_run", "cabs_device_alloc", "cabs_device_free",
             "cabs_ipc_export", "cabs_ipc_open", "cabs_ipc_close",
@@ -178,6 +178,7 @@ def load():
     lib.cabs_ipc_open.argtypes = [C.c_int, C.c_char * 64, C.POINTER(P)]
     lib.cabs_ipc_close.argtypes = [C.c_int, P]
     lib.cabs_graph_create.argtypes = [C.POINTER(GraphConfig), C.POINTER(P)]
+    lib.cabs_cross_contact.argtypes = [P, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_uint64, C.c_uint32]
     lib.cabs_graph_destroy.argtypes = [P]
     lib.cabs_graph_destroy.restype = None
     lib.cabs_graph_last_error.argtypes = [P]
@@ -310,6 +311,13 @@ class Handle(object):
         self._check(self._lib.cabs_stats_history(self._h, int(first), int(count),
                                                  out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
+
+    def cross_contact(self, other, position, other_position, contagion_distance, seed, pair_code):
+        """Contacts between this population placed at `position` and `other` at `other_position` (abs.py:352-366)."""
+        self._check(self._lib.cabs_cross_contact(self._h, other._h, int(position[0]), int(position[1]),
+                                                 int(other_position[0]), int(other_position[1]),
+                                                 float(contagion_distance), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                 int(pair_code)))
 
     def contact_pairs(self, capacity=None):
         cap = int(capacity) if capacity else 1 << 16

@@ -378,3 +378,105 @@ class Simulation(object):
 
     def __str__(self):
         return str(self.get_description())
+
+
+class MultiPopulationSimulation(Simulation):
+    """Several populations on one plane (abs.py:328-415): every `Simulation` of `simulations` steps on its own, then the
+    agents of different populations meet across the boxes placed at `positions`.
+
+    The cross contacts run on the device (`cabs_cross_contact`) under the synchronous rule of the step itself: an agent
+    infected by a cross contact starts transmitting at the next phase, not later inside the same double loop.  Offsets
+    must be integers (lattice).  The quirk of abs.py:389-410 is kept: every statistic is the LAST population's count
+    over `total_population` (each population overwrites the previous one's entry), wealth sums are the last one's.
+    """
+
+    def __init__(self, **kwargs):
+        super(MultiPopulationSimulation, self).__init__(**kwargs)
+        self.simulations = kwargs.get('simulations', [])
+        self.positions = kwargs.get('positions', [])
+        self.total_population = kwargs.get('total_population', 0)
+
+    def get_population(self):
+        population = []
+        for simulation in self.simulations:
+            population.extend(simulation.get_population())
+        return population
+
+    def append(self, simulation, position):
+        self.simulations.append(simulation)
+        self.positions.append(position)
+        self.total_population += simulation.population_size
+
+    def initialize(self):
+        if self.seed is None:
+            self.seed = int(np.random.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(np.random.randint(0, 2 ** 31 - 1))
+        for simulation in self.simulations:
+            simulation.initialize()
+        self._iteration = 0
+        self.statistics = None
+
+    def _offset(self, k):
+        px, py = self.positions[k]
+        if int(px) != px or int(py) != py:
+            raise NotImplementedError("populations are placed on the integer lattice: offsets must be integers")
+        return int(px), int(py)
+
+    def execute(self, **kwargs):
+        if self.seed is None:
+            raise RuntimeError("initialize() first")
+        for simulation in self.simulations:
+            simulation.execute()
+        self._iteration += 1
+        count = len(self.simulations)
+        for m in range(count):
+            for n in range(m + 1, count):
+                a, b = self.simulations[m], self.simulations[n]
+                a._push_params()
+                b._push_params()
+                a._handle.cross_contact(b._handle, self._offset(m), self._offset(n), self.contagion_distance,
+                                        self.seed, m * count + n)
+                for sim in (a, b):
+                    sim._invalidate_host()
+                    sim.statistics = None
+        self.statistics = None
+
+    def run(self, iterations):
+        """`iterations` x (execute(); get_statistics('all')) -> float64 [iterations, 13], columns in the key order of
+        get_statistics (the reference's dictionary has an extra, always zero, 'Exposed' entry here)."""
+        rows = []
+        for it in range(int(iterations)):
+            self.execute()
+            rows.append(list(self.get_statistics(kind='all').values()))
+        return np.array(rows, dtype=np.float64).reshape(int(iterations), -1)
+
+    def get_positions(self):
+        positions = []
+        for ct, simulation in enumerate(self.simulations):
+            h = simulation._download()
+            px, py = self.positions[ct]
+            positions.extend([[int(x) + px, int(y) + py] for x, y in zip(h["x"], h["y"])])
+        return positions
+
+    def get_description(self, complete=False):
+        out = []
+        for simulation in self.simulations:
+            out.extend(simulation.get_description(complete))
+        return out
+
+    def get_statistics(self, kind='info'):
+        if self.statistics is None:
+            if not self.simulations:
+                raise RuntimeError("no populations")
+            last = self.simulations[-1]
+            last._push_params()
+            values, counts = last._handle.stats()
+            stats = {}
+            for k, key in enumerate(STAT_KEYS):
+                if k == 4:     # abs.py:396 iterates over every InfectionSeverity, Exposed included (never assigned)
+                    stats['Exposed'] = np.float64(0.0) / self.total_population
+                if k < 7:      # S, I, R, D, Asymptomatic, Hospitalization, Severe: counts of the last population
+                    stats[key] = np.float64(counts[k]) / self.total_population
+                else:          # Q1..Q5: the last population's sums, not normalised (abs.py:403-408)
+                    stats[key] = np.float64(values[k])
+            self.statistics = stats
+        return self.filter_stats(kind)

@@ -60,6 +60,7 @@ struct cabs_sim {
   long long *pairs = nullptr;   // contact-pair output buffer (grown on demand)
   size_t pairs_cap = 0;
   unsigned long long *pair_count = nullptr;
+  unsigned char *cross_mark = nullptr;   // cabs_cross_contact: one byte per agent (allocated on first use)
   cabs_params params;
   bool have_params = false;
   bool cells_dirty = true;      // cell_start does not describe the current positions / distance
@@ -138,6 +139,7 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
   cudaFree(sim->dev_blocks);
   cudaFree(sim->ctl); cudaFree(sim->history);
   cudaFree(sim->stage); cudaFree(sim->stage_id); cudaFree(sim->pairs); cudaFree(sim->pair_count);
+  cudaFree(sim->cross_mark);
   if (sim->step_graph) cudaGraphExecDestroy(sim->step_graph);
   if (sim->slab_graph) cudaGraphExecDestroy(sim->slab_graph);
   for (cudaEvent_t e : sim->events) if (e) cudaEventDestroy(e);
@@ -890,6 +892,55 @@ extern "C" int cabs_stats_history(cabs_sim *sim, uint64_t first_step, uint64_t c
   if (rc != CABS_OK) return rc;
   for (uint64_t k = 0; k < count; ++k) convert_record(sim, recs[k], values + k * CABS_NUM_STATS, nullptr);
   return CABS_OK;
+}
+
+// MultiPopulationSimulation.execute, the loop over one pair of populations (abs.py:352-366).
+extern "C" int cabs_cross_contact(cabs_sim *a, cabs_sim *b, int32_t ax, int32_t ay, int32_t bx, int32_t by,
+                                  double contagion_distance, uint64_t seed, uint32_t pair_code) {
+  if (!a || !b || a == b) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: two different handles are needed");
+  if (!a->have_params || !b->have_params) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: call cabs_set_params first");
+  if (a->slab_on || b->slab_on) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: not defined for slab handles");
+  if (a->device != b->device) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: both populations must live on one device");
+  if (a->step != b->step) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: the populations are at different steps");
+  if (a->n == 0 || b->n == 0) return CABS_OK;
+  if (cudaSetDevice(a->device) != cudaSuccess) return fail(a, CABS_ERR_CUDA, "cabs_cross_contact: cudaSetDevice failed");
+  for (cabs_sim *s : {a, b}) {
+    if (!s->cross_mark) {
+      if (cudaMalloc(&s->cross_mark, s->capacity + kPad) != cudaSuccess)
+        return fail(a, CABS_ERR_CUDA, "cabs_cross_contact: out of device memory");
+      if (cudaMemsetAsync(s->cross_mark, 0, s->capacity + kPad, s->stream) != cudaSuccess)
+        return fail(a, CABS_ERR_CUDA, "cabs_cross_contact: memset failed");
+    }
+  }
+  // everything runs on A's stream, after what B's stream holds; B's stream continues after it
+  cudaEvent_t before = nullptr, after = nullptr;
+  if (cudaEventCreateWithFlags(&before, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&after, cudaEventDisableTiming) != cudaSuccess)
+    return fail(a, CABS_ERR_CUDA, "cabs_cross_contact: event creation failed");
+  cudaEventRecord(before, b->stream);
+  cudaStreamWaitEvent(a->stream, before, 0);
+  {
+    cabs_sim *sim = a;   // the launch macro counts on `sim`
+    const unsigned na = (unsigned)a->n;
+    LAUNCH(k_cross_contact, (na + 255u) / 256u, 256, a->ctl, a->hot[a->cur], b->ctl, b->hot[b->cur], ax - bx, ay - by,
+           contagion_distance, (uint32_t)a->step, pair_code, (uint32_t)(seed & 0xFFFFFFFFu), (uint32_t)(seed >> 32),
+           a->cross_mark, b->cross_mark);
+    LAUNCH(k_cross_apply, a->num_sms * 4, 256, a->ctl, a->hot[a->cur], a->cross_mark);
+    LAUNCH(k_cross_apply, a->num_sms * 4, 256, b->ctl, b->hot[b->cur], b->cross_mark);
+  }
+  cudaEventRecord(after, a->stream);
+  cudaStreamWaitEvent(b->stream, after, 0);
+  cudaEventDestroy(before);
+  cudaEventDestroy(after);
+  {
+    cabs_sim *sim = a;
+    CK(cudaGetLastError());
+  }
+  // the statistics record of each handle follows its population (MultiPopulationSimulation.get_statistics reads the
+  // populations after the cross contacts, abs.py:389-410); the history rows of the steps stay as they were
+  int rc = rebuild_static(a);
+  if (rc == CABS_OK) rc = rebuild_static(b);
+  return rc;
 }
 
 extern "C" int cabs_contact_pairs(cabs_sim *sim, int64_t *ij, size_t capacity_pairs, size_t *n_pairs) {

@@ -1704,6 +1704,64 @@ __global__ void k_init_ctl(Ctl *ctl, unsigned k0, unsigned k1, unsigned max_cell
 }
 
 // ------------------------------------------------------------------------------------------
+// MultiPopulationSimulation (abs.py:352-366): contacts between the agents of two populations whose boxes sit at fixed
+// offsets of a common plane.  Every agent of A against every agent of B (the reference's double loop; B streams through
+// shared memory), distance on the shifted integer positions against the same threshold T(r) as inside a population
+// (SURVEY.md A.3).  `a_i.status == Susceptible and b_j.status == Infected` -> draw <= A's contagion_rate infects a_i,
+// and the mirror image with B's rate (abs.py:365-366 call each population's own contact()).  Synchronous rule as in
+// k_contagion: only agents Infected when the phase starts transmit, so the marks go to byte arrays first and
+// k_cross_apply sets the newly-infected bit afterwards; the draw is keyed on (id in A, id in B, step, pair of
+// populations), words x / y for the two directions.
+constexpr uint32_t kStreamCross = 3;
+__global__ void __launch_bounds__(256)
+k_cross_contact(const Ctl *__restrict__ ctl_a, const uint4 *__restrict__ hot_a, const Ctl *__restrict__ ctl_b,
+                const uint4 *__restrict__ hot_b, int shift_x, int shift_y, double distance, uint32_t step,
+                uint32_t pair_code, uint32_t k0, uint32_t k1, unsigned char *__restrict__ mark_a,
+                unsigned char *__restrict__ mark_b) {
+  __shared__ uint4 s_b[256];
+  __shared__ int s_T;
+  if (threadIdx.x == 0) s_T = threshold_T(distance);
+  const unsigned na = ctl_a->n, nb = ctl_b->n;
+  const long long thr_a = ctl_a->thr_rate, thr_b = ctl_b->thr_rate;
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  const uint4 ha = i < na ? hot_a[i] : make_uint4(0, 0, 0, 0);
+  const uint32_t st_a = attr_status(attr_normalize(ha.z));
+  const long long xa = (long long)(int)ha.x + shift_x, ya = (long long)(int)ha.y + shift_y;   // in B's frame
+  bool hit_a = false;
+  for (unsigned base = 0; base < nb; base += 256u) {
+    __syncthreads();
+    if (base + threadIdx.x < nb) s_b[threadIdx.x] = hot_b[base + threadIdx.x];
+    __syncthreads();
+    const unsigned m = min(256u, nb - base);
+    const long long T = s_T;
+    if (i >= na || (st_a != ST_S && st_a != ST_I)) continue;
+    for (unsigned j = 0; j < m; ++j) {
+      const uint4 hb = s_b[j];
+      const long long dx = xa - (int)hb.x, dy = ya - (int)hb.y;
+      if (dx * dx + dy * dy > T) continue;
+      const uint32_t st_b = attr_status(attr_normalize(hb.z));
+      const bool a_from_b = st_a == ST_S && st_b == ST_I, b_from_a = st_b == ST_S && st_a == ST_I;
+      if (!a_from_b && !b_from_a) continue;
+      const uint4 r = philox4x32_10(ha.w, step, kStreamCross | (pair_code << 8), hb.w, k0, k1);
+      if (a_from_b && (long long)r.x <= thr_a) hit_a = true;
+      if (b_from_a && (long long)r.y <= thr_b) mark_b[base + j] = 1;   // several writers, one value
+    }
+  }
+  if (hit_a) mark_a[i] = 1;
+}
+
+// Marked agents become Infected the way k_contagion's victims do (bit folded by attr_normalize at the next read).
+__global__ void k_cross_apply(const Ctl *__restrict__ ctl, uint4 *__restrict__ hot, unsigned char *__restrict__ mark) {
+  const unsigned n = ctl->n;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (mark[i]) {
+      hot[i].z |= kNewlyInfected;
+      mark[i] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Host SoA (separate columns, agents.py:44-64) <-> device records.
 __global__ void k_pack(unsigned n, const int *__restrict__ x, const int *__restrict__ y,
                        const uint8_t *__restrict__ status, const uint8_t *__restrict__ severity,

@@ -239,6 +239,15 @@ int cabs_profile_enable(cabs_sim *sim, int on);
 int cabs_profile_read(cabs_sim *sim, cabs_kernel_time *out, int capacity, int *count);
 
 
+/* Replaces the loop over one pair of populations in MultiPopulationSimulation.execute (covid_abs/abs.py:352-366):
+ * `a` sits at (ax, ay) and `b` at (bx, by) of a common plane (the reference's `positions`); agents of the two within
+ * `contagion_distance` meet, a Susceptible one next to an Infected one is infected when the draw keyed on
+ * (seed, the two ids, step, pair_code) is <= the contagion_rate of ITS OWN population.  Synchronous rule: only agents
+ * Infected before the call transmit.  Both handles on one device, at the same step; afterwards cabs_stats of either
+ * handle describes its population including the new infections.  O(n_a * n_b) distance tests, like the reference. */
+int cabs_cross_contact(cabs_sim *a, cabs_sim *b, int32_t ax, int32_t ay, int32_t bx, int32_t by,
+                       double contagion_distance, uint64_t seed, uint32_t pair_code);
+
 /* ======================================================================================================
  * GraphSimulation (covid_abs/network/graph_abs.py): the hourly routine model with houses, businesses,
  * government and healthcare.  One handle holds `n_sims` independent simulations of the same capacity (a
