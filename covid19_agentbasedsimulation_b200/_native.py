@@ -26,7 +26,7 @@ EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params",
             "cabs_slab_block_bytes", "cabs_set_slab_direct", "cabs_slab_step", "cabs_slab_run", "cabs_device_alloc", "cabs_device_free",
             "cabs_ipc_export", "cabs_ipc_open", "cabs_ipc_close",
             "cabs_graph_create", "cabs_graph_destroy", "cabs_graph_last_error", "cabs_graph_upload", "cabs_graph_run",
-            "cabs_graph_sync", "cabs_graph_stats", "cabs_graph_aggregate", "cabs_graph_download",
+            "cabs_graph_sync", "cabs_graph_stats", "cabs_graph_stats_all", "cabs_graph_aggregate", "cabs_graph_download",
             "cabs_graph_last_run_ms")
 
 GRAPH_NUM_STATS, GRAPH_MAX_BUSINESS = 14, 16
@@ -188,6 +188,7 @@ def load():
     lib.cabs_graph_sync.argtypes = [P]
     lib.cabs_graph_stats.argtypes = [P, C.c_uint32, C.c_int64, C.c_uint32, C.POINTER(C.c_double)]
     lib.cabs_graph_aggregate.argtypes = [P, C.c_int64, C.c_uint32, C.POINTER(C.c_double)]
+    lib.cabs_graph_stats_all.argtypes = [P, C.c_int64, C.c_uint32, C.POINTER(C.c_double)]
     lib.cabs_graph_download.argtypes = [P, C.c_uint32, C.POINTER(GraphWorld)]
     lib.cabs_graph_last_run_ms.argtypes = [P, C.POINTER(C.c_double)]
     for name in EXPORTED:
@@ -426,6 +427,13 @@ class GraphHandle(object):
         out = np.empty((int(count), GRAPH_NUM_STATS), dtype=np.float64)
         self._check(self._lib.cabs_graph_stats(self._h, int(sim), int(first), int(count),
                                                out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def stats_all(self, first, count):
+        """Rows of every simulation of the handle -> float64 [n_sims, count, 14] (one strided copy)."""
+        out = np.empty((self.n_sims, int(count), GRAPH_NUM_STATS), dtype=np.float64)
+        self._check(self._lib.cabs_graph_stats_all(self._h, int(first), int(count),
+                                                   out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
 
     def aggregate(self, first, count):

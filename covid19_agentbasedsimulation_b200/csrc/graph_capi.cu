@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <string>
 #include <vector>
@@ -337,6 +338,40 @@ extern "C" int cabs_graph_stats(cabs_graph *g, uint32_t sim, int64_t first, uint
     const uint32_t run = (uint32_t)std::min<int64_t>(count - k, cur.hist_cap - slot);
     GCK(cudaMemcpyAsync(rows + (size_t)k * kStats, cur.history + (size_t)slot * kStats,
                         (size_t)run * kStats * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    k += run;
+  }
+  GCK(cudaStreamSynchronize(g->stream));
+  return CABS_OK;
+}
+
+// The rows of every simulation of the handle in one strided copy per contiguous piece of the ring:
+// rows[sim][k][metric], k = first_iteration + 0 .. count-1.
+extern "C" int cabs_graph_stats_all(cabs_graph *g, int64_t first, uint32_t count, double *rows) {
+  if (!g || (count && !rows)) return gfail(g, CABS_ERR_INVALID, "cabs_graph_stats_all: null argument");
+  for (uint32_t s = 0; s < g->cfg.n_sims; ++s)
+    if (!g->uploaded[s]) return gfail(g, CABS_ERR_INVALID, "cabs_graph_stats_all: every simulation of the handle must be uploaded");
+  if (count == 0) return CABS_OK;
+  GCK(cudaSetDevice(g->device));
+  Sim cur;
+  GCK(cudaMemcpyAsync(&cur, g->sims, sizeof(Sim), cudaMemcpyDeviceToHost, g->stream));
+  GCK(cudaStreamSynchronize(g->stream));
+  const int64_t last = cur.iteration;
+  if (first < -1 || first + (int64_t)count - 1 > last)
+    return gfail(g, CABS_ERR_INVALID, "cabs_graph_stats_all: iterations not executed yet");
+  if (last - first >= (int64_t)cur.hist_cap)
+    return gfail(g, CABS_ERR_CAPACITY, "cabs_graph_stats_all: rows already overwritten (history_capacity)");
+  const size_t row = kStats * sizeof(double), n_sims = g->cfg.n_sims;
+  const size_t dst_pitch = (size_t)count * row, src_pitch = (size_t)cur.hist_cap * row;
+  uint32_t k = 0;
+  if (first < 0) {   // the initial rows live in their own array, one per simulation
+    GCK(cudaMemcpy2DAsync(rows, dst_pitch, g->initial_rows, row, row, n_sims, cudaMemcpyDeviceToHost, g->stream));
+    k = 1;
+  }
+  while (k < count) {
+    const int64_t slot = (first + k) % cur.hist_cap;
+    const uint32_t run = (uint32_t)std::min<int64_t>(count - k, cur.hist_cap - slot);
+    GCK(cudaMemcpy2DAsync(rows + (size_t)k * kStats, dst_pitch, g->history + (size_t)slot * kStats, src_pitch,
+                          (size_t)run * row, n_sims, cudaMemcpyDeviceToHost, g->stream));
     k += run;
   }
   GCK(cudaStreamSynchronize(g->stream));

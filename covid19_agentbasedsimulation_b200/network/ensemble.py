@@ -64,12 +64,12 @@ class GraphEnsemble(object):
             first = self.iteration + 1
             self.handle.run(chunk)
             self.iteration += chunk
-            for k, sim in enumerate(self.sims):
+            for sim in self.sims:
                 sim.iteration = self.iteration
                 sim._world = None
                 sim._entities = None
                 sim.statistics = None
-                out[k, done:done + chunk] = self.handle.stats(k, first, chunk)
+            out[:, done:done + chunk] = self.handle.stats_all(first, chunk)
             done += chunk
         return out
 

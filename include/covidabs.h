@@ -323,6 +323,8 @@ int cabs_graph_sync(cabs_graph *g);
 /* Replaces get_statistics(kind='all') (graph_abs.py:302-324): rows after iterations
  * [first_iteration, first_iteration + count); first_iteration = -1 is the initial state. */
 int cabs_graph_stats(cabs_graph *g, uint32_t sim, int64_t first_iteration, uint32_t count, double *rows);
+/* The same rows for every simulation of the handle at once: rows[n_sims][count][CABS_GRAPH_NUM_STATS]. */
+int cabs_graph_stats_all(cabs_graph *g, int64_t first_iteration, uint32_t count, double *rows);
 /* Replaces the aggregation loop of batch_experiment (covid_abs/experiments.py:200-208) over the simulations of the
  * handle (its "experiments"): out[count][CABS_GRAPH_NUM_STATS][4] = Min, Avg, Std (ddof = 0), Max of every metric
  * after iterations [first_iteration, first_iteration + count), reduced on the device. */

@@ -164,6 +164,10 @@ def test_device_aggregate_equals_numpy_over_the_rows(native_lib):
             init = np.stack([ens.handle.stats(k, -1, 1)[0] for k in range(n_sims)])
         else:
             agg = ens.run_aggregated(iterations)
+            ens.close()
+            ens = GraphEnsemble([GraphSimulation(seed=500 + k, **kw) for k in range(n_sims)], history_capacity=cap)
+            ens.initialize(world)
+            assert np.array_equal(ens.run(iterations), table)     # strided copies of a wrapped ring
         tables.append(agg)
         ens.close()
     assert np.array_equal(tables[0], tables[1])
