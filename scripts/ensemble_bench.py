@@ -54,6 +54,14 @@ def main():
     ens.initialize(built)
     table = ens.run(args.iterations)                    # [my simulations, iterations, 14]
     ms = ens.last_run_ms()
+    # what crosses the bus afterwards: every row of every simulation, or the Min/Avg/Std/Max reduced on the device
+    t0 = time.perf_counter()
+    rows_again = ens.handle.stats_all(0, args.iterations)
+    t_rows = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    agg = ens.handle.aggregate(0, args.iterations)
+    t_agg = time.perf_counter() - t0
+    assert np.array_equal(rows_again, table) and np.array_equal(agg[:, :, 3], table.max(axis=0))
     executed = sum(1 for it in range(args.iterations) if not (it % 24 != 0 and it % 24 < 8))
     mine_rate = len(sims) * n * executed / (ms * 1e-3)
     final = np.zeros((len(sc.PAPER_SCENARIOS), 3))      # per scenario: sum of final Infected, Death, count
@@ -73,6 +81,8 @@ def main():
                    "simulation, no communication".format(args.seeds, n, args.iterations, world),
             n_sims=len(jobs), sims_per_gpu=len(sims), ms=ms, agent_updates_per_s=total, per_gpu_first_rank=mine_rate,
             host_world_build_s=t_build,
+            readback_first_rank=dict(rows_ms=t_rows * 1e3, rows_bytes=int(rows_again.nbytes),
+                                     aggregate_ms=t_agg * 1e3, aggregate_bytes=int(agg.nbytes)),
             mean_final_infected=[float(final[s, 0] / max(1.0, final[s, 2])) for s in range(final.shape[0])],
             mean_final_death=[float(final[s, 1] / max(1.0, final[s, 2])) for s in range(final.shape[0])])))
     if world > 1:
