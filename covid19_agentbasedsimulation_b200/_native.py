@@ -19,10 +19,10 @@ SYNCHRONOUS, SEQUENTIAL = 0, 1
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_DOMAIN, ERR_NOGPU = 0, -1, -2, -3, -4, -5
 
 # every symbol include/covidabs.h declares (checked by tests/test_capi_symbols.py)
-EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params", "cabs_set_triggers",
-            "cabs_upload", "cabs_download", "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_history",
+EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params", "cabs_get_params", "cabs_set_triggers",
+            "cabs_upload", "cabs_set_step", "cabs_download", "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_history",
             "cabs_contact_pairs", "cabs_cross_contact", "cabs_get_info", "cabs_event_record", "cabs_event_elapsed_ms",
-            "cabs_profile_enable", "cabs_profile_read", "cabs_set_slab", "cabs_slab_phase", "cabs_set_stream",
+            "cabs_profile_enable", "cabs_profile_read", "cabs_selftest_normals", "cabs_set_slab", "cabs_slab_phase", "cabs_set_stream",
             "cabs_slab_block_bytes", "cabs_set_slab_direct", "cabs_slab_step", "cabs_slab_run", "cabs_device_alloc", "cabs_device_free",
             "cabs_ipc_export", "cabs_ipc_open", "cabs_ipc_close",
             "cabs_graph_create", "cabs_graph_destroy", "cabs_graph_last_error", "cabs_graph_upload", "cabs_graph_run",
@@ -145,15 +145,23 @@ def load():
                           "(there is no CPU fallback for the agent step)".format(LIB_PATH))
     lib = C.CDLL(LIB_PATH)
     P = C.c_void_p
+    if os.environ.get("CABS_AB_OLD_LIB"):   # A/B timing of a library built from an older tree (scripts/ab_variants.sh)
+        class _Stub(object):
+            argtypes = restype = None
+        for name in EXPORTED:
+            if not hasattr(lib, name):
+                setattr(lib, name, _Stub())
     lib.cabs_create.argtypes = [C.POINTER(Config), C.POINTER(P)]
     lib.cabs_destroy.argtypes = [P]
     lib.cabs_destroy.restype = None
     lib.cabs_last_error.argtypes = [P]
     lib.cabs_last_error.restype = C.c_char_p
     lib.cabs_set_params.argtypes = [P, C.POINTER(Params)]
+    lib.cabs_get_params.argtypes = [P, C.POINTER(Params)]
     lib.cabs_set_triggers.argtypes = [P, C.POINTER(Trigger), C.c_int]
     lib.cabs_upload.argtypes = [P, C.POINTER(SoaHost)]
     lib.cabs_download.argtypes = [P, C.POINTER(SoaHost)]
+    lib.cabs_set_step.argtypes = [P, C.c_uint64]
     lib.cabs_step.argtypes = [P, C.c_int]
     lib.cabs_sync.argtypes = [P]
     lib.cabs_stats.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -164,6 +172,7 @@ def load():
     lib.cabs_event_elapsed_ms.argtypes = [P, C.c_int, C.c_int, C.POINTER(C.c_double)]
     lib.cabs_profile_enable.argtypes = [P, C.c_int]
     lib.cabs_profile_read.argtypes = [P, C.POINTER(KernelTime), C.c_int, C.POINTER(C.c_int)]
+    lib.cabs_selftest_normals.argtypes = [C.c_int, C.c_uint, C.POINTER(C.c_double)]
     lib.cabs_set_slab.argtypes = [P, C.POINTER(Slab)]
     lib.cabs_slab_phase.argtypes = [P, C.c_int, C.c_int]
     lib.cabs_set_stream.argtypes = [P, C.c_void_p]
@@ -218,11 +227,16 @@ class Handle(object):
             msg = self._lib.cabs_last_error(None)
             raise NativeError(rc, msg.decode() if msg else "cabs_create failed")
         self.capacity = int(capacity)
+        self.steps = 0      # mirror of the handle's step counter (draw clock / index of the statistics ring)
 
     def _check(self, rc):
         if rc != OK:
             msg = self._lib.cabs_last_error(self._h)
             raise NativeError(rc, msg.decode() if msg else "?")
+
+    def set_step(self, step):
+        self._check(self._lib.cabs_set_step(self._h, int(step)))
+        self.steps = int(step)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -237,6 +251,11 @@ class Handle(object):
 
     def set_params(self, params):
         self._check(self._lib.cabs_set_params(self._h, C.byref(params)))
+
+    def get_params(self):
+        p = Params()
+        self._check(self._lib.cabs_get_params(self._h, C.byref(p)))
+        return p
 
     def set_triggers(self, triggers):
         arr = (Trigger * max(1, len(triggers)))(*triggers)
@@ -297,6 +316,7 @@ class Handle(object):
 
     def step(self, nsteps=1):
         self._check(self._lib.cabs_step(self._h, int(nsteps)))
+        self.steps += int(nsteps)
 
     def sync(self):
         self._check(self._lib.cabs_sync(self._h))
@@ -465,6 +485,14 @@ def _util_check(rc, what):
     if rc != OK:
         msg = load().cabs_last_error(None)
         raise NativeError(rc, "{}: {}".format(what, msg.decode() if msg else "?"))
+
+
+def selftest_normals(device=0, sweep_log2=30):
+    """Measured errors of the special-function move draw against its defining arithmetic (see covidabs.h)."""
+    out = (C.c_double * 6)()
+    _util_check(load().cabs_selftest_normals(int(device), int(sweep_log2), out), "cabs_selftest_normals")
+    keys = ("radius_error_over_bound", "angle_error_over_bound", "radius_inputs_rejected", "accepted", "wrong", "draws")
+    return dict(zip(keys, out[:]))
 
 
 def slab_block_bytes(n_ranks, migrant_capacity, ghost_capacity):

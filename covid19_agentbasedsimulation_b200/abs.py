@@ -11,7 +11,10 @@ Differences a user can observe (all documented in DESIGN.md):
   * contacts are applied synchronously (an agent infected in a step starts transmitting in the next);
   * the critical-limit test (abs.py:214-217) reads the statistics of the end of the previous step,
     which is what the reference's memo holds when `batch_experiment` drives it;
-  * `triggers_population` with Python lambdas cannot run on the device and raise NotImplementedError.
+  * `triggers_population` with Python lambdas cannot run on the device and raise NotImplementedError;
+  * `get_population()` / `sim.population` return `Agent` objects materialised from a device download: they are
+    detached copies, so mutating `sim.population[i]` in place does not reach the device -- pass the edited list
+    back through `set_population()` (or use `set_population_arrays`).
 """
 import numpy as np
 
@@ -191,6 +194,27 @@ class Simulation(object):
                 h.set_triggers(native)
             self._pushed_triggers = key
 
+    def _refresh_from_device(self):
+        """A fired declarative trigger rewrote simulation attributes on the device (abs.py:267-271: the change is
+        permanent).  Mirror them into the Python attributes, and into the record of what was last pushed, so that a
+        later change of any other attribute does not send stale values back."""
+        if self._handle is None or self._pushed is None:
+            return
+        if not any(isinstance(t, Trigger) for t in self.triggers_simulation):
+            return
+        if self._param_tuple() != self._pushed:
+            return          # user code changed attributes since the last push: they win at the next _push_params()
+        p = self._targets()[0].get_params()
+        amp = [float(v) for v in p.amplitudes]
+        for status, code in STATUS_CODE.items():
+            if status in self.amplitudes:
+                keep_int = isinstance(self.amplitudes[status], int) and float(int(amp[code])) == amp[code]
+                self.amplitudes[status] = int(amp[code]) if keep_int else amp[code]
+        self.contagion_rate = float(p.contagion_rate)
+        self.contagion_distance = float(p.contagion_distance)
+        self.critical_limit = float(p.critical_limit)
+        self._pushed = self._param_tuple()
+
     def set_population_arrays(self, x, y, status, age, stratum, wealth, severity=None, infected_time=None):
         """Upload a population given as columns (codes of include/covidabs.h); ids = positions."""
         n = len(x)
@@ -303,6 +327,7 @@ class Simulation(object):
         self._handle.step(1)
         self._iteration += 1
         self._invalidate_host()
+        self._refresh_from_device()
         for trigger in self._host_triggers():  # abs.py:267-271
             if trigger['condition'](self):
                 attr = trigger['attribute']
@@ -326,12 +351,14 @@ class Simulation(object):
         if len(self.triggers_population) > 0:
             raise NotImplementedError("per-agent Python triggers cannot run on the device")
         self._push_params()
-        first = self._iteration
+        first = self._handle.info()["step"]     # the handle's clock is not reset by a re-upload
         self._handle.step(iterations)
         self._iteration += iterations
         self._invalidate_host()
         self.statistics = None
-        return self._handle.stats_history(first, iterations)
+        rows = self._handle.stats_history(first, iterations)
+        self._refresh_from_device()
+        return rows
 
     # ------------------------------------------------------------------ accessors
     def get_positions(self):

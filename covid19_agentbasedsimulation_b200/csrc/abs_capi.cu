@@ -69,7 +69,9 @@ struct cabs_sim {
   // steps is replayed without per-kernel launch gaps.  Valid while `cur == graph_cur`, `tab == graph_tab`.
   cudaGraphExec_t step_graph = nullptr;
   int graph_cur = -1, graph_tab = -1;
+  bool graph_broken = false;    // the stream refused capture once: stay on plain launches
   uint64_t n = 0, step = 0, launches = 0;
+  uint64_t hist_first = 0;      // first step whose statistics row the ring can hold (moved by cabs_set_step)
   cudaEvent_t events[CABS_NUM_EVENTS] = {};
   // per-kernel profiling: events[i] is recorded before launch i of the current batch, names[i] its kernel
   bool profiling = false;
@@ -160,6 +162,12 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   sim->num_sms = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
   sim->own_stream = sim->stream;
+  // pass B keeps 43 KB of staging per block: ask for the largest shared-memory carveout so that registers, not
+  // shared memory, decide how many of its blocks are resident
+  CK(cudaFuncSetAttribute(k_update_scatter<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_update_scatter<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_update_scatter<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_update_scatter<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   sim->capacity = cfg->capacity ? cfg->capacity : 1;
   if (sim->capacity >= (1ull << 31)) return fail(sim, CABS_ERR_CAPACITY, "capacity must be < 2^31 agents per device");
   // Two budgets for the cell table.  While few agents can transmit (or few can be infected) the contact pass is
@@ -275,6 +283,27 @@ extern "C" int cabs_set_params(cabs_sim *sim, const cabs_params *p) {
   return CABS_OK;
 }
 
+extern "C" int cabs_get_params(cabs_sim *sim, cabs_params *out) {
+  if (!sim || !out) return fail(sim, CABS_ERR_INVALID, "cabs_get_params: null argument");
+  if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_get_params: call cabs_set_params first");
+  CK(cudaSetDevice(sim->device));
+  {
+    const int rc = flush_late_close(sim);
+    if (rc != CABS_OK) return rc;
+  }
+  Ctl h;
+  CK(cudaMemcpyAsync(&h, sim->ctl, sizeof h, cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  *out = sim->params;
+  // what device-side triggers (abs.py:267-271) may have rewritten since the last cabs_set_params
+  for (int k = 0; k < 4; ++k) out->amplitudes[k] = (double)h.amp[k];
+  out->contagion_rate = h.rate;
+  out->contagion_distance = h.contagion_distance;
+  out->critical_limit = h.critical_limit;
+  sim->params = *out;
+  return CABS_OK;
+}
+
 extern "C" int cabs_set_triggers(cabs_sim *sim, const cabs_trigger *t, int count) {
   if (!sim || (count > 0 && !t)) return fail(sim, CABS_ERR_INVALID, "cabs_set_triggers: null argument");
   if (count < 0 || count > CABS_MAX_TRIGGERS) return fail(sim, CABS_ERR_INVALID, "too many triggers");
@@ -310,9 +339,15 @@ static void enqueue_build(cabs_sim *sim) {
   memset(&no_direct, 0, sizeof no_direct);
   LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl, sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list);
   LAUNCH(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
-  LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", k_update_scatter<kAdvance>, nb, kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t],
-         sim->cells[t ^ 1], sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, nullptr, nullptr,
-         (kAdvance && sequential) ? sim->tinf : nullptr, nullptr, nullptr, nullptr, no_direct);
+  if (kAdvance && sequential) {
+    LAUNCH_AS("k_update_scatter<true>", (k_update_scatter<kAdvance, true>), nb, kAgentThreads, sim->ctl, sim->hot[c], sim->w[c],
+              sim->aux, sim->cells[t], sim->cells[t ^ 1], sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, nullptr,
+              nullptr, sim->tinf, nullptr, nullptr, nullptr, no_direct);
+  } else {
+    LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", (k_update_scatter<kAdvance, false>), nb,
+              kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t], sim->cells[t ^ 1], sim->hot[o],
+              sim->w[o], sim->inf_list, sim->sqrt_tab, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, no_direct);
+  }
   if (kAdvance && sequential) {
     // rounds of label-correcting relaxation until no infection time is lowered (one host round trip each)
     for (int round = 0;; ++round) {
@@ -368,11 +403,16 @@ extern "C" int cabs_set_slab(cabs_sim *sim, const cabs_slab *slab) {
   for (int d = 0; d < 2; ++d)
     if (!slab->migrant_send[d] || !slab->migrant_recv[d] || !slab->ghost_send[d] || !slab->ghost_recv[d])
       return fail(sim, CABS_ERR_INVALID, "cabs_set_slab: null exchange buffer");
+  if (sim->have_params && sim->params.schedule == CABS_SEQUENTIAL)
+    return fail(sim, CABS_ERR_INVALID, "the sequential schedule is defined on one device only (SURVEY.md 8e)");
   CK(cudaSetDevice(sim->device));
   CK(cudaStreamSynchronize(sim->stream));
   cudaFree(sim->emig_list); cudaFree(sim->imm_rank); cudaFree(sim->tinf); cudaFree(sim->newinf_list);
   cudaFree(sim->dev_blocks);
   sim->emig_list = sim->imm_rank = nullptr;
+  sim->tinf = nullptr;
+  sim->newinf_list = nullptr;
+  sim->dev_blocks = nullptr;
   CK(cudaMalloc(&sim->emig_list, 2 * (size_t)slab->migrant_capacity * sizeof(unsigned)));
   CK(cudaMalloc(&sim->imm_rank, 2 * (size_t)slab->migrant_capacity * sizeof(unsigned)));
   for (int d = 0; d < 2; ++d) {  // headers start at count 0; outer-side receive buffers are never written again
@@ -457,7 +497,7 @@ static int slab_phase(cabs_sim *sim, int phase) {
     case 1:
       LAUNCH(k_count_immigrants, nbs, 256, sim->ctl, mr[0], mr[1], sim->cells[t], sim->imm_rank, D);
       LAUNCH(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
-      LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", k_update_scatter<kAdvance>, nb,
+      LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", (k_update_scatter<kAdvance, true>), nb,
                 kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t], sim->cells[t ^ 1],
                 sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, gs[0], gs[1], nullptr, mr[0], mr[1],
                 sim->imm_rank, D);   // the immigrants take their slots inside pass B; its last block pushes the ghosts
@@ -712,18 +752,36 @@ extern "C" int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop) {
            sim->stage + 2 * cap, sim->stage + 3 * cap, sim->stage + 4 * cap, pop->id ? sim->stage_id : nullptr,
            sim->hot[c]);
   }
-  // a new population starts a new run: step counter (part of the draw key) back to 0
-  const unsigned n32 = (unsigned)n, zero = 0;
+  // The step counter is part of the draw key (seed, agent, step) and is NOT reset here: a caller that downloads,
+  // edits and re-uploads the population every iteration (set_population, abs.py:65-69) must not see the draws of
+  // step 0 again.  A fresh handle starts at step 0; cabs_set_step restores the clock of a checkpoint.
+  if (n && pop->id && !sim->slab_on) {   // non-slab handles scatter by id on download: ids must be a permutation of 0..n-1
+    unsigned *mark = reinterpret_cast<unsigned *>(sim->aux);   // free until the next build
+    CK(cudaMemsetAsync(mark, 0, n * sizeof(unsigned), sim->stream));
+    LAUNCH(k_check_ids, agent_blocks(sim), 256, sim->ctl, sim->hot[c], (unsigned)n, mark);
+  }
+  const unsigned n32 = (unsigned)n;
   CK(cudaMemcpyAsync(&sim->ctl->n, &n32, sizeof(unsigned), cudaMemcpyHostToDevice, sim->stream));
-  CK(cudaMemcpyAsync(&sim->ctl->step, &zero, sizeof(unsigned), cudaMemcpyHostToDevice, sim->stream));
   sim->n = n;
-  sim->step = 0;
   if (sim->slab_on) {  // the caller drives the four phases of the first build (advance = 0)
     sim->cells_dirty = true;
     CK(cudaGetLastError());
     return CABS_OK;
   }
   return rebuild_static(sim);
+}
+
+extern "C" int cabs_set_step(cabs_sim *sim, uint64_t step) {
+  if (!sim) return fail(sim, CABS_ERR_INVALID, "cabs_set_step: null handle");
+  if (step >= (1ull << 32)) return fail(sim, CABS_ERR_INVALID, "cabs_set_step: the step counter is 32 bits wide");
+  if (sim->slab_on) return fail(sim, CABS_ERR_INVALID, "cabs_set_step: not defined for slab handles");
+  CK(cudaSetDevice(sim->device));
+  const unsigned s32 = (unsigned)step;
+  CK(cudaMemcpyAsync(&sim->ctl->step, &s32, sizeof(unsigned), cudaMemcpyHostToDevice, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  sim->step = step;
+  sim->hist_first = step;   // statistics rows of earlier steps belong to another clock
+  return CABS_OK;
 }
 
 extern "C" int cabs_download(cabs_sim *sim, cabs_soa_host *pop) {
@@ -779,7 +837,8 @@ extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
   }
   int s = 0;
   const bool sequential = sim->params.schedule == CABS_SEQUENTIAL;
-  if (!sim->profiling && !sequential && nsteps >= 4) {
+  const bool capturable = sim->stream != nullptr && sim->stream != cudaStreamLegacy && sim->stream != cudaStreamPerThread;
+  if (!sim->profiling && !sequential && nsteps >= 4 && capturable && !sim->graph_broken) {
     // pairs of steps through the captured graph (the kernels take every changing quantity from Ctl, so the same
     // eight launches are valid for any pair of steps that starts from the same ping/pong phase)
     if (sim->step_graph && (sim->graph_cur != sim->cur || sim->graph_tab != sim->tab)) {
@@ -790,19 +849,27 @@ extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
       cudaGraph_t graph = nullptr;
       const int cur0 = sim->cur, tab0 = sim->tab;
       const uint64_t launches0 = sim->launches;
-      CK(cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal));
-      enqueue_build<true>(sim);
-      enqueue_build<true>(sim);
-      CK(cudaStreamEndCapture(sim->stream, &graph));
-      sim->cur = cur0;              // capturing enqueued nothing: restore the host-side phase
-      sim->tab = tab0;
-      sim->launches = launches0;
-      CK(cudaGraphInstantiate(&sim->step_graph, graph, 0));
-      CK(cudaGraphDestroy(graph));
-      sim->graph_cur = cur0;
-      sim->graph_tab = tab0;
+      cudaError_t ce = cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal);
+      if (ce == cudaSuccess) {
+        enqueue_build<true>(sim);
+        enqueue_build<true>(sim);
+        ce = cudaStreamEndCapture(sim->stream, &graph);
+        sim->cur = cur0;              // capturing enqueued nothing: restore the host-side phase
+        sim->tab = tab0;
+        sim->launches = launches0;
+        if (ce == cudaSuccess) ce = cudaGraphInstantiate(&sim->step_graph, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+      }
+      if (ce != cudaSuccess) {        // a stream that cannot be captured: plain launches from now on
+        cudaGetLastError();
+        sim->step_graph = nullptr;
+        sim->graph_broken = true;
+      } else {
+        sim->graph_cur = cur0;
+        sim->graph_tab = tab0;
+      }
     }
-    for (; s + 2 <= nsteps; s += 2) {
+    for (; sim->step_graph && s + 2 <= nsteps; s += 2) {
       CK(cudaGraphLaunch(sim->step_graph, sim->stream));
       sim->launches += 8;
       sim->step += 2;
@@ -826,6 +893,11 @@ static int check_device_error(cabs_sim *sim) {
   unsigned err = 0;
   CK(cudaMemcpyAsync(&err, &sim->ctl->err, sizeof(unsigned), cudaMemcpyDeviceToHost, sim->stream));
   CK(cudaStreamSynchronize(sim->stream));
+  if (err & kErrBadIds) {
+    const unsigned clear = ~kErrBadIds;   // the population was rejected, the handle stays usable for a correct upload
+    LAUNCH(k_clear_error, 1, 32, sim->ctl, clear);
+    return fail(sim, CABS_ERR_INVALID, "cabs_upload: ids must be a permutation of 0..n-1 (they key the draws and the download order)");
+  }
   if (err & kErrDomain) return fail(sim, CABS_ERR_DOMAIN, "population bounding box exceeds the supported 2^28 lattice units");
   if (err & kErrOutOfGrid) return fail(sim, CABS_ERR_DOMAIN, "internal: an agent left the planned cell grid");
   if (err & kErrPeerTimeout)
@@ -871,6 +943,8 @@ extern "C" int cabs_stats(cabs_sim *sim, double *values, int64_t *counts) {
 extern "C" int cabs_stats_history(cabs_sim *sim, uint64_t first_step, uint64_t count, double *values) {
   if (!sim || (count && !values)) return fail(sim, CABS_ERR_INVALID, "cabs_stats_history: null argument");
   if (first_step + count > sim->step) return fail(sim, CABS_ERR_INVALID, "cabs_stats_history: steps not executed yet");
+  if (count && first_step < sim->hist_first)
+    return fail(sim, CABS_ERR_INVALID, "cabs_stats_history: steps before the last cabs_set_step are not on record");
   if (sim->step - first_step > sim->hist_cap)
     return fail(sim, CABS_ERR_CAPACITY, "cabs_stats_history: records already overwritten (history_capacity)");
   CK(cudaSetDevice(sim->device));
@@ -1044,5 +1118,26 @@ extern "C" int cabs_profile_read(cabs_sim *sim, cabs_kernel_time *out, int capac
   }
   *count = n;
   sim->prof_used = 0;
+  return CABS_OK;
+}
+
+extern "C" int cabs_selftest_normals(int device, unsigned sweep_log2, double out[6]) {
+  if (!out || sweep_log2 > 40) return CABS_ERR_INVALID;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return util_fail("cudaSetDevice", e);
+  unsigned long long *d = nullptr, h[6];
+  if ((e = cudaMalloc(&d, sizeof h)) != cudaSuccess) return util_fail("cudaMalloc", e);
+  cudaMemset(d, 0, sizeof h);
+  k_selftest_normals<<<148 * 8, 256>>>(d, sweep_log2);
+  e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return util_fail("k_selftest_normals", e);
+  for (int k = 0; k < 2; ++k) {
+    const unsigned bits = (unsigned)h[k];
+    float f;
+    memcpy(&f, &bits, sizeof f);
+    out[k] = (double)f;
+  }
+  for (int k = 2; k < 6; ++k) out[k] = (double)h[k];
   return CABS_OK;
 }

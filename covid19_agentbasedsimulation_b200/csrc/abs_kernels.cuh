@@ -40,6 +40,7 @@ constexpr uint32_t kErrOutOfGrid = 1u;     // an agent left the planned grid (in
 constexpr uint32_t kErrDomain = 2u;        // bounding box wider than 2^28
 constexpr uint32_t kErrWealthRange = 4u;   // fixed-point wealth sum would overflow
 constexpr uint32_t kErrExchange = 8u;      // slab exchange buffer overflow (migrants / ghosts)
+constexpr uint32_t kErrBadIds = 32u;       // uploaded ids are not a permutation of 0..n-1
 
 struct DevTrigger {
   int metric, op, attribute, pad;
@@ -154,7 +155,9 @@ struct StepParams {
   int gx0, gy0, eshift, ncx, ncy;
   float amp[4];
   double min_expense;
+  double me32;      // min_expense * 2^-32: folds the scaling of the income uniform (exact, a power of two)
   double bi[5];
+  double mebi[5];   // fl(min_expense * basic_income[stratum]): the daily expense of abs.py:230
   long long thr_hosp[9], thr_sev[9], thr_death[9];
   long long thr_rate;
   int T, reach, recovering_time, scale_bits, crit_active;
@@ -169,6 +172,8 @@ __device__ __forceinline__ void load_params(StepParams &P, const Ctl *ctl, bool 
   P.gx0 = g.gx0; P.gy0 = g.gy0; P.eshift = g.eshift; P.ncx = g.ncx; P.ncy = g.ncy;
   for (int i = 0; i < 4; ++i) P.amp[i] = ctl->amp[i];
   P.min_expense = ctl->min_expense;
+  P.me32 = __dmul_rn(ctl->min_expense, 0x1p-32);
+  for (int i = 0; i < 5; ++i) P.mebi[i] = __dmul_rn(ctl->min_expense, ctl->bi[i]);
   P.len_i = (int)fmin(fmax(ceil(ctl->length), -2147483647.0), 2147483647.0);
   P.hei_i = (int)fmin(fmax(ceil(ctl->height), -2147483647.0), 2147483647.0);
   for (int i = 0; i < 5; ++i) P.bi[i] = ctl->bi[i];
@@ -196,11 +201,14 @@ __device__ __forceinline__ void draw_displacement(const StepParams &P, uint32_t 
   ix = 0;
   iy = 0;
   if (mobile) {
-    float z0, z1;
-    normal_pair(w.x, w.y, z0, z1);
     const float a = P.amp[st];
-    ix = __float2int_rz(__fmul_rn(z0, a));  // int() truncates toward zero (abs.py:174-175)
-    iy = __float2int_rz(__fmul_rn(z1, a));
+#ifdef CABS_EXACT_NORMALS
+    displacement_exact(w.x, w.y, a, ix, iy);
+#else
+    // special-function evaluation with a per-draw proof that truncation agrees with the defining arithmetic;
+    // the few draws that land within the error bound of an integer are redone exactly (abs_rng.cuh)
+    if (!displacement_fast(w.x, w.y, a, ix, iy)) displacement_exact(w.x, w.y, a, ix, iy);
+#endif
   }
 }
 // abs.py:177-185: the increment, not the position, is reflected
@@ -348,7 +356,7 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, 
 constexpr int kTile = 256;    // agents per tile = consumer threads per block of the agent passes
 constexpr int kPad = kTile;   // every per-agent array is allocated with this many spare elements (whole-tile loads)
 constexpr int kConsumerWarps = kTile / 32;
-constexpr int kAgentThreads = kTile + 32;  // + one producer warp that only issues the bulk loads
+constexpr int kAgentThreads = kTile;       // threads per block of pass B
 
 // ------------------------------------------------------------------------------------------
 // Pass A: where will every agent be after this step's move?  Writes the displacement and the rank
@@ -359,6 +367,10 @@ constexpr int kScanThreads = 512;
 
 // Pass A reads one 16-byte column with plenty of resident warps, so plain vectorised loads (one agent
 // ahead) do as well as staged ones; pass B, which streams three columns at low occupancy, stages them.
+#ifndef CABS_A_PREFETCH
+#define CABS_A_PREFETCH 3
+#endif
+constexpr unsigned kPrefetchA = CABS_A_PREFETCH;
 template <bool kAdvance>
 __global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot,
                                                     uint2 *__restrict__ aux, unsigned *__restrict__ cells,
@@ -384,6 +396,11 @@ __global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const
   for (unsigned i = tid; i < P.n; i += stride) {
     const uint4 h = h_next;
     if (i + stride < P.n) h_next = __ldg(&hot[i + stride]);
+#ifndef CABS_A_NO_PREFETCH
+    // one register-held record ahead does not cover the DRAM latency at this occupancy: ask L2 for the records a
+    // few grid strides ahead (costs no registers), so that the load above finds them there
+    if (i + kPrefetchA * stride < P.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(hot + i + kPrefetchA * stride));
+#endif
     int nx = (int)h.x, ny = (int)h.y;
     uint32_t d = 0;
     if (kAdvance) {
@@ -521,57 +538,59 @@ struct BlockStats {
 };
 
 #ifndef CABS_B_MINBLOCKS
-#define CABS_B_MINBLOCKS 3
+#define CABS_B_MINBLOCKS 4
 #endif
 constexpr int kSqrtTable = 4096;  // sqrt(d2) for d2 < 4096, exact (IEEE sqrt), filled once by k_init_ctl
 
 // One agent's move + update + economy (abs.py:156-230).  ix, iy: this step's displacement.
 __device__ __forceinline__ void advance_agent(const StepParams &P, uint32_t aid, int ix, int iy, uint32_t &a,
                                               double &w, const double *__restrict__ sqrt_tab) {
-  uint32_t st = attr_status(a), sev = attr_severity(a), time = attr_time(a);
-  const uint32_t stratum = attr_stratum(a), age = attr_age(a);
-  const bool mobile = !(st == ST_D || (st == ST_I && (sev == SEV_H || sev == SEV_G)));  // abs.py:164-167
+  const uint32_t st = attr_status(a);
+  if (st == ST_D) return;   // the dead neither move (abs.py:164) nor update (abs.py:193)
+  const uint32_t sev = attr_severity(a);
+  const uint32_t stratum = min(attr_stratum(a), 4u);
   const uint2 r0 = agent_draw(aid, P.step, kStreamEconomy, P.k0, P.k1);
-  const double bi = P.bi[min(stratum, 4u)];
-  if (mobile) {
-    // abs.py:187-189: wealth += sqrt(ix^2+iy^2) * rand * minimum_expense * basic_income[stratum]
+  if (!(st == ST_I && sev >= SEV_H)) {   // mobile (abs.py:164-167)
+    // abs.py:187-189: wealth += sqrt(ix^2+iy^2) * rand * minimum_expense * basic_income[stratum], rand = (r + .5) 2^-32.
+    // The power of two rides on minimum_expense (me32): scaling by it commutes with every rounding, so the three
+    // products below round exactly like ((dist * rand) * minimum_expense) * basic_income.
     const int d2 = ix * ix + iy * iy;
     const double dist = d2 < kSqrtTable ? __ldg(&sqrt_tab[d2]) : __dsqrt_rn((double)d2);
-    const double inc = __dmul_rn(__dmul_rn(__dmul_rn(dist, u01(r0.x)), P.min_expense), bi);
-    w = __dadd_rn(w, inc);
+    const double x = __dmul_rn(dist, __dadd_rn((double)r0.x, 0.5));
+    w = __dadd_rn(w, __dmul_rn(__dmul_rn(x, P.me32), P.bi[stratum]));
   }
   // abs.py:191-230
-  if (st != ST_D) {
-    bool pays = true;
-    if (st == ST_I) {
-      time += 1;
-      const uint32_t idx = min(age > 10u ? age / 10u - 1u : 0u, 8u);  // abs.py:204
-      const long long w_sub = (long long)r0.y;
-      if (sev == SEV_A) {
-        if (w_sub < P.thr_hosp[idx]) sev = SEV_H;  // age_hospitalization_probs[idx] > u (abs.py:209)
-      } else if (sev == SEV_H) {
-        if (w_sub < P.thr_sev[idx]) {              // age_severe_probs[idx] > u (abs.py:212)
-          sev = SEV_G;
-          if (P.crit_active) {                     // abs.py:214-217
-            st = ST_D;
-            sev = SEV_A;
-          }
+  if (st == ST_I) {
+    uint32_t nst = ST_I, nsev = sev, time = attr_time(a) + 1u;
+    const uint32_t age = attr_age(a);
+    const uint32_t idx = min(age > 10u ? age / 10u - 1u : 0u, 8u);  // abs.py:204
+    const long long w_sub = (long long)r0.y;
+    if (sev == SEV_A) {
+      if (w_sub < P.thr_hosp[idx]) nsev = SEV_H;  // age_hospitalization_probs[idx] > u (abs.py:209)
+    } else if (sev == SEV_H) {
+      if (w_sub < P.thr_sev[idx]) {              // age_severe_probs[idx] > u (abs.py:212)
+        nsev = SEV_G;
+        if (P.crit_active) {                     // abs.py:214-217
+          nst = ST_D;
+          nsev = SEV_A;
         }
       }
-      const uint2 r1 = agent_draw(aid, P.step, kStreamDeath, P.k0, P.k1);
-      if ((long long)r1.x < P.thr_death[idx]) {    // age_death_probs[idx] > u (abs.py:219-223)
-        st = ST_D;
-        sev = SEV_A;
-        pays = false;
-      } else if ((int)time > P.recovering_time) {  // abs.py:225-228
-        time = 0;
-        st = ST_R;
-        sev = SEV_A;
-      }
     }
-    if (pays) w = __dadd_rn(w, -__dmul_rn(P.min_expense, bi));  // abs.py:230
+    const uint2 r1 = agent_draw(aid, P.step, kStreamDeath, P.k0, P.k1);
+    bool pays = true;
+    if ((long long)r1.x < P.thr_death[idx]) {    // age_death_probs[idx] > u (abs.py:219-223)
+      nst = ST_D;
+      nsev = SEV_A;
+      pays = false;
+    } else if ((int)time > P.recovering_time) {  // abs.py:225-228
+      time = 0;
+      nst = ST_R;
+      nsev = SEV_A;
+    }
+    a = (a & 0xFFFF00F0u) | nst | (nsev << 2) | ((time & 0xFFu) << 8);
+    if (!pays) return;                           // abs.py:223: the death of this step returns before the expense
   }
-  a = attr_pack(st, sev, stratum, time, age) | (a & 0xFF000000u);
+  w = __dadd_rn(w, -P.mebi[stratum]);            // abs.py:230
 }
 
 // An Infected agent within reach of a slab edge also pushes its contacts on the neighbour's side.
@@ -592,14 +611,36 @@ __device__ __forceinline__ void send_ghost(Ctl *ctl, const StepParams &P, const 
 }
 
 constexpr int kStagesB = 4;
+#ifndef CABS_B_GROUP
+#define CABS_B_GROUP 4
+#endif
+constexpr unsigned kGroupB = CABS_B_GROUP;   // consecutive tiles a block takes before it strides on
 struct alignas(128) StageB {
   uint4 hot[kTile];
   double w[kTile];
   uint2 aux[kTile];
 };
+// acquire-release add on a shared-memory counter: the warp that brings a stage's count to kConsumerWarps has
+// observed every other warp's release of that stage
+__device__ __forceinline__ unsigned stage_release(unsigned *counter) {
+  unsigned old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(counter)) : "memory");
+  return old;
+}
 
-template <bool kAdvance>
-__global__ void __launch_bounds__(kAgentThreads, CABS_B_MINBLOCKS)
+// kExtras = false: one device, synchronous schedule -- the instance the headline configuration runs.
+// kExtras = true: additionally the slab paths (immigrants, ghosts, direct exchange) and the infection-time array of
+// the sequential schedule; every extra is still guarded by its pointer.
+// A block owns a CONTIGUOUS run of tiles: consecutive tiles land in neighbouring cells, so the cell-start
+// gather of a tile mostly hits lines the block's previous tiles brought into L1, and the scattered record
+// stores of a block stay within a narrow band of the destination copy.
+// Input columns stream through a ring of kStagesB shared-memory stages filled by bulk copies (TMA, cp.async.bulk).
+// There is no producer warp: a warp copies its 32 records of a stage to registers, fences (the refill is an
+// async-proxy write, the reads are generic-proxy: without the fence a refill can overtake reads still queued in the
+// shared-memory pipe) and counts itself off the stage; the LAST warp to do so issues the refill, so nobody ever waits
+// for a stage to drain.
+template <bool kAdvance, bool kExtras>
+__global__ void __launch_bounds__(kTile, CABS_B_MINBLOCKS)
 k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const double *__restrict__ wealth,
                  const uint2 *__restrict__ aux, const unsigned *__restrict__ cell_start,
                  unsigned *__restrict__ stale_cells, uint4 *__restrict__ ohot, double *__restrict__ owealth,
@@ -613,12 +654,10 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
   __shared__ long long s_q[5][kTile];  // per-thread Q1..Q5 partial sums (abs.py:309-312), no bank conflicts
   __shared__ unsigned s_stale;
   __shared__ StageB s_in[kStagesB];
-  __shared__ uint64_t s_full[kStagesB], s_empty[kStagesB];
-  const bool producer = threadIdx.x >= kTile;
-  if (!producer) {
+  __shared__ uint64_t s_full[kStagesB];
+  __shared__ unsigned s_released[kStagesB];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) s_q[k][threadIdx.x] = 0;
-  }
+  for (int k = 0; k < 5; ++k) s_q[k][threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     load_params(P, ctl);
     for (int i = 0; i < 7; ++i) B.cnt[i] = 0;
@@ -628,27 +667,28 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     s_stale = ctl->cells_used[ctl->cur_table ^ 1];
     for (int k = 0; k < kStagesB; ++k) {
       mbar_init(&s_full[k], 1);
-      mbar_init(&s_empty[k], kConsumerWarps);
+      s_released[k] = 0;
     }
     mbar_fence_init();
   }
   __syncthreads();
   const unsigned ntiles = (P.n + kTile - 1) / kTile;
+  // k-th tile of this block: groups of kGroupB consecutive tiles, groups dealt round-robin over the blocks
+  auto tile_of = [&](unsigned k) -> unsigned {
+    return ((k / kGroupB) * gridDim.x + blockIdx.x) * kGroupB + (k % kGroupB);
+  };
   constexpr unsigned kStageBytes = kTile * (sizeof(uint4) + sizeof(double) + sizeof(uint2));
-  if (threadIdx.x == kTile) {
-    // producer: keeps the ring of stages full; a stage is refilled as soon as all consumer warps released it
-    unsigned k = 0;
-    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
-      const unsigned s = k % kStagesB;
-      if (k >= kStagesB) mbar_wait(&s_empty[s], ((k / kStagesB) - 1u) & 1u);
-      mbar_expect_tx(&s_full[s], kStageBytes);
-      bulk_load(s_in[s].hot, hot + (size_t)tile * kTile, kTile * sizeof(uint4), &s_full[s]);
-      bulk_load(s_in[s].w, wealth + (size_t)tile * kTile, kTile * sizeof(double), &s_full[s]);
-      bulk_load(s_in[s].aux, aux + (size_t)tile * kTile, kTile * sizeof(uint2), &s_full[s]);
+  if (threadIdx.x == 0) {   // fill the ring
+    for (unsigned k = 0; k < (unsigned)kStagesB && tile_of(k) < ntiles; ++k) {
+      const size_t off = (size_t)tile_of(k) * kTile;
+      mbar_expect_tx(&s_full[k], kStageBytes);
+      bulk_load(s_in[k].hot, hot + off, kTile * sizeof(uint4), &s_full[k]);
+      bulk_load(s_in[k].w, wealth + off, kTile * sizeof(double), &s_full[k]);
+      bulk_load(s_in[k].aux, aux + off, kTile * sizeof(uint2), &s_full[k]);
     }
   }
   // side job: zero the cell table of the step before (the next step's histogram)
-  if (!producer) {
+  {
     const unsigned m = s_stale, m4 = m >> 2;
     uint4 *c4 = reinterpret_cast<uint4 *>(stale_cells);
     const unsigned chunk = (m4 + gridDim.x - 1) / gridDim.x;
@@ -662,34 +702,49 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
   int bxmin = INT_MAX, bxmax = INT_MIN, bymin = INT_MAX, bymax = INT_MIN;
   const double qscale = (double)(1ull << P.scale_bits);
   const unsigned lane = threadIdx.x & 31;
+  const bool stand_down = kExtras && P.overflow;
+  unsigned pend_mask = 0, pend_base = 0, pend_slot = 0;   // Infected-list entries of the previous tile
 
-  unsigned k = 0;
-  for (unsigned tile = blockIdx.x; tile < ntiles && !producer; tile += gridDim.x, ++k) {
+  for (unsigned k = 0;; ++k) {
+    const unsigned tile = tile_of(k);
+    if (tile >= ntiles) break;
     const unsigned s = k % kStagesB;
     mbar_wait(&s_full[s], (k / kStagesB) & 1u);
     const uint4 h = s_in[s].hot[threadIdx.x];
     double w = s_in[s].w[threadIdx.x];
     const uint2 ax = s_in[s].aux[threadIdx.x];
-    // The stage is refilled by the bulk-copy engine (async proxy) once every warp has released it, but the reads above
-    // went through the generic proxy: without this fence the refill may overtake reads still queued in the shared-memory
-    // pipe (seen as scrambled records once a block wraps the ring, i.e. above 4 tiles per block).
     mbar_fence_async_shared();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&s_empty[s]);  // this warp is done with the stage
+    if (lane == 0 && stage_release(&s_released[s]) == kConsumerWarps - 1) {
+      // every warp has its records of this stage in registers: refill it with the tile kStagesB ahead
+      s_released[s] = 0;
+      const unsigned next = tile_of(k + kStagesB);
+      if (next < ntiles) {
+        const size_t off = (size_t)next * kTile;
+        mbar_expect_tx(&s_full[s], kStageBytes);
+        bulk_load(s_in[s].hot, hot + off, kTile * sizeof(uint4), &s_full[s]);
+        bulk_load(s_in[s].w, wealth + off, kTile * sizeof(double), &s_full[s]);
+        bulk_load(s_in[s].aux, aux + off, kTile * sizeof(uint2), &s_full[s]);
+      }
+    }
     const unsigned i = tile * kTile + threadIdx.x;
-    const bool valid = i < P.n && ax.y != kEmigrant && !P.overflow;
+    bool valid = i < P.n;
+    if (kExtras) valid = valid && ax.y != kEmigrant && !stand_down;
     int nx = (int)h.x, ny = (int)h.y;
     uint32_t a = attr_normalize(h.z);
     const uint32_t aid = h.w;
     const int ix = (int)(short)(ax.x & 0xFFFFu), iy = (int)(short)(ax.x >> 16);
     if (kAdvance) apply_displacement(P, nx, ny, ix, iy, nx, ny);
     // the destination slot only needs the new position: ask for the cell start now so that the
-    // round trip to the L2-resident table overlaps the arithmetic below
-    unsigned slot = 0;
-    if (valid) slot = __ldg(&cell_start[cell_key(P, nx, ny, &ctl->err)]) + ax.y;
+    // round trip to the table overlaps the arithmetic below
+    unsigned start = 0;
+    if (valid) start = __ldg(&cell_start[cell_key(P, nx, ny, &ctl->err)]);
     if (kAdvance && valid) advance_agent(P, aid, ix, iy, a, w, sqrt_tab);
     // partial statistics (abs.py:300-312); infections of this step are added by k_contagion
     const uint32_t st = attr_status(a), sev = attr_severity(a);
+    // The sum is tied to the updated attribute word (bit 7 is always clear here, which the compiler cannot know) so
+    // that it is scheduled after the update arithmetic: the whole of it then covers the table's round trip.
+    const unsigned slot = (start + ax.y) ^ (a & kNewlyInfected);
     if (valid) {
       c_st += 1ull << (16 * st);
       if (st != ST_D) {
@@ -701,26 +756,33 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
       bxmin = min(bxmin, nx); bxmax = max(bxmax, nx); bymin = min(bymin, ny); bymax = max(bymax, ny);
       ohot[slot] = make_uint4((uint32_t)nx, (uint32_t)ny, a, aid);
       owealth[slot] = w;
-      if (tinf) tinf[slot] = st == ST_I ? 0ull : ~0ull;   // sequential schedule: time of infection inside this step
+      if (kExtras && tinf) tinf[slot] = st == ST_I ? 0ull : ~0ull;   // sequential schedule: time of infection inside this step
     }
     // slots of the agents that can transmit in this step's contact phase (warp-aggregated append)
     const bool is_inf = valid && st == ST_I;
-    if (is_inf && ghost_left) send_ghost(ctl, P, make_uint4((uint32_t)nx, (uint32_t)ny, a, aid), ghost_left, ghost_right);
-    const unsigned m_inf = P.pull ? 0u : __ballot_sync(0xffffffffu, is_inf);   // pull mode needs no source list
-    if (m_inf) {
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(&ctl->n_inf, (unsigned)__popc(m_inf));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (is_inf) inf_list[base + __popc(m_inf & ((1u << lane) - 1u))] = slot;
+    if (kExtras && is_inf && ghost_left)
+      send_ghost(ctl, P, make_uint4((uint32_t)nx, (uint32_t)ny, a, aid), ghost_left, ghost_right);
+    // The list entries of a tile are written one tile later: the reservation (an atomic with a return value) has a
+    // whole tile of arithmetic to come back instead of stalling the warp.
+    if (pend_mask) {
+      const unsigned base = __shfl_sync(0xffffffffu, pend_base, 0);
+      if (pend_mask & (1u << lane)) inf_list[base + __popc(pend_mask & ((1u << lane) - 1u))] = pend_slot;
     }
+    pend_mask = P.pull ? 0u : __ballot_sync(0xffffffffu, is_inf);   // pull mode needs no source list
+    pend_slot = slot;
+    if (pend_mask && lane == 0) pend_base = atomicAdd(&ctl->n_inf, (unsigned)__popc(pend_mask));
+  }
+  if (pend_mask) {
+    const unsigned base = __shfl_sync(0xffffffffu, pend_base, 0);
+    if (pend_mask & (1u << lane)) inf_list[base + __popc(pend_mask & ((1u << lane) - 1u))] = pend_slot;
   }
   // Slab mode: the agents that moved in from the neighbour slabs take their slots here too (they were counted in the
   // histogram before the scan): statistics, Infected list and ghosts exactly as for the residents -- every agent is
   // accounted once, by the device that owns it after the move.  A handful of records per block, hidden behind the tiles.
-  if (!producer && recv_left) {
+  if (kExtras && recv_left) {
     const unsigned cap = ctl->mig_cap;
     const unsigned nl = min(recv_left->count, cap), nr = min(recv_right->count, cap);
-    const unsigned total = P.overflow ? 0u : nl + nr;
+    const unsigned total = stand_down ? 0u : nl + nr;
     for (unsigned t = blockIdx.x * kTile + threadIdx.x; t < total; t += gridDim.x * kTile) {
       const MigrantRecord *src = t < nl ? reinterpret_cast<const MigrantRecord *>(recv_left + 1) + t
                                         : reinterpret_cast<const MigrantRecord *>(recv_right + 1) + (t - nl);
@@ -744,7 +806,7 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     }
   }
   // block reduction: per-warp shared atomics, then one set of global atomics per block
-  if (!producer) {
+  {
     unsigned long long cnt[7];
     long long q[5];
 #pragma unroll
@@ -781,7 +843,7 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
       atomicMin(&ctl->bb_ymin, B.bb[2]); atomicMax(&ctl->bb_ymax, B.bb[3]);
     }
   }
-  if (D.enabled) {   // direct slab mode: every ghost is listed once all blocks are done; the last one hands them over
+  if (kExtras && D.enabled) {   // direct slab mode: every ghost is listed once all blocks are done; the last one hands them over
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(&ctl->imm_ticket, 1u) == gridDim.x - 1;
@@ -946,6 +1008,10 @@ __device__ void close_local(Ctl *ctl, const unsigned *cell_start, int record_sta
 // listed, then (slab mode) the ghost records received from the two neighbour slabs.
 //   finish = 1: the last block to finish closes the step (one device);
 //   finish = 2: the last block exports this slab's partial statistics row (slab mode).
+#ifndef CABS_SOURCE_LANES
+#define CABS_SOURCE_LANES 8
+#endif
+constexpr unsigned kSourceLanes = CABS_SOURCE_LANES;
 __global__ void __launch_bounds__(256)
 k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
             const unsigned *__restrict__ inf_list, const ExchangeHeader *__restrict__ ghosts_left,
@@ -1008,7 +1074,13 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
     }
   }
   if (P.T >= 0) {
-    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    // kSourceLanes adjacent lanes share one source and split its candidates: the candidate records of a source are
+    // a dependent chain of scattered loads when one thread walks them alone
+    // (only while cells are coarse -- several candidates per lane; on the fine grid of a dense epidemic a source has
+    // a handful of candidates and one lane each is the better split)
+    const unsigned lanes = (P.n >= 4u * (unsigned)P.ncx * (unsigned)P.ncy) ? kSourceLanes : 1u;
+    const unsigned sub = threadIdx.x % lanes;
+    for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) / lanes; t < total; t += stride / lanes) {
       uint4 h;
       if (t < s_local) h = hot[inf_list[t]];
       else if (t < s_local + s_left) h = reinterpret_cast<const uint4 *>(ghosts_left + 1)[t - s_local];
@@ -1019,7 +1091,7 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
       for (int row = rlo; row <= rhi; ++row) {
         const unsigned base = (unsigned)row * (unsigned)P.ncx;
         const unsigned jb = cell_start[base + clo], je = cell_start[base + chi + 1];
-        for (unsigned j = jb; j < je; ++j) {
+        for (unsigned j = jb + sub; j < je; j += lanes) {
           // positions first (8 of the 16 bytes): almost every candidate of a coarse cell is out of reach
           const uint2 cp = *reinterpret_cast<const uint2 *>(&hot[j]);
           const int ddx = (int)cp.x - xi, ddy = (int)cp.y - yi;
@@ -1775,6 +1847,22 @@ __global__ void k_pack(unsigned n, const int *__restrict__ x, const int *__restr
   }
 }
 
+// Uploaded ids of a one-device handle must be a permutation of 0..n-1: they key the draws, and cabs_download
+// scatters by id.  `mark` holds n zeroed words.
+__global__ void __launch_bounds__(256) k_check_ids(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, unsigned n,
+                                                   unsigned *__restrict__ mark) {
+  bool bad = false;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t id = hot[i].w;
+    if (id >= n) bad = true;
+    else if (atomicExch(&mark[id], 1u) != 0u) bad = true;
+  }
+  if (bad) atomicOr(&ctl->err, kErrBadIds);
+}
+__global__ void k_clear_error(Ctl *ctl, unsigned keep_mask) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) ctl->err &= keep_mask;
+}
+
 // Scatter back to id order (ids must be a permutation of 0..n-1 unless by_slot).
 __global__ void k_unpack(unsigned n, int by_slot, const uint4 *__restrict__ hot, const double *__restrict__ wealth,
                          int *__restrict__ ox, int *__restrict__ oy, uint8_t *__restrict__ status,
@@ -1785,6 +1873,7 @@ __global__ void k_unpack(unsigned n, int by_slot, const uint4 *__restrict__ hot,
     const uint4 h = hot[i];
     const uint32_t a = attr_normalize(h.z);
     const unsigned d = by_slot ? i : h.w;
+    if (d >= n) continue;   // cannot happen after k_check_ids; never write outside the buffers
     ox[d] = (int)h.x;
     oy[d] = (int)h.y;
     status[d] = (uint8_t)attr_status(a);

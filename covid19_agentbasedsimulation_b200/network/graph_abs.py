@@ -7,8 +7,10 @@ the world on the host exactly as the reference does -- the same `np.random` call
 csrc/graph_kernels.cuh through the C ABI (`cabs_graph_*`, include/covidabs.h).  There is no CPU fallback.
 
 Callbacks: the reference takes Python lambdas (run_batch.py:87-213); the behaviours it ships are named in
-`network/scenarios.py` and lowered to kernel flags.  Any other callable raises NotImplementedError -- a Python
-lambda cannot run on the device (out of scope).
+`network/scenarios.py` and lowered to kernel flags.  The reference's own callables (`lambda x: sleep(x)`,
+`lambda x: lockdown(x)`, `lambda x: pset(x, 'contagion_rate', 0.1)`, ...) are recognised by probing them with
+instrumented stand-ins (`scenarios.recognise_callbacks`), so unmodified run_batch.py scenario dictionaries work; a
+callable that matches no shipped behaviour raises NotImplementedError -- arbitrary Python cannot run on the device.
 
 Differences a user can observe: draws are counter-based (Philox keyed (seed; entity,
 iteration, stream)), money that several agents add to is fixed point, statistics read inside a step are those of
@@ -24,12 +26,15 @@ from covid19_agentbasedsimulation_b200.agents import (Status, InfectionSeverity,
 from covid19_agentbasedsimulation_b200.common import (age_hospitalization_probs, age_severe_probs, age_death_probs,
                                                       lorenz_curve, basic_income)
 from covid19_agentbasedsimulation_b200.network.agents import EconomicalStatus, Business, House, Person
-from covid19_agentbasedsimulation_b200.network.scenarios import Declarative
+from covid19_agentbasedsimulation_b200.network.scenarios import Declarative, recognise_callbacks
 from covid19_agentbasedsimulation_b200.network.util import (new_day, work_day, new_month, bed_time, work_time,  # noqa: F401
                                                             lunch_time, free_time)
 
 GRAPH_STAT_KEYS = ("Q1", "Q2", "Q3", "Q4", "Q5", "Business", "Government", "Susceptible", "Infected",
                    "Recovered_Immune", "Death", "Asymptomatic", "Hospitalization", "Severe")   # graph_abs.py:305-322
+
+
+_RECOGNISED = {}   # callbacks dicts whose Python callables have been probed already
 
 
 def default_money_bits(total_wealth):
@@ -38,14 +43,19 @@ def default_money_bits(total_wealth):
     return int(max(8, min(24, np.floor(56 - np.log2(tw)))))
 
 
-def lower_callbacks(callbacks):
-    """run_batch.py-style callbacks dict -> (mode, sleep, isolation_rate, overrides)."""
+def lower_callbacks(callbacks, sim=None):
+    """run_batch.py-style callbacks dict -> (mode, sleep, isolation_rate, overrides).  Entries are the named
+    behaviours of network/scenarios.py, or the reference's own Python callables (run_batch.py:8-50,173-175), which are
+    identified by probing (scenarios.recognise_callbacks); any other callable raises NotImplementedError."""
     mode, sleep, rate, overrides, isolation_move = _native.GRAPH_MODE_NONE, False, None, {}, False
+    if any(not isinstance(a, Declarative) for a in (callbacks or {}).values()):
+        key = tuple(sorted((e, id(a)) for e, a in callbacks.items()))
+        cached = _RECOGNISED.get(key)
+        if cached is None or cached[0] is not callbacks:      # probe once per callbacks dict, not once per call
+            cached = (callbacks, recognise_callbacks(callbacks, sim))
+            _RECOGNISED[key] = cached
+        callbacks = cached[1]
     for event, action in (callbacks or {}).items():
-        if not isinstance(action, Declarative):
-            raise NotImplementedError(
-                "callback {!r} is a Python callable; it cannot run on the device and there is no CPU fallback. Use "
-                "the named behaviours of covid19_agentbasedsimulation_b200.network.scenarios".format(event))
         kind = action.kind
         if event == 'on_execute' and kind == 'sleep':
             sleep = True
@@ -60,7 +70,10 @@ def lower_callbacks(callbacks):
         elif event == 'post_initialize' and kind == 'sample_isolated':
             rate = action.args['isolation_rate']
         elif event == 'on_initialize' and kind == 'pset':
-            overrides[action.args['attribute']] = action.args['value']
+            if 'overrides' in action.args:
+                overrides.update(action.args['overrides'])
+            else:
+                overrides[action.args['attribute']] = action.args['value']
         else:
             raise NotImplementedError("unsupported callback {} -> {}".format(event, action))
     if (rate is None) != (not isolation_move):
@@ -97,7 +110,7 @@ class GraphSimulation(Simulation):
     # ------------------------------------------------------------------ world building (graph_abs.py:89-188)
     def build_world(self):
         """The lists `initialize` builds, as columns.  Consumes np.random exactly like the reference."""
-        mode, sleep, iso_rate, overrides = lower_callbacks(self.callbacks)
+        mode, sleep, iso_rate, overrides = lower_callbacks(self.callbacks, self)
         for k, v in overrides.items():                      # on_initialize (graph_abs.py:94)
             setattr(self, k, v)
         N = int(self.population_size)
@@ -260,7 +273,7 @@ class GraphSimulation(Simulation):
     def set_world(self, world, mode=_native.GRAPH_MODE_NONE, sleep=False, handle=None, index=0):
         """Upload a world given as columns (keys of cabs_graph_world).  `handle`/`index`: slot of a shared handle."""
         self._take_seed()
-        for k, v in lower_callbacks(self.callbacks)[3].items():   # on_initialize overrides (graph_abs.py:94), idempotent
+        for k, v in lower_callbacks(self.callbacks, self)[3].items():   # on_initialize overrides (graph_abs.py:94), idempotent
             setattr(self, k, v)
         n, nh, nb = len(world["px"]), len(world["hx"]), len(world["bx"])
         if handle is None:

@@ -156,6 +156,9 @@ class SlabSimulation(Simulation):
         '''"collective": buffers move between the phases by torch.distributed send/recv + all_gather (or copies when
         the slabs share a process); "p2p" (distributed only): the kernels write into the neighbours' memory over
         NVLink peer mappings (CUDA IPC) and synchronise with flags -- no collective, one enqueue per step'''
+        if self.schedule != "synchronous" and (self.n_slabs > 1 or self.distributed):
+            raise ValueError("schedule='sequential' is defined on one device only: the in-step infection chain of the "
+                             "reference is not local to a slab (SURVEY.md 8e)")
         if self.transport not in ("collective", "p2p"):
             raise ValueError("transport must be 'collective' or 'p2p'")
         if self.transport == "p2p" and not self.distributed:
@@ -338,7 +341,7 @@ class SlabSimulation(Simulation):
         if self._host_triggers() or iterations > self.history_capacity:
             return super(SlabSimulation, self).run(iterations)
         self._push_params()
-        first = self._iteration
+        first = self._handle.info()["step"]     # the handles' clock is not reset by a re-upload
         if self.transport == "p2p":
             self._handles[0].slab_run(iterations)     # pairs of steps replay a captured CUDA graph
         else:

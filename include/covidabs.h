@@ -140,11 +140,22 @@ const char *cabs_last_error(const cabs_sim *sim);
 
 /* Sets the attributes of abs.py:17-49; callable between steps (abs.py:267-271). */
 int cabs_set_params(cabs_sim *sim, const cabs_params *params);
+/* The attributes as they are on the device now: what cabs_set_params sent, with the fields device-side triggers have
+ * rewritten since (amplitudes, contagion_rate, contagion_distance, critical_limit; abs.py:267-271 makes such a change
+ * permanent).  Waits for the enqueued steps. */
+int cabs_get_params(cabs_sim *sim, cabs_params *out);
 /* Installs up to CABS_MAX_TRIGGERS device-side simulation triggers (abs.py:74-84, 267-271). */
 int cabs_set_triggers(cabs_sim *sim, const cabs_trigger *triggers, int count);
 
-/* Replaces set_population (abs.py:65-69) / the list built by initialize (abs.py:116-139). */
+/* Replaces set_population (abs.py:65-69) / the list built by initialize (abs.py:116-139).  When `id` is given on a
+ * one-device handle it must be a permutation of 0..n-1 (checked on the device; the error surfaces as
+ * CABS_ERR_INVALID at the next synchronising call). */
 int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop);
+/* The step counter is one word of every draw key (seed, agent id, step).  It starts at 0 on a fresh handle, advances
+ * by one per executed step and is NOT reset by cabs_upload (re-uploading an edited population mid-run must not replay
+ * the draws of step 0).  cabs_set_step restores the clock of a checkpoint: (cabs_download, cabs_get_info().step) ->
+ * (cabs_upload, cabs_set_step) resumes a run bit for bit.  Statistics rows of earlier steps are dropped. */
+int cabs_set_step(cabs_sim *sim, uint64_t step);
 /* Replaces get_population (abs.py:57-63): writes the population back in id order. */
 int cabs_download(cabs_sim *sim, cabs_soa_host *pop);
 
@@ -237,6 +248,16 @@ typedef struct cabs_kernel_time {
 } cabs_kernel_time;
 int cabs_profile_enable(cabs_sim *sim, int on);
 int cabs_profile_read(cabs_sim *sim, cabs_kernel_time *out, int capacity, int *count);
+
+/* Self-test of the move draw (no reference counterpart).  The displacement of abs.py:174-175, int(randn * amplitude),
+ * is DEFINED by a Box-Muller transform in correctly rounded binary32 (csrc/abs_rng.cuh, reproduced by the CPU oracle);
+ * the kernels evaluate it on the special-function unit and fall back to the defining arithmetic whenever the result is
+ * within the proven error bound of an integer.  This call measures the actual errors on `device`, exhaustively over the
+ * 2^23 radius and 2^25 angle inputs, and compares 2^sweep_log2 sampled draws with the defining path:
+ *   out[0] worst radius error / bound, out[1] worst cos-sin error / bound (both must be < 1), out[2] radius inputs the
+ *   fast path rejects outright, out[3] sampled draws accepted by the fast path, out[4] accepted draws whose integers
+ *   differ from the defining path (must be 0), out[5] sampled draws. */
+int cabs_selftest_normals(int device, unsigned sweep_log2, double out[6]);
 
 
 /* Replaces the loop over one pair of populations in MultiPopulationSimulation.execute (covid_abs/abs.py:352-366):

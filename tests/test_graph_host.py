@@ -57,7 +57,11 @@ def test_lowering_rejects_python_callables():
     assert lower_callbacks(sc.scenario8["callbacks"])[3] == {"contagion_rate": 0.1}
     assert lower_callbacks(sc.scenario6["callbacks"])[2] == 0.5
     with pytest.raises(NotImplementedError):
-        lower_callbacks({"on_execute": lambda x: False})
+        lower_callbacks({"on_execute": lambda x: x.iteration % 2 == 0})     # not a shipped behaviour
+    with pytest.raises(NotImplementedError):
+        lower_callbacks({"on_person_move": lambda a: a.id % 2 == 0})
+    with pytest.raises(NotImplementedError):
+        lower_callbacks({"on_contact": lambda a, b: True})
     with pytest.raises(NotImplementedError):
         lower_callbacks({"post_initialize": sc.sample_isolated(.3)})
 
