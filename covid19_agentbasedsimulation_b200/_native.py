@@ -25,8 +25,8 @@ EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params",
             "cabs_profile_enable", "cabs_profile_read", "cabs_selftest_normals", "cabs_set_slab", "cabs_slab_phase", "cabs_set_stream",
             "cabs_slab_block_bytes", "cabs_set_slab_direct", "cabs_slab_step", "cabs_slab_run", "cabs_device_alloc", "cabs_device_free",
             "cabs_ipc_export", "cabs_ipc_open", "cabs_ipc_close",
-            "cabs_graph_create", "cabs_graph_destroy", "cabs_graph_last_error", "cabs_graph_upload", "cabs_graph_run",
-            "cabs_graph_sync", "cabs_graph_stats", "cabs_graph_stats_all", "cabs_graph_aggregate", "cabs_graph_download",
+            "cabs_graph_world_sizes", "cabs_graph_build_world", "cabs_graph_create", "cabs_graph_destroy", "cabs_graph_last_error", "cabs_graph_upload", "cabs_graph_run",
+            "cabs_graph_sync", "cabs_graph_stats", "cabs_graph_stats_all", "cabs_graph_aggregate", "cabs_graph_moments", "cabs_graph_download",
             "cabs_graph_last_run_ms")
 
 GRAPH_NUM_STATS, GRAPH_MAX_BUSINESS = 14, 16
@@ -132,6 +132,16 @@ class GraphWorld(C.Structure):
                 [(k, C.c_void_p) for k, _ in GRAPH_BUSINESS_COLS] + list(GRAPH_SCALARS))
 
 
+class GraphWorldSpec(C.Structure):
+    _fields_ = [("population_size", C.c_int32), ("length", C.c_int32), ("height", C.c_int32),
+                ("total_business", C.c_int32), ("homemates_avg", C.c_int32), ("homemates_std", C.c_int32),
+                ("initial_infected_perc", C.c_double), ("initial_immune_perc", C.c_double),
+                ("homeless_rate", C.c_double), ("unemployment_rate", C.c_double), ("total_wealth", C.c_double),
+                ("public_gdp_share", C.c_double), ("business_gdp_share", C.c_double), ("minimum_income", C.c_double),
+                ("minimum_expense", C.c_double), ("basic_income", C.c_double * 5), ("lorenz_curve", C.c_double * 5),
+                ("isolation_rate", C.c_double)]
+
+
 _lib = None
 
 
@@ -186,6 +196,9 @@ def load():
     lib.cabs_ipc_export.argtypes = [C.c_int, P, C.c_char * 64]
     lib.cabs_ipc_open.argtypes = [C.c_int, C.c_char * 64, C.POINTER(P)]
     lib.cabs_ipc_close.argtypes = [C.c_int, P]
+    lib.cabs_graph_world_sizes.argtypes = [C.POINTER(GraphWorldSpec), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_int32)]
+    lib.cabs_graph_build_world.argtypes = [C.POINTER(GraphWorldSpec), C.c_uint64, C.POINTER(GraphWorld)]
     lib.cabs_graph_create.argtypes = [C.POINTER(GraphConfig), C.POINTER(P)]
     lib.cabs_cross_contact.argtypes = [P, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_uint64, C.c_uint32]
     lib.cabs_graph_destroy.argtypes = [P]
@@ -198,6 +211,7 @@ def load():
     lib.cabs_graph_stats.argtypes = [P, C.c_uint32, C.c_int64, C.c_uint32, C.POINTER(C.c_double)]
     lib.cabs_graph_aggregate.argtypes = [P, C.c_int64, C.c_uint32, C.POINTER(C.c_double)]
     lib.cabs_graph_stats_all.argtypes = [P, C.c_int64, C.c_uint32, C.POINTER(C.c_double)]
+    lib.cabs_graph_moments.argtypes = [P, C.c_uint32, C.c_uint32, C.c_int64, C.c_uint32, C.POINTER(C.c_double)]
     lib.cabs_graph_download.argtypes = [P, C.c_uint32, C.POINTER(GraphWorld)]
     lib.cabs_graph_last_run_ms.argtypes = [P, C.POINTER(C.c_double)]
     for name in EXPORTED:
@@ -463,6 +477,13 @@ class GraphHandle(object):
                                                    out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
 
+    def moments(self, sim_first, sim_count, first, count):
+        """min, sum, sum of squares, max over simulations [sim_first, sim_first + sim_count) -> float64 [count, 14, 4]."""
+        out = np.empty((int(count), GRAPH_NUM_STATS, 4), dtype=np.float64)
+        self._check(self._lib.cabs_graph_moments(self._h, int(sim_first), int(sim_count), int(first), int(count),
+                                                 out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
     def download(self, sim):
         n, nh, nb = self._sizes[int(sim)]
         world = {}
@@ -478,6 +499,27 @@ class GraphHandle(object):
             if name != "reserved2":
                 world[name] = getattr(w, name)
         return world
+
+
+def build_world_native(spec, seed):
+    """cabs_graph_build_world -> dict of columns (keys of cabs_graph_world).  Host only; releases the GIL."""
+    lib = load()
+    n, nh, nb = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    _util_check(lib.cabs_graph_world_sizes(C.byref(spec), C.byref(n), C.byref(nh), C.byref(nb)), "cabs_graph_world_sizes")
+    w = GraphWorld()
+    world = {}
+    for cols, m in ((GRAPH_PERSON_COLS, n.value), (GRAPH_HOUSE_COLS, nh.value), (GRAPH_BUSINESS_COLS, nb.value)):
+        for name, dt in cols:
+            world[name] = np.zeros(m, dtype=dt)
+            setattr(w, name, world[name].ctypes.data)
+    _util_check(lib.cabs_graph_build_world(C.byref(spec), int(seed) & 0xFFFFFFFFFFFFFFFF, C.byref(w)),
+                "cabs_graph_build_world")
+    for name, _ in GRAPH_HOUSE_COLS:
+        world[name] = world[name][:w.n_houses]
+    for name, _ in GRAPH_SCALARS:
+        if name != "reserved2":
+            world[name] = getattr(w, name)
+    return world
 
 
 # ---- device memory shared between the processes of one box (exchange blocks of the direct slab transport)

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcovidabs.so")
-SOURCES = [os.path.join(CSRC, "abs_capi.cu"), os.path.join(CSRC, "graph_capi.cu")]
+SOURCES = [os.path.join(CSRC, "abs_capi.cu"), os.path.join(CSRC, "graph_capi.cu"), os.path.join(CSRC, "world_builder.cu")]
 DEPS = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "covidabs.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

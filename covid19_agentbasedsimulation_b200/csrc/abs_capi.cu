@@ -1,7 +1,9 @@
 // C ABI of the B200-native COVID-ABS step (include/covidabs.h): host orchestration of the kernels
 // in abs_kernels.cuh.  No CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <limits.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -13,6 +15,14 @@
 #include "abs_kernels.cuh"
 
 using namespace cabs;
+
+// NVTX range around every entry point that enqueues or waits for device work (the timeline
+// of a run -- uploads, steps, exchanges, statistics reads -- is readable in Nsight Systems; header-only, a no-op
+// unless a tool is attached)
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 static thread_local std::string g_create_error;
 
@@ -52,6 +62,8 @@ struct cabs_sim {
   // sequential schedule
   unsigned long long *tinf = nullptr;
   unsigned *newinf_list = nullptr;
+  unsigned *seq_round = nullptr;   // "labels lowered in round r" counters of the cooperative relaxation (3 slots)
+  int seq_grid = 0;                // its grid: every block resident (0: no cooperative launch, host-driven rounds)
   cudaStream_t own_stream = nullptr;
   Ctl *ctl = nullptr;
   StatRecord *history = nullptr;
@@ -63,6 +75,8 @@ struct cabs_sim {
   unsigned char *cross_mark = nullptr;   // cabs_cross_contact: one byte per agent (allocated on first use)
   cabs_params params;
   bool have_params = false;
+  StaticParams sp;              // step-invariant parameters, passed by value to the agent passes (constant bank)
+  uint64_t seed = 0;
   bool cells_dirty = true;      // cell_start does not describe the current positions / distance
   bool unsorted = false;        // the resident small-population kernel left the records out of cell order
   // two consecutive steps (one ping + one pong of the record / table copies) captured as a CUDA graph: a run of
@@ -106,6 +120,11 @@ static void prof_mark(cabs_sim *sim, const char *name) {
 
 static int flush_late_close(cabs_sim *sim);
 
+static void drop_graphs(cabs_sim *sim) {
+  if (sim->step_graph) { cudaGraphExecDestroy(sim->step_graph); sim->step_graph = nullptr; }
+  if (sim->slab_graph) { cudaGraphExecDestroy(sim->slab_graph); sim->slab_graph = nullptr; }
+}
+
 static int fail(cabs_sim *sim, int code, const char *msg) {
   if (sim) sim->err = msg;
   else g_create_error = msg;
@@ -138,6 +157,7 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
   cudaFree(sim->sqrt_tab);
   cudaFree(sim->cells[0]); cudaFree(sim->cells[1]); cudaFree(sim->tile_state); cudaFree(sim->inf_list);
   cudaFree(sim->emig_list); cudaFree(sim->imm_rank); cudaFree(sim->tinf); cudaFree(sim->newinf_list);
+  cudaFree(sim->seq_round);
   cudaFree(sim->dev_blocks);
   cudaFree(sim->ctl); cudaFree(sim->history);
   cudaFree(sim->stage); cudaFree(sim->stage_id); cudaFree(sim->pairs); cudaFree(sim->pair_count);
@@ -168,6 +188,12 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   CK(cudaFuncSetAttribute(k_update_scatter<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_update_scatter<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_update_scatter<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  memset(&sim->sp, 0, sizeof sim->sp);
+  sim->seed = cfg->seed;
+  sim->sp.k0 = (unsigned)(cfg->seed & 0xFFFFFFFFu);
+  sim->sp.k1 = (unsigned)(cfg->seed >> 32);
+  sim->sp.slab_lo = INT_MIN;
+  sim->sp.slab_hi = INT_MAX;
   sim->capacity = cfg->capacity ? cfg->capacity : 1;
   if (sim->capacity >= (1ull << 31)) return fail(sim, CABS_ERR_CAPACITY, "capacity must be < 2^31 agents per device");
   // Two budgets for the cell table.  While few agents can transmit (or few can be infected) the contact pass is
@@ -239,6 +265,7 @@ extern "C" int cabs_create(const cabs_config *cfg, cabs_sim **out) {
 }
 
 extern "C" int cabs_set_params(cabs_sim *sim, const cabs_params *p) {
+  NvtxRange nvtx_("cabs_set_params");
   if (!sim || !p) return fail(sim, CABS_ERR_INVALID, "cabs_set_params: null argument");
   if (p->wealth_scale_bits < 0 || p->wealth_scale_bits > 52)
     return fail(sim, CABS_ERR_INVALID, "wealth_scale_bits must be in [0, 52]");
@@ -273,6 +300,32 @@ extern "C" int cabs_set_params(cabs_sim *sim, const cabs_params *p) {
   if (p->schedule == CABS_SEQUENTIAL && !sim->tinf) {
     CK(cudaMalloc(&sim->tinf, (sim->capacity + kPad) * sizeof(unsigned long long)));
     CK(cudaMalloc(&sim->newinf_list, (sim->capacity + kPad) * sizeof(unsigned)));
+    CK(cudaMalloc(&sim->seq_round, 4 * sizeof(unsigned)));
+    CK(cudaMemsetAsync(sim->seq_round, 0, 4 * sizeof(unsigned), sim->stream));
+    // all blocks of the cooperative relaxation kernel must be resident at once
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, sim->device);
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contagion_sequential_all, 256, 0) == cudaSuccess)
+      sim->seq_grid = per_sm * sim->num_sms;
+  }
+  {   // the same values load_params derives on the device, for the by-value copy the agent passes take
+    StaticParams &sp = sim->sp;
+    sp.min_expense = p->minimum_expense;
+    sp.me32 = p->minimum_expense * 0x1p-32;
+    for (int k = 0; k < 5; ++k) {
+      sp.bi[k] = p->basic_income[k];
+      sp.mebi[k] = p->minimum_expense * p->basic_income[k];
+    }
+    for (int k = 0; k < 9; ++k) {
+      sp.thr_hosp[k] = prob_bound_lt(p->age_hospitalization_probs[k]);
+      sp.thr_sev[k] = prob_bound_lt(p->age_severe_probs[k]);
+      sp.thr_death[k] = prob_bound_lt(p->age_death_probs[k]);
+    }
+    sp.recovering_time = p->recovering_time;
+    sp.scale_bits = p->wealth_scale_bits;
+    sp.len_i = (int)fmin(fmax(ceil(p->length), -2147483647.0), 2147483647.0);
+    sp.hei_i = (int)fmin(fmax(ceil(p->height), -2147483647.0), 2147483647.0);
+    drop_graphs(sim);   // captured launches hold the old copy
   }
   LAUNCH(k_set_params, 1, 32, sim->ctl, b);
   if (sim->n > 0) LAUNCH(k_replan, 1, 32, sim->ctl, 0);  // amplitudes / distance may have changed the margin
@@ -337,19 +390,29 @@ static void enqueue_build(cabs_sim *sim) {
   const int nb = agent_blocks(sim);
   SlabDirect no_direct;
   memset(&no_direct, 0, sizeof no_direct);
-  LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl, sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list);
+  LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl, sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list, sim->sp);
   LAUNCH(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
   if (kAdvance && sequential) {
     LAUNCH_AS("k_update_scatter<true>", (k_update_scatter<kAdvance, true>), nb, kAgentThreads, sim->ctl, sim->hot[c], sim->w[c],
               sim->aux, sim->cells[t], sim->cells[t ^ 1], sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, nullptr,
-              nullptr, sim->tinf, nullptr, nullptr, nullptr, no_direct);
+              nullptr, sim->tinf, nullptr, nullptr, nullptr, no_direct, sim->sp);
   } else {
     LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", (k_update_scatter<kAdvance, false>), nb,
               kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t], sim->cells[t ^ 1], sim->hot[o],
-              sim->w[o], sim->inf_list, sim->sqrt_tab, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, no_direct);
+              sim->w[o], sim->inf_list, sim->sqrt_tab, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, no_direct, sim->sp);
   }
-  if (kAdvance && sequential) {
-    // rounds of label-correcting relaxation until no infection time is lowered (one host round trip each)
+  if (kAdvance && sequential && sim->seq_grid > 0) {
+    // every round of the label-correcting relaxation inside one cooperative launch (grid-wide barriers between the
+    // rounds); its block 0 closes the step
+    if (sim->profiling) prof_mark(sim, "k_contagion_sequential_all");
+    uint4 *hot_o = sim->hot[o];
+    unsigned *cells_t = sim->cells[t];
+    void *args[] = {&sim->ctl, &hot_o, &cells_t, &sim->tinf, &sim->inf_list, &sim->newinf_list, &sim->history,
+                    &sim->seq_round};
+    cudaLaunchCooperativeKernel((void *)k_contagion_sequential_all, dim3(sim->seq_grid), dim3(256), args, 0, sim->stream);
+    sim->launches++;
+  } else if (kAdvance && sequential) {
+    // no cooperative launch on this device: rounds driven from the host (one round trip each)
     for (int round = 0;; ++round) {
       LAUNCH(k_contagion_sequential, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->tinf,
              round == 0 ? sim->inf_list : sim->newinf_list, round == 0 ? 1 : 0, sim->newinf_list);
@@ -410,8 +473,11 @@ extern "C" int cabs_set_slab(cabs_sim *sim, const cabs_slab *slab) {
   cudaFree(sim->emig_list); cudaFree(sim->imm_rank); cudaFree(sim->tinf); cudaFree(sim->newinf_list);
   cudaFree(sim->dev_blocks);
   sim->emig_list = sim->imm_rank = nullptr;
+  cudaFree(sim->seq_round);
   sim->tinf = nullptr;
   sim->newinf_list = nullptr;
+  sim->seq_round = nullptr;
+  sim->seq_grid = 0;
   sim->dev_blocks = nullptr;
   CK(cudaMalloc(&sim->emig_list, 2 * (size_t)slab->migrant_capacity * sizeof(unsigned)));
   CK(cudaMalloc(&sim->imm_rank, 2 * (size_t)slab->migrant_capacity * sizeof(unsigned)));
@@ -424,6 +490,9 @@ extern "C" int cabs_set_slab(cabs_sim *sim, const cabs_slab *slab) {
   sim->slab = *slab;
   sim->slab_on = true;
   sim->direct = false;
+  sim->sp.slab_lo = slab->x_lo;
+  sim->sp.slab_hi = slab->x_hi;
+  drop_graphs(sim);
   LAUNCH(k_set_slab, 1, 32, sim->ctl, slab->rank, slab->n_ranks, slab->x_lo, slab->x_hi, slab->migrant_capacity,
          slab->ghost_capacity);
   if (sim->n > 0) LAUNCH(k_replan, 1, 32, sim->ctl, 0);
@@ -486,7 +555,7 @@ static int slab_phase(cabs_sim *sim, int phase) {
         LAUNCH(k_replan, 1, 32, sim->ctl, 1);
       }
       LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl,
-                sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list);
+                sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list, sim->sp);
       {   // pass A needed nothing global; pass B and the emigrants' update need the critical-limit flag
         const int rc = flush_late_close(sim);
         if (rc != CABS_OK) return rc;
@@ -500,7 +569,7 @@ static int slab_phase(cabs_sim *sim, int phase) {
       LAUNCH_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", (k_update_scatter<kAdvance, true>), nb,
                 kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t], sim->cells[t ^ 1],
                 sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, gs[0], gs[1], nullptr, mr[0], mr[1],
-                sim->imm_rank, D);   // the immigrants take their slots inside pass B; its last block pushes the ghosts
+                sim->imm_rank, D, sim->sp);   // the immigrants take their slots inside pass B; its last block pushes the ghosts
       break;
     case 2:
       if (kAdvance) {
@@ -642,6 +711,9 @@ extern "C" int cabs_set_slab_direct(cabs_sim *sim, const cabs_slab_direct *d) {
   sim->slab_on = true;
   sim->direct = true;
   sim->build_seq = 0;
+  sim->sp.slab_lo = d->x_lo;
+  sim->sp.slab_hi = d->x_hi;
+  drop_graphs(sim);
   LAUNCH(k_set_slab, 1, 32, sim->ctl, d->rank, d->n_ranks, d->x_lo, d->x_hi, d->migrant_capacity, d->ghost_capacity);
   if (sim->n > 0) LAUNCH(k_replan, 1, 32, sim->ctl, 0);
   CK(cudaGetLastError());
@@ -651,6 +723,7 @@ extern "C" int cabs_set_slab_direct(cabs_sim *sim, const cabs_slab_direct *d) {
 }
 
 extern "C" int cabs_slab_step(cabs_sim *sim, int advance) {
+  NvtxRange nvtx_("cabs_slab_step");
   if (!sim) return fail(sim, CABS_ERR_INVALID, "cabs_slab_step: null handle");
   if (!sim->slab_on || !sim->direct) return fail(sim, CABS_ERR_INVALID, "cabs_slab_step: call cabs_set_slab_direct first");
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_slab_step: call cabs_set_params first");
@@ -665,6 +738,7 @@ extern "C" int cabs_slab_step(cabs_sim *sim, int advance) {
 // `nsteps` steps of the direct mode.  Pairs of steps replay a captured CUDA graph: every launch argument is the same
 // for any two builds that start from the same ping/pong phase and flag parity (the sequence number itself lives in Ctl).
 extern "C" int cabs_slab_run(cabs_sim *sim, int nsteps) {
+  NvtxRange nvtx_("cabs_slab_run");
   if (!sim || nsteps < 0) return fail(sim, CABS_ERR_INVALID, "cabs_slab_run: bad argument");
   if (!sim->slab_on || !sim->direct) return fail(sim, CABS_ERR_INVALID, "cabs_slab_run: call cabs_set_slab_direct first");
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_slab_run: call cabs_set_params first");
@@ -727,6 +801,7 @@ static int refresh_n(cabs_sim *sim) {
 }
 
 extern "C" int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop) {
+  NvtxRange nvtx_("cabs_upload");
   if (!sim || !pop) return fail(sim, CABS_ERR_INVALID, "cabs_upload: null argument");
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_upload: call cabs_set_params first");
   if (pop->n > sim->capacity) return fail(sim, CABS_ERR_CAPACITY, "cabs_upload: population larger than capacity");
@@ -785,6 +860,7 @@ extern "C" int cabs_set_step(cabs_sim *sim, uint64_t step) {
 }
 
 extern "C" int cabs_download(cabs_sim *sim, cabs_soa_host *pop) {
+  NvtxRange nvtx_("cabs_download");
   if (!sim || !pop) return fail(sim, CABS_ERR_INVALID, "cabs_download: null argument");
   CK(cudaSetDevice(sim->device));
   {
@@ -816,6 +892,7 @@ extern "C" int cabs_download(cabs_sim *sim, cabs_soa_host *pop) {
 }
 
 extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
+  NvtxRange nvtx_("cabs_step");
   if (!sim || nsteps < 0) return fail(sim, CABS_ERR_INVALID, "cabs_step: bad argument");
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_step: call cabs_set_params first");
   if (sim->slab_on) return fail(sim, CABS_ERR_INVALID, "cabs_step: a slab handle is stepped with cabs_slab_phase");
@@ -838,7 +915,7 @@ extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
   int s = 0;
   const bool sequential = sim->params.schedule == CABS_SEQUENTIAL;
   const bool capturable = sim->stream != nullptr && sim->stream != cudaStreamLegacy && sim->stream != cudaStreamPerThread;
-  if (!sim->profiling && !sequential && nsteps >= 4 && capturable && !sim->graph_broken) {
+  if (!sim->profiling && (!sequential || sim->seq_grid > 0) && nsteps >= 4 && capturable && !sim->graph_broken) {
     // pairs of steps through the captured graph (the kernels take every changing quantity from Ctl, so the same
     // eight launches are valid for any pair of steps that starts from the same ping/pong phase)
     if (sim->step_graph && (sim->graph_cur != sim->cur || sim->graph_tab != sim->tab)) {
@@ -925,6 +1002,7 @@ static void convert_record(const cabs_sim *sim, const StatRecord &r, double *val
 }
 
 extern "C" int cabs_stats(cabs_sim *sim, double *values, int64_t *counts) {
+  NvtxRange nvtx_("cabs_stats");
   if (!sim || !values) return fail(sim, CABS_ERR_INVALID, "cabs_stats: null argument");
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_stats: call cabs_set_params first");
   CK(cudaSetDevice(sim->device));
@@ -941,6 +1019,7 @@ extern "C" int cabs_stats(cabs_sim *sim, double *values, int64_t *counts) {
 }
 
 extern "C" int cabs_stats_history(cabs_sim *sim, uint64_t first_step, uint64_t count, double *values) {
+  NvtxRange nvtx_("cabs_stats_history");
   if (!sim || (count && !values)) return fail(sim, CABS_ERR_INVALID, "cabs_stats_history: null argument");
   if (first_step + count > sim->step) return fail(sim, CABS_ERR_INVALID, "cabs_stats_history: steps not executed yet");
   if (count && first_step < sim->hist_first)
@@ -971,6 +1050,7 @@ extern "C" int cabs_stats_history(cabs_sim *sim, uint64_t first_step, uint64_t c
 // MultiPopulationSimulation.execute, the loop over one pair of populations (abs.py:352-366).
 extern "C" int cabs_cross_contact(cabs_sim *a, cabs_sim *b, int32_t ax, int32_t ay, int32_t bx, int32_t by,
                                   double contagion_distance, uint64_t seed, uint32_t pair_code) {
+  NvtxRange nvtx_("cabs_cross_contact");
   if (!a || !b || a == b) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: two different handles are needed");
   if (!a->have_params || !b->have_params) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: call cabs_set_params first");
   if (a->slab_on || b->slab_on) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: not defined for slab handles");
@@ -1018,6 +1098,7 @@ extern "C" int cabs_cross_contact(cabs_sim *a, cabs_sim *b, int32_t ax, int32_t 
 }
 
 extern "C" int cabs_contact_pairs(cabs_sim *sim, int64_t *ij, size_t capacity_pairs, size_t *n_pairs) {
+  NvtxRange nvtx_("cabs_contact_pairs");
   if (!sim || !n_pairs || (capacity_pairs && !ij)) return fail(sim, CABS_ERR_INVALID, "cabs_contact_pairs: null argument");
   CK(cudaSetDevice(sim->device));
   if (sim->cells_dirty) {

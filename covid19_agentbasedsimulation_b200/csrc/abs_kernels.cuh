@@ -28,6 +28,8 @@
 #include <limits.h>
 #include <stdint.h>
 
+#include <cooperative_groups.h>
+
 #include "abs_rng.cuh"
 
 namespace cabs {
@@ -166,6 +168,23 @@ struct StepParams {
   unsigned k0, k1, step, n;
 };
 
+// The part of StepParams that no kernel ever changes (only cabs_set_params / cabs_set_slab / the seed do): the two
+// agent passes take it BY VALUE as a kernel parameter, i.e. from the constant bank.  A value read from shared memory
+// has to be re-read after every atomic (the compiler must assume other threads may have written it), and those
+// re-reads were ~40 % of the load/store-unit traffic of the passes; constant-bank operands cost nothing there.
+// Same field names as StepParams, so the per-agent device functions take either.
+struct StaticParams {
+  double min_expense, me32;
+  double bi[5], mebi[5];
+  long long thr_hosp[9], thr_sev[9], thr_death[9];
+  int recovering_time, scale_bits;
+  int len_i, hei_i;
+  int slab_lo, slab_hi;
+  unsigned k0, k1;
+};
+
+__host__ __device__ inline long long prob_bound_lt(double p);
+
 __device__ __forceinline__ void load_params(StepParams &P, const Ctl *ctl, bool use_built = false) {
   // one thread fills the shared copy; callers __syncthreads() afterwards
   const Grid &g = use_built ? ctl->built : ctl->g;
@@ -212,16 +231,20 @@ __device__ __forceinline__ void draw_displacement(const StepParams &P, uint32_t 
   }
 }
 // abs.py:177-185: the increment, not the position, is reflected
-__device__ __forceinline__ void apply_displacement(const StepParams &P, int x, int y, int ix, int iy, int &nx,
-                                                   int &ny) {
+template <class SP>
+__device__ __forceinline__ void apply_displacement(const SP &S, int x, int y, int ix, int iy, int &nx, int &ny) {
   const int tx = x + ix, ty = y + iy;
-  nx = (tx <= 0 || tx >= P.len_i) ? x - ix : tx;
-  ny = (ty <= 0 || ty >= P.hei_i) ? y - iy : ty;
+  nx = (tx <= 0 || tx >= S.len_i) ? x - ix : tx;
+  ny = (ty <= 0 || ty >= S.hei_i) ? y - iy : ty;
 }
 
 // Cell of a lattice point.  Interior cells are 1..ncx-2 / 1..ncy-2; row/column 0 and the last one
 // are always-empty padding so that the neighbourhood of a cell never needs a bounds test.
-__device__ __forceinline__ unsigned cell_key(const StepParams &P, int x, int y, unsigned *err) {
+struct GridRegs {   // the cell grid of the build in flight, copied to registers by the agent passes
+  int gx0, gy0, eshift, ncx, ncy;
+};
+template <class G>
+__device__ __forceinline__ unsigned cell_key(const G &P, int x, int y, unsigned *err) {
   int cx = ((x - P.gx0) >> P.eshift) + 1;
   int cy = ((y - P.gy0) >> P.eshift) + 1;
   if (cx < 1 || cx > P.ncx - 2 || cy < 1 || cy > P.ncy - 2) {
@@ -367,15 +390,15 @@ constexpr int kScanThreads = 512;
 
 // Pass A reads one 16-byte column with plenty of resident warps, so plain vectorised loads (one agent
 // ahead) do as well as staged ones; pass B, which streams three columns at low occupancy, stages them.
-#ifndef CABS_A_PREFETCH
-#define CABS_A_PREFETCH 3
+#ifndef CABS_A_MINBLOCKS
+#define CABS_A_MINBLOCKS 8   // 32 registers: pass A is latency-bound and loses 15 % at 6 resident blocks (measured)
 #endif
-constexpr unsigned kPrefetchA = CABS_A_PREFETCH;
 template <bool kAdvance>
-__global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot,
+__global__ void __launch_bounds__(256, CABS_A_MINBLOCKS) k_move_count(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot,
                                                     uint2 *__restrict__ aux, unsigned *__restrict__ cells,
                                                     unsigned long long *__restrict__ tile_state,
-                                                    unsigned *__restrict__ emig_list) {
+                                                    unsigned *__restrict__ emig_list,
+                                                    const __grid_constant__ StaticParams SP) {
   __shared__ StepParams P;
   if (threadIdx.x == 0) load_params(P, ctl);
   __syncthreads();
@@ -392,26 +415,27 @@ __global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const
   unsigned p_i = 0, p_rank = 0;
   uint32_t p_d = 0;
   uint4 h_next = make_uint4(0, 0, 0, 0);
-  if (tid < P.n) h_next = __ldg(&hot[tid]);
-  for (unsigned i = tid; i < P.n; i += stride) {
-    const uint4 h = h_next;
-    if (i + stride < P.n) h_next = __ldg(&hot[i + stride]);
-#ifndef CABS_A_NO_PREFETCH
-    // one register-held record ahead does not cover the DRAM latency at this occupancy: ask L2 for the records a
-    // few grid strides ahead (costs no registers), so that the load above finds them there
-    if (i + kPrefetchA * stride < P.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(hot + i + kPrefetchA * stride));
+  const unsigned n_now = P.n, step_now = P.step;   // registers: a shared-memory value is re-read after every atomic
+#ifdef CABS_GRID_IN_SMEM
+  const StepParams &G = P;
+#else
+  const GridRegs G = {P.gx0, P.gy0, P.eshift, P.ncx, P.ncy};
 #endif
+  if (tid < n_now) h_next = __ldg(&hot[tid]);
+  for (unsigned i = tid; i < n_now; i += stride) {
+    const uint4 h = h_next;
+    if (i + stride < n_now) h_next = __ldg(&hot[i + stride]);
     int nx = (int)h.x, ny = (int)h.y;
     uint32_t d = 0;
     if (kAdvance) {
       const uint32_t a = attr_normalize(h.z);
-      const uint2 w = agent_draw(h.w, P.step, kStreamMove, P.k0, P.k1);
+      const uint2 w = agent_draw(h.w, step_now, kStreamMove, SP.k0, SP.k1);
       int ix, iy;
       draw_displacement(P, a, w, ix, iy);
-      apply_displacement(P, nx, ny, ix, iy, nx, ny);
+      apply_displacement(SP, nx, ny, ix, iy, nx, ny);
       d = ((uint32_t)ix & 0xFFFFu) | ((uint32_t)iy << 16);
     }
-    if (nx < P.slab_lo || nx >= P.slab_hi) {
+    if (nx < SP.slab_lo || nx >= SP.slab_hi) {
       // leaves the slab: k_pack_emigrants finishes its step and hands it to the neighbour
       const unsigned e = atomicAdd(&ctl->n_emig, 1u);
       if (e < 2u * ctl->mig_cap) emig_list[e] = i;
@@ -419,7 +443,7 @@ __global__ void __launch_bounds__(256) k_move_count(Ctl *__restrict__ ctl, const
       aux[i] = make_uint2(d, kEmigrant);
       continue;
     }
-    const unsigned key = cell_key(P, nx, ny, &ctl->err);
+    const unsigned key = cell_key(G, nx, ny, &ctl->err);
     if (pending) aux[p_i] = make_uint2(p_d, p_rank);
     p_rank = atomicAdd(&cells[key], 1u);
     p_d = d;
@@ -543,13 +567,15 @@ struct BlockStats {
 constexpr int kSqrtTable = 4096;  // sqrt(d2) for d2 < 4096, exact (IEEE sqrt), filled once by k_init_ctl
 
 // One agent's move + update + economy (abs.py:156-230).  ix, iy: this step's displacement.
-__device__ __forceinline__ void advance_agent(const StepParams &P, uint32_t aid, int ix, int iy, uint32_t &a,
-                                              double &w, const double *__restrict__ sqrt_tab) {
+// S: the step-invariant parameters (StepParams or StaticParams); step, crit_active: what changes every step.
+template <class SP>
+__device__ __forceinline__ void advance_agent(const SP &S, uint32_t step, int crit_active, uint32_t aid, int ix, int iy,
+                                              uint32_t &a, double &w, const double *__restrict__ sqrt_tab) {
   const uint32_t st = attr_status(a);
   if (st == ST_D) return;   // the dead neither move (abs.py:164) nor update (abs.py:193)
   const uint32_t sev = attr_severity(a);
   const uint32_t stratum = min(attr_stratum(a), 4u);
-  const uint2 r0 = agent_draw(aid, P.step, kStreamEconomy, P.k0, P.k1);
+  const uint2 r0 = agent_draw(aid, step, kStreamEconomy, S.k0, S.k1);
   if (!(st == ST_I && sev >= SEV_H)) {   // mobile (abs.py:164-167)
     // abs.py:187-189: wealth += sqrt(ix^2+iy^2) * rand * minimum_expense * basic_income[stratum], rand = (r + .5) 2^-32.
     // The power of two rides on minimum_expense (me32): scaling by it commutes with every rounding, so the three
@@ -557,7 +583,7 @@ __device__ __forceinline__ void advance_agent(const StepParams &P, uint32_t aid,
     const int d2 = ix * ix + iy * iy;
     const double dist = d2 < kSqrtTable ? __ldg(&sqrt_tab[d2]) : __dsqrt_rn((double)d2);
     const double x = __dmul_rn(dist, __dadd_rn((double)r0.x, 0.5));
-    w = __dadd_rn(w, __dmul_rn(__dmul_rn(x, P.me32), P.bi[stratum]));
+    w = __dadd_rn(w, __dmul_rn(__dmul_rn(x, S.me32), S.bi[stratum]));
   }
   // abs.py:191-230
   if (st == ST_I) {
@@ -566,23 +592,23 @@ __device__ __forceinline__ void advance_agent(const StepParams &P, uint32_t aid,
     const uint32_t idx = min(age > 10u ? age / 10u - 1u : 0u, 8u);  // abs.py:204
     const long long w_sub = (long long)r0.y;
     if (sev == SEV_A) {
-      if (w_sub < P.thr_hosp[idx]) nsev = SEV_H;  // age_hospitalization_probs[idx] > u (abs.py:209)
+      if (w_sub < S.thr_hosp[idx]) nsev = SEV_H;  // age_hospitalization_probs[idx] > u (abs.py:209)
     } else if (sev == SEV_H) {
-      if (w_sub < P.thr_sev[idx]) {              // age_severe_probs[idx] > u (abs.py:212)
+      if (w_sub < S.thr_sev[idx]) {              // age_severe_probs[idx] > u (abs.py:212)
         nsev = SEV_G;
-        if (P.crit_active) {                     // abs.py:214-217
+        if (crit_active) {                     // abs.py:214-217
           nst = ST_D;
           nsev = SEV_A;
         }
       }
     }
-    const uint2 r1 = agent_draw(aid, P.step, kStreamDeath, P.k0, P.k1);
+    const uint2 r1 = agent_draw(aid, step, kStreamDeath, S.k0, S.k1);
     bool pays = true;
-    if ((long long)r1.x < P.thr_death[idx]) {    // age_death_probs[idx] > u (abs.py:219-223)
+    if ((long long)r1.x < S.thr_death[idx]) {    // age_death_probs[idx] > u (abs.py:219-223)
       nst = ST_D;
       nsev = SEV_A;
       pays = false;
-    } else if ((int)time > P.recovering_time) {  // abs.py:225-228
+    } else if ((int)time > S.recovering_time) {  // abs.py:225-228
       time = 0;
       nst = ST_R;
       nsev = SEV_A;
@@ -590,7 +616,7 @@ __device__ __forceinline__ void advance_agent(const StepParams &P, uint32_t aid,
     a = (a & 0xFFFF00F0u) | nst | (nsev << 2) | ((time & 0xFFu) << 8);
     if (!pays) return;                           // abs.py:223: the death of this step returns before the expense
   }
-  w = __dadd_rn(w, -P.mebi[stratum]);            // abs.py:230
+  w = __dadd_rn(w, -S.mebi[stratum]);            // abs.py:230
 }
 
 // An Infected agent within reach of a slab edge also pushes its contacts on the neighbour's side.
@@ -647,7 +673,8 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
                  unsigned *__restrict__ inf_list, const double *__restrict__ sqrt_tab,
                  ExchangeHeader *__restrict__ ghost_left, ExchangeHeader *__restrict__ ghost_right,
                  unsigned long long *__restrict__ tinf, const ExchangeHeader *__restrict__ recv_left,
-                 const ExchangeHeader *__restrict__ recv_right, const unsigned *__restrict__ imm_rank, SlabDirect D) {
+                 const ExchangeHeader *__restrict__ recv_right, const unsigned *__restrict__ imm_rank, SlabDirect D,
+                 const __grid_constant__ StaticParams SP) {
   __shared__ StepParams P;
   __shared__ BlockStats B;
   __shared__ unsigned s_last;
@@ -700,9 +727,17 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
   // for any population the 2^31 capacity allows: n / (gridDim * 256) < 2^31 / (148*8*256))
   unsigned long long c_st = 0, c_sev = 0;  // status S,I,R,D and severity A,H,G counts
   int bxmin = INT_MAX, bxmax = INT_MIN, bymin = INT_MAX, bymax = INT_MIN;
-  const double qscale = (double)(1ull << P.scale_bits);
+  const double qscale = (double)(1ull << SP.scale_bits);
   const unsigned lane = threadIdx.x & 31;
   const bool stand_down = kExtras && P.overflow;
+  const unsigned n_now = P.n, step_now = P.step;      // registers: shared-memory values are re-read after every atomic
+  const int crit_now = P.crit_active;
+  const bool pull_now = P.pull != 0;
+#ifdef CABS_GRID_IN_SMEM
+  const StepParams &G = P;
+#else
+  const GridRegs G = {P.gx0, P.gy0, P.eshift, P.ncx, P.ncy};
+#endif
   unsigned pend_mask = 0, pend_base = 0, pend_slot = 0;   // Infected-list entries of the previous tile
 
   for (unsigned k = 0;; ++k) {
@@ -728,18 +763,18 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
       }
     }
     const unsigned i = tile * kTile + threadIdx.x;
-    bool valid = i < P.n;
+    bool valid = i < n_now;
     if (kExtras) valid = valid && ax.y != kEmigrant && !stand_down;
     int nx = (int)h.x, ny = (int)h.y;
     uint32_t a = attr_normalize(h.z);
     const uint32_t aid = h.w;
     const int ix = (int)(short)(ax.x & 0xFFFFu), iy = (int)(short)(ax.x >> 16);
-    if (kAdvance) apply_displacement(P, nx, ny, ix, iy, nx, ny);
+    if (kAdvance) apply_displacement(SP, nx, ny, ix, iy, nx, ny);
     // the destination slot only needs the new position: ask for the cell start now so that the
     // round trip to the table overlaps the arithmetic below
     unsigned start = 0;
-    if (valid) start = __ldg(&cell_start[cell_key(P, nx, ny, &ctl->err)]);
-    if (kAdvance && valid) advance_agent(P, aid, ix, iy, a, w, sqrt_tab);
+    if (valid) start = __ldg(&cell_start[cell_key(G, nx, ny, &ctl->err)]);
+    if (kAdvance && valid) advance_agent(SP, step_now, crit_now, aid, ix, iy, a, w, sqrt_tab);
     // partial statistics (abs.py:300-312); infections of this step are added by k_contagion
     const uint32_t st = attr_status(a), sev = attr_severity(a);
     // The sum is tied to the updated attribute word (bit 7 is always clear here, which the compiler cannot know) so
@@ -768,7 +803,7 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
       const unsigned base = __shfl_sync(0xffffffffu, pend_base, 0);
       if (pend_mask & (1u << lane)) inf_list[base + __popc(pend_mask & ((1u << lane) - 1u))] = pend_slot;
     }
-    pend_mask = P.pull ? 0u : __ballot_sync(0xffffffffu, is_inf);   // pull mode needs no source list
+    pend_mask = pull_now ? 0u : __ballot_sync(0xffffffffu, is_inf);   // pull mode needs no source list
     pend_slot = slot;
     if (pend_mask && lane == 0) pend_base = atomicAdd(&ctl->n_inf, (unsigned)__popc(pend_mask));
   }
@@ -909,7 +944,7 @@ k_pack_emigrants(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     const int ix = (int)(short)(ax.x & 0xFFFFu), iy = (int)(short)(ax.x >> 16);
     if (kAdvance) {
       apply_displacement(P, nx, ny, ix, iy, nx, ny);
-      advance_agent(P, h.w, ix, iy, a, w, sqrt_tab);
+      advance_agent(P, P.step, P.crit_active, h.w, ix, iy, a, w, sqrt_tab);
     }
     const bool to_left = nx < P.slab_lo;
     ExchangeHeader *dst = to_left ? send_left : send_right;   // the local header counts; records may go remote
@@ -1201,6 +1236,73 @@ k_contagion_sequential(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const uns
   }
 }
 
+// The same relaxation with every round on the device: ONE cooperative launch per step.  All blocks are resident
+// (the host sizes the grid with the occupancy calculator), a grid-wide barrier separates the rounds, and the
+// "did this round lower a label" counters rotate over three slots so that clearing one never races with a block that
+// is still adding to, or reading, another.  The last round's closing (statistics record, triggers, next grid) runs
+// in block 0 after the final barrier, so a sequential step is four launches and has no host round trip.
+//   seq_round[3]: labels lowered in round r are counted in slot r % 3.
+__global__ void __launch_bounds__(256)
+k_contagion_sequential_all(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
+                           unsigned long long *__restrict__ tinf, const unsigned *__restrict__ inf_list,
+                           unsigned *__restrict__ newinf_list, StatRecord *__restrict__ history,
+                           unsigned *__restrict__ seq_round) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  __shared__ StepParams P;
+  __shared__ unsigned s_count;
+  if (threadIdx.x == 0) load_params(P, ctl);
+  __syncthreads();
+  for (unsigned round = 0;; ++round) {
+    unsigned *changed = seq_round + round % 3u;
+    if (P.T >= 0) {
+      if (threadIdx.x == 0) s_count = round == 0 ? ctl->n_inf : *(volatile unsigned *)&ctl->n_newinf;
+      __syncthreads();
+      const unsigned count = s_count;  // snapshot: agents appended during this round are picked up by the next one
+      const unsigned *sources = round == 0 ? inf_list : newinf_list;
+      const unsigned lanes = (P.n >= 4u * (unsigned)P.ncx * (unsigned)P.ncy) ? kSourceLanes : 1u;
+      const unsigned sub = threadIdx.x % lanes;
+      for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) / lanes; t < count; t += gridDim.x * blockDim.x / lanes) {
+        const unsigned s = __ldcg(&sources[t]);
+        const uint4 h = __ldcg(&hot[s]);
+        const unsigned long long ts = *reinterpret_cast<volatile unsigned long long *>(&tinf[s]);
+        const int xi = (int)h.x, yi = (int)h.y;
+        int clo, chi, rlo, rhi;
+        contact_cells(P, xi, yi, clo, chi, rlo, rhi);
+        for (int row = rlo; row <= rhi; ++row) {
+          const unsigned base = (unsigned)row * (unsigned)P.ncx;
+          const unsigned jb = cell_start[base + clo], je = cell_start[base + chi + 1];
+          for (unsigned j = jb + sub; j < je; j += lanes) {
+            const uint4 c = __ldcg(&hot[j]);
+            if ((c.z & 3u) != ST_S || j == s) continue;   // Susceptible at the start of the phase (marked or not)
+            const long long dx = (int)c.x - xi, dy = (int)c.y - yi;
+            if (dx * dx + dy * dy > (long long)P.T) continue;
+            const unsigned long long rank = pair_rank(h.w, c.w);
+            if (rank <= ts) continue;                      // the pair was walked before the source was infected
+            const uint4 r = philox4x32_10(min(h.w, c.w), P.step, kStreamContact, max(h.w, c.w), P.k0, P.k1);
+            if ((long long)r.x > P.thr_rate) continue;     // contagion_test <= contagion_rate (abs.py:150-153)
+            const unsigned long long old = atomicMin(&tinf[j], rank);
+            if (rank < old) {
+              atomicAdd(changed, 1u);
+              if (old == ~0ull) {
+                atomicOr(reinterpret_cast<uint32_t *>(&hot[j]) + 2, kNewlyInfected);
+                atomicAdd(&ctl->newinf, 1ull);
+                newinf_list[atomicAdd(&ctl->n_newinf, 1u)] = j;
+              }
+            }
+          }
+        }
+      }
+    }
+    __threadfence();
+    grid.sync();
+    const unsigned lowered = *(volatile unsigned *)changed;
+    if (blockIdx.x == 0 && threadIdx.x == 0) seq_round[(round + 2u) % 3u] = 0;   // next used two rounds from now
+    if (lowered == 0 || P.T < 0) break;
+  }
+  // the loop ends on a round that lowered nothing, so all three slots are zero again for the next launch
+  if (blockIdx.x == 0 && threadIdx.x == 0) close_step(ctl, history, 1);
+}
+
 // ------------------------------------------------------------------------------------------
 // Test hook for the pair loop of abs.py:253-259: every (i, j), i < j, within contagion_distance.
 __global__ void __launch_bounds__(256)
@@ -1295,7 +1397,7 @@ __device__ inline double stat_value(const Ctl *ctl, const StatRecord &r, int met
   return (double)r.q[metric - 7] / (double)(1ull << ctl->scale_bits);
 }
 
-__device__ inline long long prob_bound_lt(double p) {   // p > u  <=>  w < bound
+__host__ __device__ inline long long prob_bound_lt(double p) {   // p > u  <=>  w < bound
   const double t = ceil(p * 4294967296.0 - 0.5);
   return t <= 0.0 ? 0ll : t >= 4294967296.0 ? 4294967296ll : (long long)t;
 }
@@ -1616,7 +1718,7 @@ k_small_run(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, double *__restrict__
       int ix, iy;
       draw_displacement(P, a, r, ix, iy);
       apply_displacement(P, nx, ny, ix, iy, nx, ny);
-      advance_agent(P, h.w, ix, iy, a, w, sqrt_tab);
+      advance_agent(P, P.step, P.crit_active, h.w, ix, iy, a, w, sqrt_tab);
       // statistics (abs.py:300-312)
       const uint32_t st = attr_status(a), sev = attr_severity(a);
       atomicAdd(&s_cnt[st], 1ull);

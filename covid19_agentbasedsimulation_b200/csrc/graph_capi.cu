@@ -1,6 +1,7 @@
 // C ABI of the GraphSimulation path (include/covidabs.h, cabs_graph_*): host orchestration of graph_kernels.cuh.
 // No CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -14,6 +15,12 @@
 #include "graph_kernels.cuh"
 
 using namespace cabs::graph;
+
+// NVTX range around every entry point that enqueues or waits for device work (see abs_capi.cu)
+struct NvtxRangeG {
+  explicit NvtxRangeG(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRangeG() { nvtxRangePop(); }
+};
 
 static thread_local std::string g_graph_create_error;
 
@@ -175,6 +182,7 @@ static cudaError_t up_money(long long *dst, const double *src, size_t n, double 
 }
 
 extern "C" int cabs_graph_upload(cabs_graph *g, uint32_t sim, const cabs_graph_world *w, const cabs_graph_params *p) {
+  NvtxRangeG nvtx_("cabs_graph_upload");
   if (!g || !w || !p) return gfail(g, CABS_ERR_INVALID, "cabs_graph_upload: null argument");
   if (sim >= g->cfg.n_sims) return gfail(g, CABS_ERR_INVALID, "cabs_graph_upload: simulation index out of range");
   if (w->n_persons < 0 || (uint32_t)w->n_persons > g->cfg.max_persons || w->n_houses < 0 ||
@@ -281,6 +289,7 @@ extern "C" int cabs_graph_upload(cabs_graph *g, uint32_t sim, const cabs_graph_w
 }
 
 extern "C" int cabs_graph_run(cabs_graph *g, int iterations) {
+  NvtxRangeG nvtx_("cabs_graph_run");
   if (!g || iterations < 0) return gfail(g, CABS_ERR_INVALID, "cabs_graph_run: bad argument");
   for (char u : g->uploaded)
     if (!u) return gfail(g, CABS_ERR_INVALID, "cabs_graph_run: every simulation of the handle must be uploaded first");
@@ -315,6 +324,7 @@ extern "C" int cabs_graph_last_run_ms(cabs_graph *g, double *ms) {
 }
 
 extern "C" int cabs_graph_stats(cabs_graph *g, uint32_t sim, int64_t first, uint32_t count, double *rows) {
+  NvtxRangeG nvtx_("cabs_graph_stats");
   if (!g || (count && !rows)) return gfail(g, CABS_ERR_INVALID, "cabs_graph_stats: null argument");
   if (sim >= g->cfg.n_sims || !g->uploaded[sim]) return gfail(g, CABS_ERR_INVALID, "cabs_graph_stats: bad simulation index");
   GCK(cudaSetDevice(g->device));
@@ -347,6 +357,7 @@ extern "C" int cabs_graph_stats(cabs_graph *g, uint32_t sim, int64_t first, uint
 // The rows of every simulation of the handle in one strided copy per contiguous piece of the ring:
 // rows[sim][k][metric], k = first_iteration + 0 .. count-1.
 extern "C" int cabs_graph_stats_all(cabs_graph *g, int64_t first, uint32_t count, double *rows) {
+  NvtxRangeG nvtx_("cabs_graph_stats_all");
   if (!g || (count && !rows)) return gfail(g, CABS_ERR_INVALID, "cabs_graph_stats_all: null argument");
   for (uint32_t s = 0; s < g->cfg.n_sims; ++s)
     if (!g->uploaded[s]) return gfail(g, CABS_ERR_INVALID, "cabs_graph_stats_all: every simulation of the handle must be uploaded");
@@ -379,6 +390,7 @@ extern "C" int cabs_graph_stats_all(cabs_graph *g, int64_t first, uint32_t count
 }
 
 extern "C" int cabs_graph_aggregate(cabs_graph *g, int64_t first, uint32_t count, double *out) {
+  NvtxRangeG nvtx_("cabs_graph_aggregate");
   if (!g || (count && !out)) return gfail(g, CABS_ERR_INVALID, "cabs_graph_aggregate: null argument");
   for (uint32_t s = 0; s < g->cfg.n_sims; ++s)
     if (!g->uploaded[s]) return gfail(g, CABS_ERR_INVALID, "cabs_graph_aggregate: every simulation of the handle must be uploaded");
@@ -406,12 +418,45 @@ extern "C" int cabs_graph_aggregate(cabs_graph *g, int64_t first, uint32_t count
   return CABS_OK;
 }
 
+extern "C" int cabs_graph_moments(cabs_graph *g, uint32_t sim_first, uint32_t sim_count, int64_t first, uint32_t count,
+                                  double *out) {
+  NvtxRangeG nvtx_("cabs_graph_moments");
+  if (!g || (count && !out)) return gfail(g, CABS_ERR_INVALID, "cabs_graph_moments: null argument");
+  if (sim_count == 0 || sim_first + (uint64_t)sim_count > g->cfg.n_sims)
+    return gfail(g, CABS_ERR_INVALID, "cabs_graph_moments: simulation range outside the handle");
+  for (uint32_t s = sim_first; s < sim_first + sim_count; ++s)
+    if (!g->uploaded[s]) return gfail(g, CABS_ERR_INVALID, "cabs_graph_moments: every simulation of the range must be uploaded");
+  if (count == 0) return CABS_OK;
+  GCK(cudaSetDevice(g->device));
+  Sim cur;
+  GCK(cudaMemcpyAsync(&cur, g->sims, sizeof(Sim), cudaMemcpyDeviceToHost, g->stream));
+  GCK(cudaStreamSynchronize(g->stream));
+  const int64_t last = cur.iteration;
+  if (first < 0 || first + (int64_t)count - 1 > last)
+    return gfail(g, CABS_ERR_INVALID, "cabs_graph_moments: iterations not executed yet");
+  if (last - first >= (int64_t)cur.hist_cap)
+    return gfail(g, CABS_ERR_CAPACITY, "cabs_graph_moments: rows already overwritten (history_capacity)");
+  double *dev = nullptr;
+  const size_t bytes = (size_t)count * kStats * 4 * sizeof(double);
+  GCK(cudaMalloc(&dev, bytes));
+  k_graph_moments<<<count, kStats * 32, 0, g->stream>>>(g->history, (int)sim_first, (int)sim_count, cur.hist_cap,
+                                                        (long long)first, dev);
+  g->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, g->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+  cudaFree(dev);
+  GCK(e);
+  return CABS_OK;
+}
+
 template <typename T>
 static cudaError_t down(T *dst, const T *src, size_t n, cudaStream_t s) {
   return (n && dst) ? cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, s) : cudaSuccess;
 }
 
 extern "C" int cabs_graph_download(cabs_graph *g, uint32_t sim, cabs_graph_world *w) {
+  NvtxRangeG nvtx_("cabs_graph_download");
   if (!g || !w) return gfail(g, CABS_ERR_INVALID, "cabs_graph_download: null argument");
   if (sim >= g->cfg.n_sims || !g->uploaded[sim]) return gfail(g, CABS_ERR_INVALID, "cabs_graph_download: bad simulation index");
   const size_t n = g->np[sim], nh = g->nh[sim], nb = g->nb[sim];

@@ -858,5 +858,36 @@ k_graph_aggregate(const double *__restrict__ history, const double *__restrict__
   }
 }
 
+// The same reduction in mergeable form over a RANGE of the handle's simulations: out[iteration][metric] =
+// {min, sum, sum of squares, max}.  A scenario x seed sweep keeps the seeds of a scenario in consecutive simulations;
+// every GPU reduces its part of each scenario and the parts merge with min / + / + / max (three tiny all-reduces).
+__global__ void __launch_bounds__(kStats * 32)
+k_graph_moments(const double *__restrict__ history, int sim_first, int sim_count, int hist_cap, long long first,
+                double *__restrict__ out) {
+  const long long it = first + blockIdx.x;
+  const int m = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double *base = history + (size_t)(it % hist_cap) * kStats + (size_t)sim_first * hist_cap * kStats;
+  const size_t stride = (size_t)hist_cap * kStats;
+  double mn = INFINITY, mx = -INFINITY, sum = 0.0, sq = 0.0;
+  for (int s = lane; s < sim_count; s += 32) {
+    const double v = base[(size_t)s * stride + m];
+    mn = fmin(mn, v);
+    mx = fmax(mx, v);
+    sum = __dadd_rn(sum, v);
+    sq = __dadd_rn(sq, __dmul_rn(v, v));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+    sq = __dadd_rn(sq, __shfl_xor_sync(0xffffffffu, sq, o));
+  }
+  if (lane == 0) {
+    double *o4 = out + ((size_t)blockIdx.x * kStats + m) * 4;
+    o4[0] = mn; o4[1] = sum; o4[2] = sq; o4[3] = mx;
+  }
+}
+
 }  // namespace graph
 }  // namespace cabs

@@ -47,7 +47,7 @@ enum { CABS_EXPOSED = 0, CABS_ASYMPTOMATIC = 1, CABS_HOSPITALIZATION = 2, CABS_S
 enum {
   CABS_SYNCHRONOUS = 0, /* one neighbour scan: only agents infected before the contact phase transmit */
   CABS_SEQUENTIAL = 1   /* abs.py:261-265 order: in-step chains along increasing (i,j) rank; exact, by rounds
-                           of relaxation with one host round trip each (cabs_step waits); one device only     */
+                           of relaxation inside one cooperative launch (no host round trip); one device only  */
 };
 
 /* statistics slots, in the key order of abs.py:300-312 */
@@ -333,6 +333,23 @@ typedef struct cabs_graph_world {
   int32_t reserved2;
 } cabs_graph_world;
 
+/* Host-side world builder: the construction of GraphSimulation.initialize (graph_abs.py:89-188 with
+ * network/agents.py:36-42,186-194 -- every rule and quirk, in the same order over the persons) with counter-based draws
+ * keyed by `seed`, in C++: a 10^5-person world in milliseconds instead of the ~1 s of the Python loop, re-entrant so that
+ * the worlds of an ensemble are built concurrently.  Same distribution as the reference's worlds, not the same draws (the
+ * Python mirror network/graph_abs.py::build_world keeps np.random's order for that).  Needs no GPU. */
+typedef struct cabs_graph_world_spec {
+  int32_t population_size, length, height, total_business, homemates_avg, homemates_std;
+  double initial_infected_perc, initial_immune_perc, homeless_rate, unemployment_rate;
+  double total_wealth, public_gdp_share, business_gdp_share, minimum_income, minimum_expense;
+  double basic_income[5], lorenz_curve[5];   /* common.py:24-27 */
+  double isolation_rate;                     /* run_batch.py:31-35 sample_isolated; < 0: nobody is isolated */
+} cabs_graph_world_spec;
+/* Array sizes a caller must allocate for cabs_graph_build_world (houses: an upper bound; n_houses is set on return). */
+int cabs_graph_world_sizes(const cabs_graph_world_spec *spec, int32_t *n_persons, int32_t *max_houses,
+                           int32_t *n_business);
+int cabs_graph_build_world(const cabs_graph_world_spec *spec, uint64_t seed, cabs_graph_world *world);
+
 int cabs_graph_create(const cabs_graph_config *cfg, cabs_graph **out);
 void cabs_graph_destroy(cabs_graph *g);
 const char *cabs_graph_last_error(const cabs_graph *g);
@@ -350,6 +367,11 @@ int cabs_graph_stats_all(cabs_graph *g, int64_t first_iteration, uint32_t count,
  * handle (its "experiments"): out[count][CABS_GRAPH_NUM_STATS][4] = Min, Avg, Std (ddof = 0), Max of every metric
  * after iterations [first_iteration, first_iteration + count), reduced on the device. */
 int cabs_graph_aggregate(cabs_graph *g, int64_t first_iteration, uint32_t count, double *out);
+/* The same reduction in mergeable form over simulations [sim_first, sim_first + sim_count) of the handle:
+ * out[count][CABS_GRAPH_NUM_STATS][4] = min, sum, sum of squares, max.  A scenario x seed sweep sharded over several
+ * GPUs reduces its part of every scenario on each device and merges the parts with min / + / + / max. */
+int cabs_graph_moments(cabs_graph *g, uint32_t sim_first, uint32_t sim_count, int64_t first_iteration, uint32_t count,
+                       double *out);
 /* Current state of simulation `sim` (caller-allocated arrays of at least the uploaded sizes). */
 int cabs_graph_download(cabs_graph *g, uint32_t sim, cabs_graph_world *world);
 /* Device time of the last cabs_graph_run (CUDA events on the handle's stream); waits for it. */
