@@ -348,7 +348,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         ok, bad_rows, bad_agents, resident = slab_invariance(local_rank, world, args.transport)
         invariance = {"slab_invariance": ok, "mismatching_statistics_rows": bad_rows, "mismatching_agents": bad_agents,
-                      "agents": resident, "steps": 12,
+                      "agents": resident, "invariance_steps": 12,
                       "what": "3e5 agents, unmasked (r = 1, rate .9) with the conditional-lockdown triggers, stepped on "
                               "{} slabs (one per rank, transport {}) and on one device by every rank: every "
                               "statistics row and every agent record (position, status, severity, infected_time, "

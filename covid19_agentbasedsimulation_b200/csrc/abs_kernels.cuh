@@ -376,6 +376,15 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, 
                : "memory");
 }
 
+// Programmatic dependent launch (opt-in, CABS_PDL=1; measured slower than plain graph edges, see abs_capi.cu): the
+// kernels of a step can be chained with cudaLaunchAttributeProgrammaticStreamSerialization, so that the blocks of the
+// next kernel are resident and parked at pdl_wait() while the tail of the previous one drains.  pdl_wait()
+// returns once every block of the preceding kernel has finished and its writes are visible, so nothing produced by
+// it may be touched before; pdl_trigger() lets the successor's blocks be scheduled (they park at their own wait).
+// Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr int kTile = 256;    // agents per tile = consumer threads per block of the agent passes
 constexpr int kPad = kTile;   // every per-agent array is allocated with this many spare elements (whole-tile loads)
 constexpr int kConsumerWarps = kTile / 32;
@@ -400,6 +409,7 @@ __global__ void __launch_bounds__(256, CABS_A_MINBLOCKS) k_move_count(Ctl *__res
                                                     unsigned *__restrict__ emig_list,
                                                     const __grid_constant__ StaticParams SP) {
   __shared__ StepParams P;
+  pdl_wait();
   if (threadIdx.x == 0) load_params(P, ctl);
   __syncthreads();
   const unsigned stride = gridDim.x * blockDim.x;
@@ -450,6 +460,7 @@ __global__ void __launch_bounds__(256, CABS_A_MINBLOCKS) k_move_count(Ctl *__res
     p_i = i;
     pending = true;
   }
+  pdl_trigger();
   if (pending) aux[p_i] = make_uint2(p_d, p_rank);
 }
 
@@ -464,6 +475,8 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_cells(Ctl *__restrict__ c
                                                              unsigned long long *__restrict__ tile_state) {
   __shared__ unsigned warp_sums[kScanThreads / 32];
   __shared__ unsigned s_tile, s_prefix;
+  pdl_wait();
+  pdl_trigger();   // few blocks, short: let pass B's blocks take their places right away
   const unsigned m = ctl->g.ncells + 1;
   const unsigned ntiles = (m + kScanTile - 1) / kScanTile;
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -685,6 +698,7 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
   __shared__ unsigned s_released[kStagesB];
 #pragma unroll
   for (int k = 0; k < 5; ++k) s_q[k][threadIdx.x] = 0;
+  pdl_wait();
   if (threadIdx.x == 0) {
     load_params(P, ctl);
     for (int i = 0; i < 7; ++i) B.cnt[i] = 0;
@@ -807,6 +821,7 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     pend_slot = slot;
     if (pend_mask && lane == 0) pend_base = atomicAdd(&ctl->n_inf, (unsigned)__popc(pend_mask));
   }
+  pdl_trigger();
   if (pend_mask) {
     const unsigned base = __shfl_sync(0xffffffffu, pend_base, 0);
     if (pend_mask & (1u << lane)) inf_list[base + __popc(pend_mask & ((1u << lane) - 1u))] = pend_slot;
@@ -927,6 +942,7 @@ k_pack_emigrants(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
                  const double *__restrict__ sqrt_tab, SlabDirect D) {
   __shared__ StepParams P;
   __shared__ unsigned s_last;
+  pdl_wait();
   if (threadIdx.x == 0) load_params(P, ctl);
   __syncthreads();
   const unsigned count = min(ctl->n_emig, 2u * ctl->mig_cap);
@@ -993,6 +1009,7 @@ k_count_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ rec
                    const ExchangeHeader *__restrict__ recv_right, unsigned *__restrict__ cells,
                    unsigned *__restrict__ imm_rank, SlabDirect D) {
   __shared__ StepParams P;
+  pdl_wait();
   if (threadIdx.x == 0) {
     load_params(P, ctl);
     if (D.enabled) {   // the neighbours' migrants of this build have landed in my block
@@ -1054,6 +1071,7 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
             long long *__restrict__ rows, int finish, SlabDirect D, ExchangeHeader *__restrict__ send_reset) {
   __shared__ StepParams P;
   __shared__ unsigned s_new, s_local, s_left, s_right;
+  pdl_wait();
   if (threadIdx.x == 0) {
     load_params(P, ctl);
     if (D.enabled) {   // the neighbours' ghosts of this build have landed in my block
@@ -1146,6 +1164,7 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
       }
     }
   }
+  pdl_trigger();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) newinf += __shfl_xor_sync(0xffffffffu, newinf, o);
   if ((threadIdx.x & 31) == 0 && newinf) atomicAdd(&s_new, newinf);
@@ -1499,6 +1518,7 @@ __device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats) {
 }
 
 __global__ void k_finalize(Ctl *ctl, StatRecord *history, int record_stats) {
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   close_step(ctl, history, record_stats);
 }
@@ -1533,6 +1553,7 @@ __device__ void slab_export(Ctl *ctl, long long *rows, SlabDirect D) {
 }
 
 __global__ void k_slab_export(Ctl *ctl, long long *rows, SlabDirect D) {
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   slab_export(ctl, rows, D);
 }
@@ -1625,12 +1646,14 @@ __device__ void close_global(Ctl *ctl, const long long *rows, StatRecord *histor
 
 __global__ void k_slab_close_local(Ctl *ctl, const unsigned *cell_start, int record_stats, ExchangeHeader *s0,
                                    ExchangeHeader *s1, ExchangeHeader *s2, ExchangeHeader *s3) {
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   s0->count = 0; s1->count = 0; s2->count = 0; s3->count = 0;
   close_local(ctl, cell_start, record_stats);
 }
 
 __global__ void k_slab_close_global(Ctl *ctl, StatRecord *history, int record_stats, SlabDirect D) {
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
   const unsigned dseq = ctl->build_seq + D.seq;   // D.seq = 0: the build that has just been closed locally
@@ -1643,6 +1666,7 @@ __global__ void k_slab_close_global(Ctl *ctl, StatRecord *history, int record_st
 __global__ void k_slab_close(Ctl *ctl, const long long *rows, const unsigned *cell_start, StatRecord *history,
                              int record_stats, ExchangeHeader *s0, ExchangeHeader *s1, ExchangeHeader *s2,
                              ExchangeHeader *s3, SlabDirect D) {
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (D.enabled) {   // every rank's row of this build has landed in my block
     const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);

@@ -1,9 +1,10 @@
 set -x
-bash scripts/ab_variants.sh 2>&1 | tee gpurun_out/ab_r2_5.log
-timeout 900 python -m pytest tests/test_gpu_graph.py tests/test_gpu_api.py -m gpu -x -q 2>&1 | tail -3
-timeout 1200 python bench.py --workload ensemble > gpurun_out/bench_ens_r2_a.json 2> gpurun_out/bench_ens_r2_a.err; tail -5 gpurun_out/bench_ens_r2_a.err
-python - <<'PY'
-import json
-d=json.load(open("gpurun_out/bench_ens_r2_a.json"))
-print(json.dumps({k:v for k,v in d.items() if k not in ("config",)}, indent=None)[:3000])
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for pdl in 0 1; do
+CABS_NO_PDL=$pdl python bench.py --steps 100 --no-cpu-baseline --no-other-configs --e2e-steps 3 > gpurun_out/pdl_$pdl.json 2>/dev/null
+python - $pdl <<'PY'
+import json,sys
+d=json.load(open("gpurun_out/pdl_%s.json"%sys.argv[1]))
+print("CABS_NO_PDL=%s  step %.4f ms  value %.4g  e2e_python %.4f" % (sys.argv[1], d["ms_per_step"], d["value"], d["e2e_python"]["ms_per_step"]))
 PY
+done

@@ -65,6 +65,48 @@ def test_simulation_ensemble_matches_reference(native_lib, case, schedule):
             assert p > 0.05, (case, when, key, p)
 
 
+@pytest.mark.parametrize("schedule", ["synchronous", "sequential"])
+@pytest.mark.parametrize("case", ["config3_masks", "config3_masks_i20"])
+def test_config3_parameters_meet_the_strict_criterion_on_both_schedules(native_lib, case, schedule):
+    """The headline configuration's own rules (masks: distance .05, rate .1; density 0.2; conditional-lockdown
+    triggers) at N = 300, where the unmodified reference can run 256 seeds (oracle/gen_config3_ensemble.py).  With
+    contacts only between agents on the same lattice point and a transmission probability of 0.1, an in-step
+    infection chain needs two rare events in one step, so the synchronous schedule -- the one every bench number is
+    measured on -- is held to the north star's FULL criterion here, exactly like the sequential one: >= 90 % of the
+    (iteration, metric) cells inside 1.96 combined standard errors, none beyond 4.5, KS p > 0.05 at the middle and the
+    last iteration."""
+    from covid19_agentbasedsimulation_b200.abs import Simulation, Trigger
+    from covid19_agentbasedsimulation_b200.agents import Status
+    path = os.path.join(GOLDEN, "simulation_config3_ensemble.json")
+    if not os.path.exists(path):
+        pytest.skip("config-3 ensemble fixture not generated")
+    with open(path) as f:
+        ens = json.load(f)[case]
+    keys, iters, seeds = ens["keys"], ens["iterations"], len(ens["seeds"])
+    assert seeds >= 256
+    amp = lambda v: {Status.Susceptible: v, Status.Recovered_Immune: v, Status.Infected: v}
+    rows = np.empty((seeds, iters, len(keys)))
+    for s in range(seeds):
+        np.random.seed(s)
+        sim = Simulation(schedule=schedule, amplitudes=amp(5),
+                         triggers_simulation=[Trigger('Infected', '>=', .2, 'amplitudes', amp(1.5)),
+                                              Trigger('Infected', '<=', .05, 'amplitudes', amp(5))], **ens["kwargs"])
+        sim.initialize()
+        rows[s] = sim.run(iters)
+    z = _z_table(rows, np.array(ens["mean"]), np.array(ens["std"]), seeds)
+    live = np.array(ens["std"]) > 0
+    frac_inside = float(np.mean(z[live] < 1.96))
+    assert frac_inside >= 0.90, (case, schedule, frac_inside)
+    assert float(z[live].max()) < 4.5, (case, schedule, float(z[live].max()))
+    for when, sample in (("mid", iters // 2), ("final", iters - 1)):
+        ref = np.array(ens[when])
+        for k, key in enumerate(keys[:7]):
+            if np.ptp(ref[:, k]) == 0 and np.ptp(rows[:, sample, k]) == 0:
+                continue
+            p = stats.ks_2samp(rows[:, sample, k], ref[:, k]).pvalue
+            assert p > 0.05, (case, schedule, when, key, p)
+
+
 def test_graph_ensemble_matches_reference(native_lib):
     from covid19_agentbasedsimulation_b200.network.graph_abs import GraphSimulation
     from covid19_agentbasedsimulation_b200.network.ensemble import GraphEnsemble
