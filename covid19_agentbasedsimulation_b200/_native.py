@@ -20,7 +20,8 @@ OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_DOMAIN, ERR_NOGPU = 0, -1, -2, -3, 
 
 # every symbol include/covidabs.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params", "cabs_get_params", "cabs_set_triggers",
-            "cabs_upload", "cabs_set_step", "cabs_download", "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_history",
+            "cabs_upload", "cabs_upload_f64", "cabs_download_positions_f64", "cabs_set_rules", "cabs_set_step", "cabs_download",
+            "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_history",
             "cabs_contact_pairs", "cabs_cross_contact", "cabs_get_info", "cabs_event_record", "cabs_event_elapsed_ms",
             "cabs_profile_enable", "cabs_profile_read", "cabs_selftest_normals", "cabs_set_slab", "cabs_slab_phase", "cabs_set_stream",
             "cabs_slab_block_bytes", "cabs_set_slab_direct", "cabs_slab_step", "cabs_slab_run", "cabs_device_alloc", "cabs_device_free",
@@ -61,6 +62,18 @@ class Params(C.Structure):
 class Trigger(C.Structure):
     _fields_ = [("metric", C.c_int32), ("op", C.c_int32), ("threshold", C.c_double), ("attribute", C.c_int32),
                 ("reserved", C.c_int32), ("value", C.c_double * 4)]
+
+
+FLAG_F64_POSITIONS = 1
+RULE_MOVE_STAY, RULE_MOVE_POINT, RULE_ATTRIBUTE = 1, 2, 3
+RATTR = {"status": 0, "infected_status": 1, "infected_time": 2, "age": 3, "social_stratum": 4, "wealth": 5}
+RULE_CONDITION_WORDS, MAX_RULES = 250, 8
+
+
+class Rule(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("attribute", C.c_int32), ("target_x", C.c_double), ("target_y", C.c_double),
+                ("sigma", C.c_double), ("p", C.c_double), ("q", C.c_double),
+                ("condition", C.c_uint32 * RULE_CONDITION_WORDS), ("reserved", C.c_uint32 * 2)]
 
 
 class SoaHost(C.Structure):
@@ -172,6 +185,9 @@ def load():
     lib.cabs_upload.argtypes = [P, C.POINTER(SoaHost)]
     lib.cabs_download.argtypes = [P, C.POINTER(SoaHost)]
     lib.cabs_set_step.argtypes = [P, C.c_uint64]
+    lib.cabs_upload_f64.argtypes = [P, C.POINTER(SoaHost), C.c_void_p, C.c_void_p]
+    lib.cabs_download_positions_f64.argtypes = [P, C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.cabs_set_rules.argtypes = [P, C.POINTER(Rule), C.c_int, C.c_int]
     lib.cabs_step.argtypes = [P, C.c_int]
     lib.cabs_sync.argtypes = [P]
     lib.cabs_stats.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -231,11 +247,12 @@ SOA_DTYPES = (("x", np.int32), ("y", np.int32), ("status", np.uint8), ("severity
 class Handle(object):
     """Owns one `cabs_sim*`."""
 
-    def __init__(self, capacity, seed=0, device=0, max_cells=0, history_capacity=4096):
+    def __init__(self, capacity, seed=0, device=0, max_cells=0, history_capacity=4096, f64=False):
         self._lib = load()
         self._h = C.c_void_p()
+        self.f64 = bool(f64)
         cfg = Config(ABI_VERSION, int(device), int(capacity), int(max_cells), int(seed) & 0xFFFFFFFFFFFFFFFF,
-                     int(history_capacity), 0)
+                     int(history_capacity), FLAG_F64_POSITIONS if f64 else 0)
         rc = self._lib.cabs_create(C.byref(cfg), C.byref(self._h))
         if rc != OK:
             msg = self._lib.cabs_last_error(None)
@@ -293,6 +310,25 @@ class Handle(object):
         n = len(cols["x"])
         s = self._soa(cols, n)
         self._check(self._lib.cabs_upload(self._h, C.byref(s)))
+
+    def upload_f64(self, cols, xf, yf):
+        """Like upload(), with binary64 positions (off-lattice handles); cols need no 'x' / 'y'."""
+        n = len(cols["status"])
+        xf = np.ascontiguousarray(xf, dtype=np.float64)
+        yf = np.ascontiguousarray(yf, dtype=np.float64)
+        assert xf.shape == (n,) and yf.shape == (n,)
+        s = self._soa({k: v for k, v in cols.items() if k not in ("x", "y")}, n)
+        self._check(self._lib.cabs_upload_f64(self._h, C.byref(s), xf.ctypes.data, yf.ctypes.data))
+
+    def download_positions(self, n):
+        xf, yf = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
+        self._check(self._lib.cabs_download_positions_f64(self._h, xf.ctypes.data, yf.ctypes.data, n))
+        return xf, yf
+
+    def set_rules(self, move_rules, attr_rules):
+        rules = list(move_rules) + list(attr_rules)
+        arr = (Rule * max(1, len(rules)))(*rules)
+        self._check(self._lib.cabs_set_rules(self._h, arr, len(move_rules), len(attr_rules)))
 
     def upload_pointers(self, n, ptrs):
         """Upload from raw host addresses (e.g. pinned torch tensors): ptrs maps column name -> int address."""

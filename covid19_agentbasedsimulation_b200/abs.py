@@ -11,7 +11,11 @@ Differences a user can observe (all documented in DESIGN.md):
   * contacts are applied synchronously (an agent infected in a step starts transmitting in the next);
   * the critical-limit test (abs.py:214-217) reads the statistics of the end of the previous step,
     which is what the reference's memo holds when `batch_experiment` drives it;
-  * `triggers_population` with Python lambdas cannot run on the device and raise NotImplementedError;
+  * `triggers_population` (abs.py:86-95) run on the device as declarative rules (`rules.MoveRule`, `AttributeRule`);
+    the reference's own dict-of-lambdas entries are recognised by probing when they have the shipped shape (condition on
+    status / infected_status / age / social_stratum; move action = point + np.random.normal(0, sigma); attribute
+    action = constant, or scale * wealth + shift), anything else raises NotImplementedError.  With a population trigger
+    the positions are binary64, as in the reference once a move action has assigned a float (`positions="float64"`);
   * `get_population()` / `sim.population` return `Agent` objects materialised from a device download: they are
     detached copies, so mutating `sim.population[i]` in place does not reach the device -- pass the edited list
     back through `set_population()` (or use `set_population_arrays`).
@@ -24,6 +28,7 @@ from covid19_agentbasedsimulation_b200.agents import (Status, InfectionSeverity,
 from covid19_agentbasedsimulation_b200.common import *  # noqa: F401,F403  (the reference does the same, abs.py:6)
 from covid19_agentbasedsimulation_b200.common import (age_hospitalization_probs, age_severe_probs, age_death_probs,
                                                       lorenz_curve, basic_income)
+from covid19_agentbasedsimulation_b200.rules import MoveRule, AttributeRule, When, lower_trigger  # noqa: F401
 
 STAT_KEYS = ("Susceptible", "Infected", "Recovered_Immune", "Death", "Asymptomatic", "Hospitalization", "Severe",
              "Q1", "Q2", "Q3", "Q4", "Q5")
@@ -88,6 +93,8 @@ _EXTRA_KWARGS = (
     ("placement", "reference"),       # "reference": abs.py:97-114 from np.random in the reference's order; "uniform": x, y ~ U{0..L}
     ("schedule", "synchronous"),      # or "sequential": the reference's pair order with in-step chains (abs.py:261-265), exact, slower
     ("max_cells", 0), ("history_capacity", 4096),
+    ("positions", "lattice"),         # "float64": binary64 positions and the reference's floating-point contact test
+                                      # (chosen automatically as soon as a population trigger or a float position appears)
 )
 
 
@@ -105,6 +112,7 @@ class Simulation(object):
         self._handle = None
         self._pushed = None          # last parameter tuple sent to the device
         self._pushed_triggers = None
+        self._pushed_rules = None
         self._host = None            # cached download of the population (dict of columns)
         self._agents = None          # cached list of Agent objects
         self._iteration = 0
@@ -141,10 +149,48 @@ class Simulation(object):
             if self.seed is None:
                 self.seed = int(np.random.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(np.random.randint(0, 2 ** 31 - 1))
             self._handle = _native.Handle(capacity=max(1, n), seed=self.seed, device=self.device,
-                                          max_cells=self.max_cells, history_capacity=self.history_capacity)
+                                          max_cells=self.max_cells, history_capacity=self.history_capacity,
+                                          f64=self._wants_f64())
             self._pushed = None
             self._pushed_triggers = None
+            self._pushed_rules = None
         return self._handle
+
+    def _wants_f64(self):
+        if self.positions not in ("lattice", "float64"):
+            raise ValueError("positions must be 'lattice' or 'float64'")
+        return self.positions == "float64" or len(self.triggers_population) > 0
+
+    def _push_rules(self):
+        """Population triggers (abs.py:86-95) as device rules; switches the handle to binary64 positions when the
+        first one appears on a lattice handle."""
+        if not self.triggers_population:
+            if self._pushed_rules:
+                self._handle.set_rules([], [])
+                self._pushed_rules = None
+            return
+        rules = [lower_trigger(t) for t in self.triggers_population]
+        key = tuple(r.key() for r in rules)
+        if not self._handle.f64:
+            self._to_float64()
+        if key != self._pushed_rules:
+            self._handle.set_rules([r.native() for r in rules if isinstance(r, MoveRule)],
+                                   [r.native() for r in rules if isinstance(r, AttributeRule)])
+            self._pushed_rules = key
+
+    def _to_float64(self):
+        """Re-create the handle in off-lattice mode with the same population and the same draw clock."""
+        cols = self._handle.download(int(self.population_size))
+        step = self._handle.info()["step"]
+        self._handle.close()
+        self._handle = None
+        self.positions = "float64"
+        self._ensure_handle(len(cols["x"]))
+        self._push_params()
+        xf, yf = cols.pop("x").astype(np.float64), cols.pop("y").astype(np.float64)
+        self._handle.upload_f64(cols, xf, yf)
+        self._handle.set_step(step)
+        self._invalidate_host()
 
     def _targets(self):
         """Handles that hold a part of this population (several in slab mode)."""
@@ -218,8 +264,13 @@ class Simulation(object):
     def set_population_arrays(self, x, y, status, age, stratum, wealth, severity=None, infected_time=None):
         """Upload a population given as columns (codes of include/covidabs.h); ids = positions."""
         n = len(x)
+        xa, ya = np.asarray(x), np.asarray(y)
+        fractional = (xa.dtype.kind == 'f' and bool(np.any(xa != np.floor(xa)))) or \
+                     (ya.dtype.kind == 'f' and bool(np.any(ya != np.floor(ya))))
+        if fractional:
+            self.positions = "float64"
         cols = {
-            "x": np.ascontiguousarray(x, dtype=np.int32), "y": np.ascontiguousarray(y, dtype=np.int32),
+            "x": np.ascontiguousarray(np.floor(xa), dtype=np.int32), "y": np.ascontiguousarray(np.floor(ya), dtype=np.int32),
             "status": np.ascontiguousarray(status, dtype=np.uint8),
             "severity": (np.full(n, 1, dtype=np.uint8) if severity is None
                          else np.ascontiguousarray(severity, dtype=np.uint8)),
@@ -230,9 +281,15 @@ class Simulation(object):
             "wealth": np.ascontiguousarray(wealth, dtype=np.float64),
         }
         self.population_size = n
+        if self._handle is not None and self._handle.f64 != self._wants_f64():
+            self._handle.close()
+            self._handle = None
         self._ensure_handle(n)
         self._push_params()
-        self._handle.upload(cols)
+        if self._handle.f64:
+            self._handle.upload_f64(cols, np.asarray(xa, dtype=np.float64), np.asarray(ya, dtype=np.float64))
+        else:
+            self._handle.upload(cols)
         self._invalidate_host()
         self.statistics = None
 
@@ -246,13 +303,16 @@ class Simulation(object):
                 self._host = {name: np.zeros(0, dtype=dt) for name, dt in _native.SOA_DTYPES}
             else:
                 self._host = self._handle.download(int(self.population_size))
+                if self._handle.f64:   # the exact positions (the int columns hold their floors)
+                    self._host["x"], self._host["y"] = self._handle.download_positions(len(self._host["x"]))
         return self._host
 
     def get_population(self):
         """Current population as `Agent` objects, materialised from a device download (abs.py:57-63)."""
         if self._agents is None:
             h = self._download()
-            self._agents = [Agent(id=int(h["id"][k]), x=int(h["x"][k]), y=int(h["y"][k]),
+            num = float if h["x"].dtype.kind == 'f' else int
+            self._agents = [Agent(id=int(h["id"][k]), x=num(h["x"][k]), y=num(h["y"][k]),
                                   status=STATUS_LIST[h["status"][k]],
                                   infected_status=SEVERITY_LIST[h["severity"][k]],
                                   infected_time=int(h["infected_time"][k]), age=int(h["age"][k]),
@@ -264,7 +324,8 @@ class Simulation(object):
         """Replace the population with a list of Agent-like objects (abs.py:65-69)."""
         pop = list(pop)
         self.set_population_arrays(
-            [int(a.x) for a in pop], [int(a.y) for a in pop], [STATUS_CODE[a.status] for a in pop],
+            [float(np.asarray(a.x).ravel()[0]) for a in pop], [float(np.asarray(a.y).ravel()[0]) for a in pop],
+            [STATUS_CODE[a.status] for a in pop],
             [int(a.age) for a in pop], [int(a.social_stratum) for a in pop],
             [float(np.asarray(a.wealth).ravel()[0]) for a in pop],
             severity=[SEVERITY_CODE[a.infected_status] for a in pop],
@@ -320,10 +381,8 @@ class Simulation(object):
         """One iteration (abs.py:232-273): move, update, contacts on the GPU; simulation triggers after."""
         if self._handle is None:
             raise RuntimeError("initialize() or set_population() first")
-        if len(self.triggers_population) > 0:
-            raise NotImplementedError("per-agent Python triggers (abs.py:244-247) cannot run on the device and "
-                                      "there is no CPU fallback; see DESIGN.md (out of scope rows)")
         self._push_params()
+        self._push_rules()
         self._handle.step(1)
         self._iteration += 1
         self._invalidate_host()
@@ -348,9 +407,8 @@ class Simulation(object):
                 s = self.get_statistics(kind='all')
                 rows[it] = [s[k] for k in STAT_KEYS]
             return rows
-        if len(self.triggers_population) > 0:
-            raise NotImplementedError("per-agent Python triggers cannot run on the device")
         self._push_params()
+        self._push_rules()
         first = self._handle.info()["step"]     # the handle's clock is not reset by a re-upload
         self._handle.step(iterations)
         self._iteration += iterations
@@ -364,7 +422,14 @@ class Simulation(object):
     def get_positions(self):
         """abs.py:275-277."""
         h = self._download()
-        return [[int(a), int(b)] for a, b in zip(h["x"], h["y"])]
+        num = float if h["x"].dtype.kind == 'f' else int
+        return [[num(a), num(b)] for a, b in zip(h["x"], h["y"])]
+
+    def remove_trigger_population(self, attribute):
+        """Drop the population triggers on `attribute` (used by run_batch.py's commented scenarios)."""
+        def attr_of(t):
+            return t['attribute'] if isinstance(t, dict) else ('move' if isinstance(t, MoveRule) else t.attribute)
+        self.triggers_population = [t for t in self.triggers_population if attr_of(t) != attribute]
 
     def get_description(self, complete=False):
         """abs.py:279-289."""

@@ -39,6 +39,12 @@ struct cabs_sim {
   uint4 *hot[2] = {nullptr, nullptr};
   double *w[2] = {nullptr, nullptr};
   uint2 *aux = nullptr;         // {displacement, rank in destination cell}: pass A -> pass B
+  // off-lattice mode (cabs_config.flags & CABS_FLAG_F64_POSITIONS): exact positions (ping/pong with hot) + the moved ones
+  bool f64 = false;
+  double2 *pos[2] = {nullptr, nullptr};
+  double2 *npos = nullptr;
+  DevRule *rules = nullptr;     // kMaxRules declarative per-agent rules: move rules first, then attribute rules
+  int n_move_rules = 0, n_attr_rules = 0;
   double *sqrt_tab = nullptr;   // exact sqrt of small integers (income of abs.py:187)
   int cur = 0;
   unsigned *cells[2] = {nullptr, nullptr};  // histogram / cell_start (ping/pong), max_cells + 8 entries each
@@ -173,6 +179,7 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
     cudaFree(sim->hot[b]); cudaFree(sim->w[b]);
   }
   cudaFree(sim->aux);
+  cudaFree(sim->pos[0]); cudaFree(sim->pos[1]); cudaFree(sim->npos); cudaFree(sim->rules);
   cudaFree(sim->sqrt_tab);
   cudaFree(sim->cells[0]); cudaFree(sim->cells[1]); cudaFree(sim->tile_state); cudaFree(sim->inf_list);
   cudaFree(sim->emig_list); cudaFree(sim->imm_rank); cudaFree(sim->tinf); cudaFree(sim->newinf_list);
@@ -252,6 +259,16 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   }
   CK(cudaMalloc(&sim->aux, capp * sizeof(uint2)));
   CK(cudaMemsetAsync(sim->aux, 0, capp * sizeof(uint2), sim->stream));
+  sim->f64 = (cfg->flags & CABS_FLAG_F64_POSITIONS) != 0;
+  if (sim->f64) {
+    for (int b = 0; b < 2; ++b) {
+      CK(cudaMalloc(&sim->pos[b], capp * sizeof(double2)));
+      CK(cudaMemsetAsync(sim->pos[b], 0, capp * sizeof(double2), sim->stream));
+    }
+    CK(cudaMalloc(&sim->npos, capp * sizeof(double2)));
+    CK(cudaMalloc(&sim->rules, kMaxRules * sizeof(DevRule)));
+    CK(cudaMemsetAsync(sim->rules, 0, kMaxRules * sizeof(DevRule), sim->stream));
+  }
   CK(cudaMalloc(&sim->inf_list, cap * sizeof(unsigned)));
   CK(cudaMalloc(&sim->sqrt_tab, kSqrtTable * sizeof(double)));
   for (int b = 0; b < 2; ++b) {
@@ -268,6 +285,7 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   CK(cudaMemsetAsync(sim->history, 0, (size_t)sim->hist_cap * sizeof(StatRecord), sim->stream));
   LAUNCH(k_init_ctl, 1, 256, sim->ctl, (unsigned)(cfg->seed & 0xFFFFFFFFu), (unsigned)(cfg->seed >> 32),
          sim->max_cells, sim->coarse_cells, sim->hist_cap, (unsigned)sim->capacity, sim->sqrt_tab);
+  if (sim->f64) LAUNCH(k_set_rules, 1, 32, sim->ctl, 1, 0, 1, 0, 1, 0);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(sim->stream));
   return CABS_OK;
@@ -348,6 +366,8 @@ extern "C" int cabs_set_params(cabs_sim *sim, const cabs_params *p) {
     }
     sp.recovering_time = p->recovering_time;
     sp.scale_bits = p->wealth_scale_bits;
+    sp.length = p->length;
+    sp.height = p->height;
     sp.len_i = (int)fmin(fmax(ceil(p->length), -2147483647.0), 2147483647.0);
     sp.hei_i = (int)fmin(fmax(ceil(p->height), -2147483647.0), 2147483647.0);
     drop_graphs(sim);   // captured launches hold the old copy
@@ -415,10 +435,24 @@ static void enqueue_build(cabs_sim *sim) {
   const int nb = agent_blocks(sim);
   SlabDirect no_direct;
   memset(&no_direct, 0, sizeof no_direct);
-  LAUNCH_PDL_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl,
-                (const uint4 *)sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list, sim->sp);
+  const double2 *pos_o = sim->f64 ? sim->pos[o] : nullptr;   // exact positions the contact kernels test (off-lattice mode)
+  if (sim->f64) {
+    LAUNCH_AS(kAdvance ? "k_move_count_f64<true>" : "k_move_count_f64<false>", k_move_count_f64<kAdvance>, nb, 256,
+              sim->ctl, sim->hot[c], sim->pos[c], sim->npos, sim->aux, sim->cells[t], sim->tile_state, sim->rules,
+              sim->n_move_rules, sim->sp);
+    LAUNCH(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
+    LAUNCH_AS(kAdvance ? "k_update_scatter_f64<true>" : "k_update_scatter_f64<false>", k_update_scatter_f64<kAdvance>, nb,
+              256, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->npos, sim->cells[t], sim->cells[t ^ 1], sim->hot[o],
+              sim->w[o], sim->pos[o], sim->inf_list, sim->sqrt_tab, (kAdvance && sequential) ? sim->tinf : nullptr,
+              sim->rules, sim->n_move_rules, sim->n_attr_rules, sim->sp);
+  } else {
+  LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl,
+            sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list, sim->sp);
   LAUNCH_PDL_AS("k_scan_cells", k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
-  if (kAdvance && sequential) {
+  }
+  if (sim->f64) {
+    // pass B ran above
+  } else if (kAdvance && sequential) {
     LAUNCH_AS("k_update_scatter<true>", (k_update_scatter<kAdvance, true>), nb, kAgentThreads, sim->ctl, sim->hot[c], sim->w[c],
               sim->aux, sim->cells[t], sim->cells[t ^ 1], sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, nullptr,
               nullptr, sim->tinf, nullptr, nullptr, nullptr, no_direct, sim->sp);
@@ -437,14 +471,14 @@ static void enqueue_build(cabs_sim *sim) {
     uint4 *hot_o = sim->hot[o];
     unsigned *cells_t = sim->cells[t];
     void *args[] = {&sim->ctl, &hot_o, &cells_t, &sim->tinf, &sim->inf_list, &sim->newinf_list, &sim->history,
-                    &sim->seq_round};
+                    &sim->seq_round, &pos_o};
     cudaLaunchCooperativeKernel((void *)k_contagion_sequential_all, dim3(sim->seq_grid), dim3(256), args, 0, sim->stream);
     sim->launches++;
   } else if (kAdvance && sequential) {
     // no cooperative launch on this device: rounds driven from the host (one round trip each)
     for (int round = 0;; ++round) {
       LAUNCH(k_contagion_sequential, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->tinf,
-             round == 0 ? sim->inf_list : sim->newinf_list, round == 0 ? 1 : 0, sim->newinf_list);
+             round == 0 ? sim->inf_list : sim->newinf_list, round == 0 ? 1 : 0, sim->newinf_list, pos_o);
       unsigned changed = 0;
       if (cudaMemcpyAsync(&changed, &sim->ctl->seq_changed, sizeof changed, cudaMemcpyDeviceToHost, sim->stream) !=
               cudaSuccess || cudaStreamSynchronize(sim->stream) != cudaSuccess)
@@ -458,7 +492,7 @@ static void enqueue_build(cabs_sim *sim) {
     memset(&none, 0, sizeof none);
     LAUNCH_PDL_AS("k_contagion", k_contagion, nb, 256, sim->ctl, sim->hot[o], (const unsigned *)sim->cells[t],
                   (const unsigned *)sim->inf_list, (const ExchangeHeader *)nullptr, (const ExchangeHeader *)nullptr,
-                  sim->history, (long long *)nullptr, 1, none, (ExchangeHeader *)nullptr);
+                  sim->history, (long long *)nullptr, 1, none, (ExchangeHeader *)nullptr, pos_o);
   } else {
     LAUNCH(k_finalize, 1, 32, sim->ctl, sim->history, 0);
   }
@@ -491,6 +525,7 @@ extern "C" int cabs_set_slab(cabs_sim *sim, const cabs_slab *slab) {
   if (!sim || !slab) return fail(sim, CABS_ERR_INVALID, "cabs_set_slab: null argument");
   if (slab->n_ranks < 1 || slab->rank < 0 || slab->rank >= slab->n_ranks || slab->x_lo >= slab->x_hi)
     return fail(sim, CABS_ERR_INVALID, "cabs_set_slab: bad rank / bounds");
+  if (sim->f64) return fail(sim, CABS_ERR_INVALID, "cabs_set_slab: the off-lattice mode runs on one device");
   if (slab->migrant_capacity == 0 || slab->ghost_capacity == 0 || !slab->stats_rows)
     return fail(sim, CABS_ERR_INVALID, "cabs_set_slab: capacities and stats_rows are required");
   for (int d = 0; d < 2; ++d)
@@ -608,12 +643,12 @@ static int slab_phase(cabs_sim *sim, int phase) {
           SlabDirect none;
           memset(&none, 0, sizeof none);
           LAUNCH_PDLN(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, nullptr, nullptr,
-                 sim->history, rows, 0, none, nullptr);
+                 sim->history, rows, 0, none, nullptr, nullptr);
           LAUNCH_PDL_AS("k_contagion(ghosts)", k_contagion, nbs, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list,
-                    gr[0], gr[1], sim->history, rows, 8 | 3, D, (ExchangeHeader *)sim->blocks[sl.rank]);
+                    gr[0], gr[1], sim->history, rows, 8 | 3, D, (ExchangeHeader *)sim->blocks[sl.rank], nullptr);
         } else {
           LAUNCH_PDLN(k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t], sim->inf_list, gr[0], gr[1], sim->history,
-                 rows, 2, D, nullptr);
+                 rows, 2, D, nullptr, nullptr);
         }
       } else {
         LAUNCH_PDLN(k_slab_export, 1, 32, sim->ctl, rows, D);
@@ -720,6 +755,7 @@ extern "C" int cabs_set_slab_direct(cabs_sim *sim, const cabs_slab_direct *d) {
     return fail(sim, CABS_ERR_INVALID, "cabs_set_slab_direct: bad rank / bounds (at most 16 ranks)");
   if (d->migrant_capacity == 0 || d->ghost_capacity == 0)
     return fail(sim, CABS_ERR_INVALID, "cabs_set_slab_direct: capacities are required");
+  if (sim->f64) return fail(sim, CABS_ERR_INVALID, "cabs_set_slab_direct: the off-lattice mode runs on one device");
   for (int r = 0; r < d->n_ranks; ++r)
     if (!d->blocks[r]) return fail(sim, CABS_ERR_INVALID, "cabs_set_slab_direct: null exchange block");
   if (sim->have_params && sim->params.schedule == CABS_SEQUENTIAL)
@@ -830,13 +866,26 @@ static int refresh_n(cabs_sim *sim) {
   return CABS_OK;
 }
 
+static int upload_impl(cabs_sim *sim, const cabs_soa_host *pop, const double *xf, const double *yf);
+
 extern "C" int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop) {
   NvtxRange nvtx_("cabs_upload");
+  return upload_impl(sim, pop, nullptr, nullptr);
+}
+
+extern "C" int cabs_upload_f64(cabs_sim *sim, const cabs_soa_host *pop, const double *x, const double *y) {
+  NvtxRange nvtx_("cabs_upload_f64");
+  if (sim && !sim->f64) return fail(sim, CABS_ERR_INVALID, "cabs_upload_f64: the handle was not created with CABS_FLAG_F64_POSITIONS");
+  if (sim && pop && pop->n && (!x || !y)) return fail(sim, CABS_ERR_INVALID, "cabs_upload_f64: null position column");
+  return upload_impl(sim, pop, x, y);
+}
+
+static int upload_impl(cabs_sim *sim, const cabs_soa_host *pop, const double *xf, const double *yf) {
   if (!sim || !pop) return fail(sim, CABS_ERR_INVALID, "cabs_upload: null argument");
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_upload: call cabs_set_params first");
   if (pop->n > sim->capacity) return fail(sim, CABS_ERR_CAPACITY, "cabs_upload: population larger than capacity");
   const size_t n = pop->n;
-  if (n && (!pop->x || !pop->y || !pop->status || !pop->severity || !pop->infected_time || !pop->age ||
+  if (n && ((!xf && (!pop->x || !pop->y)) || !pop->status || !pop->severity || !pop->infected_time || !pop->age ||
             !pop->stratum || !pop->wealth))
     return fail(sim, CABS_ERR_INVALID, "cabs_upload: null column");
   CK(cudaSetDevice(sim->device));
@@ -844,8 +893,13 @@ extern "C" int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop) {
   const size_t cap = sim->capacity;
   int *sx = reinterpret_cast<int *>(sim->hot[c ^ 1]), *sy = sx + cap;  // the other copy is free: scratch
   if (n) {
-    CK(cudaMemcpyAsync(sx, pop->x, n * sizeof(int), cudaMemcpyHostToDevice, sim->stream));
-    CK(cudaMemcpyAsync(sy, pop->y, n * sizeof(int), cudaMemcpyHostToDevice, sim->stream));
+    if (pop->x && pop->y) {
+      CK(cudaMemcpyAsync(sx, pop->x, n * sizeof(int), cudaMemcpyHostToDevice, sim->stream));
+      CK(cudaMemcpyAsync(sy, pop->y, n * sizeof(int), cudaMemcpyHostToDevice, sim->stream));
+    } else {   // binary64 positions follow (cabs_upload_f64): the lattice columns are derived from them on the device
+      CK(cudaMemsetAsync(sx, 0, n * sizeof(int), sim->stream));
+      CK(cudaMemsetAsync(sy, 0, n * sizeof(int), sim->stream));
+    }
     CK(cudaMemcpyAsync(sim->w[c], pop->wealth, n * sizeof(double), cudaMemcpyHostToDevice, sim->stream));
     CK(cudaMemcpyAsync(sim->stage + 0 * cap, pop->status, n, cudaMemcpyHostToDevice, sim->stream));
     CK(cudaMemcpyAsync(sim->stage + 1 * cap, pop->severity, n, cudaMemcpyHostToDevice, sim->stream));
@@ -856,6 +910,16 @@ extern "C" int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop) {
     LAUNCH(k_pack, agent_blocks(sim), 256, (unsigned)n, sx, sy, sim->stage + 0 * cap, sim->stage + 1 * cap,
            sim->stage + 2 * cap, sim->stage + 3 * cap, sim->stage + 4 * cap, pop->id ? sim->stage_id : nullptr,
            sim->hot[c]);
+  }
+  if (n && sim->f64) {   // exact positions: the caller's binary64 columns, or the lattice points themselves
+    double *dxf = nullptr, *dyf = nullptr;
+    if (xf) {            // staged through the moved-position array (free between builds)
+      dxf = reinterpret_cast<double *>(sim->npos);
+      dyf = dxf + cap;
+      CK(cudaMemcpyAsync(dxf, xf, n * sizeof(double), cudaMemcpyHostToDevice, sim->stream));
+      CK(cudaMemcpyAsync(dyf, yf, n * sizeof(double), cudaMemcpyHostToDevice, sim->stream));
+    }
+    LAUNCH(k_pack_pos, agent_blocks(sim), 256, (unsigned)n, dxf, dyf, sim->hot[c], sim->pos[c], sim->ctl);
   }
   // The step counter is part of the draw key (seed, agent, step) and is NOT reset here: a caller that downloads,
   // edits and re-uploads the population every iteration (set_population, abs.py:65-69) must not see the draws of
@@ -921,13 +985,71 @@ extern "C" int cabs_download(cabs_sim *sim, cabs_soa_host *pop) {
   return CABS_OK;
 }
 
+extern "C" int cabs_download_positions_f64(cabs_sim *sim, double *x, double *y, uint64_t capacity) {
+  NvtxRange nvtx_("cabs_download_positions_f64");
+  if (!sim || !x || !y) return fail(sim, CABS_ERR_INVALID, "cabs_download_positions_f64: null argument");
+  if (!sim->f64) return fail(sim, CABS_ERR_INVALID, "cabs_download_positions_f64: the handle holds lattice positions");
+  if (capacity < sim->n) return fail(sim, CABS_ERR_CAPACITY, "cabs_download_positions_f64: host buffers smaller than the population");
+  CK(cudaSetDevice(sim->device));
+  const size_t n = sim->n, cap = sim->capacity;
+  if (n == 0) return CABS_OK;
+  double *dx = reinterpret_cast<double *>(sim->npos), *dy = dx + cap;   // free between builds
+  LAUNCH(k_unpack_pos, agent_blocks(sim), 256, (unsigned)n, sim->hot[sim->cur], sim->pos[sim->cur], dx, dy);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(x, dx, n * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaMemcpyAsync(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  return CABS_OK;
+}
+
+extern "C" int cabs_set_rules(cabs_sim *sim, const cabs_rule *rules, int n_move, int n_attr) {
+  if (!sim || ((n_move + n_attr) > 0 && !rules)) return fail(sim, CABS_ERR_INVALID, "cabs_set_rules: null argument");
+  if (!sim->f64) return fail(sim, CABS_ERR_INVALID, "cabs_set_rules: per-agent rules need a handle created with CABS_FLAG_F64_POSITIONS");
+  if (n_move < 0 || n_attr < 0 || n_move + n_attr > kMaxRules) return fail(sim, CABS_ERR_INVALID, "cabs_set_rules: at most 8 rules");
+  static_assert(sizeof(cabs_rule) == sizeof(DevRule), "cabs_rule and DevRule share one layout");
+  int margin = 0, box[4] = {1, 0, 1, 0};
+  for (int k = 0; k < n_move + n_attr; ++k) {
+    const cabs_rule &r = rules[k];
+    const bool move = k < n_move;
+    if (move && r.kind != CABS_RULE_MOVE_STAY && r.kind != CABS_RULE_MOVE_POINT)
+      return fail(sim, CABS_ERR_INVALID, "cabs_set_rules: the first n_move rules must be move rules");
+    if (!move && (r.kind != CABS_RULE_ATTRIBUTE || r.attribute < 0 || r.attribute > CABS_RATTR_WEALTH))
+      return fail(sim, CABS_ERR_INVALID, "cabs_set_rules: bad attribute rule");
+    if (move) {
+      if (!(r.sigma >= 0.0 && r.sigma < 1e6)) return fail(sim, CABS_ERR_INVALID, "cabs_set_rules: sigma out of range");
+      const int m = (int)ceil(5.78 * r.sigma) + 2;   // the largest |normal| the draw map returns is 5.78
+      if (r.kind == CABS_RULE_MOVE_STAY) {
+        margin = margin > m ? margin : m;
+      } else {
+        if (!(fabs(r.target_x) < 2e8 && fabs(r.target_y) < 2e8)) return fail(sim, CABS_ERR_DOMAIN, "cabs_set_rules: target outside the supported box");
+        const int x0 = (int)floor(r.target_x) - m, x1 = (int)floor(r.target_x) + m;
+        const int y0 = (int)floor(r.target_y) - m, y1 = (int)floor(r.target_y) + m;
+        if (box[0] > box[1]) { box[0] = x0; box[1] = x1; box[2] = y0; box[3] = y1; }
+        else { box[0] = box[0] < x0 ? box[0] : x0; box[1] = box[1] > x1 ? box[1] : x1;
+               box[2] = box[2] < y0 ? box[2] : y0; box[3] = box[3] > y1 ? box[3] : y1; }
+      }
+    }
+  }
+  CK(cudaSetDevice(sim->device));
+  if (n_move + n_attr > 0)
+    CK(cudaMemcpyAsync(sim->rules, rules, (size_t)(n_move + n_attr) * sizeof(DevRule), cudaMemcpyHostToDevice, sim->stream));
+  LAUNCH(k_set_rules, 1, 32, sim->ctl, 1, margin, box[0], box[1], box[2], box[3]);
+  if (sim->n > 0) LAUNCH(k_replan, 1, 32, sim->ctl, 0);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(sim->stream));   // `rules` is the caller's memory
+  sim->n_move_rules = n_move;
+  sim->n_attr_rules = n_attr;
+  drop_graphs(sim);     // captured launches hold the old rule counts
+  return CABS_OK;
+}
+
 extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
   NvtxRange nvtx_("cabs_step");
   if (!sim || nsteps < 0) return fail(sim, CABS_ERR_INVALID, "cabs_step: bad argument");
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_step: call cabs_set_params first");
   if (sim->slab_on) return fail(sim, CABS_ERR_INVALID, "cabs_step: a slab handle is stepped with cabs_slab_phase");
   CK(cudaSetDevice(sim->device));
-  if (sim->n > 0 && sim->n <= (uint64_t)kSmallMax && sim->params.schedule == CABS_SYNCHRONOUS && nsteps > 0) {
+  if (sim->n > 0 && sim->n <= (uint64_t)kSmallMax && sim->params.schedule == CABS_SYNCHRONOUS && nsteps > 0 && !sim->f64) {
     // the whole run in one launch of one resident block (small populations are launch-latency bound otherwise)
     LAUNCH(k_small_run, 1, kSmallMax, sim->ctl, sim->hot[sim->cur], sim->w[sim->cur], sim->history, sim->sqrt_tab,
            nsteps);
@@ -968,6 +1090,7 @@ extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
         if (graph) cudaGraphDestroy(graph);
       }
       if (ce != cudaSuccess) {        // a stream that cannot be captured: plain launches from now on
+        if (getenv("CABS_DEBUG")) fprintf(stderr, "cabs_step: graph capture failed (%s), falling back to plain launches\n", cudaGetErrorString(ce));
         cudaGetLastError();
         sim->step_graph = nullptr;
         sim->graph_broken = true;
@@ -1084,6 +1207,7 @@ extern "C" int cabs_cross_contact(cabs_sim *a, cabs_sim *b, int32_t ax, int32_t 
   if (!a || !b || a == b) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: two different handles are needed");
   if (!a->have_params || !b->have_params) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: call cabs_set_params first");
   if (a->slab_on || b->slab_on) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: not defined for slab handles");
+  if (a->f64 || b->f64) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: populations are placed on the integer lattice");
   if (a->device != b->device) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: both populations must live on one device");
   if (a->step != b->step) return fail(a, CABS_ERR_INVALID, "cabs_cross_contact: the populations are at different steps");
   if (a->n == 0 || b->n == 0) return CABS_OK;
@@ -1146,7 +1270,7 @@ extern "C" int cabs_contact_pairs(cabs_sim *sim, int64_t *ij, size_t capacity_pa
   CK(cudaMemsetAsync(sim->pair_count, 0, sizeof(unsigned long long), sim->stream));
   const int c = sim->cur;
   LAUNCH(k_contact_pairs, agent_blocks(sim), 256, sim->ctl, sim->hot[c], sim->cells[sim->tab ^ 1], sim->pairs,
-         (unsigned long long)capacity_pairs, sim->pair_count);
+         (unsigned long long)capacity_pairs, sim->pair_count, sim->f64 ? sim->pos[c] : nullptr);
   CK(cudaGetLastError());
   unsigned long long total = 0;
   CK(cudaMemcpyAsync(&total, sim->pair_count, sizeof total, cudaMemcpyDeviceToHost, sim->stream));

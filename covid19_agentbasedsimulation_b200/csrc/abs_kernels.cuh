@@ -128,6 +128,10 @@ struct Ctl {
   DevTrigger trig[kMaxTriggers];
   unsigned err;
   unsigned hist_cap;
+  // ---- off-lattice mode: binary64 positions, declarative per-agent rules (abs.py:86-95)
+  int f64;                 // positions are binary64 (pos arrays); hot.x, hot.y hold their floors
+  int rule_margin;         // lattice units a `stay` move rule can displace an agent (5.78 sigma, rounded up)
+  int rule_box[4];         // bounding box of the points `point` move rules send agents to (xmin > xmax: none)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -163,6 +167,8 @@ struct StepParams {
   long long thr_hosp[9], thr_sev[9], thr_death[9];
   long long thr_rate;
   int T, reach, recovering_time, scale_bits, crit_active;
+  int f64;          // off-lattice mode: `reach` is one more than on the lattice and the distance test is binary64
+  double r;         // contagion_distance (abs.py:27), for that test
   int len_i, hei_i;  // x >= length  <=>  x >= ceil(length) for integer x (abs.py:177,182)
   int slab_lo, slab_hi, overflow, pull;
   unsigned k0, k1, step, n;
@@ -181,6 +187,7 @@ struct StaticParams {
   int len_i, hei_i;
   int slab_lo, slab_hi;
   unsigned k0, k1;
+  double length, height;   // abs.py:177,182 compare binary64 positions with these in off-lattice mode
 };
 
 __host__ __device__ inline long long prob_bound_lt(double p);
@@ -205,7 +212,10 @@ __device__ __forceinline__ void load_params(StepParams &P, const Ctl *ctl, bool 
   int reach = P.T > 0 ? (int)__dsqrt_rn((double)P.T) : 0;
   while ((long long)reach * reach > (long long)P.T) --reach;
   while ((long long)(reach + 1) * (reach + 1) <= (long long)P.T) ++reach;
-  P.reach = reach;
+  // off the lattice |xi - xj| <= r only bounds the floors by floor(r) + 1
+  P.f64 = ctl->f64;
+  P.r = ctl->contagion_distance;
+  P.reach = reach + (ctl->f64 ? 1 : 0);
   P.recovering_time = ctl->recovering_time; P.scale_bits = ctl->scale_bits;
   P.crit_active = ctl->crit_active;
   P.slab_lo = ctl->slab_lo; P.slab_hi = ctl->slab_hi; P.overflow = ctl->overflow; P.pull = ctl->pull_mode;
@@ -583,13 +593,14 @@ constexpr int kSqrtTable = 4096;  // sqrt(d2) for d2 < 4096, exact (IEEE sqrt), 
 // S: the step-invariant parameters (StepParams or StaticParams); step, crit_active: what changes every step.
 template <class SP>
 __device__ __forceinline__ void advance_agent(const SP &S, uint32_t step, int crit_active, uint32_t aid, int ix, int iy,
-                                              uint32_t &a, double &w, const double *__restrict__ sqrt_tab) {
+                                              uint32_t &a, double &w, const double *__restrict__ sqrt_tab,
+                                              bool moved_by_rule = false) {
   const uint32_t st = attr_status(a);
   if (st == ST_D) return;   // the dead neither move (abs.py:164) nor update (abs.py:193)
   const uint32_t sev = attr_severity(a);
   const uint32_t stratum = min(attr_stratum(a), 4u);
   const uint2 r0 = agent_draw(aid, step, kStreamEconomy, S.k0, S.k1);
-  if (!(st == ST_I && sev >= SEV_H)) {   // mobile (abs.py:164-167)
+  if (!(st == ST_I && sev >= SEV_H) && !moved_by_rule) {   // mobile (abs.py:164-167); a move trigger returns before the income (169-172)
     // abs.py:187-189: wealth += sqrt(ix^2+iy^2) * rand * minimum_expense * basic_income[stratum], rand = (r + .5) 2^-32.
     // The power of two rides on minimum_expense (me32): scaling by it commutes with every rounding, so the three
     // products below round exactly like ((dist * rand) * minimum_expense) * basic_income.
@@ -1050,6 +1061,13 @@ __device__ __forceinline__ void contact_cells(const StepParams &P, int x, int y,
   rhi = min(max(((y + P.reach - P.gy0) >> P.eshift) + 1, 0), P.ncy - 1);
 }
 
+// The reference's own predicate on binary64 positions (abs.py:9-10,258): sqrt((xi - xj)^2 + (yi - yj)^2) <= r, every
+// operation rounded once (no FMA contraction), SURVEY.md A.3.
+__device__ __forceinline__ bool within_f64(const double2 a, const double2 b, double r) {
+  const double dx = __dadd_rn(a.x, -b.x), dy = __dadd_rn(a.y, -b.y);
+  return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) <= r;
+}
+
 __device__ void close_step(Ctl *ctl, StatRecord *history, int record_stats);
 __device__ void slab_export(Ctl *ctl, long long *rows, SlabDirect D);
 __device__ void close_local(Ctl *ctl, const unsigned *cell_start, int record_stats);
@@ -1068,7 +1086,8 @@ __global__ void __launch_bounds__(256)
 k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
             const unsigned *__restrict__ inf_list, const ExchangeHeader *__restrict__ ghosts_left,
             const ExchangeHeader *__restrict__ ghosts_right, StatRecord *__restrict__ history,
-            long long *__restrict__ rows, int finish, SlabDirect D, ExchangeHeader *__restrict__ send_reset) {
+            long long *__restrict__ rows, int finish, SlabDirect D, ExchangeHeader *__restrict__ send_reset,
+            const double2 *__restrict__ pos) {
   __shared__ StepParams P;
   __shared__ unsigned s_new, s_local, s_left, s_right;
   pdl_wait();
@@ -1135,8 +1154,11 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
     const unsigned sub = threadIdx.x % lanes;
     for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) / lanes; t < total; t += stride / lanes) {
       uint4 h;
-      if (t < s_local) h = hot[inf_list[t]];
-      else if (t < s_local + s_left) h = reinterpret_cast<const uint4 *>(ghosts_left + 1)[t - s_local];
+      double2 pi = make_double2(0.0, 0.0);
+      if (t < s_local) {
+        h = hot[inf_list[t]];
+        if (pos) pi = pos[inf_list[t]];
+      } else if (t < s_local + s_left) h = reinterpret_cast<const uint4 *>(ghosts_left + 1)[t - s_local];
       else h = reinterpret_cast<const uint4 *>(ghosts_right + 1)[t - s_local - s_left];
       const int xi = (int)h.x, yi = (int)h.y;
       int clo, chi, rlo, rhi;
@@ -1150,7 +1172,9 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
           const int ddx = (int)cp.x - xi, ddy = (int)cp.y - yi;
           if ((unsigned)(ddx + P.reach) > 2u * (unsigned)P.reach || (unsigned)(ddy + P.reach) > 2u * (unsigned)P.reach)
             continue;
-          if (ddx * ddx + ddy * ddy > P.T) continue;     // |ddx|, |ddy| <= reach <= 16000: no overflow
+          if (pos) {                                      // off the lattice: the binary64 predicate on the exact positions
+            if (!within_f64(pi, pos[j], P.r)) continue;
+          } else if (ddx * ddx + ddy * ddy > P.T) continue;  // |ddx|, |ddy| <= reach <= 16000: no overflow
           const uint2 cq = *(reinterpret_cast<const uint2 *>(&hot[j]) + 1);
           const uint4 c = make_uint4(cp.x, cp.y, cq.x, cq.y);
           if ((c.z & (3u | kNewlyInfected)) != ST_S) continue;  // only a still Susceptible agent can be infected
@@ -1212,7 +1236,7 @@ __device__ __forceinline__ unsigned long long pair_rank(uint32_t a, uint32_t b) 
 __global__ void __launch_bounds__(256)
 k_contagion_sequential(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
                        unsigned long long *__restrict__ tinf, const unsigned *__restrict__ sources, int first_round,
-                       unsigned *__restrict__ newinf_list) {
+                       unsigned *__restrict__ newinf_list, const double2 *__restrict__ pos) {
   __shared__ StepParams P;
   __shared__ unsigned s_count;
   if (threadIdx.x == 0) {
@@ -1236,7 +1260,9 @@ k_contagion_sequential(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const uns
         const uint4 c = hot[j];
         if ((c.z & 3u) != ST_S || j == s) continue;   // Susceptible at the start of the phase (marked or not)
         const long long dx = (int)c.x - xi, dy = (int)c.y - yi;
-        if (dx * dx + dy * dy > (long long)P.T) continue;
+        if (pos) {
+          if (!within_f64(pos[s], pos[j], P.r)) continue;
+        } else if (dx * dx + dy * dy > (long long)P.T) continue;
         const unsigned long long rank = pair_rank(h.w, c.w);
         if (rank <= ts) continue;                      // the pair was walked before the source was infected
         const uint4 r = philox4x32_10(min(h.w, c.w), P.step, kStreamContact, max(h.w, c.w), P.k0, P.k1);
@@ -1265,7 +1291,7 @@ __global__ void __launch_bounds__(256)
 k_contagion_sequential_all(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
                            unsigned long long *__restrict__ tinf, const unsigned *__restrict__ inf_list,
                            unsigned *__restrict__ newinf_list, StatRecord *__restrict__ history,
-                           unsigned *__restrict__ seq_round) {
+                           unsigned *__restrict__ seq_round, const double2 *__restrict__ pos) {
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   __shared__ StepParams P;
   __shared__ unsigned s_count;
@@ -1294,7 +1320,9 @@ k_contagion_sequential_all(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const
             const uint4 c = __ldcg(&hot[j]);
             if ((c.z & 3u) != ST_S || j == s) continue;   // Susceptible at the start of the phase (marked or not)
             const long long dx = (int)c.x - xi, dy = (int)c.y - yi;
-            if (dx * dx + dy * dy > (long long)P.T) continue;
+            if (pos) {
+              if (!within_f64(pos[s], pos[j], P.r)) continue;
+            } else if (dx * dx + dy * dy > (long long)P.T) continue;
             const unsigned long long rank = pair_rank(h.w, c.w);
             if (rank <= ts) continue;                      // the pair was walked before the source was infected
             const uint4 r = philox4x32_10(min(h.w, c.w), P.step, kStreamContact, max(h.w, c.w), P.k0, P.k1);
@@ -1326,7 +1354,8 @@ k_contagion_sequential_all(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const
 // Test hook for the pair loop of abs.py:253-259: every (i, j), i < j, within contagion_distance.
 __global__ void __launch_bounds__(256)
 k_contact_pairs(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const unsigned *__restrict__ cell_start,
-                long long *__restrict__ out, unsigned long long capacity, unsigned long long *__restrict__ count) {
+                long long *__restrict__ out, unsigned long long capacity, unsigned long long *__restrict__ count,
+                const double2 *__restrict__ pos) {
   __shared__ StepParams P;
   if (threadIdx.x == 0) load_params(P, ctl, true);
   __syncthreads();
@@ -1344,7 +1373,9 @@ k_contact_pairs(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const unsi
         const uint4 c = hot[j];
         if (c.w <= h.w) continue;
         const long long dx = (int)c.x - xi, dy = (int)c.y - yi;
-        if (dx * dx + dy * dy > (long long)P.T) continue;
+        if (pos) {
+          if (!within_f64(pos[i], pos[j], P.r)) continue;
+        } else if (dx * dx + dy * dy > (long long)P.T) continue;
         const unsigned long long slot = atomicAdd(count, 1ull);
         if (slot < capacity) {
           out[2 * slot] = (long long)h.w;
@@ -1365,6 +1396,11 @@ __device__ inline void plan_grid(Ctl *ctl, int xmin, int xmax, int ymin, int yma
     for (int k = 0; k < 3; ++k) amax = fmaxf(amax, fabsf(ctl->amp[k]));
     margin = (int)(kMaxAbsNormal * amax) + 2;
   }
+  if (add_margin) margin = max(margin, ctl->rule_margin);
+  if (add_margin && ctl->rule_box[0] <= ctl->rule_box[1]) {   // agents a `point` rule may teleport
+    xmin = min(xmin, ctl->rule_box[0]); xmax = max(xmax, ctl->rule_box[1]);
+    ymin = min(ymin, ctl->rule_box[2]); ymax = max(ymax, ctl->rule_box[3]);
+  }
   long long x0 = (long long)xmin - margin, x1 = (long long)xmax + margin;
   const long long y0 = (long long)ymin - margin, y1 = (long long)ymax + margin;
   // a slab's residents and immigrants are inside [slab_lo, slab_hi) by construction
@@ -1378,8 +1414,14 @@ __device__ inline void plan_grid(Ctl *ctl, int xmin, int xmax, int ymin, int yma
   // cell edge: power of two, at least floor(sqrt(T)) so contacts never skip a cell, grown until
   // the grid fits max_cells (keeps the cell table L2-resident)
   int eshift = 0;
-  const int T = ctl->T;
-  while (T > 0 && ((1ll << eshift) * (1ll << eshift)) < (long long)T && eshift < 28) ++eshift;
+  long long T = ctl->T;
+  if (ctl->f64 && T >= 0) {   // floors of two positions within r differ by at most floor(r) + 1
+    long long reach = (long long)__dsqrt_rn((double)T);
+    while (reach * reach > T) --reach;
+    while ((reach + 1) * (reach + 1) <= T) ++reach;
+    T = (reach + 1) * (reach + 1);
+  }
+  while (T > 0 && ((1ll << eshift) * (1ll << eshift)) < T && eshift < 28) ++eshift;
   // (1<<eshift)^2 >= T  =>  1<<eshift >= sqrt(T) >= any |dx| of a contact
   for (;;) {
     const long long ncx = ((x1 - x0) >> eshift) + 3, ncy = ((y1 - y0) >> eshift) + 3;
@@ -1457,7 +1499,8 @@ __device__ __forceinline__ int ld_acc(const int *p) { return __ldcg(p); }
 __device__ inline void choose_cell_budget(Ctl *ctl, const StatRecord &cur) {
   const unsigned long long lesser = min(cur.cnt[ST_S], cur.cnt[ST_I]);
   ctl->cell_budget = (lesser * 16ull > ctl->pop_size && ctl->T >= 0) ? ctl->max_cells : ctl->coarse_cells;
-  ctl->pull_mode = (ctl->schedule == 0 && 4ull * cur.cnt[ST_I] > (unsigned long long)CABS_PULL_X4 * cur.cnt[ST_S]) ? 1 : 0;
+  ctl->pull_mode = (ctl->schedule == 0 && !ctl->f64 &&
+                    4ull * cur.cnt[ST_I] > (unsigned long long)CABS_PULL_X4 * cur.cnt[ST_S]) ? 1 : 0;
 }
 
 // Statistics half of the closing: the step's record, triggers on the memo of the step before, critical-limit flag.
@@ -1896,6 +1939,8 @@ __global__ void k_init_ctl(Ctl *ctl, unsigned k0, unsigned k1, unsigned max_cell
   ctl->slab_lo = INT_MIN; ctl->slab_hi = INT_MAX;
   ctl->overflow = 0; ctl->mig_cap = 0; ctl->ghost_cap = 0;
   ctl->pending_step = 0; ctl->glob_ymin = INT_MAX; ctl->glob_ymax = INT_MIN;
+  ctl->f64 = 0; ctl->rule_margin = 0;
+  ctl->rule_box[0] = ctl->rule_box[2] = 1; ctl->rule_box[1] = ctl->rule_box[3] = 0;   // empty
   reset_accumulators(ctl);
   plan_grid(ctl, 0, 0, 0, 0, false);
   ctl->built = ctl->g;
@@ -2010,6 +2055,275 @@ __global__ void k_unpack(unsigned n, int by_slot, const uint4 *__restrict__ hot,
     owealth[d] = wealth[i];
     oid[d] = h.w;
   }
+}
+
+
+// ==========================================================================================================
+// Off-lattice mode: binary64 positions and declarative per-agent rules.
+//
+// The reference keeps agents on the integer lattice only as long as nothing assigns them a float: a population
+// trigger with attribute 'move' (abs.py:86-95, applied at abs.py:169-172) replaces the random walk of an agent by
+// whatever position its action returns -- the shipped idiom is "some point + np.random.normal(0, sigma)" (run_batch.py:
+// 446-450) -- and from then on x, y are binary64: the walk adds integer increments to them (abs.py:177-185), and the
+// contact test is sqrt((xi-xj)^2 + (yi-yj)^2) <= contagion_distance in binary64 (abs.py:9-10,258).  Other population
+// triggers rewrite an attribute after update() (abs.py:244-247).
+//
+// A Python lambda cannot run here, so rules are declarative (DevRule): a condition tabulated over the discrete
+// attributes (status x severity x age x stratum, 8 000 bits -- any predicate of those four is representable) and
+//   move rules       new position = target + N(0, sigma) per axis, target = the agent's own position or a fixed point;
+//                    the first matching rule wins and the agent earns no move income (abs.py:169-172 returns early);
+//   attribute rules  status / severity / infected_time / age / stratum := value, or wealth := p * wealth + q,
+//                    applied in order after the update of the step.
+// Layout: pos[2] (double2, ping/pong with hot) holds the exact positions, hot.x / hot.y their floors -- the cell list,
+// the bounding box and the candidate pre-filter stay integer work; only the final distance test reads pos.  These
+// kernels are the plain grid-stride form of passes A and B (no staging ring): the mode exists for drop-in coverage
+// of the reference's API, the lattice path is the one that is tuned.
+constexpr int kRuleWords = 250;   // 8 000 condition bits
+constexpr int kMaxRules = 8;
+enum { RULE_MOVE_STAY = 1, RULE_MOVE_POINT = 2, RULE_ATTRIBUTE = 3 };
+enum { RATTR_STATUS = 0, RATTR_SEVERITY = 1, RATTR_TIME = 2, RATTR_AGE = 3, RATTR_STRATUM = 4, RATTR_WEALTH = 5 };
+struct DevRule {
+  int kind, attribute;
+  double tx, ty, sigma;    // move rules
+  double p, q;             // attribute rules: discrete attributes take (int)q, wealth becomes p * wealth + q
+  uint32_t cond[kRuleWords];
+  uint32_t pad[2];
+};
+__device__ __forceinline__ bool rule_matches(const DevRule &r, uint32_t a) {
+  const uint32_t idx = ((attr_status(a) * 4u + attr_severity(a)) * 100u + min(attr_age(a), 99u)) * 5u +
+                       min(attr_stratum(a), 4u);
+  return (__ldg(&r.cond[idx >> 5]) >> (idx & 31u)) & 1u;
+}
+constexpr unsigned kRuleMoved = 0x80000000u;   // aux.y bit: this step's position came from a move rule
+
+__device__ __forceinline__ bool floor_to_lattice(double v, int &out) {
+  if (!(v > -268435456.0 && v < 268435456.0)) return false;   // also NaN
+  out = __double2int_rd(v);
+  return true;
+}
+
+template <bool kAdvance>
+__global__ void __launch_bounds__(256)
+k_move_count_f64(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const double2 *__restrict__ pos,
+                 double2 *__restrict__ npos, uint2 *__restrict__ aux, unsigned *__restrict__ cells,
+                 unsigned long long *__restrict__ tile_state, const DevRule *__restrict__ rules, int n_move_rules,
+                 const __grid_constant__ StaticParams SP) {
+  __shared__ StepParams P;
+  if (threadIdx.x == 0) load_params(P, ctl);
+  __syncthreads();
+  const unsigned stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  {
+    const unsigned nscan = ((unsigned)P.ncx * (unsigned)P.ncy + 1u + kScanTile - 1) / kScanTile;
+    for (unsigned t = tid; t < nscan; t += stride) tile_state[t] = 0ull;
+  }
+  const unsigned n_now = P.n, step_now = P.step;
+  const GridRegs G = {P.gx0, P.gy0, P.eshift, P.ncx, P.ncy};
+  for (unsigned i = tid; i < n_now; i += stride) {
+    const uint4 h = hot[i];
+    const double2 p = pos[i];
+    double nx = p.x, ny = p.y;
+    uint32_t d = 0, flag = 0;
+    if (kAdvance) {
+      const uint32_t a = attr_normalize(h.z);
+      const uint32_t st = attr_status(a), sev = attr_severity(a);
+      const bool mobile = !(st == ST_D || (st == ST_I && (sev == SEV_H || sev == SEV_G)));   // abs.py:164-167
+      if (mobile) {
+        const uint2 w = agent_draw(h.w, step_now, kStreamMove, SP.k0, SP.k1);
+        int hit = -1;
+        for (int k = 0; k < n_move_rules && hit < 0; ++k)
+          if (rule_matches(rules[k], a)) hit = k;                                             // abs.py:169-172
+        if (hit >= 0) {
+          float z0, z1;
+          normal_pair(w.x, w.y, z0, z1);
+          const bool stay = rules[hit].kind == RULE_MOVE_STAY;
+          const double sigma = rules[hit].sigma;
+          nx = __dadd_rn(stay ? p.x : rules[hit].tx, __dmul_rn((double)z0, sigma));
+          ny = __dadd_rn(stay ? p.y : rules[hit].ty, __dmul_rn((double)z1, sigma));
+          flag = kRuleMoved;
+        } else {
+          int ix, iy;
+          draw_displacement(P, a, w, ix, iy);
+          // abs.py:177-185 on binary64: the increment, not the position, is reflected
+          const double tx = __dadd_rn(p.x, (double)ix), ty = __dadd_rn(p.y, (double)iy);
+          nx = (tx <= 0.0 || tx >= SP.length) ? __dadd_rn(p.x, -(double)ix) : tx;
+          ny = (ty <= 0.0 || ty >= SP.height) ? __dadd_rn(p.y, -(double)iy) : ty;
+          d = ((uint32_t)ix & 0xFFFFu) | ((uint32_t)iy << 16);
+        }
+      }
+    }
+    npos[i] = make_double2(nx, ny);
+    int fx = 0, fy = 0;
+    if (!floor_to_lattice(nx, fx) || !floor_to_lattice(ny, fy)) atomicOr(&ctl->err, kErrDomain);
+    const unsigned key = cell_key(G, fx, fy, &ctl->err);
+    aux[i] = make_uint2(d, atomicAdd(&cells[key], 1u) | flag);
+  }
+}
+
+template <bool kAdvance>
+__global__ void __launch_bounds__(256)
+k_update_scatter_f64(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const double *__restrict__ wealth,
+                     const uint2 *__restrict__ aux, const double2 *__restrict__ npos,
+                     const unsigned *__restrict__ cell_start, unsigned *__restrict__ stale_cells,
+                     uint4 *__restrict__ ohot, double *__restrict__ owealth, double2 *__restrict__ opos,
+                     unsigned *__restrict__ inf_list, const double *__restrict__ sqrt_tab,
+                     unsigned long long *__restrict__ tinf, const DevRule *__restrict__ rules, int n_move_rules,
+                     int n_attr_rules, const __grid_constant__ StaticParams SP) {
+  __shared__ StepParams P;
+  __shared__ BlockStats B;
+  __shared__ long long s_q[5][256];
+  __shared__ unsigned s_stale;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) s_q[k][threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    load_params(P, ctl);
+    for (int i = 0; i < 7; ++i) B.cnt[i] = 0;
+    for (int i = 0; i < 5; ++i) B.q[i] = 0;
+    B.bb[0] = B.bb[2] = INT_MAX;
+    B.bb[1] = B.bb[3] = INT_MIN;
+    s_stale = ctl->cells_used[ctl->cur_table ^ 1];
+  }
+  __syncthreads();
+  {   // zero the cell table of the step before (the next step's histogram)
+    const unsigned m = s_stale;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) stale_cells[i] = 0;
+  }
+  unsigned long long c_st = 0, c_sev = 0;
+  int bxmin = INT_MAX, bxmax = INT_MIN, bymin = INT_MAX, bymax = INT_MIN;
+  const double qscale = (double)(1ull << SP.scale_bits);
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned n_now = P.n, step_now = P.step;
+  const int crit_now = P.crit_active;
+  const GridRegs G = {P.gx0, P.gy0, P.eshift, P.ncx, P.ncy};
+  // whole warps iterate together (the Infected-list append below is warp-aggregated)
+  const unsigned n_round = (n_now + 31u) & ~31u;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const bool valid = i < n_now;
+    uint4 h = make_uint4(0, 0, 0, 0);
+    double w = 0.0;
+    uint2 ax = make_uint2(0, 0);
+    double2 np = make_double2(0.0, 0.0);
+    if (valid) { h = hot[i]; w = wealth[i]; ax = aux[i]; np = npos[i]; }
+    uint32_t a = attr_normalize(h.z);
+    const int ix = (int)(short)(ax.x & 0xFFFFu), iy = (int)(short)(ax.x >> 16);
+    int fx = 0, fy = 0;
+    floor_to_lattice(np.x, fx);
+    floor_to_lattice(np.y, fy);
+    unsigned slot = 0;
+    if (valid) slot = cell_start[cell_key(G, fx, fy, &ctl->err)] + (ax.y & ~kRuleMoved);
+    if (kAdvance && valid) {
+      advance_agent(SP, step_now, crit_now, h.w, ix, iy, a, w, sqrt_tab, (ax.y & kRuleMoved) != 0);
+      // population triggers on other attributes (abs.py:244-247), in order, on the updated agent
+      for (int k = n_move_rules; k < n_move_rules + n_attr_rules; ++k) {
+        const DevRule &r = rules[k];
+        if (!rule_matches(r, a)) continue;
+        const uint32_t v = (uint32_t)(int)r.q;
+        switch (r.attribute) {
+          case RATTR_STATUS: a = (a & ~3u) | (v & 3u); break;
+          case RATTR_SEVERITY: a = (a & ~0xCu) | ((v & 3u) << 2); break;
+          case RATTR_TIME: a = (a & ~0xFF00u) | ((v & 0xFFu) << 8); break;
+          case RATTR_AGE: a = (a & ~0xFF0000u) | ((v & 0xFFu) << 16); break;
+          case RATTR_STRATUM: a = (a & ~0x70u) | ((min(v, 4u) & 7u) << 4); break;
+          default: w = __dadd_rn(__dmul_rn(r.p, w), r.q); break;
+        }
+      }
+    }
+    const uint32_t st = attr_status(a), sev = attr_severity(a);
+    if (valid) {
+      c_st += 1ull << (16 * st);
+      if (st != ST_D) {
+        c_sev += (sev != SEV_E) ? (1ull << (16 * (sev - 1))) : 0ull;
+        if (attr_age(a) >= 18u) s_q[min(attr_stratum(a), 4u)][threadIdx.x] += __double2ll_rn(__dmul_rn(w, qscale));
+      }
+      bxmin = min(bxmin, fx); bxmax = max(bxmax, fx); bymin = min(bymin, fy); bymax = max(bymax, fy);
+      ohot[slot] = make_uint4((uint32_t)fx, (uint32_t)fy, a, h.w);
+      owealth[slot] = w;
+      opos[slot] = np;
+      if (tinf) tinf[slot] = st == ST_I ? 0ull : ~0ull;
+    }
+    const bool is_inf = valid && st == ST_I;
+    const unsigned m_inf = __ballot_sync(0xffffffffu, is_inf);
+    if (m_inf) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(&ctl->n_inf, (unsigned)__popc(m_inf));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (is_inf) inf_list[base + __popc(m_inf & ((1u << lane) - 1u))] = slot;
+    }
+    // a thread's 16-bit count fields hold 65 535 agents; flush long before (grid-stride loops can be long here)
+    if ((c_st & 0xFFFFull) > 60000ull || ((c_st >> 16) & 0xFFFFull) > 60000ull || ((c_st >> 32) & 0xFFFFull) > 60000ull ||
+        (c_st >> 48) > 60000ull) {
+      for (int k = 0; k < 4; ++k) atomicAdd(&ctl->cnt[k], (c_st >> (16 * k)) & 0xFFFFull);
+      for (int k = 0; k < 3; ++k) atomicAdd(&ctl->cnt[4 + k], (c_sev >> (16 * k)) & 0xFFFFull);
+      c_st = c_sev = 0;
+    }
+  }
+  {
+    unsigned long long cnt[7];
+    long long q[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) q[k] = s_q[k][threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cnt[k] = (c_st >> (16 * k)) & 0xFFFFull;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cnt[4 + k] = (c_sev >> (16 * k)) & 0xFFFFull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], o);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+      bxmin = min(bxmin, __shfl_xor_sync(0xffffffffu, bxmin, o));
+      bxmax = max(bxmax, __shfl_xor_sync(0xffffffffu, bxmax, o));
+      bymin = min(bymin, __shfl_xor_sync(0xffffffffu, bymin, o));
+      bymax = max(bymax, __shfl_xor_sync(0xffffffffu, bymax, o));
+    }
+    if (lane == 0) {
+      for (int k = 0; k < 7; ++k) atomicAdd(&B.cnt[k], cnt[k]);
+      for (int k = 0; k < 5; ++k) atomicAdd((unsigned long long *)&B.q[k], (unsigned long long)q[k]);
+      atomicMin(&B.bb[0], bxmin); atomicMax(&B.bb[1], bxmax); atomicMin(&B.bb[2], bymin); atomicMax(&B.bb[3], bymax);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 7; ++k)
+      if (B.cnt[k]) atomicAdd(&ctl->cnt[k], B.cnt[k]);
+    for (int k = 0; k < 5; ++k)
+      if (B.q[k]) atomicAdd((unsigned long long *)&ctl->q[k], (unsigned long long)B.q[k]);
+    if (B.bb[0] <= B.bb[1]) {
+      atomicMin(&ctl->bb_xmin, B.bb[0]); atomicMax(&ctl->bb_xmax, B.bb[1]);
+      atomicMin(&ctl->bb_ymin, B.bb[2]); atomicMax(&ctl->bb_ymax, B.bb[3]);
+    }
+  }
+}
+
+// Exact positions in and out (cabs_upload_f64 / cabs_download_positions_f64): records are in storage order on upload
+// (before the first build) and scattered back to id order on download.
+__global__ void k_pack_pos(unsigned n, const double *__restrict__ xf, const double *__restrict__ yf,
+                           uint4 *__restrict__ hot, double2 *__restrict__ pos, Ctl *__restrict__ ctl) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint4 h = hot[i];
+    double2 p = xf ? make_double2(xf[i], yf[i]) : make_double2((double)(int)h.x, (double)(int)h.y);
+    int fx = 0, fy = 0;
+    if (!floor_to_lattice(p.x, fx) || !floor_to_lattice(p.y, fy)) atomicOr(&ctl->err, kErrDomain);
+    h.x = (uint32_t)fx;
+    h.y = (uint32_t)fy;
+    hot[i] = h;
+    pos[i] = p;
+  }
+}
+__global__ void k_unpack_pos(unsigned n, const uint4 *__restrict__ hot, const double2 *__restrict__ pos,
+                             double *__restrict__ xf, double *__restrict__ yf) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned d = hot[i].w;
+    if (d >= n) continue;
+    xf[d] = pos[i].x;
+    yf[d] = pos[i].y;
+  }
+}
+__global__ void k_set_rules(Ctl *ctl, int f64, int rule_margin, int bx0, int bx1, int by0, int by1) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctl->f64 = f64;
+  ctl->rule_margin = rule_margin;
+  ctl->rule_box[0] = bx0; ctl->rule_box[1] = bx1; ctl->rule_box[2] = by0; ctl->rule_box[3] = by1;
 }
 
 }  // namespace cabs

@@ -60,6 +60,9 @@ enum {
 
 typedef struct cabs_sim cabs_sim;
 
+/* cabs_config.flags */
+#define CABS_FLAG_F64_POSITIONS 1u /* off-lattice mode: positions are binary64 (see cabs_upload_f64, cabs_set_rules) */
+
 /* creation-time configuration (sizes of the device allocations) */
 typedef struct cabs_config {
   uint32_t abi_version;      /* CABS_ABI_VERSION                                                  */
@@ -68,7 +71,7 @@ typedef struct cabs_config {
   uint64_t max_cells;        /* cap on cell-list cells (0 = auto: capacity/8 while the epidemic is sparse, 1.5*capacity when dense; explicit = fixed) */
   uint64_t seed;             /* Philox key; draws are keyed (seed, agent id, step)                */
   uint32_t history_capacity; /* per-step statistics records kept on the device (ring)             */
-  uint32_t flags;            /* reserved, 0                                                       */
+  uint32_t flags;            /* CABS_FLAG_*                                                       */
 } cabs_config;
 
 /* Simulation attributes a step reads: covid_abs/abs.py:17-49 and covid_abs/common.py:13-27.
@@ -158,6 +161,39 @@ int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop);
 int cabs_set_step(cabs_sim *sim, uint64_t step);
 /* Replaces get_population (abs.py:57-63): writes the population back in id order. */
 int cabs_download(cabs_sim *sim, cabs_soa_host *pop);
+
+/* ---- off-lattice mode (handles created with CABS_FLAG_F64_POSITIONS; one device, no slabs) ----------------------
+ * Population triggers (abs.py:86-95): an entry with attribute 'move' replaces the random walk of the agents its
+ * condition selects by the position its action returns (abs.py:169-172; the shipped idiom is a point plus
+ * np.random.normal(0, sigma), run_batch.py:446-450), after which x and y are binary64 and the contact test is the
+ * reference's floating-point one (abs.py:9-10,258); any other entry rewrites an attribute after update()
+ * (abs.py:244-247).  A Python lambda cannot run on the device, so rules are declarative:
+ *   condition   any predicate of (status, severity, age, stratum), tabulated as 8 000 bits, bit index
+ *               ((status * 4 + severity) * 100 + min(age, 99)) * 5 + stratum;
+ *   move rule   new position = target + N(0, sigma) per axis (the move stream's two normals), target = the agent's
+ *               own position (CABS_RULE_MOVE_STAY) or (target_x, target_y); the first matching rule wins and the agent
+ *               earns no move income, like the early return of abs.py:172;
+ *   attribute   status / severity / infected_time / age / stratum := (int)q, or wealth := p * wealth + q; applied in
+ *               order after the step's update. */
+enum { CABS_RULE_MOVE_STAY = 1, CABS_RULE_MOVE_POINT = 2, CABS_RULE_ATTRIBUTE = 3 };
+enum { CABS_RATTR_STATUS = 0, CABS_RATTR_SEVERITY = 1, CABS_RATTR_INFECTED_TIME = 2, CABS_RATTR_AGE = 3,
+       CABS_RATTR_STRATUM = 4, CABS_RATTR_WEALTH = 5 };
+#define CABS_RULE_CONDITION_WORDS 250
+#define CABS_MAX_RULES 8
+typedef struct cabs_rule {
+  int32_t kind;                 /* CABS_RULE_*                                   */
+  int32_t attribute;            /* CABS_RATTR_* (attribute rules)                */
+  double target_x, target_y, sigma;
+  double p, q;
+  uint32_t condition[CABS_RULE_CONDITION_WORDS];
+  uint32_t reserved[2];
+} cabs_rule;
+/* rules[0 .. n_move) are move rules, rules[n_move .. n_move + n_attr) attribute rules, each group in trigger order. */
+int cabs_set_rules(cabs_sim *sim, const cabs_rule *rules, int n_move, int n_attr);
+/* cabs_upload with binary64 positions (x, y in the order of pop's columns; pop->x / pop->y may be NULL). */
+int cabs_upload_f64(cabs_sim *sim, const cabs_soa_host *pop, const double *x, const double *y);
+/* The exact positions in id order (cabs_download returns their floors in x, y). */
+int cabs_download_positions_f64(cabs_sim *sim, double *x, double *y, uint64_t capacity);
 
 /* Replaces `nsteps` calls of Simulation.execute (abs.py:232-273): move, update, contacts,
  * triggers.  Asynchronous. */

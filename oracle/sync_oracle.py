@@ -85,6 +85,42 @@ class Trigger(object):
         self.metric, self.op, self.threshold, self.attribute, self.value = metric, op, float(threshold), attribute, value
 
 
+def contact_pairs_float(x, y, r, brute_limit=3000):
+    """Off-lattice positions: all (i, j), i < j, with the reference's own binary64 predicate
+    sqrt((xi - xj)**2 + (yi - yj)**2) <= r (abs.py:9-10,258), every operation rounded once."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n = len(x)
+    r = np.float64(r)
+    if not (r >= 0.0) or n < 2:
+        return np.zeros((0, 2), dtype=np.int64)
+    if n <= brute_limit:
+        dx = x[:, None] - x[None, :]
+        dy = y[:, None] - y[None, :]
+        ii, jj = np.nonzero(np.triu(np.sqrt(dx * dx + dy * dy) <= r, k=1))
+        return np.stack([ii, jj], axis=1).astype(np.int64)
+    from scipy.spatial import cKDTree
+    tree = cKDTree(np.stack([x, y], axis=1))
+    cand = tree.query_pairs(float(r) * (1 + 1e-9) + 1e-9, output_type='ndarray').astype(np.int64)
+    if len(cand) == 0:
+        return np.zeros((0, 2), dtype=np.int64)
+    lo = np.minimum(cand[:, 0], cand[:, 1])
+    hi = np.maximum(cand[:, 0], cand[:, 1])
+    dx = x[lo] - x[hi]
+    dy = y[lo] - y[hi]
+    keep = np.sqrt(dx * dx + dy * dy) <= r
+    lo, hi = lo[keep], hi[keep]
+    order = np.lexsort((hi, lo))
+    return np.stack([lo[order], hi[order]], axis=1)
+
+
+class _AgentView(object):
+    """What a population-trigger condition sees (abs.py:86-95)."""
+
+    def __init__(self, status, infected_status, age, social_stratum):
+        self.status, self.infected_status, self.age, self.social_stratum = status, infected_status, age, social_stratum
+
+
 class SyncSimulation(object):
     def __init__(self, seed=0, wealth_scale_bits=None, **kwargs):
         self.seed = int(seed)
@@ -108,12 +144,22 @@ class SyncSimulation(object):
         self.step_index = 0
         self.prev_stats = None
         self.last_pairs = None
+        # population triggers (abs.py:86-95), declarative: dicts
+        #   {'kind': 'move', 'when': callable(view) -> bool, 'target': 'stay' | (x, y), 'sigma': s}
+        #   {'kind': 'attr', 'when': ..., 'attribute': name, 'p': p, 'q': q}   (discrete: := int(q); wealth: p * w + q)
+        # `when` receives status / infected_status codes of this module, age, social_stratum
+        self.rules = list(kwargs.get("rules", []))
+        self.float_positions = bool(kwargs.get("float_positions", False)) or len(self.rules) > 0
+
+    def _matches(self, when, st, sev, k):
+        return bool(when(_AgentView(int(st[k]), int(sev[k]), int(self.age[k]), int(self.stratum[k]))))
 
     def set_population(self, x, y, status, age, stratum, wealth, severity=None, infected_time=None):
         n = len(x)
         self.population_size = n
-        self.x = np.array(x, dtype=np.int64)
-        self.y = np.array(y, dtype=np.int64)
+        ptype = np.float64 if self.float_positions else np.int64
+        self.x = np.array(x, dtype=ptype)
+        self.y = np.array(y, dtype=ptype)
         self.status = np.array(status, dtype=np.int64)
         self.age = np.array(age, dtype=np.int64)
         self.stratum = np.array(stratum, dtype=np.int64)
@@ -147,15 +193,41 @@ class SyncSimulation(object):
         iy = np.trunc(z1 * amp).astype(np.int64)
         ix = np.where(mobile, ix, 0)
         iy = np.where(mobile, iy, 0)
-        nx = self.x + ix
-        ny = self.y + iy
-        bx = (nx <= 0) | (nx >= self.length)
-        by = (ny <= 0) | (ny >= self.height)
-        self.x = np.where(bx, self.x - ix, nx)
-        self.y = np.where(by, self.y - iy, ny)
+        # population triggers with attribute 'move' (abs.py:169-172): the first whose condition holds replaces the walk
+        moved_by_rule = np.zeros(n, dtype=bool)
+        move_rules = [r for r in self.rules if r['kind'] == 'move']
+        if move_rules:
+            rx, ry = self.x.copy(), self.y.copy()
+            for k in np.nonzero(mobile)[0]:
+                for r in move_rules:
+                    if self._matches(r['when'], st, sev, k):
+                        tx, ty = (self.x[k], self.y[k]) if r['target'] == 'stay' else r['target']
+                        rx[k] = np.float64(tx) + np.float64(z0[k]) * np.float64(r['sigma'])
+                        ry[k] = np.float64(ty) + np.float64(z1[k]) * np.float64(r['sigma'])
+                        moved_by_rule[k] = True
+                        break
+        if self.float_positions:                       # abs.py:177-185 on binary64 positions
+            fx, fy = ix.astype(np.float64), iy.astype(np.float64)
+            nx = self.x + fx
+            ny = self.y + fy
+            bx = (nx <= 0) | (nx >= np.float64(self.length))
+            by = (ny <= 0) | (ny >= np.float64(self.height))
+            wx = np.where(bx, self.x - fx, nx)
+            wy = np.where(by, self.y - fy, ny)
+            if move_rules:
+                wx = np.where(moved_by_rule, rx, wx)
+                wy = np.where(moved_by_rule, ry, wy)
+            self.x, self.y = wx, wy
+        else:
+            nx = self.x + ix
+            ny = self.y + iy
+            bx = (nx <= 0) | (nx >= self.length)
+            by = (ny <= 0) | (ny >= self.height)
+            self.x = np.where(bx, self.x - ix, nx)
+            self.y = np.where(by, self.y - iy, ny)
         dist = np.sqrt((ix * ix + iy * iy).astype(np.float64))
         inc = ((dist * philox.u01(w2)) * np.float64(self.minimum_expense)) * BASIC_INCOME[self.stratum]
-        self.wealth = np.where(mobile, self.wealth + inc, self.wealth)
+        self.wealth = np.where(mobile & ~moved_by_rule, self.wealth + inc, self.wealth)
         # ---- update (abs.py:191-230)
         idx = np.where(self.age > 10, self.age // 10 - 1, 0)
         idx = np.minimum(idx, 8)
@@ -186,8 +258,32 @@ class SyncSimulation(object):
         self.wealth = np.where(pays, self.wealth - expense, self.wealth)
         self.infected_time = time
         self.severity = sev
+        # ---- population triggers on other attributes (abs.py:244-247), in order, on the updated agent
+        attr_rules = [r for r in self.rules if r['kind'] == 'attr']
+        if attr_rules:
+            st = st.copy()
+            sev = sev.copy()
+            for k in range(n):                            # every agent, the dead included (the loop is in execute())
+                for r in attr_rules:
+                    if not self._matches(r['when'], st, sev, k):
+                        continue
+                    a, v = r['attribute'], int(r['q'])
+                    if a == 'status':
+                        st[k] = v & 3
+                    elif a == 'infected_status':
+                        sev[k] = v & 3
+                    elif a == 'infected_time':
+                        self.infected_time[k] = v & 0xFF
+                    elif a == 'age':
+                        self.age[k] = v & 0xFF
+                    elif a == 'social_stratum':
+                        self.stratum[k] = min(v, 4)
+                    else:
+                        self.wealth[k] = np.float64(r['p']) * self.wealth[k] + np.float64(r['q'])
+            self.severity = sev
         # ---- contacts (abs.py:249-265), synchronous
-        pairs = contact_pairs(self.x, self.y, self.contagion_distance)
+        pairs = (contact_pairs_float(self.x, self.y, self.contagion_distance) if self.float_positions
+                 else contact_pairs(self.x, self.y, self.contagion_distance))
         self.last_pairs = pairs
         if len(pairs):
             a, b = pairs[:, 0], pairs[:, 1]

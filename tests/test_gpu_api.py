@@ -99,10 +99,15 @@ def test_history_ring_and_error_paths(native_lib):
     assert e.value.code == _native.ERR_CAPACITY
     with pytest.raises(_native.NativeError):
         sim._handle.stats_history(27, 5)            # not executed yet
-    # per-agent Python triggers cannot run on the device
-    sim.append_trigger_population(lambda a: True, 'wealth', lambda w: 0)
+    # per-agent triggers the device cannot express are refused (no CPU fallback); the expressible ones run
+    # (tests/test_offlattice.py)
+    sim.append_trigger_population(lambda a: a.wealth > 10, 'wealth', lambda w: 0)     # condition on wealth: not tabulable
     with pytest.raises(NotImplementedError):
         sim.execute()
+    sim.triggers_population = []
+    sim.append_trigger_population(lambda a: True, 'wealth', lambda w: 0)
+    sim.execute()
+    assert sum(float(sim.get_statistics('all')[k]) for k in ("Q1", "Q2", "Q3", "Q4", "Q5")) == 0.0
     # coordinates beyond the supported box are reported, not silently wrapped
     far = Simulation(seed=1, population_size=2, length=10, height=10)
     far.set_population_arrays([0, 2 ** 29], [0, 0], [0, 1], [30, 30], [1, 1], [1.0, 1.0])
