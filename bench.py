@@ -501,6 +501,26 @@ def run_ours(args, rank, world, local_rank):
                       "unit": "agent-updates/s", "clock": "host wall clock around the loop",
                       "fraction_of_value": (n * k_py / wall) / value}
 
+    # ---- the same call chain with the inputs ALREADY on the device (cabs_bind_device: torch tensors' data_ptr()):
+    #      what a pipeline that produces populations on the GPU pays -- no PCIe copy, one pack pass + the first sort
+    e2e_device = None
+    if world == 1:
+        dev_cols = {k: t.cuda(local_rank) for k, t in pinned.items()}
+        dev_ptrs = {k: t.data_ptr() for k, t in dev_cols.items()}
+        torch.cuda.synchronize()
+
+        def dev_once():
+            h.bind_device(n, dev_ptrs)
+            step(1)
+            h.stats()
+
+        dev_once()
+        dms = timed(h, lambda: [dev_once() for _ in range(e2e_steps)])
+        e2e_device = {"what": "cabs_bind_device (device-resident columns, no host copy) + cabs_step(1) + cabs_stats, every step",
+                      "steps": e2e_steps, "ms_per_step": dms / e2e_steps, "value": n * e2e_steps / (dms * 1e-3),
+                      "unit": "agent-updates/s", "h2d_bytes_per_step": 0}
+        del dev_cols
+
     other = None
     if not args.no_other_configs:
         other = {}
@@ -573,6 +593,7 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": 12 * 8 + 7 * 8 + 4, "steps": e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps},
             "e2e_python": e2e_python,
+            "e2e_device_inputs": e2e_device,
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,

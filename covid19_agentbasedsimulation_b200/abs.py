@@ -293,6 +293,34 @@ class Simulation(object):
         self._invalidate_host()
         self.statistics = None
 
+    def set_population_tensors(self, x, y, status, age, stratum, wealth, severity=None, infected_time=None):
+        """Like set_population_arrays for columns that already live on the GPU: torch CUDA tensors (int32 x / y, uint8
+        status / age / stratum / severity / infected_time, float64 wealth) on this simulation's device.  They are
+        packed straight into the device records (cabs_bind_device): nothing crosses the PCIe bus."""
+        import torch
+        n = int(x.numel())
+        dev = torch.device("cuda", int(self.device))
+        want = (("x", x, torch.int32), ("y", y, torch.int32), ("status", status, torch.uint8), ("age", age, torch.uint8),
+                ("stratum", stratum, torch.uint8), ("wealth", wealth, torch.float64),
+                ("severity", torch.ones(n, dtype=torch.uint8, device=dev) if severity is None else severity, torch.uint8),
+                ("infected_time", torch.zeros(n, dtype=torch.uint8, device=dev) if infected_time is None else infected_time,
+                 torch.uint8))
+        cols = {}
+        for name, t, dt in want:
+            if t.device != dev or t.dtype != dt or t.numel() != n:
+                raise ValueError("{}: expected a {} tensor of {} elements on {}".format(name, dt, n, dev))
+            cols[name] = t.contiguous()
+        self.population_size = n
+        if self._handle is not None and self._handle.f64:
+            raise NotImplementedError("device columns are lattice positions; use set_population_arrays for float64")
+        self._ensure_handle(n)
+        self._push_params()
+        torch.cuda.current_stream(dev).synchronize()      # the columns are complete before the library's stream reads them
+        self._handle.bind_device(n, {k: t.data_ptr() for k, t in cols.items()})
+        self._handle.sync()                               # ... and consumed before the caller may free them
+        self._invalidate_host()
+        self.statistics = None
+
     def _invalidate_host(self):
         self._host = None
         self._agents = None

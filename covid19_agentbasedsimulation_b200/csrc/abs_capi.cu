@@ -866,11 +866,32 @@ static int refresh_n(cabs_sim *sim) {
   return CABS_OK;
 }
 
-static int upload_impl(cabs_sim *sim, const cabs_soa_host *pop, const double *xf, const double *yf);
+static int upload_impl(cabs_sim *sim, const cabs_soa_host *pop, const double *xf, const double *yf,
+                       bool on_device = false);
 
 extern "C" int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop) {
   NvtxRange nvtx_("cabs_upload");
   return upload_impl(sim, pop, nullptr, nullptr);
+}
+
+static bool device_pointer(const cabs_sim *sim, const void *p) {
+  if (!p) return true;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return (a.type == cudaMemoryTypeDevice && a.device == sim->device) || a.type == cudaMemoryTypeManaged;
+}
+
+extern "C" int cabs_bind_device(cabs_sim *sim, const cabs_soa_host *pop) {
+  NvtxRange nvtx_("cabs_bind_device");
+  if (!sim || !pop) return fail(sim, CABS_ERR_INVALID, "cabs_bind_device: null argument");
+  for (const void *p : {(const void *)pop->x, (const void *)pop->y, (const void *)pop->status, (const void *)pop->severity,
+                        (const void *)pop->infected_time, (const void *)pop->age, (const void *)pop->stratum,
+                        (const void *)pop->wealth, (const void *)pop->id})
+    if (!device_pointer(sim, p)) return fail(sim, CABS_ERR_INVALID, "cabs_bind_device: every column must be device memory of the handle's device");
+  return upload_impl(sim, pop, nullptr, nullptr, true);
 }
 
 extern "C" int cabs_upload_f64(cabs_sim *sim, const cabs_soa_host *pop, const double *x, const double *y) {
@@ -880,7 +901,7 @@ extern "C" int cabs_upload_f64(cabs_sim *sim, const cabs_soa_host *pop, const do
   return upload_impl(sim, pop, x, y);
 }
 
-static int upload_impl(cabs_sim *sim, const cabs_soa_host *pop, const double *xf, const double *yf) {
+static int upload_impl(cabs_sim *sim, const cabs_soa_host *pop, const double *xf, const double *yf, bool on_device) {
   if (!sim || !pop) return fail(sim, CABS_ERR_INVALID, "cabs_upload: null argument");
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_upload: call cabs_set_params first");
   if (pop->n > sim->capacity) return fail(sim, CABS_ERR_CAPACITY, "cabs_upload: population larger than capacity");
@@ -892,7 +913,14 @@ static int upload_impl(cabs_sim *sim, const cabs_soa_host *pop, const double *xf
   const int c = sim->cur;
   const size_t cap = sim->capacity;
   int *sx = reinterpret_cast<int *>(sim->hot[c ^ 1]), *sy = sx + cap;  // the other copy is free: scratch
-  if (n) {
+  if (n && on_device) {
+    // the columns are device memory already (e.g. torch tensors): pack the records straight from them, no staging copy
+    if (!pop->x || !pop->y) return fail(sim, CABS_ERR_INVALID, "cabs_bind_device: null column");
+    CK(cudaMemcpyAsync(sim->w[c], pop->wealth, n * sizeof(double), cudaMemcpyDeviceToDevice, sim->stream));
+    LAUNCH(k_pack, agent_blocks(sim), 256, (unsigned)n, (const int *)pop->x, (const int *)pop->y,
+           (const uint8_t *)pop->status, (const uint8_t *)pop->severity, (const uint8_t *)pop->infected_time,
+           (const uint8_t *)pop->age, (const uint8_t *)pop->stratum, (const uint32_t *)pop->id, sim->hot[c]);
+  } else if (n) {
     if (pop->x && pop->y) {
       CK(cudaMemcpyAsync(sx, pop->x, n * sizeof(int), cudaMemcpyHostToDevice, sim->stream));
       CK(cudaMemcpyAsync(sy, pop->y, n * sizeof(int), cudaMemcpyHostToDevice, sim->stream));

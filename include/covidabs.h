@@ -154,6 +154,11 @@ int cabs_set_triggers(cabs_sim *sim, const cabs_trigger *triggers, int count);
  * one-device handle it must be a permutation of 0..n-1 (checked on the device; the error surfaces as
  * CABS_ERR_INVALID at the next synchronising call). */
 int cabs_upload(cabs_sim *sim, const cabs_soa_host *pop);
+/* cabs_upload for columns that ALREADY live in device memory of the handle's device (e.g. the data_ptr() of torch
+ * tensors): the records are packed straight from them -- no host staging, no host-to-device copy.  `pop` holds device
+ * pointers; the columns must be complete when the call is made (synchronise the stream that produced them, or run the
+ * handle on that stream with cabs_set_stream).  The handle keeps no reference to them afterwards. */
+int cabs_bind_device(cabs_sim *sim, const cabs_soa_host *pop);
 /* The step counter is one word of every draw key (seed, agent id, step).  It starts at 0 on a fresh handle, advances
  * by one per executed step and is NOT reset by cabs_upload (re-uploading an edited population mid-run must not replay
  * the draws of step 0).  cabs_set_step restores the clock of a checkpoint: (cabs_download, cabs_get_info().step) ->

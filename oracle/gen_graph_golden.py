@@ -52,7 +52,12 @@ CASES = [  # name, scenario, np seed, draw seed, iterations, overrides
     ("graph_fewbusiness", "conditional_lockdown", 11, 85, 200,
      dict(population_size=80, initial_infected_perc=0.08, total_business=4, incubation_time=2, contagion_time=6,
           recovering_time=9, business_distance=60)),
+    # BASELINE.json configs[1] at its own shape: 1 000 persons (333 houses, 9 businesses), scenario2 (lockdown), past the
+    # first monthly accounting (iteration 720).  ~20 minutes of the reference's O(N^2) loop: generated on request only
+    # (`python oracle/gen_graph_golden.py graph_config2`)
+    ("graph_config2", "lockdown", 21, 90, 760, dict(population_size=1000)),
 ]
+SLOW = {"graph_config2"}
 
 
 def jsonable(o):
@@ -75,7 +80,7 @@ def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     only = sys.argv[1:]
     for name, scenario, np_seed, seed, iters, over in CASES:
-        if only and name not in only:
+        if (only and name not in only) or (not only and name in SLOW):
             continue
         sim, iso = reference_simulation(MODS, scenario, np_seed, **over)
         world = world_from_reference(sim, mode=MODES[scenario], sleep=True, isolated_ids=iso)

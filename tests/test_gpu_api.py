@@ -153,3 +153,21 @@ def test_small_population_kernel_and_tiled_path_agree(native_lib):
     h = small._download()
     assert np.array_equal(h["x"], orc.x) and np.array_equal(h["status"], orc.status)
     assert h["wealth"].tobytes() == orc.wealth.tobytes()
+
+
+def test_bind_device_equals_host_upload(native_lib):
+    """cabs_bind_device: columns that already live on the GPU (torch tensors) give the same run as the host upload."""
+    import torch
+    from covid19_agentbasedsimulation_b200 import _native
+    from covid19_agentbasedsimulation_b200.abs import Simulation
+    pop, tw = _pop(30000, 400, 11)
+    host = _gpu(pop, tw, 400, seed=5)
+    dev = Simulation(seed=5, population_size=30000, length=400, height=400, total_wealth=tw)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).cuda()
+    dev.set_population_tensors(t(pop["x"], np.int32), t(pop["y"], np.int32), t(pop["status"], np.uint8),
+                               t(pop["age"], np.uint8), t(pop["stratum"], np.uint8), t(pop["wealth"], np.float64))
+    assert np.array_equal(host.run(6), dev.run(6))
+    a, b = host._download(), dev._download()
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    with pytest.raises(_native.NativeError):        # a host pointer is refused, not dereferenced on the device
+        dev._handle.bind_device(4, {k: np.zeros(4, dtype=dt).ctypes.data for k, dt in _native.SOA_DTYPES})

@@ -52,7 +52,7 @@ def test_reference_trajectories(native_lib, path):
     assert sim.world()["px"].tolist() == fix["final"]["px"] and sim.world()["status"].tolist() == fix["final"]["status"]
 
 
-@pytest.mark.parametrize("scenario,n", [("scenario1", 1500), ("scenario3", 1000), ("scenario6", 800)])
+@pytest.mark.parametrize("scenario,n", [("scenario1", 1500), ("scenario2", 1000), ("scenario3", 1000), ("scenario6", 800)])
 def test_built_world_stepwise_equals_batched_equals_oracle(native_lib, scenario, n):
     from covid19_agentbasedsimulation_b200.network.graph_abs import GraphSimulation, GRAPH_STAT_KEYS, default_money_bits
     from covid19_agentbasedsimulation_b200.network import scenarios as sc

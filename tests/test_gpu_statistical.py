@@ -134,3 +134,45 @@ def test_graph_ensemble_matches_reference(native_lib):
         frac_inside = float(np.mean(z[live] < 1.96))
         assert frac_inside >= 0.90, (case["scenario"], frac_inside)
         assert float(z[live].max()) < 4.5, (case["scenario"], float(z[live].max()))
+
+
+def test_graph_ensemble_256_seeds_with_ks(native_lib):
+    """North-star criterion for GraphSimulation at the reference's own size: run_batch.py scenario1 / 2 / 3 with the
+    shipped global_parameters (300 persons), 256 seeds x 480 hourly iterations of the UNMODIFIED reference
+    (oracle/gen_graph_ensemble256.py) against 256 device simulations, each with its own world: >= 90 % of the
+    (iteration, metric) cells inside 1.96 combined standard errors, none beyond 4.5, and two-sample KS p > 0.05 on
+    the per-seed epidemiological fractions at four sample iterations."""
+    from covid19_agentbasedsimulation_b200.network.graph_abs import GraphSimulation
+    from covid19_agentbasedsimulation_b200.network.ensemble import GraphEnsemble
+    from covid19_agentbasedsimulation_b200.network import scenarios as sc
+    path = os.path.join(GOLDEN, "ensemble_graph256.json")
+    if not os.path.exists(path):
+        pytest.skip("256-seed graph ensemble fixture not generated")
+    fix = json.load(open(path))
+    scen = {"none": sc.scenario1, "lockdown": sc.scenario2, "conditional_lockdown": sc.scenario3}
+    for case in fix["cases"]:
+        kw = dict(sc.global_parameters)
+        kw.update(scen[case["scenario"]])
+        kw.pop("name")
+        kw.update(case["overrides"])
+        n_seeds = 256
+        np.random.seed(4242)
+        sims = [GraphSimulation(seed=9000 + k, **kw) for k in range(n_seeds)]
+        ens = GraphEnsemble(sims, history_capacity=1024)
+        ens.initialize()                       # 256 worlds drawn like graph_abs.py:89-188
+        rows = ens.run(case["iterations"])
+        ens.close()
+        mean_ref, std_ref = np.array(case["mean"]), np.array(case["std"])
+        z = _z_table(rows, mean_ref, std_ref, case["seeds"])
+        live = std_ref > 0
+        frac_inside = float(np.mean(z[live] < 1.96))
+        assert frac_inside >= 0.90, (case["scenario"], frac_inside)
+        assert float(z[live].max()) < 4.5, (case["scenario"], float(z[live].max()))
+        for when, ref_rows in case["rows_at"].items():
+            ref = np.array(ref_rows)
+            ours = rows[:, int(when), :]
+            for k in range(7, 14):                # Susceptible .. Severe
+                if np.ptp(ref[:, k]) == 0 and np.ptp(ours[:, k]) == 0:
+                    continue
+                p = stats.ks_2samp(ours[:, k], ref[:, k]).pvalue
+                assert p > 0.05, (case["scenario"], when, fix["stat_keys"][k], p)
