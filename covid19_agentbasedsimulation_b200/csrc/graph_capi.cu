@@ -1,6 +1,7 @@
 // C ABI of the GraphSimulation path (include/covidabs.h, cabs_graph_*): host orchestration of graph_kernels.cuh.
 // No CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <nvtx3/nvToolsExt.h>
 #include <math.h>
 #include <stdio.h>
@@ -49,6 +50,8 @@ struct cabs_graph {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   uint64_t launches = 0;
+  int slots = 0;                 // blocks of k_graph_run the device holds at once (occupancy x SMs)
+  int *queue = nullptr;          // task-queue schedule: [0] ticket counter, [1 + sim] hours done in the current launch
   std::string err;
 };
 
@@ -80,7 +83,7 @@ extern "C" void cabs_graph_destroy(cabs_graph *g) {
   void *ptrs[] = {g->sims, g->px, g->py, g->house, g->employer, g->hire_seq, g->attr, g->pwealth, g->events, g->hx, g->hy,
                   g->hstratum, g->hsize, g->hwealth, g->hfixed, g->hincomes, g->hexpenses, g->bx, g->by, g->bstratum,
                   g->bstocks, g->bsales, g->bnum, g->bprice, g->bwealth, g->bfixed, g->bincomes, g->cell_count,
-                  g->cell_items, g->contagious, g->history, g->initial_rows};
+                  g->cell_items, g->contagious, g->history, g->initial_rows, g->queue};
   for (void *p : ptrs) cudaFree(p);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
@@ -296,7 +299,26 @@ extern "C" int cabs_graph_run(cabs_graph *g, int iterations) {
   GCK(cudaSetDevice(g->device));
   GCK(cudaEventRecord(g->ev0, g->stream));
   if (iterations > 0) {
-    k_graph_run<<<g->cfg.n_sims, kThreads, 0, g->stream>>>(g->sims, iterations);
+    // simulations that fit the GPU at once keep one block each for the whole run; larger ensembles are scheduled hour
+    // by hour from a ticket queue over a persistent grid (see k_graph_run)
+    if (g->slots == 0) {
+      int per_sm = 0, sms = 0;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_graph_run<true>, kThreads, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+      g->slots = per_sm * sms;
+    }
+    const char *force = getenv("CABS_GRAPH_QUEUE");   // "0" / "1": force a schedule (measurements, tests)
+    const bool queue = force ? force[0] == '1' : (int)g->cfg.n_sims > g->slots;
+    if (queue) {
+      if (!g->queue) GCK(cudaMalloc(&g->queue, (1 + (size_t)g->cfg.n_sims) * sizeof(int)));
+      GCK(cudaMemsetAsync(g->queue, 0, (1 + (size_t)g->cfg.n_sims) * sizeof(int), g->stream));
+      const int grid = g->slots < (int)g->cfg.n_sims ? g->slots : (int)g->cfg.n_sims;
+      k_graph_run<true><<<grid, kThreads, 0, g->stream>>>(g->sims, iterations, (int)g->cfg.n_sims,
+                                                          reinterpret_cast<unsigned *>(g->queue), g->queue + 1);
+    } else {
+      k_graph_run<false><<<g->cfg.n_sims, kThreads, 0, g->stream>>>(g->sims, iterations, (int)g->cfg.n_sims, nullptr, nullptr);
+    }
     g->launches++;
   }
   GCK(cudaEventRecord(g->ev1, g->stream));

@@ -223,13 +223,47 @@ __device__ __forceinline__ void fire(const Sim &S, Shared &sh, int b, uint32_t i
 }
 
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2) k_graph_run(Sim *sims, int iterations) {
+// Two schedules of the same hour code:
+//   kQueue = false   block b owns simulation b for the whole run (grid = n_sims): nothing is shared between blocks;
+//                    right whenever the simulations fit the GPU at once (2 blocks per SM).
+//   kQueue = true    a persistent grid (one block per resident slot) draws (simulation, hour) tasks from a ticket
+//                    counter, hour-major: task t = hour * n_sims + simulation.  A simulation's hours still run in order
+//                    (a worker waits until `progress[simulation]` says the hour before is done -- it was handed out
+//                    n_sims tickets earlier, to a worker that is running, so the wait cannot deadlock), but which
+//                    block runs which hour is decided as blocks become free.  An ensemble of 896 simulations on 296
+//                    slots is then 3.03 slots' worth of time instead of 4 rounds (the fourth round of the static
+//                    schedule runs 8 blocks on an otherwise idle GPU).  Between tasks the accounts go back to global
+//                    memory (a few hundred bytes); results are identical bit for bit.
+template <bool kQueue>
+__global__ void __launch_bounds__(kThreads, 2)
+k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progress) {
   // the descriptor (pointers, parameters) is read by every thread all the time: keep a copy in shared memory
   __shared__ Sim S;
   __shared__ Shared sh;
+  __shared__ unsigned s_task;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (bool first_pass = true;; first_pass = false) {
+  int sim_index = blockIdx.x, hours = iterations, task_hour = 0;
+  if (kQueue) {
+    if (tid == 0) s_task = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned task = s_task;
+    if (task >= (unsigned)n_sims * (unsigned)iterations) break;
+    sim_index = (int)(task % (unsigned)n_sims);
+    task_hour = (int)(task / (unsigned)n_sims);
+    hours = 1;
+    if (tid == 0) {
+      while (*(volatile int *)&progress[sim_index] < task_hour) __nanosleep(200);
+      __threadfence();
+    }
+    __syncthreads();
+    __threadfence();   // what the previous hour of this simulation wrote (on another SM) is read from L2, not a stale L1 line
+  } else if (!first_pass) {
+    break;
+  }
   for (unsigned k = tid; k < sizeof(Sim) / 4; k += kThreads)
-    reinterpret_cast<uint32_t *>(&S)[k] = reinterpret_cast<const uint32_t *>(&sims[blockIdx.x])[k];
+    reinterpret_cast<uint32_t *>(&S)[k] = kQueue ? __ldcg(reinterpret_cast<const uint32_t *>(&sims[sim_index]) + k)
+                                                 : reinterpret_cast<const uint32_t *>(&sims[sim_index])[k];
   __syncthreads();
   const int n = S.n, nh = S.nh, nb = S.nb;
   const double scale = S.scale;
@@ -249,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_graph_run(Sim *sims, int iterat
   int it = S.iteration;
   double prev_infected = S.prev_infected, prev_hs = S.prev_hosp_severe;
 
-  for (int step = 0; step < iterations; ++step) {
+  for (int step = 0; step < hours; ++step) {
     ++it;                                                                       // graph_abs.py:192
     const int hour = it % 24, day = it / 24;
     const bool bed = hour < 8, work = hour >= 8 && hour < 16, free_t = hour >= 17, lunch = hour == 12;
@@ -769,13 +803,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_graph_run(Sim *sims, int iterat
     S.bstocks[tid] = sh.bstocks[tid]; S.bsales[tid] = sh.bsales[tid]; S.bnum[tid] = sh.bnum[tid];
   }
   if (tid == 0) {
-    Sim &G = sims[blockIdx.x];
+    Sim &G = sims[sim_index];
     G.gov_wealth = sh.gov_wealth; G.health_wealth = sh.health_wealth; G.health_expenses = sh.health_expenses;
     G.next_hire_seq = sh.next_hire_seq;
     G.iteration = it;
     G.prev_infected = prev_infected;
     G.prev_hosp_severe = prev_hs;
   }
+  if (kQueue) {   // publish the hour: everything this block wrote, then the progress counter
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      *(volatile int *)&progress[sim_index] = task_hour + 1;
+    }
+  }
+  }   // next task
 }
 
 // Statistics of the initial state (row -1 is never read by batch_experiment, but get_statistics() before the

@@ -74,7 +74,14 @@ def test_config3_parameters_meet_the_strict_criterion_on_both_schedules(native_l
     infection chain needs two rare events in one step, so the synchronous schedule -- the one every bench number is
     measured on -- is held to the north star's FULL criterion here, exactly like the sequential one: >= 90 % of the
     (iteration, metric) cells inside 1.96 combined standard errors, none beyond 4.5, KS p > 0.05 at the middle and the
-    last iteration."""
+    last iteration.
+
+    The cells of one ensemble are strongly autocorrelated (Recovered is cumulative: one early fluctuation moves every
+    later cell), so the "fraction inside" of ONE 256-seed ensemble is itself noisy: four independent Philox seed
+    families of the sequential schedule -- the reference's own schedule, exact -- gave 0.81, 0.93, 0.99, 0.91 on the
+    20 % case, the synchronous one 0.91, 0.93, 0.99, 0.91 (scripts/diag_config3_stats.py, B200).  The test therefore runs
+    three independent families and asks the MEDIAN fraction to be >= 0.90; the bound on the worst cell and the KS test
+    must hold in every family."""
     from covid19_agentbasedsimulation_b200.abs import Simulation, Trigger
     from covid19_agentbasedsimulation_b200.agents import Status
     path = os.path.join(GOLDEN, "simulation_config3_ensemble.json")
@@ -85,26 +92,28 @@ def test_config3_parameters_meet_the_strict_criterion_on_both_schedules(native_l
     keys, iters, seeds = ens["keys"], ens["iterations"], len(ens["seeds"])
     assert seeds >= 256
     amp = lambda v: {Status.Susceptible: v, Status.Recovered_Immune: v, Status.Infected: v}
-    rows = np.empty((seeds, iters, len(keys)))
-    for s in range(seeds):
-        np.random.seed(s)
-        sim = Simulation(schedule=schedule, amplitudes=amp(5),
-                         triggers_simulation=[Trigger('Infected', '>=', .2, 'amplitudes', amp(1.5)),
-                                              Trigger('Infected', '<=', .05, 'amplitudes', amp(5))], **ens["kwargs"])
-        sim.initialize()
-        rows[s] = sim.run(iters)
-    z = _z_table(rows, np.array(ens["mean"]), np.array(ens["std"]), seeds)
-    live = np.array(ens["std"]) > 0
-    frac_inside = float(np.mean(z[live] < 1.96))
-    assert frac_inside >= 0.90, (case, schedule, frac_inside)
-    assert float(z[live].max()) < 4.5, (case, schedule, float(z[live].max()))
-    for when, sample in (("mid", iters // 2), ("final", iters - 1)):
-        ref = np.array(ens[when])
-        for k, key in enumerate(keys[:7]):
-            if np.ptp(ref[:, k]) == 0 and np.ptp(rows[:, sample, k]) == 0:
-                continue
-            p = stats.ks_2samp(rows[:, sample, k], ref[:, k]).pvalue
-            assert p > 0.05, (case, schedule, when, key, p)
+    fractions = []
+    for family in (None, 1000003, 2000003):      # None: the Philox seed follows np.random, like every other test
+        rows = np.empty((seeds, iters, len(keys)))
+        for s in range(seeds):
+            np.random.seed(s)                     # same initial populations as the reference runs (abs.py:116-139)
+            sim = Simulation(schedule=schedule, seed=None if family is None else family + s, amplitudes=amp(5),
+                             triggers_simulation=[Trigger('Infected', '>=', .2, 'amplitudes', amp(1.5)),
+                                                  Trigger('Infected', '<=', .05, 'amplitudes', amp(5))], **ens["kwargs"])
+            sim.initialize()
+            rows[s] = sim.run(iters)
+        z = _z_table(rows, np.array(ens["mean"]), np.array(ens["std"]), seeds)
+        live = np.array(ens["std"]) > 0
+        fractions.append(float(np.mean(z[live] < 1.96)))
+        assert float(z[live].max()) < 4.5, (case, schedule, family, float(z[live].max()))
+        for when, sample in (("mid", iters // 2), ("final", iters - 1)):
+            ref = np.array(ens[when])
+            for k, key in enumerate(keys[:7]):
+                if np.ptp(ref[:, k]) == 0 and np.ptp(rows[:, sample, k]) == 0:
+                    continue
+                p = stats.ks_2samp(rows[:, sample, k], ref[:, k]).pvalue
+                assert p > 0.05, (case, schedule, family, when, key, p)
+    assert float(np.median(fractions)) >= 0.90, (case, schedule, fractions)
 
 
 def test_graph_ensemble_matches_reference(native_lib):
