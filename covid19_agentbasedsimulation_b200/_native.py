@@ -20,7 +20,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_DOMAIN, ERR_NOGPU = 0, -1, -2, -3, 
 
 # every symbol include/covidabs.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params", "cabs_get_params", "cabs_set_triggers",
-            "cabs_upload", "cabs_bind_device", "cabs_upload_f64", "cabs_download_positions_f64", "cabs_set_rules", "cabs_set_step", "cabs_download",
+            "cabs_upload", "cabs_bind_device", "cabs_snapshot", "cabs_upload_f64", "cabs_download_positions_f64", "cabs_set_rules", "cabs_set_step", "cabs_download",
             "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_history",
             "cabs_contact_pairs", "cabs_cross_contact", "cabs_get_info", "cabs_event_record", "cabs_event_elapsed_ms",
             "cabs_profile_enable", "cabs_profile_read", "cabs_selftest_normals", "cabs_set_slab", "cabs_slab_phase", "cabs_set_stream",
@@ -185,6 +185,8 @@ def load():
     lib.cabs_upload.argtypes = [P, C.POINTER(SoaHost)]
     lib.cabs_download.argtypes = [P, C.POINTER(SoaHost)]
     lib.cabs_bind_device.argtypes = [P, C.POINTER(SoaHost)]
+    lib.cabs_snapshot.argtypes = [P, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                  C.POINTER(C.c_uint64)]
     lib.cabs_set_step.argtypes = [P, C.c_uint64]
     lib.cabs_upload_f64.argtypes = [P, C.POINTER(SoaHost), C.c_void_p, C.c_void_p]
     lib.cabs_download_positions_f64.argtypes = [P, C.c_void_p, C.c_void_p, C.c_uint64]
@@ -347,6 +349,16 @@ class Handle(object):
         for name, _ in SOA_DTYPES:
             setattr(s, name, ptrs.get(name))
         self._check(self._lib.cabs_bind_device(self._h, C.byref(s)))
+
+    def snapshot(self, n, stride=1):
+        """Position and status of every stride-th agent of the population list (the live-view feed)."""
+        m = (int(n) + int(stride) - 1) // int(stride)
+        out = {"x": np.empty(m, dtype=np.int32), "y": np.empty(m, dtype=np.int32),
+               "status": np.empty(m, dtype=np.uint8), "severity": np.empty(m, dtype=np.uint8)}
+        count = C.c_uint64(0)
+        self._check(self._lib.cabs_snapshot(self._h, int(stride), out["x"].ctypes.data, out["y"].ctypes.data,
+                                            out["status"].ctypes.data, out["severity"].ctypes.data, m, C.byref(count)))
+        return {k: v[:count.value] for k, v in out.items()}
 
     def download(self, n):
         cols = {name: np.empty(n, dtype=dt) for name, dt in SOA_DTYPES}

@@ -447,11 +447,22 @@ class Simulation(object):
         return rows
 
     # ------------------------------------------------------------------ accessors
-    def get_positions(self):
-        """abs.py:275-277."""
+    def get_positions(self, stride=1):
+        """abs.py:275-277.  stride > 1: every stride-th agent only (what an animation of millions of agents can draw:
+        `cabs_snapshot` moves 10 bytes per sampled agent instead of the whole population)."""
+        if stride > 1:
+            s = self.snapshot(stride)
+            return [[int(a), int(b)] for a, b in zip(s["x"], s["y"])]
         h = self._download()
         num = float if h["x"].dtype.kind == 'f' else int
         return [[num(a), num(b)] for a, b in zip(h["x"], h["y"])]
+
+    def snapshot(self, stride=1):
+        """Columns x, y, status, severity (codes of include/covidabs.h) of every stride-th agent of the population list:
+        the per-frame feed of graphics.py:113-142,241-276 (`get_positions()` + `get_description()`), strided."""
+        if self._handle is None:
+            raise RuntimeError("initialize() or set_population() first")
+        return self._handle.snapshot(int(self.population_size), int(stride))
 
     def remove_trigger_population(self, attribute):
         """Drop the population triggers on `attribute` (used by run_batch.py's commented scenarios)."""
@@ -459,8 +470,14 @@ class Simulation(object):
             return t['attribute'] if isinstance(t, dict) else ('move' if isinstance(t, MoveRule) else t.attribute)
         self.triggers_population = [t for t in self.triggers_population if attr_of(t) != attribute]
 
-    def get_description(self, complete=False):
-        """abs.py:279-289."""
+    def get_description(self, complete=False, stride=1):
+        """abs.py:279-289 (stride > 1: every stride-th agent, see get_positions)."""
+        if stride > 1:
+            s = self.snapshot(stride)
+            if complete:
+                return [STATUS_LIST[a].name if STATUS_LIST[a] != Status.Infected else
+                        "{}({})".format(STATUS_LIST[a].name, SEVERITY_LIST[b].name) for a, b in zip(s["status"], s["severity"])]
+            return [STATUS_LIST[a].name for a in s["status"]]
         if complete:
             return [a.get_description() for a in self.get_population()]
         h = self._download()

@@ -1013,6 +1013,27 @@ extern "C" int cabs_download(cabs_sim *sim, cabs_soa_host *pop) {
   return CABS_OK;
 }
 
+extern "C" int cabs_snapshot(cabs_sim *sim, uint32_t stride, int32_t *x, int32_t *y, uint8_t *status, uint8_t *severity,
+                             uint64_t capacity, uint64_t *count) {
+  NvtxRange nvtx_("cabs_snapshot");
+  if (!sim || !count || stride == 0) return fail(sim, CABS_ERR_INVALID, "cabs_snapshot: bad argument");
+  if (sim->slab_on) return fail(sim, CABS_ERR_INVALID, "cabs_snapshot: not defined for slab handles (ids are global there)");
+  CK(cudaSetDevice(sim->device));
+  const size_t n = sim->n, cap = sim->capacity, m = (n + stride - 1) / stride;
+  *count = m;
+  if (m == 0) return CABS_OK;
+  if (capacity < m) return fail(sim, CABS_ERR_CAPACITY, "cabs_snapshot: host buffers smaller than the sample");
+  int *sx = reinterpret_cast<int *>(sim->hot[sim->cur ^ 1]), *sy = sx + cap;   // the other copy is free between steps
+  LAUNCH(k_snapshot, agent_blocks(sim), 256, (unsigned)n, stride, sim->hot[sim->cur], sx, sy, sim->stage, sim->stage + cap);
+  CK(cudaGetLastError());
+  if (x) CK(cudaMemcpyAsync(x, sx, m * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
+  if (y) CK(cudaMemcpyAsync(y, sy, m * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
+  if (status) CK(cudaMemcpyAsync(status, sim->stage, m, cudaMemcpyDeviceToHost, sim->stream));
+  if (severity) CK(cudaMemcpyAsync(severity, sim->stage + cap, m, cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  return CABS_OK;
+}
+
 extern "C" int cabs_download_positions_f64(cabs_sim *sim, double *x, double *y, uint64_t capacity) {
   NvtxRange nvtx_("cabs_download_positions_f64");
   if (!sim || !x || !y) return fail(sim, CABS_ERR_INVALID, "cabs_download_positions_f64: null argument");

@@ -2319,6 +2319,21 @@ __global__ void k_unpack_pos(unsigned n, const uint4 *__restrict__ hot, const do
     yf[d] = pos[i].y;
   }
 }
+// Live-view feed (graphics.py:113-142,241-276 read every agent's position and status per frame): every stride-th
+// agent of the reference's population list, in list order.
+__global__ void k_snapshot(unsigned n, unsigned stride, const uint4 *__restrict__ hot, int *__restrict__ ox,
+                           int *__restrict__ oy, uint8_t *__restrict__ status, uint8_t *__restrict__ severity) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint4 h = hot[i];
+    if (h.w % stride != 0u || h.w >= n) continue;
+    const unsigned d = h.w / stride;
+    const uint32_t a = attr_normalize(h.z);
+    ox[d] = (int)h.x;
+    oy[d] = (int)h.y;
+    status[d] = (uint8_t)attr_status(a);
+    severity[d] = (uint8_t)attr_severity(a);
+  }
+}
 __global__ void k_set_rules(Ctl *ctl, int f64, int rule_margin, int bx0, int bx1, int by0, int by1) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ctl->f64 = f64;

@@ -200,6 +200,13 @@ int cabs_upload_f64(cabs_sim *sim, const cabs_soa_host *pop, const double *x, co
 /* The exact positions in id order (cabs_download returns their floors in x, y). */
 int cabs_download_positions_f64(cabs_sim *sim, double *x, double *y, uint64_t capacity);
 
+/* Live-view feed: what the reference's animations read per frame (graphics.py:113-142,241-276: every agent's
+ * position and status) for every stride-th agent of the population list, in list order -- count = ceil(n / stride)
+ * records of 10 bytes cross the bus instead of the whole population.  Any of x, y, status, severity may be NULL.
+ * (Off-lattice handles report the floors of the positions.) */
+int cabs_snapshot(cabs_sim *sim, uint32_t stride, int32_t *x, int32_t *y, uint8_t *status, uint8_t *severity,
+                  uint64_t capacity, uint64_t *count);
+
 /* Replaces `nsteps` calls of Simulation.execute (abs.py:232-273): move, update, contacts,
  * triggers.  Asynchronous. */
 int cabs_step(cabs_sim *sim, int nsteps);

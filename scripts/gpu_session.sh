@@ -1,1 +1,1 @@
-python scripts/diag_config3_stats.py 2>&1 | grep -v Warning | cut -c1-260 | tail -18
+timeout 1500 python -m pytest tests/test_gpu_statistical.py tests/test_gpu_graph.py -m gpu -q 2>&1 | tail -12

@@ -171,3 +171,19 @@ def test_bind_device_equals_host_upload(native_lib):
     assert all(np.array_equal(a[k], b[k]) for k in a)
     with pytest.raises(_native.NativeError):        # a host pointer is refused, not dereferenced on the device
         dev._handle.bind_device(4, {k: np.zeros(4, dtype=dt).ctypes.data for k, dt in _native.SOA_DTYPES})
+
+
+def test_strided_snapshot_is_the_live_view_feed(native_lib):
+    """graphics.py reads get_positions() + get_description() per frame; the strided snapshot is the same data for
+    every stride-th agent of the population list."""
+    pop, tw = _pop(50000, 500, 13)
+    sim = _gpu(pop, tw, 500, seed=6)
+    sim.run(5)
+    full_pos, full_desc, full_c = sim.get_positions(), sim.get_description(), sim.get_description(complete=True)
+    for stride in (1, 7, 1000):
+        s = sim.snapshot(stride)
+        assert len(s["x"]) == (50000 + stride - 1) // stride
+        assert [[int(a), int(b)] for a, b in zip(s["x"], s["y"])] == full_pos[::stride]
+    assert sim.get_positions(stride=7) == full_pos[::7]
+    assert sim.get_description(stride=7) == full_desc[::7]
+    assert sim.get_description(complete=True, stride=7) == full_c[::7]
