@@ -21,7 +21,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_DOMAIN, ERR_NOGPU = 0, -1, -2, -3, 
 # every symbol include/covidabs.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = ("cabs_create", "cabs_destroy", "cabs_last_error", "cabs_set_params", "cabs_get_params", "cabs_set_triggers",
             "cabs_upload", "cabs_bind_device", "cabs_snapshot", "cabs_upload_f64", "cabs_download_positions_f64", "cabs_set_rules", "cabs_set_step", "cabs_download",
-            "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_history",
+            "cabs_step", "cabs_sync", "cabs_stats", "cabs_stats_ex", "cabs_stats_history",
             "cabs_contact_pairs", "cabs_cross_contact", "cabs_get_info", "cabs_event_record", "cabs_event_elapsed_ms",
             "cabs_profile_enable", "cabs_profile_read", "cabs_selftest_normals", "cabs_set_slab", "cabs_slab_phase", "cabs_set_stream",
             "cabs_slab_block_bytes", "cabs_set_slab_direct", "cabs_slab_step", "cabs_slab_run", "cabs_device_alloc", "cabs_device_free",
@@ -194,6 +194,7 @@ def load():
     lib.cabs_step.argtypes = [P, C.c_int]
     lib.cabs_sync.argtypes = [P]
     lib.cabs_stats.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.cabs_stats_ex.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(Params), C.POINTER(C.c_uint64)]
     lib.cabs_stats_history.argtypes = [P, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]
     lib.cabs_contact_pairs.argtypes = [P, C.POINTER(C.c_int64), C.c_size_t, C.POINTER(C.c_size_t)]
     lib.cabs_get_info.argtypes = [P, C.POINTER(Info)]
@@ -398,6 +399,15 @@ class Handle(object):
         c = (C.c_int64 * 7)()
         self._check(self._lib.cabs_stats(self._h, v, c))
         return np.array(v[:], dtype=np.float64), np.array(c[:], dtype=np.int64)
+
+    def stats_ex(self):
+        """(values[12], counts[7], Params as on the device now, trigger epoch) from one copy and one synchronisation."""
+        v = (C.c_double * NUM_STATS)()
+        c = (C.c_int64 * 7)()
+        p = Params()
+        e = C.c_uint64(0)
+        self._check(self._lib.cabs_stats_ex(self._h, v, c, C.byref(p), C.byref(e)))
+        return np.array(v[:], dtype=np.float64), np.array(c[:], dtype=np.int64), p, int(e.value)
 
     def stats_history(self, first, count):
         out = np.empty((int(count), NUM_STATS), dtype=np.float64)

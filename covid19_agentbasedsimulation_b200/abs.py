@@ -113,6 +113,8 @@ class Simulation(object):
         self._pushed = None          # last parameter tuple sent to the device
         self._pushed_triggers = None
         self._pushed_rules = None
+        self._trigger_epoch = 0      # device-side trigger firings already mirrored into the attributes
+        self._stats_values = None    # statistics fetched together with the trigger state, valid until the next step
         self._host = None            # cached download of the population (dict of columns)
         self._agents = None          # cached list of Agent objects
         self._iteration = 0
@@ -243,14 +245,20 @@ class Simulation(object):
     def _refresh_from_device(self):
         """A fired declarative trigger rewrote simulation attributes on the device (abs.py:267-271: the change is
         permanent).  Mirror them into the Python attributes, and into the record of what was last pushed, so that a
-        later change of any other attribute does not send stale values back."""
+        later change of any other attribute does not send stale values back.  One copy and one synchronisation fetch
+        the statistics of the step as well (kept for the get_statistics() that follows), and the attributes are only
+        touched when the device says a trigger has fired since the last look."""
         if self._handle is None or self._pushed is None:
             return
         if not any(isinstance(t, Trigger) for t in self.triggers_simulation):
             return
         if self._param_tuple() != self._pushed:
             return          # user code changed attributes since the last push: they win at the next _push_params()
-        p = self._targets()[0].get_params()
+        values, _, p, epoch = self._targets()[0].stats_ex()
+        self._stats_values = values
+        if epoch == self._trigger_epoch:
+            return
+        self._trigger_epoch = epoch
         amp = [float(v) for v in p.amplitudes]
         for status, code in STATUS_CODE.items():
             if status in self.amplitudes:
@@ -324,6 +332,7 @@ class Simulation(object):
     def _invalidate_host(self):
         self._host = None
         self._agents = None
+        self._stats_values = None
 
     def _download(self):
         if self._host is None:
@@ -496,7 +505,9 @@ class Simulation(object):
             if self._handle is None:
                 raise RuntimeError("initialize() or set_population() first")
             self._push_params()
-            values, _ = self._handle.stats()
+            values = self._stats_values
+            if values is None:
+                values, _ = self._handle.stats()
             self.statistics = {k: np.float64(v) for k, v in zip(STAT_KEYS, values)}
         return self.filter_stats(kind)
 

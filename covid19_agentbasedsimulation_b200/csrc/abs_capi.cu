@@ -73,6 +73,7 @@ struct cabs_sim {
   int seq_grid = 0;                // its grid: every block resident (0: no cooperative launch, host-driven rounds)
   cudaStream_t own_stream = nullptr;
   Ctl *ctl = nullptr;
+  Ctl *host_ctl = nullptr;      // pinned mirror: statistics, error bits and trigger-rewritten attributes in ONE copy + ONE sync
   StatRecord *history = nullptr;
   uint8_t *stage = nullptr;     // byte-column staging for upload/download: 5 * capacity
   uint32_t *stage_id = nullptr;
@@ -186,6 +187,7 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
   cudaFree(sim->seq_round);
   cudaFree(sim->dev_blocks);
   cudaFree(sim->ctl); cudaFree(sim->history);
+  cudaFreeHost(sim->host_ctl);
   cudaFree(sim->stage); cudaFree(sim->stage_id); cudaFree(sim->pairs); cudaFree(sim->pair_count);
   cudaFree(sim->cross_mark);
   if (sim->step_graph) cudaGraphExecDestroy(sim->step_graph);
@@ -277,6 +279,7 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   }
   CK(cudaMalloc(&sim->tile_state, ((size_t)sim->max_cells / kScanTile + 2) * sizeof(unsigned long long)));
   CK(cudaMalloc(&sim->ctl, sizeof(Ctl)));
+  CK(cudaHostAlloc(&sim->host_ctl, sizeof(Ctl), cudaHostAllocDefault));
   CK(cudaMalloc(&sim->history, (size_t)sim->hist_cap * sizeof(StatRecord)));
   CK(cudaMalloc(&sim->stage, cap * 5));
   CK(cudaMalloc(&sim->stage_id, cap * sizeof(uint32_t)));
@@ -1164,6 +1167,19 @@ extern "C" int cabs_step(cabs_sim *sim, int nsteps) {
   return CABS_OK;
 }
 
+static int report_device_error(cabs_sim *sim, unsigned err);
+
+// The whole control block into the pinned mirror: one copy, one synchronisation; then the sticky error bits.
+static int fetch_ctl(cabs_sim *sim) {
+  {
+    const int rc = flush_late_close(sim);
+    if (rc != CABS_OK) return rc;
+  }
+  CK(cudaMemcpyAsync(sim->host_ctl, sim->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  return report_device_error(sim, sim->host_ctl->err);
+}
+
 static int check_device_error(cabs_sim *sim) {
   {
     const int rc = flush_late_close(sim);
@@ -1172,6 +1188,10 @@ static int check_device_error(cabs_sim *sim) {
   unsigned err = 0;
   CK(cudaMemcpyAsync(&err, &sim->ctl->err, sizeof(unsigned), cudaMemcpyDeviceToHost, sim->stream));
   CK(cudaStreamSynchronize(sim->stream));
+  return report_device_error(sim, err);
+}
+
+static int report_device_error(cabs_sim *sim, unsigned err) {
   if (err & kErrBadIds) {
     const unsigned clear = ~kErrBadIds;   // the population was rejected, the handle stays usable for a correct upload
     LAUNCH(k_clear_error, 1, 32, sim->ctl, clear);
@@ -1203,21 +1223,30 @@ static void convert_record(const cabs_sim *sim, const StatRecord &r, double *val
   for (int k = 0; k < 5; ++k) values[7 + k] = (double)r.q[k] / scale;  // abs.py:309-312
 }
 
-extern "C" int cabs_stats(cabs_sim *sim, double *values, int64_t *counts) {
+extern "C" int cabs_stats_ex(cabs_sim *sim, double *values, int64_t *counts, cabs_params *params_now,
+                             uint64_t *trigger_epoch) {
   NvtxRange nvtx_("cabs_stats");
   if (!sim || !values) return fail(sim, CABS_ERR_INVALID, "cabs_stats: null argument");
   if (!sim->have_params) return fail(sim, CABS_ERR_INVALID, "cabs_stats: call cabs_set_params first");
   CK(cudaSetDevice(sim->device));
-  {
-    const int rc = flush_late_close(sim);
-    if (rc != CABS_OK) return rc;
-  }
-  StatRecord r;
-  CK(cudaMemcpyAsync(&r, &sim->ctl->cur, sizeof r, cudaMemcpyDeviceToHost, sim->stream));
-  const int rc = check_device_error(sim);  // synchronises
+  const int rc = fetch_ctl(sim);   // synchronises
   if (rc != CABS_OK) return rc;
-  convert_record(sim, r, values, counts);
+  const Ctl &h = *sim->host_ctl;
+  convert_record(sim, h.cur, values, counts);
+  if (params_now) {
+    *params_now = sim->params;
+    for (int k = 0; k < 4; ++k) params_now->amplitudes[k] = (double)h.amp[k];
+    params_now->contagion_rate = h.rate;
+    params_now->contagion_distance = h.contagion_distance;
+    params_now->critical_limit = h.critical_limit;
+    sim->params = *params_now;
+  }
+  if (trigger_epoch) *trigger_epoch = h.trig_epoch;
   return CABS_OK;
+}
+
+extern "C" int cabs_stats(cabs_sim *sim, double *values, int64_t *counts) {
+  return cabs_stats_ex(sim, values, counts, nullptr, nullptr);
 }
 
 extern "C" int cabs_stats_history(cabs_sim *sim, uint64_t first_step, uint64_t count, double *values) {

@@ -129,6 +129,7 @@ struct Ctl {
   unsigned err;
   unsigned hist_cap;
   // ---- off-lattice mode: binary64 positions, declarative per-agent rules (abs.py:86-95)
+  unsigned trig_epoch;     // bumped whenever a device-side trigger fires (the host mirrors the attributes it rewrote)
   int f64;                 // positions are binary64 (pos arrays); hot.x, hot.y hold their floors
   int rule_margin;         // lattice units a `stay` move rule can displace an agent (5.78 sigma, rounded up)
   int rule_box[4];         // bounding box of the points `point` move rules send agents to (xmin > xmax: none)
@@ -1523,6 +1524,7 @@ __device__ void close_stats(Ctl *ctl, StatRecord *history, int record_stats) {
       const bool hit = tr.op == 0 ? v >= tr.threshold : tr.op == 1 ? v <= tr.threshold
                      : tr.op == 2 ? v > tr.threshold : v < tr.threshold;
       if (!hit) continue;
+      ctl->trig_epoch += 1;
       if (tr.attribute == 0) {
         for (int k = 0; k < 4; ++k) ctl->amp[k] = (float)tr.value[k];
       } else if (tr.attribute == 1) {
@@ -1621,6 +1623,7 @@ __device__ void close_local(Ctl *ctl, const unsigned *cell_start, int record_sta
       const bool hit = tr.op == 0 ? v >= tr.threshold : tr.op == 1 ? v <= tr.threshold
                      : tr.op == 2 ? v > tr.threshold : v < tr.threshold;
       if (!hit) continue;
+      ctl->trig_epoch += 1;
       if (tr.attribute == 0) {
         for (int k = 0; k < 4; ++k) ctl->amp[k] = (float)tr.value[k];
       } else if (tr.attribute == 1) {

@@ -216,6 +216,10 @@ int cabs_sync(cabs_sim *sim);
 /* Replaces get_statistics(kind='all') (abs.py:291-314) for the current state.
  * `values`: CABS_NUM_STATS doubles in abs.py key order; `counts` (optional): the 7 raw counts. */
 int cabs_stats(cabs_sim *sim, double *values, int64_t *counts);
+/* cabs_stats plus, from the same single copy and synchronisation: the attributes as they are on the device now
+ * (`params_now`, see cabs_get_params; may be NULL) and the number of times a device-side trigger has fired on this handle
+ * (`trigger_epoch`; may be NULL) -- a host mirror refreshes its attributes only when that number moves. */
+int cabs_stats_ex(cabs_sim *sim, double *values, int64_t *counts, cabs_params *params_now, uint64_t *trigger_epoch);
 /* Statistics after each of steps [first_step, first_step+count) (the rows batch_experiment appends,
  * experiments.py:193-196); `values` holds count*CABS_NUM_STATS doubles. */
 int cabs_stats_history(cabs_sim *sim, uint64_t first_step, uint64_t count, double *values);
