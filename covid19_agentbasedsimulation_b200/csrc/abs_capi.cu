@@ -149,6 +149,12 @@ static inline int agent_blocks(const cabs_sim *sim) { return sim->num_sms * 8; }
     sim->launches++;                                    \
   } while (0)
 #define LAUNCH(kernel, grid, block, ...) LAUNCH_AS(#kernel, kernel, grid, block, __VA_ARGS__)
+#define LAUNCH_SMEM_AS(name, kernel, grid, block, smem, ...)   \
+  do {                                                        \
+    if (sim->profiling) prof_mark(sim, name);                 \
+    kernel<<<(grid), (block), (smem), sim->stream>>>(__VA_ARGS__); \
+    sim->launches++;                                          \
+  } while (0)
 // The same with programmatic dependent launch on the preceding kernel of the stream (see pdl_wait in abs_kernels.cuh).
 #define LAUNCH_PDL_AS(name, kernel, grid, block, ...)                          \
   do {                                                                        \
@@ -216,6 +222,10 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   CK(cudaFuncSetAttribute(k_update_scatter<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_update_scatter<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_update_scatter<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_update_scatter<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassBSmem));
+  CK(cudaFuncSetAttribute(k_update_scatter<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassBSmem));
+  CK(cudaFuncSetAttribute(k_update_scatter<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassBSmem));
+  CK(cudaFuncSetAttribute(k_update_scatter<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassBSmem));
   memset(&sim->sp, 0, sizeof sim->sp);
   sim->seed = cfg->seed;
   {   // measured on B200 (gpurun_out/session7.log): 0.314 ms/step with the programmatic edges against 0.279 ms/step
@@ -456,12 +466,12 @@ static void enqueue_build(cabs_sim *sim) {
   if (sim->f64) {
     // pass B ran above
   } else if (kAdvance && sequential) {
-    LAUNCH_AS("k_update_scatter<true>", (k_update_scatter<kAdvance, true>), nb, kAgentThreads, sim->ctl, sim->hot[c], sim->w[c],
+    LAUNCH_SMEM_AS("k_update_scatter<true>", (k_update_scatter<kAdvance, true>), nb, kAgentThreads, kPassBSmem, sim->ctl, sim->hot[c], sim->w[c],
               sim->aux, sim->cells[t], sim->cells[t ^ 1], sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, nullptr,
               nullptr, sim->tinf, nullptr, nullptr, nullptr, no_direct, sim->sp);
   } else {
-    LAUNCH_PDL_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", (k_update_scatter<kAdvance, false>),
-                  nb, kAgentThreads, sim->ctl, (const uint4 *)sim->hot[c], (const double *)sim->w[c],
+    LAUNCH_SMEM_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", (k_update_scatter<kAdvance, false>),
+                  nb, kAgentThreads, kPassBSmem, sim->ctl, (const uint4 *)sim->hot[c], (const double *)sim->w[c],
                   (const uint2 *)sim->aux, (const unsigned *)sim->cells[t], sim->cells[t ^ 1], sim->hot[o], sim->w[o],
                   sim->inf_list, (const double *)sim->sqrt_tab, (ExchangeHeader *)nullptr, (ExchangeHeader *)nullptr,
                   (unsigned long long *)nullptr, (const ExchangeHeader *)nullptr, (const ExchangeHeader *)nullptr,
@@ -634,8 +644,8 @@ static int slab_phase(cabs_sim *sim, int phase) {
     case 1:
       LAUNCH_PDLN(k_count_immigrants, nbs, 256, sim->ctl, mr[0], mr[1], sim->cells[t], sim->imm_rank, D);
       LAUNCH_PDLN(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
-      LAUNCH_PDL_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", (k_update_scatter<kAdvance, true>), nb,
-                kAgentThreads, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t], sim->cells[t ^ 1],
+      LAUNCH_SMEM_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", (k_update_scatter<kAdvance, true>), nb,
+                kAgentThreads, kPassBSmem, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t], sim->cells[t ^ 1],
                 sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, gs[0], gs[1], nullptr, mr[0], mr[1],
                 sim->imm_rank, D, sim->sp);   // the immigrants take their slots inside pass B; its last block pushes the ghosts
       break;
@@ -968,7 +978,16 @@ static int upload_impl(cabs_sim *sim, const cabs_soa_host *pop, const double *xf
     CK(cudaGetLastError());
     return CABS_OK;
   }
-  return rebuild_static(sim);
+  if (sim->f64 || getenv("CABS_EAGER_SORT")) return rebuild_static(sim);
+  // No sort here: the first step's pass B scatters into cell order from whatever order it reads.  One pass for the
+  // statistics and the bounding box, then the closing that plans the first grid (k_upload_stats / k_close_upload).
+  // (the accumulators are clean here: every closing, k_replan and k_init_ctl leave them reset)
+  LAUNCH(k_upload_stats, agent_blocks(sim), 256, sim->ctl, sim->hot[c], sim->w[c]);
+  LAUNCH(k_close_upload, 1, 32, sim->ctl);
+  CK(cudaGetLastError());
+  sim->cells_dirty = true;
+  sim->unsorted = false;
+  return CABS_OK;
 }
 
 extern "C" int cabs_set_step(cabs_sim *sim, uint64_t step) {

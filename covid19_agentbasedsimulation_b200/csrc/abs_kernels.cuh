@@ -442,17 +442,34 @@ __global__ void __launch_bounds__(256, CABS_A_MINBLOCKS) k_move_count(Ctl *__res
 #else
   const GridRegs G = {P.gx0, P.gy0, P.eshift, P.ncx, P.ncy};
 #endif
+#ifdef CABS_A_PREFETCH2
+  // two records ahead in registers: the load queues behind the atomics of the iterations before it in the load/store
+  // unit, and one iteration of arithmetic does not cover that
+  uint4 h_next2 = make_uint4(0, 0, 0, 0);
+  if (tid < n_now) h_next = __ldg(&hot[tid]);
+  if (tid + stride < n_now) h_next2 = __ldg(&hot[tid + stride]);
+  for (unsigned i = tid; i < n_now; i += stride) {
+    const uint4 h = h_next;
+    h_next = h_next2;
+    if (i + 2 * stride < n_now) h_next2 = __ldg(&hot[i + 2 * stride]);
+#else
   if (tid < n_now) h_next = __ldg(&hot[tid]);
   for (unsigned i = tid; i < n_now; i += stride) {
     const uint4 h = h_next;
     if (i + stride < n_now) h_next = __ldg(&hot[i + stride]);
+#endif
     int nx = (int)h.x, ny = (int)h.y;
     uint32_t d = 0;
     if (kAdvance) {
       const uint32_t a = attr_normalize(h.z);
+#ifdef CABS_DIAG_A_NODRAW     // timing diagnostics only: no Philox rounds, no Box-Muller
+      const uint2 w = make_uint2(h.w * 0x9E3779B9u, h.w * 0x85EBCA6Bu + step_now);
+      int ix = (int)(w.x >> 29) - 4, iy = (int)(w.y >> 29) - 4;
+#else
       const uint2 w = agent_draw(h.w, step_now, kStreamMove, SP.k0, SP.k1);
       int ix, iy;
       draw_displacement(P, a, w, ix, iy);
+#endif
       apply_displacement(SP, nx, ny, ix, iy, nx, ny);
       d = ((uint32_t)ix & 0xFFFFu) | ((uint32_t)iy << 16);
     }
@@ -466,7 +483,11 @@ __global__ void __launch_bounds__(256, CABS_A_MINBLOCKS) k_move_count(Ctl *__res
     }
     const unsigned key = cell_key(G, nx, ny, &ctl->err);
     if (pending) aux[p_i] = make_uint2(p_d, p_rank);
+#ifdef CABS_DIAG_A_NOATOMIC   // timing diagnostics only: a plain load in place of the returning atomic
+    p_rank = __ldcg(&cells[key]);
+#else
     p_rank = atomicAdd(&cells[key], 1u);
+#endif
     p_d = d;
     p_i = i;
     pending = true;
@@ -592,10 +613,15 @@ constexpr int kSqrtTable = 4096;  // sqrt(d2) for d2 < 4096, exact (IEEE sqrt), 
 
 // One agent's move + update + economy (abs.py:156-230).  ix, iy: this step's displacement.
 // S: the step-invariant parameters (StepParams or StaticParams); step, crit_active: what changes every step.
+// sqrt(ix^2 + iy^2) of the move income (abs.py:187), exact: table for the displacements that occur, IEEE sqrt beyond
+__device__ __forceinline__ double move_distance(int ix, int iy, const double *__restrict__ sqrt_tab) {
+  const int d2 = ix * ix + iy * iy;
+  return d2 < kSqrtTable ? __ldg(&sqrt_tab[d2]) : __dsqrt_rn((double)d2);
+}
+
 template <class SP>
-__device__ __forceinline__ void advance_agent(const SP &S, uint32_t step, int crit_active, uint32_t aid, int ix, int iy,
-                                              uint32_t &a, double &w, const double *__restrict__ sqrt_tab,
-                                              bool moved_by_rule = false) {
+__device__ __forceinline__ void advance_agent(const SP &S, uint32_t step, int crit_active, uint32_t aid, double dist,
+                                              uint32_t &a, double &w, bool moved_by_rule = false) {
   const uint32_t st = attr_status(a);
   if (st == ST_D) return;   // the dead neither move (abs.py:164) nor update (abs.py:193)
   const uint32_t sev = attr_severity(a);
@@ -605,8 +631,6 @@ __device__ __forceinline__ void advance_agent(const SP &S, uint32_t step, int cr
     // abs.py:187-189: wealth += sqrt(ix^2+iy^2) * rand * minimum_expense * basic_income[stratum], rand = (r + .5) 2^-32.
     // The power of two rides on minimum_expense (me32): scaling by it commutes with every rounding, so the three
     // products below round exactly like ((dist * rand) * minimum_expense) * basic_income.
-    const int d2 = ix * ix + iy * iy;
-    const double dist = d2 < kSqrtTable ? __ldg(&sqrt_tab[d2]) : __dsqrt_rn((double)d2);
     const double x = __dmul_rn(dist, __dadd_rn((double)r0.x, 0.5));
     w = __dadd_rn(w, __dmul_rn(__dmul_rn(x, S.me32), S.bi[stratum]));
   }
@@ -661,7 +685,11 @@ __device__ __forceinline__ void send_ghost(Ctl *ctl, const StepParams &P, const 
   }
 }
 
-constexpr int kStagesB = 4;
+#ifndef CABS_B_STAGES
+#define CABS_B_STAGES 3   // measured 3 / 4 / 5 / 6 stages: 0.156 / 0.160 / 0.162 / 0.157 ms (profiles/r2_ab_ring_depth.log)
+#endif
+constexpr int kStagesB = CABS_B_STAGES;
+constexpr int kInfStage = 1024;   // Infected-list entries a block of pass B collects before it appends them in one piece
 #ifndef CABS_B_GROUP
 #define CABS_B_GROUP 4
 #endif
@@ -671,6 +699,8 @@ struct alignas(128) StageB {
   double w[kTile];
   uint2 aux[kTile];
 };
+// dynamic shared memory of pass B: the ring, the Q partial sums, the block's Infected list
+constexpr size_t kPassBSmem = kStagesB * sizeof(StageB) + 5 * kTile * sizeof(long long) + kInfStage * sizeof(unsigned);
 // acquire-release add on a shared-memory counter: the warp that brings a stage's count to kConsumerWarps has
 // observed every other warp's release of that stage
 __device__ __forceinline__ unsigned stage_release(unsigned *counter) {
@@ -703,13 +733,22 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
   __shared__ StepParams P;
   __shared__ BlockStats B;
   __shared__ unsigned s_last;
-  __shared__ long long s_q[5][kTile];  // per-thread Q1..Q5 partial sums (abs.py:309-312), no bank conflicts
   __shared__ unsigned s_stale;
-  __shared__ StageB s_in[kStagesB];
   __shared__ uint64_t s_full[kStagesB];
   __shared__ unsigned s_released[kStagesB];
+  __shared__ unsigned s_inf_n, s_inf_base, s_inf_valid;
+  // dynamic shared memory (more than the 48 KB a static allocation may take): the staging ring, the per-thread
+  // Q1..Q5 partial sums (abs.py:309-312; one column per thread: no bank conflicts) and the block's Infected list
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  StageB *s_in = reinterpret_cast<StageB *>(s_dyn);
+  long long (*s_q)[kTile] = reinterpret_cast<long long (*)[kTile]>(s_dyn + kStagesB * sizeof(StageB));
+  unsigned *s_inf = reinterpret_cast<unsigned *>(s_dyn + kStagesB * sizeof(StageB) + 5 * kTile * sizeof(long long));
 #pragma unroll
   for (int k = 0; k < 5; ++k) s_q[k][threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    s_inf_n = 0;
+    s_inf_valid = kInfStage;
+  }
   pdl_wait();
   if (threadIdx.x == 0) {
     load_params(P, ctl);
@@ -764,7 +803,6 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
 #else
   const GridRegs G = {P.gx0, P.gy0, P.eshift, P.ncx, P.ncy};
 #endif
-  unsigned pend_mask = 0, pend_base = 0, pend_slot = 0;   // Infected-list entries of the previous tile
 
   for (unsigned k = 0;; ++k) {
     const unsigned tile = tile_of(k);
@@ -799,13 +837,23 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     // the destination slot only needs the new position: ask for the cell start now so that the
     // round trip to the table overlaps the arithmetic below
     unsigned start = 0;
+#ifndef CABS_DIAG_B_NOGATHER
     if (valid) start = __ldg(&cell_start[cell_key(G, nx, ny, &ctl->err)]);
-    if (kAdvance && valid) advance_agent(SP, step_now, crit_now, aid, ix, iy, a, w, sqrt_tab);
+#endif
+    // the distance of the move income is a table lookup too: asked for here, consumed after the draw of the update
+    const double dist = kAdvance ? move_distance(ix, iy, sqrt_tab) : 0.0;
+#ifndef CABS_DIAG_B_NOCOMPUTE   // timing diagnostics only (scripts/ab_variants.sh): results are wrong with any CABS_DIAG_*
+    if (kAdvance && valid) advance_agent(SP, step_now, crit_now, aid, dist, a, w);
+#endif
     // partial statistics (abs.py:300-312); infections of this step are added by k_contagion
     const uint32_t st = attr_status(a), sev = attr_severity(a);
     // The sum is tied to the updated attribute word (bit 7 is always clear here, which the compiler cannot know) so
     // that it is scheduled after the update arithmetic: the whole of it then covers the table's round trip.
+#ifdef CABS_DIAG_B_NOSCATTER
+    const unsigned slot = i ^ ((start + ax.y) >> 31) ^ (a & kNewlyInfected);   // coalesced stores, same dependencies
+#else
     const unsigned slot = (start + ax.y) ^ (a & kNewlyInfected);
+#endif
     if (valid) {
       c_st += 1ull << (16 * st);
       if (st != ST_D) {
@@ -823,20 +871,40 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     const bool is_inf = valid && st == ST_I;
     if (kExtras && is_inf && ghost_left)
       send_ghost(ctl, P, make_uint4((uint32_t)nx, (uint32_t)ny, a, aid), ghost_left, ghost_right);
-    // The list entries of a tile are written one tile later: the reservation (an atomic with a return value) has a
-    // whole tile of arithmetic to come back instead of stalling the warp.
-    if (pend_mask) {
-      const unsigned base = __shfl_sync(0xffffffffu, pend_base, 0);
-      if (pend_mask & (1u << lane)) inf_list[base + __popc(pend_mask & ((1u << lane) - 1u))] = pend_slot;
+    // Every warp of every block appending to ONE global counter serialises in L2 (87 000 same-address atomics per
+    // launch at 0.4 % Infected: the reservation came back a whole tile late and still stalled the warp).  A block
+    // collects its entries in shared memory and appends them in one piece at its end; a block that finds more than
+    // kInfStage of them (a dense epidemic) spills the rest straight to the global list.
+    const unsigned m_inf = pull_now ? 0u : __ballot_sync(0xffffffffu, is_inf);   // pull mode needs no source list
+    if (m_inf) {
+      unsigned base = 0;
+      const unsigned cnt = (unsigned)__popc(m_inf);
+      if (lane == 0) base = atomicAdd(&s_inf_n, cnt);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + cnt <= (unsigned)kInfStage) {
+        if (is_inf) s_inf[base + __popc(m_inf & ((1u << lane) - 1u))] = slot;
+      } else {   // no room.  The counter only grows, so every later reservation starts beyond the capacity too: the
+                 // stored entries are exactly [0, first overflowing base) -- remember that base, append globally
+        unsigned gbase = 0;
+        if (lane == 0) {
+          atomicMin(&s_inf_valid, base);
+          gbase = atomicAdd(&ctl->n_inf, cnt);
+        }
+        gbase = __shfl_sync(0xffffffffu, gbase, 0);
+        if (is_inf) inf_list[gbase + __popc(m_inf & ((1u << lane) - 1u))] = slot;
+      }
     }
-    pend_mask = pull_now ? 0u : __ballot_sync(0xffffffffu, is_inf);   // pull mode needs no source list
-    pend_slot = slot;
-    if (pend_mask && lane == 0) pend_base = atomicAdd(&ctl->n_inf, (unsigned)__popc(pend_mask));
   }
   pdl_trigger();
-  if (pend_mask) {
-    const unsigned base = __shfl_sync(0xffffffffu, pend_base, 0);
-    if (pend_mask & (1u << lane)) inf_list[base + __popc(pend_mask & ((1u << lane) - 1u))] = pend_slot;
+  __syncthreads();
+  {   // append the block's list: one reservation, coalesced stores
+    if (threadIdx.x == 0) {
+      s_inf_n = min(s_inf_n, s_inf_valid);
+      s_inf_base = s_inf_n ? atomicAdd(&ctl->n_inf, s_inf_n) : 0u;
+    }
+    __syncthreads();
+    const unsigned cnt = s_inf_n, base = s_inf_base;
+    for (unsigned k = threadIdx.x; k < cnt; k += kTile) inf_list[base + k] = s_inf[k];
   }
   // Slab mode: the agents that moved in from the neighbour slabs take their slots here too (they were counted in the
   // histogram before the scan): statistics, Infected list and ghosts exactly as for the residents -- every agent is
@@ -972,7 +1040,7 @@ k_pack_emigrants(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
     const int ix = (int)(short)(ax.x & 0xFFFFu), iy = (int)(short)(ax.x >> 16);
     if (kAdvance) {
       apply_displacement(P, nx, ny, ix, iy, nx, ny);
-      advance_agent(P, P.step, P.crit_active, h.w, ix, iy, a, w, sqrt_tab);
+      advance_agent(P, P.step, P.crit_active, h.w, move_distance(ix, iy, sqrt_tab), a, w);
     }
     const bool to_left = nx < P.slab_lo;
     ExchangeHeader *dst = to_left ? send_left : send_right;   // the local header counts; records may go remote
@@ -1788,7 +1856,7 @@ k_small_run(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, double *__restrict__
       int ix, iy;
       draw_displacement(P, a, r, ix, iy);
       apply_displacement(P, nx, ny, ix, iy, nx, ny);
-      advance_agent(P, P.step, P.crit_active, h.w, ix, iy, a, w, sqrt_tab);
+      advance_agent(P, P.step, P.crit_active, h.w, move_distance(ix, iy, sqrt_tab), a, w);
       // statistics (abs.py:300-312)
       const uint32_t st = attr_status(a), sev = attr_severity(a);
       atomicAdd(&s_cnt[st], 1ull);
@@ -2214,7 +2282,7 @@ k_update_scatter_f64(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const
     unsigned slot = 0;
     if (valid) slot = cell_start[cell_key(G, fx, fy, &ctl->err)] + (ax.y & ~kRuleMoved);
     if (kAdvance && valid) {
-      advance_agent(SP, step_now, crit_now, h.w, ix, iy, a, w, sqrt_tab, (ax.y & kRuleMoved) != 0);
+      advance_agent(SP, step_now, crit_now, h.w, move_distance(ix, iy, sqrt_tab), a, w, (ax.y & kRuleMoved) != 0);
       // population triggers on other attributes (abs.py:244-247), in order, on the updated agent
       for (int k = n_move_rules; k < n_move_rules + n_attr_rules; ++k) {
         const DevRule &r = rules[k];
@@ -2322,6 +2390,84 @@ __global__ void k_unpack_pos(unsigned n, const uint4 *__restrict__ hot, const do
     yf[d] = pos[i].y;
   }
 }
+// Upload without a sort: statistics (abs.py:291-314) and bounding box of the uploaded records in one pass over them.
+// The first step after an upload sorts anyway (its pass B scatters into cell order whatever order it reads), so
+// cabs_upload no longer builds a cell list of its own -- that was a second full scatter of the population, a third of
+// the device time of an upload-step-statistics cycle.  The cell list of the uploaded positions is built on demand
+// (contact-pair hook).
+__global__ void __launch_bounds__(256)
+k_upload_stats(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const double *__restrict__ wealth) {
+  __shared__ BlockStats B;
+  __shared__ long long s_q[5][256];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) s_q[k][threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 7; ++i) B.cnt[i] = 0;
+    for (int i = 0; i < 5; ++i) B.q[i] = 0;
+    B.bb[0] = B.bb[2] = INT_MAX;
+    B.bb[1] = B.bb[3] = INT_MIN;
+  }
+  __syncthreads();
+  unsigned long long cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+  int bxmin = INT_MAX, bxmax = INT_MIN, bymin = INT_MAX, bymax = INT_MIN;
+  const double qscale = (double)(1ull << ctl->scale_bits);
+  const unsigned n = ctl->n, lane = threadIdx.x & 31;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint4 h = hot[i];
+    const uint32_t a = attr_normalize(h.z), st = attr_status(a), sev = attr_severity(a);
+    cnt[st] += 1;
+    if (st != ST_D) {
+      if (sev != SEV_E) cnt[3 + sev] += 1;
+      if (attr_age(a) >= 18u) s_q[min(attr_stratum(a), 4u)][threadIdx.x] += __double2ll_rn(__dmul_rn(wealth[i], qscale));
+    }
+    bxmin = min(bxmin, (int)h.x); bxmax = max(bxmax, (int)h.x);
+    bymin = min(bymin, (int)h.y); bymax = max(bymax, (int)h.y);
+  }
+  long long q[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) q[k] = s_q[k][threadIdx.x];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], o);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+    bxmin = min(bxmin, __shfl_xor_sync(0xffffffffu, bxmin, o));
+    bxmax = max(bxmax, __shfl_xor_sync(0xffffffffu, bxmax, o));
+    bymin = min(bymin, __shfl_xor_sync(0xffffffffu, bymin, o));
+    bymax = max(bymax, __shfl_xor_sync(0xffffffffu, bymax, o));
+  }
+  if (lane == 0) {
+    for (int k = 0; k < 7; ++k) atomicAdd(&B.cnt[k], cnt[k]);
+    for (int k = 0; k < 5; ++k) atomicAdd((unsigned long long *)&B.q[k], (unsigned long long)q[k]);
+    atomicMin(&B.bb[0], bxmin); atomicMax(&B.bb[1], bxmax); atomicMin(&B.bb[2], bymin); atomicMax(&B.bb[3], bymax);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 7; ++k)
+      if (B.cnt[k]) atomicAdd(&ctl->cnt[k], B.cnt[k]);
+    for (int k = 0; k < 5; ++k)
+      if (B.q[k]) atomicAdd((unsigned long long *)&ctl->q[k], (unsigned long long)B.q[k]);
+    if (B.bb[0] <= B.bb[1]) {
+      atomicMin(&ctl->bb_xmin, B.bb[0]); atomicMax(&ctl->bb_xmax, B.bb[1]);
+      atomicMin(&ctl->bb_ymin, B.bb[2]); atomicMax(&ctl->bb_ymax, B.bb[3]);
+    }
+  }
+}
+// ... and its closing: the statistics become the memo the first step's triggers and critical-limit test read, the
+// grid of the first build is planned around the uploaded positions.  No cell table was built: the tables keep their state.
+__global__ void k_close_upload(Ctl *ctl) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctl->overflow = 0;
+  close_stats(ctl, nullptr, 0);
+  const int bx0 = ld_acc(&ctl->bb_xmin), bx1 = ld_acc(&ctl->bb_xmax);
+  const int by0 = ld_acc(&ctl->bb_ymin), by1 = ld_acc(&ctl->bb_ymax);
+  ctl->last_bb[0] = bx0; ctl->last_bb[1] = bx1; ctl->last_bb[2] = by0; ctl->last_bb[3] = by1;
+  ctl->T = threshold_T(ctl->contagion_distance);
+  plan_grid(ctl, bx0, bx1, by0, by1, true);
+  reset_accumulators(ctl);
+}
+
 // Live-view feed (graphics.py:113-142,241-276 read every agent's position and status per frame): every stride-th
 // agent of the reference's population list, in list order.
 __global__ void k_snapshot(unsigned n, unsigned stride, const uint4 *__restrict__ hot, int *__restrict__ ox,

@@ -38,8 +38,9 @@ struct cabs_graph {
   uint32_t *attr = nullptr;
   long long *pwealth = nullptr;
   unsigned long long *events = nullptr;
-  int *hx = nullptr, *hy = nullptr, *hstratum = nullptr, *hsize = nullptr;
-  long long *hwealth = nullptr, *hfixed = nullptr, *hincomes = nullptr, *hexpenses = nullptr;
+  HouseRec *hrec = nullptr;
+  int *hstratum = nullptr, *hsize = nullptr;
+  long long *hfixed = nullptr;
   int *bx = nullptr, *by = nullptr, *bstratum = nullptr, *bstocks = nullptr, *bsales = nullptr, *bnum = nullptr;
   double *bprice = nullptr;
   long long *bwealth = nullptr, *bfixed = nullptr, *bincomes = nullptr;
@@ -80,8 +81,8 @@ extern "C" void cabs_graph_destroy(cabs_graph *g) {
   if (!g) return;
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
-  void *ptrs[] = {g->sims, g->px, g->py, g->house, g->employer, g->hire_seq, g->attr, g->pwealth, g->events, g->hx, g->hy,
-                  g->hstratum, g->hsize, g->hwealth, g->hfixed, g->hincomes, g->hexpenses, g->bx, g->by, g->bstratum,
+  void *ptrs[] = {g->sims, g->px, g->py, g->house, g->employer, g->hire_seq, g->attr, g->pwealth, g->events, g->hrec,
+                  g->hstratum, g->hsize, g->hfixed, g->bx, g->by, g->bstratum,
                   g->bstocks, g->bsales, g->bnum, g->bprice, g->bwealth, g->bfixed, g->bincomes, g->cell_count,
                   g->cell_items, g->contagious, g->history, g->initial_rows, g->queue};
   for (void *p : ptrs) cudaFree(p);
@@ -124,8 +125,8 @@ static int graph_create_impl(cabs_graph *g, const cabs_graph_config *cfg) {
   GCK(alloc(&g->sims, S));
   GCK(alloc(&g->px, P)); GCK(alloc(&g->py, P)); GCK(alloc(&g->house, P)); GCK(alloc(&g->employer, P));
   GCK(alloc(&g->hire_seq, P)); GCK(alloc(&g->attr, P)); GCK(alloc(&g->pwealth, P)); GCK(alloc(&g->events, P));
-  GCK(alloc(&g->hx, H)); GCK(alloc(&g->hy, H)); GCK(alloc(&g->hstratum, H)); GCK(alloc(&g->hsize, H));
-  GCK(alloc(&g->hwealth, H)); GCK(alloc(&g->hfixed, H)); GCK(alloc(&g->hincomes, H)); GCK(alloc(&g->hexpenses, H));
+  GCK(alloc(&g->hrec, H)); GCK(alloc(&g->hstratum, H)); GCK(alloc(&g->hsize, H));
+  GCK(alloc(&g->hfixed, H));
   GCK(alloc(&g->bx, B)); GCK(alloc(&g->by, B)); GCK(alloc(&g->bstratum, B)); GCK(alloc(&g->bstocks, B));
   GCK(alloc(&g->bsales, B)); GCK(alloc(&g->bnum, B)); GCK(alloc(&g->bprice, B)); GCK(alloc(&g->bwealth, B));
   GCK(alloc(&g->bfixed, B)); GCK(alloc(&g->bincomes, B));
@@ -222,12 +223,16 @@ extern "C" int cabs_graph_upload(cabs_graph *g, uint32_t sim, const cabs_graph_w
   GCK(up(g->house + op, w->house, n, g->stream)); GCK(up(g->employer + op, w->employer, n, g->stream));
   GCK(up(g->hire_seq + op, w->hire_seq, n, g->stream)); GCK(up(g->attr + op, attr.data(), n, g->stream));
   GCK(up_money(g->pwealth + op, w->pwealth, n, scale, g->stream, keep));
-  GCK(up(g->hx + oh, w->hx, nh, g->stream)); GCK(up(g->hy + oh, w->hy, nh, g->stream));
+  std::vector<HouseRec> hrec(nh);   // outlives the async copy: the call synchronises before returning
+  for (size_t h = 0; h < nh; ++h) {
+    hrec[h].x = w->hx[h]; hrec[h].y = w->hy[h];
+    hrec[h].wealth = to_fx(w->hwealth[h], scale);
+    hrec[h].expenses = w->hexpenses ? to_fx(w->hexpenses[h], scale) : 0;
+    hrec[h].incomes = w->hincomes ? to_fx(w->hincomes[h], scale) : 0;
+  }
+  GCK(up(g->hrec + oh, hrec.data(), nh, g->stream));
   GCK(up(g->hstratum + oh, w->hstratum, nh, g->stream)); GCK(up(g->hsize + oh, w->hsize, nh, g->stream));
-  GCK(up_money(g->hwealth + oh, w->hwealth, nh, scale, g->stream, keep));
   GCK(up_money(g->hfixed + oh, w->hfixed, nh, scale, g->stream, keep));
-  GCK(up_money(g->hincomes + oh, w->hincomes, nh, scale, g->stream, keep));
-  GCK(up_money(g->hexpenses + oh, w->hexpenses, nh, scale, g->stream, keep));
   GCK(up(g->bx + ob, w->bx, nb, g->stream)); GCK(up(g->by + ob, w->by, nb, g->stream));
   GCK(up(g->bstratum + ob, w->bstratum, nb, g->stream)); GCK(up(g->bstocks + ob, w->bstocks, nb, g->stream));
   GCK(up(g->bnum + ob, w->bnum_employees, nb, g->stream)); GCK(up(g->bprice + ob, w->bprice, nb, g->stream));
@@ -242,8 +247,8 @@ extern "C" int cabs_graph_upload(cabs_graph *g, uint32_t sim, const cabs_graph_w
   s.n = (int)n; s.nh = (int)nh; s.nb = (int)nb;
   s.px = g->px + op; s.py = g->py + op; s.attr = g->attr + op; s.house = g->house + op; s.employer = g->employer + op;
   s.hire_seq = g->hire_seq + op; s.pwealth = g->pwealth + op; s.events = g->events + op;
-  s.hx = g->hx + oh; s.hy = g->hy + oh; s.hstratum = g->hstratum + oh; s.hsize = g->hsize + oh;
-  s.hwealth = g->hwealth + oh; s.hfixed = g->hfixed + oh; s.hincomes = g->hincomes + oh; s.hexpenses = g->hexpenses + oh;
+  s.hrec = g->hrec + oh; s.hstratum = g->hstratum + oh; s.hsize = g->hsize + oh;
+  s.hfixed = g->hfixed + oh;
   s.bx = g->bx + ob; s.by = g->by + ob; s.bstratum = g->bstratum + ob; s.bstocks = g->bstocks + ob;
   s.bsales = g->bsales + ob; s.bnum = g->bnum + ob; s.bprice = g->bprice + ob; s.bwealth = g->bwealth + ob;
   s.bfixed = g->bfixed + ob; s.bincomes = g->bincomes + ob;
@@ -489,15 +494,15 @@ extern "C" int cabs_graph_download(cabs_graph *g, uint32_t sim, cabs_graph_world
   Sim cur;
   GCK(cudaMemcpyAsync(&cur, g->sims + sim, sizeof(Sim), cudaMemcpyDeviceToHost, g->stream));
   std::vector<uint32_t> attr(n);
-  std::vector<long long> pw(n), hw(nh), hf(nh), hi(nh), he(nh), bw(nb), bf(nb), bi(nb);
+  std::vector<long long> pw(n), hf(nh), bw(nb), bf(nb), bi(nb);
+  std::vector<HouseRec> hrec(nh);
   GCK(down(w->px, s.px, n, g->stream)); GCK(down(w->py, s.py, n, g->stream));
   GCK(down(w->house, s.house, n, g->stream)); GCK(down(w->employer, s.employer, n, g->stream));
   GCK(down(w->hire_seq, s.hire_seq, n, g->stream)); GCK(down(attr.data(), s.attr, n, g->stream));
   GCK(down(pw.data(), s.pwealth, n, g->stream));
-  GCK(down(w->hx, s.hx, nh, g->stream)); GCK(down(w->hy, s.hy, nh, g->stream));
+  GCK(down(hrec.data(), s.hrec, nh, g->stream));
   GCK(down(w->hstratum, s.hstratum, nh, g->stream)); GCK(down(w->hsize, s.hsize, nh, g->stream));
-  GCK(down(hw.data(), s.hwealth, nh, g->stream)); GCK(down(hf.data(), s.hfixed, nh, g->stream));
-  GCK(down(hi.data(), s.hincomes, nh, g->stream)); GCK(down(he.data(), s.hexpenses, nh, g->stream));
+  GCK(down(hf.data(), s.hfixed, nh, g->stream));
   GCK(down(w->bx, s.bx, nb, g->stream)); GCK(down(w->by, s.by, nb, g->stream));
   GCK(down(w->bstratum, s.bstratum, nb, g->stream)); GCK(down(w->bstocks, s.bstocks, nb, g->stream));
   GCK(down(w->bsales, s.bsales, nb, g->stream)); GCK(down(w->bnum_employees, s.bnum, nb, g->stream));
@@ -518,10 +523,12 @@ extern "C" int cabs_graph_download(cabs_graph *g, uint32_t sim, cabs_graph_world
     if (w->pwealth) w->pwealth[i] = (double)pw[i] / scale;
   }
   for (size_t h = 0; h < nh; ++h) {
-    if (w->hwealth) w->hwealth[h] = (double)hw[h] / scale;
+    if (w->hx) w->hx[h] = hrec[h].x;
+    if (w->hy) w->hy[h] = hrec[h].y;
+    if (w->hwealth) w->hwealth[h] = (double)hrec[h].wealth / scale;
     if (w->hfixed) w->hfixed[h] = (double)hf[h] / scale;
-    if (w->hincomes) w->hincomes[h] = (double)hi[h] / scale;
-    if (w->hexpenses) w->hexpenses[h] = (double)he[h] / scale;
+    if (w->hincomes) w->hincomes[h] = (double)hrec[h].incomes / scale;
+    if (w->hexpenses) w->hexpenses[h] = (double)hrec[h].expenses / scale;
   }
   for (size_t b = 0; b < nb; ++b) {
     if (w->bwealth) w->bwealth[b] = (double)bw[b] / scale;

@@ -54,6 +54,11 @@ __device__ __forceinline__ uint32_t a_set(uint32_t a, uint32_t st, uint32_t sev,
   return (a & 0xFFFF0070u) | (st & 3u) | ((sev & 3u) << 2) | ((time & 0xFFu) << 8);
 }
 
+struct alignas(32) HouseRec {
+  int x, y;
+  long long wealth, expenses, incomes;
+};
+
 // Per-simulation descriptor (device memory).  Arrays are this simulation's segments.
 struct Sim {
   int n, nh, nb;
@@ -63,9 +68,12 @@ struct Sim {
   int *house, *employer, *hire_seq;
   long long *pwealth;
   unsigned long long *events;   // scratch: one nibble per business (0 none, 1..9 request, 15 check-in)
-  // houses
-  int *hx, *hy, *hstratum, *hsize;
-  long long *hwealth, *hfixed, *hincomes, *hexpenses;
+  // houses: position and the three accounts persons touch every hour share ONE 32-byte sector (a person's house is a
+  // random index: as four separate arrays every check-in cost four scattered sectors -- half of the kernel's DRAM
+  // traffic in lockdown and night hours, profiles/r2_graph_summary.md)
+  HouseRec *hrec;
+  int *hstratum, *hsize;
+  long long *hfixed;
   // businesses
   int *bx, *by, *bstratum, *bstocks, *bsales, *bnum;
   double *bprice;
@@ -162,8 +170,8 @@ __device__ __forceinline__ double person_incomes(const Sim &S, uint32_t a) {
 
 __device__ __forceinline__ void house_checkin(const Sim &S, int h, uint32_t a) {   // network/agents.py:202-207
   const long long v = fx(__ddiv_rn(person_expenses(S, a), 720.0), S.scale);
-  atom_add(&S.hwealth[h], -v);
-  atom_add(&S.hexpenses[h], v);
+  atom_add(&S.hrec[h].wealth, -v);
+  atom_add(&S.hrec[h].expenses, v);
 }
 
 __device__ __forceinline__ void move_freely(const Sim &S, uint32_t i, uint32_t it, uint32_t stream, uint32_t a, int &x,
@@ -185,8 +193,8 @@ __device__ __forceinline__ void move_to_home(const Sim &S, uint32_t i, uint32_t 
     const uint4 w = philox4x32_10(i, it, stream, 0u, S.k0, S.k1);
     float z0, z1;
     normal_pair(w.x, w.y, z0, z1);
-    x = trunc_add(S.hx[h], z0, 0.25);
-    y = trunc_add(S.hy[h], z1, 0.25);
+    x = trunc_add(S.hrec[h].x, z0, 0.25);
+    y = trunc_add(S.hrec[h].y, z1, 0.25);
   } else {
     atom_add(&S.pwealth[i], -fx(__ddiv_rn(person_incomes(S, a), 720.0), S.scale));
     move_freely(S, i, it, stream, a, x, y);
@@ -196,16 +204,16 @@ __device__ __forceinline__ void move_to_home(const Sim &S, uint32_t i, uint32_t 
 // Person.supply (network/agents.py:286-291): income goes to the house, or to the person if homeless
 __device__ __forceinline__ void person_supply(const Sim &S, uint32_t i, int h, long long v) {
   if (h >= 0) {
-    atom_add(&S.hwealth[h], v);
-    atom_add(&S.hincomes[h], v);
+    atom_add(&S.hrec[h].wealth, v);
+    atom_add(&S.hrec[h].incomes, v);
   } else {
     atom_add(&S.pwealth[i], v);
   }
 }
 __device__ __forceinline__ void person_demand(const Sim &S, uint32_t i, int h, long long v) {   // 279-284
   if (h >= 0) {
-    atom_add(&S.hwealth[h], -v);
-    atom_add(&S.hexpenses[h], v);
+    atom_add(&S.hrec[h].wealth, -v);
+    atom_add(&S.hrec[h].expenses, v);
   } else {
     atom_add(&S.pwealth[i], -v);
   }
@@ -363,7 +371,7 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
                 st = D_;
                 sev = SEV_A_;
                 if (h >= 0) {                                                        // remove_mate, 196-200
-                  atom_add(&S.hwealth[h], -fx(__ddiv_rn(fl(S.pwealth[i], scale), 2.0), scale));
+                  atom_add(&S.hrec[h].wealth, -fx(__ddiv_rn(fl(S.pwealth[i], scale), 2.0), scale));
                   atomicSub(&S.hsize[h], 1);
                   atom_add(&S.hfixed[h], -fx(__dmul_rn(__ddiv_rn(person_expenses(S, a), 720.0), 24.0), scale));
                 } else {
@@ -610,11 +618,11 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
         if (new_day) gov += fx(__ddiv_rn(fl(S.hfixed[h], scale), 10.0), scale);
         if (monthly) {
           const long long tax = fx(__dadd_rn(__dmul_rn(S.gov_price, (double)S.hsize[h]),
-                                             __ddiv_rn(fl(S.hexpenses[h], scale), 10.0)), scale);
+                                             __ddiv_rn(fl(S.hrec[h].expenses, scale), 10.0)), scale);
           gov += tax;
-          S.hwealth[h] -= tax;
-          S.hincomes[h] = 0;
-          S.hexpenses[h] = 0;
+          S.hrec[h].wealth -= tax;
+          S.hrec[h].incomes = 0;
+          S.hrec[h].expenses = 0;
         }
       }
       gov = block_sum(gov, sh.red);
@@ -763,7 +771,7 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
       long long q[5] = {0, 0, 0, 0, 0};
       for (int h = tid; h < nh; h += kThreads) {
         const int s = S.hstratum[h];
-        if (s >= 0 && s < 5) q[s] += S.hwealth[h];
+        if (s >= 0 && s < 5) q[s] += S.hrec[h].wealth;
       }
       if (tid < 8) sh.cnt[tid] = 0;
       __syncthreads();
@@ -836,7 +844,7 @@ __global__ void __launch_bounds__(kThreads) k_graph_initial_stats(Sim *sims, dou
   }
   for (int h = tid; h < S.nh; h += kThreads) {
     const int s = S.hstratum[h];
-    if (s >= 0 && s < 5) v[7 + s] += S.hwealth[h];
+    if (s >= 0 && s < 5) v[7 + s] += S.hrec[h].wealth;
   }
   for (int k = 0; k < 12; ++k) {
     const long long t = block_sum(v[k], red);
