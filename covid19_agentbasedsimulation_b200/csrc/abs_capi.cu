@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <string>
 #include <vector>
@@ -58,6 +59,8 @@ struct cabs_sim {
   unsigned char *blocks[CABS_MAX_RANKS] = {};
   unsigned char **dev_blocks = nullptr;
   unsigned build_seq = 0;
+  bool fused_pack = false;      // direct mode: this build's pass A packed the emigrants itself (set by phase 0)
+  bool slab_unfused = true;     // default: separate exchange kernels; CABS_SLAB_FUSED=1 folds them into pass A / one contact launch (measured slower)
   bool late_pending = false;    // direct mode: the global half of the last build's closing has not been enqueued
   unsigned late_offset = 0;     // its sequence number relative to Ctl::build_seq (0 once the local half has run)
   int late_record = 0;
@@ -216,12 +219,21 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   sim->num_sms = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
   sim->own_stream = sim->stream;
-  // pass B keeps 43 KB of staging per block: ask for the largest shared-memory carveout so that registers, not
-  // shared memory, decide how many of its blocks are resident
-  CK(cudaFuncSetAttribute(k_update_scatter<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k_update_scatter<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k_update_scatter<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k_update_scatter<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  // pass B: shared memory for CABS_B_MINBLOCKS resident blocks (ring + partial sums + Infected list + 2 KB of static
+  // and reserved space each) and the REST of the 256 KB to L1 -- its cell-start gather is the most expensive part of
+  // the kernel (measured without it: 0.109 ms against 0.144 ms) and lives on L1 hits
+  {
+#ifdef CABS_B_CARVEOUT
+    const int pct = CABS_B_CARVEOUT;
+#else
+    const size_t want = (size_t)CABS_B_MINBLOCKS * (kPassBSmem + 2048);
+    const int pct = (int)std::min<size_t>(100, (want * 100 + prop.sharedMemPerMultiprocessor - 1) / prop.sharedMemPerMultiprocessor);
+#endif
+    CK(cudaFuncSetAttribute(k_update_scatter<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    CK(cudaFuncSetAttribute(k_update_scatter<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    CK(cudaFuncSetAttribute(k_update_scatter<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    CK(cudaFuncSetAttribute(k_update_scatter<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+  }
   CK(cudaFuncSetAttribute(k_update_scatter<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassBSmem));
   CK(cudaFuncSetAttribute(k_update_scatter<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassBSmem));
   CK(cudaFuncSetAttribute(k_update_scatter<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassBSmem));
@@ -233,6 +245,10 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
       // running, which costs more than the launch gaps inside the captured graph were worth.  Opt-in only.
     const char *pdl = getenv("CABS_PDL");
     sim->use_pdl = pdl && pdl[0] == '1';
+    // Folding the emigrants' update + pack into pass A and the ghost contacts into the local contact launch saves two
+    // launches per step but doubles pass A's registers: 2 GPUs 0.391 ms/step against 0.297 ms.
+    const char *fused = getenv("CABS_SLAB_FUSED");
+    sim->slab_unfused = !(fused && fused[0] == '1');
   }
   sim->sp.k0 = (unsigned)(cfg->seed & 0xFFFFFFFFu);
   sim->sp.k1 = (unsigned)(cfg->seed >> 32);
@@ -459,8 +475,9 @@ static void enqueue_build(cabs_sim *sim) {
               sim->w[o], sim->pos[o], sim->inf_list, sim->sqrt_tab, (kAdvance && sequential) ? sim->tinf : nullptr,
               sim->rules, sim->n_move_rules, sim->n_attr_rules, sim->sp);
   } else {
-  LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl,
-            sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list, sim->sp);
+  LAUNCH_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", (k_move_count<kAdvance, false>), nb, 256, sim->ctl,
+            sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list, sim->sp, nullptr, nullptr, nullptr,
+            nullptr, SlabDirect(), 0);
   LAUNCH_PDL_AS("k_scan_cells", k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
   }
   if (sim->f64) {
@@ -632,8 +649,20 @@ static int slab_phase(cabs_sim *sim, int phase) {
         LAUNCH_PDLN(k_bbox, nb, 256, sim->ctl, sim->hot[c]);
         LAUNCH_PDLN(k_replan, 1, 32, sim->ctl, 1);
       }
-      LAUNCH_PDL_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", k_move_count<kAdvance>, nb, 256, sim->ctl,
-                sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list, sim->sp);
+      // Steady state of the direct mode (the build before was a step whose global closing is still pending, or nothing
+      // is pending): pass A updates and sends the emigrants itself, and the global closing rides on
+      // k_count_immigrants -- two launches fewer per step (opt-in, CABS_SLAB_FUSED=1).
+      sim->fused_pack = kAdvance && sim->direct && !sim->slab_unfused &&
+                        (!sim->late_pending || (sim->late_offset == 0 && sim->late_record == 1));
+      if (sim->fused_pack) {
+        LAUNCH_PDL_AS("k_move_count<true,pack>", (k_move_count<kAdvance, true>), nb, 256, sim->ctl, sim->hot[c], sim->aux,
+                      sim->cells[t], sim->tile_state, sim->emig_list, sim->sp, (const double *)sim->w[c], ms[0], ms[1],
+                      (const double *)sim->sqrt_tab, D, sim->late_pending ? 1 : 0);
+        break;
+      }
+      LAUNCH_PDL_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", (k_move_count<kAdvance, false>), nb, 256,
+                    sim->ctl, sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list, sim->sp, nullptr,
+                    nullptr, nullptr, nullptr, SlabDirect(), 0);
       {   // pass A needed nothing global; pass B and the emigrants' update need the critical-limit flag
         const int rc = flush_late_close(sim);
         if (rc != CABS_OK) return rc;
@@ -641,17 +670,33 @@ static int slab_phase(cabs_sim *sim, int phase) {
       LAUNCH_PDL_AS("k_pack_emigrants", k_pack_emigrants<kAdvance>, nbs, 256, sim->ctl, sim->hot[c], sim->w[c], sim->aux,
                 sim->emig_list, ms[0], ms[1], sim->sqrt_tab, D);
       break;
-    case 1:
-      LAUNCH_PDLN(k_count_immigrants, nbs, 256, sim->ctl, mr[0], mr[1], sim->cells[t], sim->imm_rank, D);
+    case 1: {
+      SlabDirect C;   // the rows the global closing reads: the build that was closed locally (sequence offset 0)
+      memset(&C, 0, sizeof C);
+      int close_first = 0;
+      if (sim->fused_pack && sim->late_pending) {
+        C.self = sim->blocks[sl.rank];
+        C.enabled = 1;
+        close_first = 1;
+        sim->late_pending = false;
+      }
+      LAUNCH_PDLN(k_count_immigrants, nbs, 256, sim->ctl, mr[0], mr[1], sim->cells[t], sim->imm_rank, D, close_first, C,
+                  sim->history);
       LAUNCH_PDLN(k_scan_cells, sim->num_sms * 3, kScanThreads, sim->ctl, sim->cells[t], sim->tile_state);
       LAUNCH_SMEM_AS(kAdvance ? "k_update_scatter<true>" : "k_update_scatter<false>", (k_update_scatter<kAdvance, true>), nb,
                 kAgentThreads, kPassBSmem, sim->ctl, sim->hot[c], sim->w[c], sim->aux, sim->cells[t], sim->cells[t ^ 1],
                 sim->hot[o], sim->w[o], sim->inf_list, sim->sqrt_tab, gs[0], gs[1], nullptr, mr[0], mr[1],
                 sim->imm_rank, D, sim->sp);   // the immigrants take their slots inside pass B; its last block pushes the ghosts
       break;
+    }
     case 2:
       if (kAdvance) {
-        if (sim->direct) {
+        if (sim->direct && !sim->slab_unfused) {
+          // one launch: every block pushes its share of the local sources first, which hides the wait for the ghosts
+          LAUNCH_PDL_AS("k_contagion(local+ghosts)", k_contagion, nb, 256, sim->ctl, sim->hot[o], sim->cells[t],
+                        sim->inf_list, gr[0], gr[1], sim->history, rows, 16 | 3, D, (ExchangeHeader *)sim->blocks[sl.rank],
+                        nullptr);
+        } else if (sim->direct) {
           // the local sources need nothing from the neighbours: their launch hides the wait for the ghosts
           SlabDirect none;
           memset(&none, 0, sizeof none);

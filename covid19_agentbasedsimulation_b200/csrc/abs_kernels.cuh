@@ -408,18 +408,37 @@ constexpr int kAgentThreads = kTile;       // threads per block of pass B
 constexpr int kScanTile = 4096;      // histogram entries per scan tile (512 threads x 8)
 constexpr int kScanThreads = 512;
 
+// Direct slab mode, steady state: an agent whose move takes it out of the slab finishes its step right where pass A
+// finds it and travels at once (k_pack_emigrants does the same from a list, in a launch of its own: two launches and
+// ~25 us per step at 8 GPUs for ~16 000 agents).  Out of line, so that the registers of the update do not count
+// against pass A's 32.  The critical-limit flag of abs.py:214 belongs to the statistics of the step before, whose global
+// half (k_slab_close_global) has not run yet when pass A does: the few threads that get here read the ranks' rows
+// themselves -- the same sum, the same comparison (close_global below).
+__device__ __noinline__ void pack_emigrant_inline(Ctl *ctl, const StaticParams &SP, unsigned step, uint4 h, int nx, int ny,
+                                                  int ix, int iy, double w, ExchangeHeader *send_left,
+                                                  ExchangeHeader *send_right, const double *sqrt_tab, const SlabDirect &D,
+                                                  int late);
+
 // Pass A reads one 16-byte column with plenty of resident warps, so plain vectorised loads (one agent
 // ahead) do as well as staged ones; pass B, which streams three columns at low occupancy, stages them.
 #ifndef CABS_A_MINBLOCKS
 #define CABS_A_MINBLOCKS 8   // 32 registers: pass A is latency-bound and loses 15 % at 6 resident blocks (measured)
 #endif
-template <bool kAdvance>
+// kPack (direct slab mode, steady state): emigrants are updated and sent from here (pack_emigrant_inline), the last
+// block publishes the counts and raises the neighbours' flags -- no k_pack_emigrants launch.
+template <bool kAdvance, bool kPack = false>
 __global__ void __launch_bounds__(256, CABS_A_MINBLOCKS) k_move_count(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot,
                                                     uint2 *__restrict__ aux, unsigned *__restrict__ cells,
                                                     unsigned long long *__restrict__ tile_state,
                                                     unsigned *__restrict__ emig_list,
-                                                    const __grid_constant__ StaticParams SP) {
+                                                    const __grid_constant__ StaticParams SP,
+                                                    const double *__restrict__ wealth = nullptr,
+                                                    ExchangeHeader *__restrict__ send_left = nullptr,
+                                                    ExchangeHeader *__restrict__ send_right = nullptr,
+                                                    const double *__restrict__ sqrt_tab = nullptr,
+                                                    const __grid_constant__ SlabDirect D = SlabDirect(), int late = 0) {
   __shared__ StepParams P;
+  __shared__ unsigned s_last_a;
   pdl_wait();
   if (threadIdx.x == 0) load_params(P, ctl);
   __syncthreads();
@@ -474,16 +493,27 @@ __global__ void __launch_bounds__(256, CABS_A_MINBLOCKS) k_move_count(Ctl *__res
       d = ((uint32_t)ix & 0xFFFFu) | ((uint32_t)iy << 16);
     }
     if (nx < SP.slab_lo || nx >= SP.slab_hi) {
-      // leaves the slab: k_pack_emigrants finishes its step and hands it to the neighbour
-      const unsigned e = atomicAdd(&ctl->n_emig, 1u);
-      if (e < 2u * ctl->mig_cap) emig_list[e] = i;
-      else atomicOr(&ctl->err, kErrExchange);
+      if (kPack) {   // leaves the slab: finishes its step here and goes straight into the neighbour's receive buffer
+        atomicAdd(&ctl->n_emig, 1u);
+        pack_emigrant_inline(ctl, SP, step_now, h, nx, ny, (int)(short)(d & 0xFFFFu), (int)(short)(d >> 16),
+                             __ldg(&wealth[i]), send_left, send_right, sqrt_tab, D, late);
+      } else {       // k_pack_emigrants finishes its step and hands it to the neighbour
+        const unsigned e = atomicAdd(&ctl->n_emig, 1u);
+        if (e < 2u * ctl->mig_cap) emig_list[e] = i;
+        else atomicOr(&ctl->err, kErrExchange);
+      }
       aux[i] = make_uint2(d, kEmigrant);
       continue;
     }
     const unsigned key = cell_key(G, nx, ny, &ctl->err);
+#ifdef CABS_DIAG_A_NOSTORE
+    if (pending && p_rank == 0xFFFFFFF0u) aux[p_i] = make_uint2(p_d, p_rank);
+#else
     if (pending) aux[p_i] = make_uint2(p_d, p_rank);
-#ifdef CABS_DIAG_A_NOATOMIC   // timing diagnostics only: a plain load in place of the returning atomic
+#endif
+#if defined(CABS_DIAG_A_NOATOMIC) && defined(CABS_DIAG_A_NOGATHER)
+    p_rank = key >> 31;   // 0, but the compiler cannot know
+#elif defined(CABS_DIAG_A_NOATOMIC)   // timing diagnostics only: a plain load in place of the returning atomic
     p_rank = __ldcg(&cells[key]);
 #else
     p_rank = atomicAdd(&cells[key], 1u);
@@ -494,6 +524,27 @@ __global__ void __launch_bounds__(256, CABS_A_MINBLOCKS) k_move_count(Ctl *__res
   }
   pdl_trigger();
   if (pending) aux[p_i] = make_uint2(p_d, p_rank);
+  if (kPack) {   // every block has fenced its remote stores; the last one publishes counts and flags (as k_pack_emigrants)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last_a = atomicAdd(&ctl->pack_ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last_a && threadIdx.x < 2) {
+      __threadfence_system();
+      const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
+      const unsigned dseq = ctl->build_seq + D.seq;
+      const unsigned par = dseq & 1u;
+      const int to_left = threadIdx.x == 0;
+      unsigned char *peer = to_left ? D.left : D.right;
+      if (peer) {
+        const int from_dir = to_left ? 1 : 0;
+        const unsigned cnt = min(__ldcg(&(to_left ? send_left : send_right)->count), ctl->mig_cap);
+        reinterpret_cast<ExchangeHeader *>(peer + L.mig_recv + (from_dir * 2 + par) * L.mig_bytes)->count = cnt;
+        __threadfence_system();
+        *(reinterpret_cast<volatile unsigned *>(peer) + FLAG_MIG + from_dir * 2 + par) = dseq;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -686,10 +737,13 @@ __device__ __forceinline__ void send_ghost(Ctl *ctl, const StepParams &P, const 
 }
 
 #ifndef CABS_B_STAGES
-#define CABS_B_STAGES 3   // measured 3 / 4 / 5 / 6 stages: 0.156 / 0.160 / 0.162 / 0.157 ms (profiles/r2_ab_ring_depth.log)
+#define CABS_B_STAGES 1   // measured 1 / 2 / 3 / 4 stages: 0.143 / 0.147 / 0.153 / 0.157 ms (profiles/r2_ab_carveout_stages.log)
 #endif
 constexpr int kStagesB = CABS_B_STAGES;
-constexpr int kInfStage = 1024;   // Infected-list entries a block of pass B collects before it appends them in one piece
+#ifndef CABS_B_INFSTAGE
+#define CABS_B_INFSTAGE 1024
+#endif
+constexpr int kInfStage = CABS_B_INFSTAGE;   // Infected-list entries a block of pass B collects before it appends them in one piece
 #ifndef CABS_B_GROUP
 #define CABS_B_GROUP 4
 #endif
@@ -1011,6 +1065,46 @@ k_update_scatter(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
   }
 }
 
+__device__ __noinline__ void pack_emigrant_inline(Ctl *ctl, const StaticParams &SP, unsigned step, uint4 h, int nx, int ny,
+                                                  int ix, int iy, double w, ExchangeHeader *send_left,
+                                                  ExchangeHeader *send_right, const double *sqrt_tab, const SlabDirect &D,
+                                                  int late) {
+  const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
+  int crit = ctl->crit_active;
+  if (late) {   // the statistics of the step before: every rank's row of the build that was closed locally (D.seq = 0 there)
+    const unsigned cseq = ctl->build_seq, cpar = cseq & 1u;
+    const long long *rows = reinterpret_cast<const long long *>(D.self + L.rows) + (size_t)cpar * kMaxRanks * kSlabRow;
+    unsigned long long c5 = 0, c6 = 0;
+    for (int g = 0; g < ctl->n_ranks; ++g) {
+      wait_flag(D.self, FLAG_ROW + cpar * kMaxRanks + g, cseq, &ctl->err);
+      c5 += (unsigned long long)__ldcg(rows + (size_t)g * kSlabRow + 5);
+      c6 += (unsigned long long)__ldcg(rows + (size_t)g * kSlabRow + 6);
+    }
+    const double n = (double)ctl->pop_size;   // abs.py:215, as close_global evaluates it
+    crit = ((double)c6 / n + (double)c5 / n) >= ctl->critical_limit;
+  }
+  uint32_t a = attr_normalize(h.z);
+  advance_agent(SP, step, crit, h.w, move_distance(ix, iy, sqrt_tab), a, w, false);
+  const bool to_left = nx < SP.slab_lo;
+  ExchangeHeader *dst = to_left ? send_left : send_right;   // the local header counts; the record goes remote
+  const unsigned k = atomicAdd(&dst->count, 1u);
+  if (k >= ctl->mig_cap) {
+    atomicOr(&ctl->err, kErrExchange);
+    return;
+  }
+  MigrantRecord r;
+  r.hot = make_uint4((uint32_t)nx, (uint32_t)ny, a, h.w);
+  r.w = w;
+  r.pad = 0;
+  const unsigned par = (ctl->build_seq + D.seq) & 1u;
+  unsigned char *peer = to_left ? D.left : D.right;
+  MigrantRecord *out = reinterpret_cast<MigrantRecord *>(dst + 1);
+  if (peer)   // what goes left arrives there "from the right" (dir 1)
+    out = reinterpret_cast<MigrantRecord *>(peer + L.mig_recv + ((to_left ? 1 : 0) * 2 + par) * L.mig_bytes +
+                                            sizeof(ExchangeHeader));
+  out[k] = r;
+}
+
 // ------------------------------------------------------------------------------------------
 // Slab exchange 1, sender side: the agents pass A found leaving the slab finish their step here
 // (abs.py:156-230) and are appended, as complete records, to the buffer of the neighbour they move to.
@@ -1084,12 +1178,24 @@ k_pack_emigrants(Ctl *__restrict__ ctl, const uint4 *__restrict__ hot, const dou
 
 // Slab exchange 1, receiver side, before the scan: count the immigrants in the histogram and keep
 // their ranks; check that residents + immigrants fit.
+// close_first (direct mode, steady state): block 0 first runs the global half of the previous step's closing
+// (k_slab_close_global's work: every rank's row has long arrived) -- it sets the critical-limit flag pass B reads, and
+// nothing this kernel uses.
+__device__ void close_global(Ctl *ctl, const long long *rows, StatRecord *history, int record_stats);
 __global__ void __launch_bounds__(256)
 k_count_immigrants(Ctl *__restrict__ ctl, const ExchangeHeader *__restrict__ recv_left,
                    const ExchangeHeader *__restrict__ recv_right, unsigned *__restrict__ cells,
-                   unsigned *__restrict__ imm_rank, SlabDirect D) {
+                   unsigned *__restrict__ imm_rank, SlabDirect D, int close_first, SlabDirect C,
+                   StatRecord *__restrict__ history) {
   __shared__ StepParams P;
   pdl_wait();
+  if (close_first && blockIdx.x == 0 && threadIdx.x == 32) {   // its own warp: thread 0 waits for the neighbours meanwhile
+    const BlockLayout L = block_layout(ctl->n_ranks, ctl->mig_cap, ctl->ghost_cap);
+    const unsigned cseq = ctl->build_seq + C.seq;
+    const unsigned cpar = cseq & 1u;
+    for (int g = 0; g < ctl->n_ranks; ++g) wait_flag(C.self, FLAG_ROW + cpar * kMaxRanks + g, cseq, &ctl->err);
+    close_global(ctl, reinterpret_cast<const long long *>(C.self + L.rows) + (size_t)cpar * kMaxRanks * kSlabRow, history, 1);
+  }
   if (threadIdx.x == 0) {
     load_params(P, ctl);
     if (D.enabled) {   // the neighbours' migrants of this build have landed in my block
@@ -1160,9 +1266,10 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
   __shared__ StepParams P;
   __shared__ unsigned s_new, s_local, s_left, s_right;
   pdl_wait();
+  const bool ghosts_late = (finish & 16) != 0;   // bit 16: local sources first, then wait for the ghosts (one launch)
   if (threadIdx.x == 0) {
     load_params(P, ctl);
-    if (D.enabled) {   // the neighbours' ghosts of this build have landed in my block
+    if (D.enabled && !ghosts_late) {   // the neighbours' ghosts of this build have landed in my block
       const unsigned dseq = ctl->build_seq + D.seq;
       const unsigned par = dseq & 1u;
       if (D.left) wait_flag(D.self, FLAG_GHOST + 0 * 2 + par, dseq, &ctl->err);
@@ -1171,13 +1278,13 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
     s_new = 0;
     s_local = (finish & 8) ? 0u : ctl->n_inf;   // bit 8: ghost sources only (the local ones ran in their own launch);
                                                 // in pull mode pass B listed nobody, so this is 0
-    s_left = ghosts_left ? min(ghosts_left->count, ctl->ghost_cap) : 0u;
-    s_right = ghosts_right ? min(ghosts_right->count, ctl->ghost_cap) : 0u;
+    s_left = (ghosts_left && !ghosts_late) ? min(ghosts_left->count, ctl->ghost_cap) : 0u;
+    s_right = (ghosts_right && !ghosts_late) ? min(ghosts_right->count, ctl->ghost_cap) : 0u;
   }
   __syncthreads();
   unsigned newinf = 0;
   const unsigned stride = gridDim.x * blockDim.x;
-  const unsigned total = s_local + s_left + s_right;
+  unsigned total = s_local + s_left + s_right;
   if (P.T >= 0 && P.pull && !(finish & 8) && *(const volatile unsigned long long *)&ctl->cnt[ST_S] > 0) {
     // pull: every Susceptible agent (in cell order: neighbouring threads share cells) looks for an agent that was
     // Infected before this phase and stops at the first contact that transmits
@@ -1221,7 +1328,23 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
     // a handful of candidates and one lane each is the better split)
     const unsigned lanes = (P.n >= 4u * (unsigned)P.ncx * (unsigned)P.ncy) ? kSourceLanes : 1u;
     const unsigned sub = threadIdx.x % lanes;
-    for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) / lanes; t < total; t += stride / lanes) {
+    unsigned first = 0;
+    for (int part = 0; part < (ghosts_late ? 2 : 1); ++part) {
+    if (part == 1) {   // the local sources are done: now the neighbours' ghosts of this build (they have had that long to land)
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned dseq = ctl->build_seq + D.seq;
+        const unsigned par = dseq & 1u;
+        if (D.left) wait_flag(D.self, FLAG_GHOST + 0 * 2 + par, dseq, &ctl->err);
+        if (D.right) wait_flag(D.self, FLAG_GHOST + 1 * 2 + par, dseq, &ctl->err);
+        s_left = ghosts_left ? min(*(const volatile unsigned *)&ghosts_left->count, ctl->ghost_cap) : 0u;
+        s_right = ghosts_right ? min(*(const volatile unsigned *)&ghosts_right->count, ctl->ghost_cap) : 0u;
+      }
+      __syncthreads();
+      first = s_local;
+      total = s_local + s_left + s_right;
+    }
+    for (unsigned t = first + (blockIdx.x * blockDim.x + threadIdx.x) / lanes; t < total; t += stride / lanes) {
       uint4 h;
       double2 pi = make_double2(0.0, 0.0);
       if (t < s_local) {
@@ -1255,6 +1378,7 @@ k_contagion(Ctl *__restrict__ ctl, uint4 *__restrict__ hot, const unsigned *__re
           }
         }
       }
+    }
     }
   }
   pdl_trigger();

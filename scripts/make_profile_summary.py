@@ -45,6 +45,10 @@ def main():
         for r in rows[2:]:
             w.writerow([r[i] for i in idx])
     launches_of = collections.Counter(r[h.index("Kernel Name")] for r in rows[2:])
+    inst_of = {}    # executed warp instructions of ONE launch, from the raw page (the source page sums over the launches)
+    if "smsp__inst_executed.sum" in h:
+        for r in rows[2:]:
+            inst_of.setdefault(r[h.index("Kernel Name")], float(r[h.index("smsp__inst_executed.sum")] or 0))
     srows = list(csv.reader(open(sass)))
     kernels, cur, hdr = collections.OrderedDict(), None, None
     for r in srows:
@@ -61,7 +65,11 @@ def main():
            "issues per 32 agents, spin-wait iterations included.\n".format(agents)]
     for name, lines in kernels.items():
         short = name.split("(")[0].replace("cabs::", "").replace("void ", "")
-        nl = max(1, sum(v for k, v in launches_of.items() if short.split("<")[0] in k))
+        base = short.split("<")[0]
+        nl = max(1, sum(v for k, v in launches_of.items() if base in k))
+        one = [v for k, v in inst_of.items() if base in k and v > 0]
+        if one:
+            nl = max(1, round(sum(I(r[ci]) for r in lines) / one[0]))
         tot = sum(I(r[ci]) for r in lines) / nl
         samples = sum(I(r[cs]) for r in lines)
         ops = collections.Counter()

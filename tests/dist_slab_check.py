@@ -26,6 +26,9 @@ def main():
     pop, tw = synthetic_population(n, side, side, seed=4, infected=0.05, immune=0.01)
     kw = dict(seed=21, population_size=n, length=side, height=side, total_wealth=tw, contagion_distance=1.0,
               contagion_rate=0.9, device=local)
+    if os.environ.get("SLAB_CRIT"):   # a critical limit that is crossed during the run: abs.py:214-217 kills the severe
+        kw["critical_limit"] = float(os.environ["SLAB_CRIT"])   # cases, on every rank from the SAME global statistics
+        steps = 30
     transport = os.environ.get("SLAB_TRANSPORT", "collective")
     sim = SlabSimulation(distributed=True, slab_devices=[local], transport=transport, **kw)
     mine = owner_of(pop["x"], side, world) == rank

@@ -85,7 +85,7 @@ def test_migrant_overflow_is_reported(native_lib):
         sim.get_statistics('all')
 
 
-@pytest.mark.parametrize("transport", ["collective", "p2p"])
+@pytest.mark.parametrize("transport", ["collective", "p2p", "p2p-critical", "p2p-fused", "p2p-fused-critical"])
 def test_two_process_nccl_slabs_match_single_device(native_lib, transport):
     """One slab per process (needs >= 2 GPUs; skipped on a one-GPU box): buffers exchanged by NCCL send/recv +
     all_gather ("collective") or written straight into the neighbour's memory over NVLink ("p2p")."""
@@ -98,7 +98,13 @@ def test_two_process_nccl_slabs_match_single_device(native_lib, transport):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dist_slab_check.py")]
-    env = dict(os.environ, SLAB_TRANSPORT=transport)
+    env = dict(os.environ)
+    if "critical" in transport:         # the critical-limit flag flips mid-run: the emigrants updated in the exchange
+        env["SLAB_CRIT"] = "0.005"      # kernels (or inside pass A) must see it exactly as the residents in pass B do
+    if "fused" in transport:            # emigrants packed inside pass A, one contact launch (opt-in: measured slower)
+        env["CABS_SLAB_FUSED"] = "1"
+    transport = transport.split("-")[0]
+    env["SLAB_TRANSPORT"] = transport
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=600,
                          env=env)
     assert res.returncode == 0 and "DIST_SLAB_CHECK {} OK".format(transport) in res.stdout, res.stdout[-3000:]
