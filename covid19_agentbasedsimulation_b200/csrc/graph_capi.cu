@@ -44,10 +44,12 @@ struct cabs_graph {
   int *bx = nullptr, *by = nullptr, *bstratum = nullptr, *bstocks = nullptr, *bsales = nullptr, *bnum = nullptr;
   double *bprice = nullptr;
   long long *bwealth = nullptr, *bfixed = nullptr, *bincomes = nullptr;
-  unsigned *cell_count = nullptr, *contagious = nullptr;
-  int4 *cell_items = nullptr;
+  unsigned *cell_count = nullptr;
+  unsigned long long *cell_keys = nullptr;
+  int4 *cell_items = nullptr, *src_list = nullptr;
   double *history = nullptr, *initial_rows = nullptr;
   unsigned cell_cap = 0;
+  size_t pstride = 0;            // persons per simulation in the device arrays: max_persons rounded up to 4 (16-byte loads)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   uint64_t launches = 0;
@@ -84,7 +86,7 @@ extern "C" void cabs_graph_destroy(cabs_graph *g) {
   void *ptrs[] = {g->sims, g->px, g->py, g->house, g->employer, g->hire_seq, g->attr, g->pwealth, g->events, g->hrec,
                   g->hstratum, g->hsize, g->hfixed, g->bx, g->by, g->bstratum,
                   g->bstocks, g->bsales, g->bnum, g->bprice, g->bwealth, g->bfixed, g->bincomes, g->cell_count,
-                  g->cell_items, g->contagious, g->history, g->initial_rows, g->queue};
+                  g->cell_items, g->src_list, g->cell_keys, g->history, g->initial_rows, g->queue};
   for (void *p : ptrs) cudaFree(p);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
@@ -113,14 +115,14 @@ static int graph_create_impl(cabs_graph *g, const cabs_graph_config *cfg) {
   GCK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
   GCK(cudaEventCreate(&g->ev0));
   GCK(cudaEventCreate(&g->ev1));
-  const size_t S = cfg->n_sims, P = S * cfg->max_persons, H = S * (cfg->max_houses ? cfg->max_houses : 1),
+  g->pstride = ((size_t)cfg->max_persons + 3) & ~(size_t)3;
+  const size_t S = cfg->n_sims, P = S * g->pstride, H = S * (cfg->max_houses ? cfg->max_houses : 1),
                B = S * cfg->max_business;
-  unsigned cc = cfg->cell_capacity;
-  if (cc == 0) {
-    cc = cfg->max_persons / 2;
-    if (cc < 1024) cc = 1024;
-    if (cc > (1u << 20)) cc = 1u << 20;
-  }
+  // slots of the contact table (graph_kernels.cuh): a power of two >= 2 x max_persons, so that the cells holding a
+  // source (at most one per person) never load it beyond one half; cfg->cell_capacity can only raise it
+  unsigned cc = 1024;
+  while (cc < 2u * cfg->max_persons && cc < (1u << 30)) cc <<= 1;
+  while (cc < cfg->cell_capacity && cc < (1u << 30)) cc <<= 1;
   g->cell_cap = cc;
   GCK(alloc(&g->sims, S));
   GCK(alloc(&g->px, P)); GCK(alloc(&g->py, P)); GCK(alloc(&g->house, P)); GCK(alloc(&g->employer, P));
@@ -130,7 +132,7 @@ static int graph_create_impl(cabs_graph *g, const cabs_graph_config *cfg) {
   GCK(alloc(&g->bx, B)); GCK(alloc(&g->by, B)); GCK(alloc(&g->bstratum, B)); GCK(alloc(&g->bstocks, B));
   GCK(alloc(&g->bsales, B)); GCK(alloc(&g->bnum, B)); GCK(alloc(&g->bprice, B)); GCK(alloc(&g->bwealth, B));
   GCK(alloc(&g->bfixed, B)); GCK(alloc(&g->bincomes, B));
-  GCK(alloc(&g->cell_count, S * ((size_t)cc + 2))); GCK(alloc(&g->cell_items, P)); GCK(alloc(&g->contagious, P));
+  GCK(alloc(&g->cell_count, S * ((size_t)cc + 2))); GCK(alloc(&g->cell_keys, S * (size_t)cc)); GCK(alloc(&g->cell_items, P)); GCK(alloc(&g->src_list, P));
   GCK(alloc(&g->history, S * (size_t)g->cfg.history_capacity * kStats));
   GCK(alloc(&g->initial_rows, S * kStats));
   g->host_sims.assign(S, Sim());
@@ -206,7 +208,7 @@ extern "C" int cabs_graph_upload(cabs_graph *g, uint32_t sim, const cabs_graph_w
     return gfail(g, CABS_ERR_INVALID, "cabs_graph_upload: null business column");
   GCK(cudaSetDevice(g->device));
   const double scale = ldexp(1.0, p->money_bits);
-  const size_t op = (size_t)sim * g->cfg.max_persons, oh = (size_t)sim * (g->cfg.max_houses ? g->cfg.max_houses : 1),
+  const size_t op = (size_t)sim * g->pstride, oh = (size_t)sim * (g->cfg.max_houses ? g->cfg.max_houses : 1),
                ob = (size_t)sim * g->cfg.max_business;
   std::vector<std::vector<long long>> keep;  // staging that must outlive the async copies
   std::vector<uint32_t> attr(n);
@@ -280,7 +282,8 @@ extern "C" int cabs_graph_upload(cabs_graph *g, uint32_t sim, const cabs_graph_w
   s.iteration = w->iteration;
   s.next_hire_seq = max_seq + 1;
   s.cell_count = g->cell_count + (size_t)sim * ((size_t)g->cell_cap + 2);
-  s.cell_items = g->cell_items + op; s.contagious = g->contagious + op;
+  s.cell_keys = g->cell_keys + (size_t)sim * (size_t)g->cell_cap;
+  s.cell_items = g->cell_items + op; s.src_list = g->src_list + op;
   s.cell_cap = (int)g->cell_cap;
   s.history = g->history + (size_t)sim * g->cfg.history_capacity * kStats;
   s.hist_cap = (int)g->cfg.history_capacity;
@@ -543,3 +546,13 @@ extern "C" int cabs_graph_download(cabs_graph *g, uint32_t sim, cabs_graph_world
   w->iteration = cur.iteration;
   return CABS_OK;
 }
+
+#ifdef CABS_GRAPH_TIMERS
+// timing-only build: read and reset the per-phase clocks (graph_kernels.cuh); not part of include/covidabs.h
+extern "C" int cabs_graph_phase_clocks(unsigned long long *out32) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(out32, cabs::graph::g_graph_phase_clk, 32 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  unsigned long long zero[32] = {};
+  return cudaMemcpyToSymbol(cabs::graph::g_graph_phase_clk, zero, sizeof zero) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -13,9 +13,10 @@
 //   2 stocks      Business.supply / checkin stock arithmetic (network/agents.py:82-93,101-102) resolved in the
 //                 reference's person order with a block-wide scan of the max-plus maps s -> max(s + a, m)
 //   3 accounts    Business/House/Government daily update and monthly accounting (network/agents.py:108-168,227-245)
-//   4 contacts    cell list over the block's persons, contact() pushed from the contagious persons
-//                 (graph_abs.py:256-300)
-//   5 statistics  GraphSimulation.get_statistics (graph_abs.py:302-324) -> one row of the history
+//   4 contacts    the contagious persons (listed by phase 1) are grouped by hashed cell (graph_abs.py:256-300)
+//   5 statistics  every Susceptible person PULLS contact() from the contagious persons within reach and stops at the
+//                 first success (graph_abs.py:278-300: the outcome is an OR over pair-keyed draws, so the early exit is
+//                 exact); GraphSimulation.get_statistics (graph_abs.py:302-324) -> one row of the history
 //
 // Money that several threads add to is 64-bit fixed point (`money_bits` fractional bits, every flow rounded
 // to nearest-even once), so the sums do not depend on the order of the additions; the CPU restatement the tests check against
@@ -32,6 +33,8 @@ namespace graph {
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxBusiness = 16;
+constexpr int kBGrid = 32;
+constexpr int kSrcBits = 32768;
 constexpr int kStats = 14;
 
 enum : uint32_t { S_ = 0, I_ = 1, R_ = 2, D_ = 3 };
@@ -94,10 +97,11 @@ struct Sim {
   int iteration;          // graph_abs.py:25 starts at -1
   int next_hire_seq;
   double prev_infected, prev_hosp_severe;   // memo of the previous executed hour (statistics fractions)
-  // contact cell list scratch
-  unsigned *cell_count;   // cell_cap + 1
-  int4 *cell_items;       // n: {x, y, person, -} of the Susceptible persons, grouped by cell
-  unsigned *contagious;   // n
+  // contact scratch: the contagious persons of the hour as {x, y, person, infected_time}
+  unsigned long long *cell_keys;   // cell_cap: open-addressing table of the cells that hold a source (key = cell)
+  unsigned *cell_count;   // cell_cap + 2: sources per slot of that table, then the end of the slot's run in cell_items
+  int4 *cell_items;       // n: the sources grouped by cell
+  int4 *src_list;         // n: the sources in the order phase 1 met them
   int cell_cap;
   // output
   double *history;        // hist_cap rows of kStats doubles, row = iteration % hist_cap
@@ -114,6 +118,41 @@ __device__ __forceinline__ int trunc_add(int base, float z, double sigma) {
 __device__ __forceinline__ uint32_t mulhi_pick(uint32_t w, uint32_t n) { return __umulhi(w, n); }
 __device__ __forceinline__ void atom_add(long long *p, long long v) {
   atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
+}
+
+// k-th component of a 16-byte vector held in registers (k is a loop counter, not a constant: selects, not an array)
+template <typename V>
+__device__ __forceinline__ auto vget(const V &v, int k) -> decltype(v.x) {
+  return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w;
+}
+template <typename V, typename T>
+__device__ __forceinline__ void vset(V &v, int k, T t) {
+  if (k == 0) v.x = t; else if (k == 1) v.y = t; else if (k == 2) v.z = t; else v.w = t;
+}
+// four consecutive elements from `p + i0` (16-byte aligned): one 16-byte load for a whole group, guarded scalar loads
+// for the last, partial one
+template <typename V, typename T>
+__device__ __forceinline__ V load4(const T *p, int i0, int n, T fill) {
+  V v;
+  if (i0 + 3 < n) {
+    v = *reinterpret_cast<const V *>(p + i0);
+  } else {
+    v.x = p[i0];
+    v.y = i0 + 1 < n ? p[i0 + 1] : fill;
+    v.z = i0 + 2 < n ? p[i0 + 2] : fill;
+    v.w = fill;
+  }
+  return v;
+}
+template <typename V, typename T>
+__device__ __forceinline__ void store4(T *p, int i0, int n, const V &v) {
+  if (i0 + 3 < n) {
+    *reinterpret_cast<V *>(p + i0) = v;
+  } else {
+    p[i0] = v.x;
+    if (i0 + 1 < n) p[i0 + 1] = v.y;
+    if (i0 + 2 < n) p[i0 + 2] = v.z;
+  }
 }
 
 // block-wide helpers ---------------------------------------------------------------------------------
@@ -138,8 +177,18 @@ struct Shared {
   long long acc[8];
   int wa[kWarps][kMaxBusiness], wm[kWarps][kMaxBusiness];   // per-warp max-plus totals
   int ws[kWarps][kMaxBusiness];                              // stock before each warp of the current chunk
-  unsigned present;          // businesses with an event in the current chunk
-  int bb[4];
+  unsigned present_req[3];   // businesses with a purchase request in the current chunk (the order-dependent ones)
+  // which businesses can be within business_distance of a position: kBGrid x kBGrid cells over the bounding box of the
+  // businesses (+- reach), one bit per business.  A person outside the box, or in a cell with no bit, has none in reach.
+  unsigned bgrid[kBGrid][kBGrid];
+  int bg_x0, bg_y0, bg_shift;
+  // check-ins at work per (business, stratum): the amount a check-in takes from the business depends on the stratum only
+  // (network/agents.py:101-103), so the hour's check-ins are COUNTED with native 32-bit shared atomics and charged once
+  // (a 64-bit shared atomicAdd is a compare-and-swap loop, and 7 000 colleagues hit the same word every working hour)
+  unsigned ci_cnt[kMaxBusiness][5];
+  // one bit per hashed cell that holds a source of this hour's contacts: most Susceptible persons learn from these
+  // bits (shared memory) that nobody is near and never touch the bucket table
+  unsigned sbits[kSrcBits / 32];
   unsigned n_contagious;
   unsigned cnt[8];
   int sel;                   // result slot of block-wide selections
@@ -148,10 +197,117 @@ struct Shared {
 
 constexpr int kNegInf = -(1 << 29);
 
+// Timing-only build (-DCABS_GRAPH_TIMERS): clocks of thread 0 between the phases of an executed hour, summed over all
+// blocks into g_graph_phase_clk[hour class][phase] (class 0 = hour 0, 1 = working hours 8..16, 2 = evening 17..23).
+#ifdef CABS_GRAPH_TIMERS
+__device__ unsigned long long g_graph_phase_clk[4][8];
+#define GT_BEGIN() long long gt_prev = clock64(); const int gt_cls = hour == 0 ? 0 : (hour < 17 ? 1 : 2)
+#define GT_MARK(k)                                                                   \
+  do {                                                                               \
+    if (tid == 0) {                                                                  \
+      const long long gt_now = clock64();                                            \
+      atomicAdd(&g_graph_phase_clk[gt_cls][k], (unsigned long long)(gt_now - gt_prev)); \
+      gt_prev = gt_now;                                                              \
+    }                                                                                \
+  } while (0)
+#define GT_PULL_PARAM , unsigned *gt_cnt
+#define GT_PULL_ARG , gt_cnt
+#define GT_COUNT(k) (++gt_cnt[k])
+#else
+#define GT_BEGIN() do { } while (0)
+#define GT_MARK(k) do { } while (0)
+#define GT_PULL_PARAM
+#define GT_PULL_ARG
+#define GT_COUNT(k) ((void)0)
+#endif
+
 // compose max-plus maps: apply (a1, m1) first, then (a2, m2):  s -> max(max(s + a1, m1) + a2, m2)
 __device__ __forceinline__ void compose(int a1, int m1, int a2, int m2, int &a, int &m) {
   a = a1 + a2;
   m = max(m1 > kNegInf / 2 ? m1 + a2 : kNegInf, m2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Contacts (graph_abs.py:256-300).  The reference walks the pairs (i, j) within contagion_distance and calls contact()
+// for a Susceptible / contagious pair; a Susceptible person ends the hour Infected if ANY of its pairs succeeds, and the
+// draws are keyed by the pair, so neither the order of the pairs nor skipping the pairs of a person that is already
+// infected changes anything.  The sources are grouped by cell of a grid whose edge is a power of two >= reach; the cells
+// that hold a source live in an open-addressing hash table (key = the cell, linear probing, 2^k slots with k chosen
+// every hour for a load factor <= 1/2: no bounding box, nothing to clamp).  Every Susceptible person then looks up the
+// <= 9 cells around it and stops at the first contact that infects.  Persons pile up on single lattice points
+// (thousands of colleagues at the four points of a workplace, the hospitalised at the hospital): pushed from the
+// sources that is sources x targets pair draws per pile, pulled with the early exit it is about one draw per target;
+// and because a slot is exactly one cell, nobody ever walks a pile it is not next to (with plain hashed buckets the
+// few persons whose lookups collided with the hospital's bucket walked 13 000 records each while their block waited).
+constexpr unsigned long long kEmptyCell = 0x8000000080000000ull;
+__device__ __forceinline__ unsigned long long cell_key(int cx, int cy) {
+  return ((unsigned long long)(unsigned)cx << 32) | (unsigned long long)(unsigned)cy;
+}
+__device__ __forceinline__ unsigned cell_hash(int cx, int cy) {
+  unsigned h = (unsigned)cx * 0x9E3779B1u ^ (unsigned)cy * 0x85EBCA77u;
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  return h ^ (h >> 13);
+}
+// bit of a cell in the shared "a source is here" map: the cell coordinates modulo 256 x 128 (no hash to compute for
+// the nine cells a Susceptible person tests every hour; aliases only cost a lookup in the table)
+__device__ __forceinline__ unsigned cell_bit(int cx, int cy) { return ((unsigned)(cy & 127) << 8) | (unsigned)(cx & 255); }
+__device__ __forceinline__ bool is_source(const Sim &S, uint32_t a) {
+  // Infected persons whose infected_time can fall inside the window for some (low, up) of graph_abs.py:289-290
+  return a_status(a) == I_ && (int)a_time(a) >= S.incubation - 1 && (int)a_time(a) <= S.contagion_time;
+}
+// Structured control flow on purpose (flags in the loop conditions, no early return): with a return from inside the
+// nested loops the compiler reconverges a warp only at the exit of the CALLER's person loop, and the lanes that had a
+// lookup to do ran the rest of the hour one or two at a time (measured: 1.9 active lanes per instruction, 17 x the
+// instructions of the converged loop, profiles/r2_graph_divergence.md).
+__device__ __forceinline__ bool pull_contact(const Sim &S, const unsigned *sbits, const unsigned long long *keys,
+                                             const unsigned *table, const int4 *items, unsigned mask, int eshift,
+                                             unsigned qmask, int i, int x, int y, uint32_t it GT_PULL_PARAM) {
+  const int cx = x >> eshift, cy = y >> eshift;
+  const long long T = S.T;
+  bool infected = false;
+  // qmask: the cells of the 3 x 3 neighbourhood that can hold somebody within reach.  With cells of edge 1 (reach 1,
+  // every shipped scenario) that is a property of the offset alone -- the diagonals are out -- and was worked out once
+  // per hour; with larger cells it depends on where in its cell the person stands and is tested below.
+#pragma unroll 1
+  for (unsigned qm = qmask; qm && !infected; qm &= qm - 1u) {
+    const int q = __ffs(qm) - 1, oy = (q * 11) >> 5, ccx = cx + (q - 3 * oy) - 1, ccy = cy + oy - 1;
+    const unsigned hb = cell_bit(ccx, ccy);
+    bool look = (sbits[hb >> 5] >> (hb & 31u)) & 1u;
+    if (look && eshift > 0) {     // nearest lattice point of the cell: a cell out of reach as a whole is not looked up
+      const int edge1 = (1 << eshift) - 1, lox = ccx << eshift, loy = ccy << eshift;
+      const long long ddx = x < lox ? lox - x : (x > lox + edge1 ? x - lox - edge1 : 0);
+      const long long ddy = y < loy ? loy - y : (y > loy + edge1 ? y - loy - edge1 : 0);
+      look = ddx * ddx + ddy * ddy <= T;
+    }
+    if (look) {
+      GT_COUNT(1);
+      const unsigned long long key = cell_key(ccx, ccy);
+      unsigned b = cell_hash(ccx, ccy) & mask;
+      unsigned long long kk = __ldcg(keys + b);
+      while (kk != key && kk != kEmptyCell) {      // linear probing: the cell's slot, or an empty one (no source there)
+        b = (b + 1u) & mask;
+        kk = __ldcg(keys + b);
+      }
+      if (kk == key) {
+        const unsigned je = __ldcg(table + b);     // table[b]: END of the run of slot b
+        unsigned k = b ? __ldcg(table + b - 1) : 0u;
+        for (; k < je && !infected; ++k) {
+          const int4 c = items[k];
+          GT_COUNT(2);
+          const long long dx = c.x - x, dy = c.y - y;
+          if (dx * dx + dy * dy <= T) {
+            GT_COUNT(3);
+            const int j = c.z, tj = c.w;
+            const uint4 w = philox4x32_10((uint32_t)min(i, j), it, ST_CONTACT, (uint32_t)max(i, j), S.k0, S.k1);
+            const int low = -1 + (int)(w.x >> 31), up = -1 + (int)(w.y >> 31);           // np.random.randint(-1, 1)
+            infected = tj >= S.incubation + low && tj <= S.contagion_time + up && (long long)w.z <= S.thr_rate;
+          }                                                                              // graph_abs.py:292-297
+        }
+      }
+    }
+  }
+  return infected;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -288,6 +444,30 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
   }
   __syncthreads();
 
+  int bus_reach = S.T_bus > 0 ? (int)__dsqrt_rn((double)S.T_bus) + 1 : 0;         // >= floor(sqrt(T_bus))
+  if (S.T_bus < 0) bus_reach = -1;                                                  // nothing is in reach
+  for (int c = tid; c < kBGrid * kBGrid; c += kThreads) (&sh.bgrid[0][0])[c] = 0u;
+  if (tid == 0) {
+    int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
+    for (int b = 0; b < nb; ++b) {
+      x0 = min(x0, sh.bx[b]); x1 = max(x1, sh.bx[b]); y0 = min(y0, sh.by[b]); y1 = max(y1, sh.by[b]);
+    }
+    const int r = max(bus_reach, 0);
+    x0 -= r; y0 -= r; x1 += r; y1 += r;
+    int shift = 0;
+    while (nb > 0 && ((((long long)x1 - x0) >> shift) >= kBGrid || (((long long)y1 - y0) >> shift) >= kBGrid)) ++shift;
+    sh.bg_x0 = x0; sh.bg_y0 = y0; sh.bg_shift = shift;
+  }
+  __syncthreads();
+  if (tid < nb && bus_reach >= 0) {
+    const int sft = sh.bg_shift;
+    const int cx0 = (sh.bx[tid] - bus_reach - sh.bg_x0) >> sft, cx1 = (sh.bx[tid] + bus_reach - sh.bg_x0) >> sft;
+    const int cy0 = (sh.by[tid] - bus_reach - sh.bg_y0) >> sft, cy1 = (sh.by[tid] + bus_reach - sh.bg_y0) >> sft;
+    for (int cy = cy0; cy <= cy1; ++cy)
+      for (int cx = cx0; cx <= cx1; ++cx) atomicOr(&sh.bgrid[cy][cx], 1u << tid);
+  }
+  __syncthreads();
+
   int it = S.iteration;
   double prev_infected = S.prev_infected, prev_hs = S.prev_hosp_severe;
 
@@ -305,26 +485,42 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
       __syncthreads();
       continue;
     }
+    GT_BEGIN();
     const bool lock_all = S.mode == MODE_LOCKDOWN || (S.mode == MODE_CONDITIONAL && prev_infected > 0.05);
     const bool crit_active = prev_hs >= S.critical_limit;                        // network/agents.py:389-390
     const bool monthly = it > 1 && new_month;
-    int bus_reach = S.T_bus > 0 ? (int)__dsqrt_rn((double)S.T_bus) + 1 : 0;       // >= floor(sqrt(T_bus))
-    if (S.T_bus < 0) bus_reach = -1;                                                // nothing is in reach
-    if (tid == 0) {
-      sh.bb[0] = sh.bb[2] = INT_MAX; sh.bb[1] = sh.bb[3] = INT_MIN;
-      sh.n_contagious = 0;
-    }
+    const bool contacts_on = S.T >= 0;
+    if (tid == 0) sh.n_contagious = 0;
+    if (tid < kMaxBusiness * 5) (&sh.ci_cnt[0][0])[tid] = 0u;
     __syncthreads();
 
     // ================= phase 1: persons (graph_abs.py:210-233) =================
-    int bxmin = INT_MAX, bxmax = INT_MIN, bymin = INT_MAX, bymax = INT_MIN;
-    for (int i = tid; i < n; i += kThreads) {
-      uint32_t a = S.attr[i];
-      int x = S.px[i], y = S.py[i];
+    // A thread takes FOUR consecutive persons at a time: their five columns arrive as five 16-byte loads (four times the
+    // bytes in flight per thread of a person-per-thread loop -- the hour is bound by memory latency, not by bandwidth),
+    // the three columns that change and the event words leave the same way.
+    // Every thread makes the same number of trips and the warp is brought back together after every person (see
+    // pull_contact: lanes that leave a loop early otherwise stay apart until the next block-wide barrier).
+    for (int base = 0; base < n; base += kThreads * 4) {
+      const int i0 = base + tid * 4;
+      uint4 A4 = make_uint4(D_, D_, D_, D_);
+      int4 X4 = make_int4(0, 0, 0, 0), Y4 = X4, H4 = make_int4(-1, -1, -1, -1), E4 = H4;
+      if (i0 < n) {
+        A4 = load4<uint4, uint32_t>(S.attr, i0, n, (uint32_t)D_);
+        X4 = load4<int4, int>(S.px, i0, n, 0); Y4 = load4<int4, int>(S.py, i0, n, 0);
+        H4 = load4<int4, int>(S.house, i0, n, -1); E4 = load4<int4, int>(S.employer, i0, n, -1);
+      }
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k;
+      // the person of this trip sits in component .x; the vectors are rotated by one at the end of the trip (after four
+      // trips they are back in place, updated): moves instead of selects on a loop counter
+      uint32_t a = A4.x;
+      int x = X4.x, y = Y4.x;
+      const int h = H4.x, emp0 = E4.x;
+      if (i < n) {
       unsigned long long ev = 0ull;
       if (a_status(a) != D_) {
-        const int h = S.house[i];
-        int checked_in = -1;
+        int checked_in = -1, emp = emp0;   // emp: -1 once the critical-limit rule below has fired the person
         // ---- on_person_move (run_batch.py:16-50) or the default routine (graph_abs.py:212-220)
         if (lock_all || (S.mode == MODE_VERTICAL && !(a & kActive))) {
           if (h >= 0) house_checkin(S, h, a);
@@ -334,14 +530,14 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
           move_freely(S, i, it, ST_MOVE, a, x, y);
         } else if (work_day && work) {                                           // move_to_work, 293-310
           if (a_sev(a) == SEV_A_ && (a & kActive)) {
-            const int b = S.employer[i];
+            const int b = emp0;
             if (b >= 0) {
               const uint4 w = philox4x32_10(i, it, ST_MOVE, 0u, S.k0, S.k1);
               float z0, z1;
               normal_pair(w.x, w.y, z0, z1);
               x = trunc_add(sh.bx[b], z0, 0.25);
               y = trunc_add(sh.by[b], z1, 0.25);
-              atom_add(&sh.bwealth[b], -fx(__ddiv_rn(person_expenses(S, a), 720.0), scale));   // checkin, 101-103
+              atomicAdd(&sh.ci_cnt[b][min(a_stratum(a), 4u)], 1u);                        // checkin, 101-103
               checked_in = b;
             } else {
               move_freely(S, i, it, ST_MOVE, a, x, y);
@@ -377,9 +573,12 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
                 } else {
                   atom_add(&sh.gov_wealth, -fx(person_expenses(S, a), scale));
                 }
-                const int b = S.employer[i];
-                if (b >= 0) fire(S, sh, b, i, a);
-                else atom_add(&sh.gov_wealth, -fx(person_expenses(S, a), scale));
+                if (emp >= 0) {
+                  fire(S, sh, emp, i, a);
+                  emp = -1;
+                } else {
+                  atom_add(&sh.gov_wealth, -fx(person_expenses(S, a), scale));
+                }
               }
             }
           }
@@ -401,16 +600,15 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
         // ---- purchase requests at every business in reach other than the employer (graph_abs.py:230-233)
         if (checked_in >= 0) ev |= 15ull << (4 * checked_in);
         if (a_sev(a) == SEV_A_) {
-          const int emp = S.employer[i];
           uint4 q4 = make_uint4(0, 0, 0, 0);
           int have = -1;
-          for (int b = 0; b < nb; ++b) {
-            // cheap box test first: almost every (person, business) pair is far apart
-            const int ddx = sh.bx[b] - x, ddy = sh.by[b] - y;
-            if (b == emp || (unsigned)(ddx + bus_reach) > 2u * (unsigned)bus_reach ||
-                (unsigned)(ddy + bus_reach) > 2u * (unsigned)bus_reach)
-              continue;
-            const long long dx = ddx, dy = ddy;
+          // the businesses whose box of reach covers this cell (almost always none), in ascending order
+          const int gx = (x - sh.bg_x0) >> sh.bg_shift, gy = (y - sh.bg_y0) >> sh.bg_shift;
+          unsigned near = ((unsigned)gx < (unsigned)kBGrid && (unsigned)gy < (unsigned)kBGrid) ? sh.bgrid[gy][gx] : 0u;
+          for (; near; near &= near - 1u) {
+            const int b = __ffs(near) - 1;
+            if (b == emp) continue;
+            const long long dx = sh.bx[b] - x, dy = sh.by[b] - y;
             if (dx * dx + dy * dy > (long long)S.T_bus) continue;
             if (have != (b >> 2)) {
               q4 = philox4x32_10(i, it, ST_SHOP + (b >> 2), 0u, S.k0, S.k1);
@@ -420,88 +618,122 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
             ev |= (unsigned long long)(1u + mulhi_pick(w, 9u)) << (4 * b);            // np.random.randint(1, 10)
           }
         }
-        S.attr[i] = a;
-        S.px[i] = x;
-        S.py[i] = y;
+        // ---- the sources of this hour's contacts (graph_abs.py:278-290): position and infected_time are final here
+        if (contacts_on && is_source(S, a)) {
+          const unsigned m = __activemask();          // the lanes that are here together share one reservation
+          const int leader = __ffs(m) - 1;
+          unsigned at = 0;
+          if (lane == leader) at = atomicAdd(&sh.n_contagious, (unsigned)__popc(m));
+          at = __shfl_sync(m, at, leader) + (unsigned)__popc(m & ((1u << lane) - 1u));
+          S.src_list[at] = make_int4(x, y, i, (int)a_time(a));
+        }
       }
       S.events[i] = ev;
-      bxmin = min(bxmin, x); bxmax = max(bxmax, x); bymin = min(bymin, y); bymax = max(bymax, y);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      bxmin = min(bxmin, __shfl_xor_sync(0xffffffffu, bxmin, o)); bxmax = max(bxmax, __shfl_xor_sync(0xffffffffu, bxmax, o));
-      bymin = min(bymin, __shfl_xor_sync(0xffffffffu, bymin, o)); bymax = max(bymax, __shfl_xor_sync(0xffffffffu, bymax, o));
-    }
-    if (lane == 0 && bxmin <= bxmax) {
-      atomicMin(&sh.bb[0], bxmin); atomicMax(&sh.bb[1], bxmax); atomicMin(&sh.bb[2], bymin); atomicMax(&sh.bb[3], bymax);
+      }
+      A4 = make_uint4(A4.y, A4.z, A4.w, a);
+      X4 = make_int4(X4.y, X4.z, X4.w, x);
+      Y4 = make_int4(Y4.y, Y4.z, Y4.w, y);
+      H4 = make_int4(H4.y, H4.z, H4.w, h);
+      E4 = make_int4(E4.y, E4.z, E4.w, emp0);
+      __syncwarp();
+      }
+      if (i0 < n) {
+        store4<uint4, uint32_t>(S.attr, i0, n, A4);
+        store4<int4, int>(S.px, i0, n, X4);
+        store4<int4, int>(S.py, i0, n, Y4);
+      }
     }
     __syncthreads();
+    if (tid < nb) {   // Business.checkin (network/agents.py:101-103): expenses / 720 of every employee that came in
+      long long total = 0;
+      for (int k = 0; k < 5; ++k)
+        total += (long long)sh.ci_cnt[tid][k] * fx(__ddiv_rn(__dmul_rn(S.bi[k], S.min_expense), 720.0), scale);
+      sh.bwealth[tid] -= total;
+    }
+    __syncthreads();
+    GT_MARK(1);
 
     // ================= phase 2: stocks in person order (network/agents.py:82-93,101-102) =================
-    for (int base = 0; base < n; base += kThreads) {
-      const int i = base + tid;
-      const unsigned long long ev = i < n ? S.events[i] : 0ull;
-      if (tid == 0) sh.present = 0;
+    // Only a purchase request reads the stock (min(quantity, stock)); check-ins just add one.  Per chunk of kThreads
+    // persons the businesses that got a request are scanned in person order (their check-ins included); for every
+    // other business the check-ins of the chunk are simply counted.  `present_req` rotates through three slots so
+    // that one barrier per chunk is enough (slot k+1 is cleared while chunk k-1 may still be read and chunk k is set).
+    {
+      if (tid < 3) sh.present_req[tid] = 0u;
       __syncthreads();
-      unsigned mine = 0;
-      for (int b = 0; b < nb; ++b)
-        if ((ev >> (4 * b)) & 15ull) mine |= 1u << b;
-      mine = __reduce_or_sync(0xffffffffu, mine);
-      if (lane == 0 && mine) atomicOr(&sh.present, mine);
-      __syncthreads();
-      const unsigned present = sh.present;
-      __syncthreads();   // everyone has read it before the next chunk resets it
-      if (!present) continue;
-      int ea[kMaxBusiness], em[kMaxBusiness];  // inclusive prefix inside the warp, per business
-      for (int b = 0; b < nb; ++b) {
-        if (!((present >> b) & 1u)) continue;
-        const unsigned nib = (unsigned)((ev >> (4 * b)) & 15ull);
-        int a = nib == 15u ? 1 : -(int)nib;
-        int m = (nib >= 1u && nib <= 9u) ? 0 : kNegInf;
+      unsigned long long ev_next = tid < n ? S.events[tid] : 0ull;
+      int slot = 0;
+      for (int base = 0; base < n; base += kThreads, slot = slot == 2 ? 0 : slot + 1) {
+        const int i = base + tid;
+        const unsigned long long ev = ev_next;
+        ev_next = i + kThreads < n ? S.events[i + kThreads] : 0ull;      // the next chunk is on its way during this one
+        if (tid == 0) sh.present_req[slot == 2 ? 0 : slot + 1] = 0u;
+        unsigned req = 0, ci = 0;
+        for (unsigned long long e = ev; e;) {
+          const int b = (__ffsll((long long)e) - 1) >> 2;
+          const unsigned nib = (unsigned)(e >> (4 * b)) & 15u;
+          if (nib == 15u) ci |= 1u << b; else req |= 1u << b;
+          e &= ~(15ull << (4 * b));
+        }
+        const unsigned wreq = __reduce_or_sync(0xffffffffu, req);
+        unsigned wci = __reduce_or_sync(0xffffffffu, ci);
+        if (lane == 0 && wreq) atomicOr(&sh.present_req[slot], wreq);
+        __syncthreads();
+        const unsigned present = sh.present_req[slot];
+        for (wci &= ~present; wci; wci &= wci - 1u) {                     // check-ins nobody's request can observe
+          const int b = __ffs(wci) - 1;
+          const unsigned who = __ballot_sync(0xffffffffu, (ci >> b) & 1u);
+          if (lane == 0) atomicAdd(&sh.bstocks[b], __popc(who));
+        }
+        if (!present) continue;
+        // the requested businesses one after the other (almost always none or one): scan inside the warps, carry the
+        // stock through the warps, apply -- everything of a business stays in registers
+        for (unsigned todo = present; todo; todo &= todo - 1u) {
+          const int b = __ffs(todo) - 1;
+          const unsigned nib = (unsigned)((ev >> (4 * b)) & 15ull);
+          int ea = nib == 15u ? 1 : -(int)nib;
+          int em = (nib >= 1u && nib <= 9u) ? 0 : kNegInf;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int pa = __shfl_up_sync(0xffffffffu, a, o), pm = __shfl_up_sync(0xffffffffu, m, o);
-          if (lane >= o) compose(pa, pm, a, m, a, m);
-        }
-        ea[b] = a;
-        em[b] = m;
-        if (lane == 31) {
-          sh.wa[wid][b] = a;
-          sh.wm[wid][b] = m;
-        }
-      }
-      __syncthreads();
-      // one thread per business carries the stock through the warps of the chunk: ws[w][b] = stock before warp w
-      if (tid < nb && ((present >> tid) & 1u)) {
-        int s0 = sh.bstocks[tid];
-        for (int w = 0; w < kWarps; ++w) {
-          sh.ws[w][tid] = s0;
-          s0 = max(s0 + sh.wa[w][tid], sh.wm[w][tid]);
-        }
-        sh.bstocks[tid] = s0;
-      }
-      __syncthreads();
-      for (int b = 0; b < nb; ++b) {
-        if (!((present >> b) & 1u)) continue;
-        const unsigned nib = (unsigned)((ev >> (4 * b)) & 15ull);
-        const int s0 = sh.ws[wid][b];
-        const int after = max(s0 + ea[b], em[b]);
-        // exclusive prefix = inclusive prefix of the lane before
-        const int pa = __shfl_up_sync(0xffffffffu, ea[b], 1), pm = __shfl_up_sync(0xffffffffu, em[b], 1);
-        if (nib >= 1u && nib <= 9u) {
-          const int before = lane == 0 ? s0 : max(s0 + pa, pm);
-          const int taken = before - after;                                           // min(qty, stocks)
-          const uint32_t a = S.attr[i];
-          const long long value = fx(__dmul_rn(__dmul_rn(sh.bprice[b], (double)a_stratum(a)), (double)taken), scale);
-          person_demand(S, i, S.house[i], value);
-          atom_add(&sh.bwealth[b], value);
-          atom_add(&sh.bincomes[b], value);
-          atomicAdd(&sh.bsales[b], taken);
+          for (int o = 1; o < 32; o <<= 1) {
+            const int pa = __shfl_up_sync(0xffffffffu, ea, o), pm = __shfl_up_sync(0xffffffffu, em, o);
+            if (lane >= o) compose(pa, pm, ea, em, ea, em);
+          }
+          if (lane == 31) {
+            sh.wa[wid][0] = ea;
+            sh.wm[wid][0] = em;
+          }
+          __syncthreads();
+          // one thread carries the stock through the warps of the chunk: ws[w] = stock before warp w
+          if (tid == 0) {
+            int s0 = sh.bstocks[b];
+            for (int w = 0; w < kWarps; ++w) {
+              sh.ws[w][0] = s0;
+              s0 = max(s0 + sh.wa[w][0], sh.wm[w][0]);
+            }
+            sh.bstocks[b] = s0;
+          }
+          __syncthreads();
+          const int s0 = sh.ws[wid][0];
+          const int after = max(s0 + ea, em);
+          // exclusive prefix = inclusive prefix of the lane before
+          const int pa = __shfl_up_sync(0xffffffffu, ea, 1), pm = __shfl_up_sync(0xffffffffu, em, 1);
+          if (nib >= 1u && nib <= 9u) {
+            const int before = lane == 0 ? s0 : max(s0 + pa, pm);
+            const int taken = before - after;                                           // min(qty, stocks)
+            const uint32_t a = S.attr[i];
+            const long long value = fx(__dmul_rn(__dmul_rn(sh.bprice[b], (double)a_stratum(a)), (double)taken), scale);
+            person_demand(S, i, S.house[i], value);
+            atom_add(&sh.bwealth[b], value);
+            atom_add(&sh.bincomes[b], value);
+            atomicAdd(&sh.bsales[b], taken);
+          }
+          __syncthreads();   // ws / wa / wm are free again
         }
       }
       __syncthreads();
     }
 
+    GT_MARK(2);
     // ================= phase 3: accounts (graph_abs.py:235-254) =================
     // ---- businesses: daily update (network/agents.py:147-153)
     if (new_day && tid < nb) {
@@ -669,122 +901,194 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
       __syncthreads();
     }
 
-    // ================= phase 4: contacts (graph_abs.py:256-300) =================
-    if (S.T >= 0) {
-      // cell grid over the bounding box, edge a power of two >= reach, grown to fit cell_cap
-      int eshift = 0;
-      while ((1 << eshift) < S.reach) ++eshift;
-      const int x0 = sh.bb[0], y0 = sh.bb[2];
-      int ncx, ncy;
-      for (;;) {
-        ncx = ((sh.bb[1] - x0) >> eshift) + 3;
-        ncy = ((sh.bb[3] - y0) >> eshift) + 3;
-        if ((long long)ncx * ncy <= (long long)S.cell_cap || eshift >= 30) break;
-        ++eshift;
+    GT_MARK(3);
+    // ================= phase 4: contacts, the sources grouped by hashed cell (graph_abs.py:256-300) =================
+    const unsigned nsrc = sh.n_contagious;
+    int eshift = 0;
+    while ((1 << eshift) < S.reach && eshift < 30) ++eshift;
+    unsigned qmask = 0x1FFu;                                  // which of the 3 x 3 cells can be within reach at all
+    if (eshift == 0) {
+      qmask = 0u;
+      for (int q = 0; q < 9; ++q) {
+        const long long ox = q % 3 - 1, oy = q / 3 - 1;
+        if (ox * ox + oy * oy <= (long long)S.T) qmask |= 1u << q;
       }
-      const int ncells = (int)min((long long)ncx * ncy, (long long)S.cell_cap);
-      if (n > 0 && sh.bb[0] <= sh.bb[1]) {
-        for (int c = tid; c <= ncells; c += kThreads) S.cell_count[c] = 0;
-        __syncthreads();
-        // the cell list holds the possible targets only (Susceptible persons); the possible sources are listed
-        for (int i = tid; i < n; i += kThreads) {
-          const uint32_t a = S.attr[i];
-          if (a_status(a) == S_) {
-            const int cx = ((S.px[i] - x0) >> eshift) + 1, cy = ((S.py[i] - y0) >> eshift) + 1;
-            atomicAdd(&S.cell_count[cy * ncx + cx], 1u);
-          } else if (a_status(a) == I_ && (int)a_time(a) >= S.incubation - 1 && (int)a_time(a) <= S.contagion_time) {
-            // Infected persons whose infected_time can fall inside the window for some (low, up)
-            S.contagious[atomicAdd(&sh.n_contagious, 1u)] = i;
+    }
+    unsigned cmask = 255u;                                    // slots: a power of two >= 2 x sources (<= cell_cap)
+    while (cmask + 1u < 2u * nsrc && 2u * (cmask + 1u) <= (unsigned)S.cell_cap) cmask = 2u * cmask + 1u;
+    if (nsrc) {
+      const int nbuckets = (int)cmask + 1;
+      for (int c = tid; c <= nbuckets; c += kThreads) S.cell_count[c] = 0;
+      for (int c = tid; c < nbuckets; c += kThreads) S.cell_keys[c] = kEmptyCell;
+      for (int c = tid; c < kSrcBits / 32; c += kThreads) sh.sbits[c] = 0u;
+      __syncthreads();
+      for (unsigned base = 0; base < nsrc; base += kThreads) {
+        const unsigned t = base + tid;
+        if (t < nsrc) {
+          const int4 r = S.src_list[t];
+          const int ccx = r.x >> eshift, ccy = r.y >> eshift;
+          const unsigned h = cell_hash(ccx, ccy), hb = cell_bit(ccx, ccy);
+          const unsigned long long key = cell_key(ccx, ccy);
+          unsigned b = h & cmask;
+          unsigned long long prev = atomicCAS(&S.cell_keys[b], kEmptyCell, key);   // claim the cell's slot or find it
+          while (prev != kEmptyCell && prev != key) {
+            b = (b + 1u) & cmask;
+            prev = atomicCAS(&S.cell_keys[b], kEmptyCell, key);
           }
+          atomicAdd(&S.cell_count[b], 1u);
+          atomicOr(&sh.sbits[hb >> 5], 1u << (hb & 31u));
         }
-        __syncthreads();
-        // exclusive scan of cell_count[0..ncells] (chunked, running carry)
-        unsigned carry = 0;
-        for (int base = 0; base <= ncells; base += kThreads) {
-          const int c = base + tid;
-          const unsigned v = c <= ncells ? S.cell_count[c] : 0u;
-          unsigned inc = v;
+        __syncwarp();
+      }
+      __syncthreads();
+      // exclusive scan of cell_count[0..nbuckets] (chunked, running carry)
+      unsigned carry = 0;
+      for (int base = 0; base <= nbuckets; base += kThreads) {
+        const int c = base + tid;
+        const unsigned v = c <= nbuckets ? __ldcg(S.cell_count + c) : 0u;
+        unsigned inc = v;
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-          }
-          if (lane == 31) sh.wa[wid][0] = (int)inc;
-          __syncthreads();
-          unsigned before = carry, total = 0;
-          for (int k = 0; k < kWarps; ++k) {
-            if (k < wid) before += (unsigned)sh.wa[k][0];
-            total += (unsigned)sh.wa[k][0];
-          }
-          if (c <= ncells) S.cell_count[c] = before + inc - v;
-          carry += total;
-          __syncthreads();
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
         }
-        // fill: cell_count[c] is advanced to the end of cell c, i.e. becomes the start of cell c + 1
-        for (int i = tid; i < n; i += kThreads) {
-          if (a_status(S.attr[i]) != S_) continue;
-          const int x = S.px[i], y = S.py[i];
-          const int cx = ((x - x0) >> eshift) + 1, cy = ((y - y0) >> eshift) + 1;
-          S.cell_items[atomicAdd(&S.cell_count[cy * ncx + cx], 1u)] = make_int4(x, y, i, 0);
-        }
+        if (lane == 31) sh.wa[wid][0] = (int)inc;
         __syncthreads();
-        // after the fill, items of cell c are [c == 0 ? 0 : cell_count[c - 1], cell_count[c]).  One warp per
-        // source, lanes over the candidates: persons pile up on single lattice points (homes, workplaces), so
-        // a source can have thousands of candidates while most have a handful.
-        const unsigned nsrc = sh.n_contagious;
-        for (unsigned t = wid; t < nsrc; t += kWarps) {
-          const int j = (int)S.contagious[t];
-          const int xj = S.px[j], yj = S.py[j], tj = (int)a_time(S.attr[j]);
-          const int clo = max(((xj - S.reach - x0) >> eshift) + 1, 0), chi = min(((xj + S.reach - x0) >> eshift) + 1, ncx - 1);
-          const int rlo = max(((yj - S.reach - y0) >> eshift) + 1, 0), rhi = min(((yj + S.reach - y0) >> eshift) + 1, ncy - 1);
-          for (int r = rlo; r <= rhi; ++r) {
-            const int c0 = r * ncx + clo, c1 = r * ncx + chi;
-            const unsigned jb = c0 == 0 ? 0u : S.cell_count[c0 - 1], je = S.cell_count[c1];
-            for (unsigned k = jb + lane; k < je; k += 32) {
-              const int4 c = S.cell_items[k];
-              const long long dx = c.x - xj, dy = c.y - yj;
-              if (dx * dx + dy * dy > (long long)S.T) continue;
-              const int s = c.z;
-              const uint4 w = philox4x32_10((uint32_t)min(s, j), it, ST_CONTACT, (uint32_t)max(s, j), S.k0, S.k1);
-              const int low = -1 + (int)(w.x >> 31), up = -1 + (int)(w.y >> 31);       // np.random.randint(-1, 1)
-              if (tj >= S.incubation + low && tj <= S.contagion_time + up && (long long)w.z <= S.thr_rate)
-                atomicOr(&S.attr[s], kNew);                                            // graph_abs.py:292-297
+        unsigned before = carry, total = 0;
+        for (int k = 0; k < kWarps; ++k) {
+          if (k < wid) before += (unsigned)sh.wa[k][0];
+          total += (unsigned)sh.wa[k][0];
+        }
+        if (c <= nbuckets) S.cell_count[c] = before + inc - v;
+        carry += total;
+        __syncthreads();
+      }
+      // fill: cell_count[b] is advanced to the end of the run of slot b, i.e. becomes the start of slot b + 1
+      for (unsigned base = 0; base < nsrc; base += kThreads) {
+        const unsigned t = base + tid;
+        if (t < nsrc) {
+          const int4 r = S.src_list[t];
+          const int ccx = r.x >> eshift, ccy = r.y >> eshift;
+          const unsigned long long key = cell_key(ccx, ccy);
+          unsigned b = cell_hash(ccx, ccy) & cmask;
+          while (__ldcg(S.cell_keys + b) != key) b = (b + 1u) & cmask;
+          S.cell_items[atomicAdd(&S.cell_count[b], 1u)] = r;
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+    }
+
+    GT_MARK(4);
+    // ================= phase 5: statistics (graph_abs.py:302-324) =================
+    {
+      // per-thread counts packed 16 bits each (a thread sees n / kThreads persons): no dynamically indexed local array
+      unsigned long long c_st = 0ull, c_sev = 0ull;
+#ifdef CABS_GRAPH_TIMERS
+      unsigned gt_cnt[5] = {0, 0, 0, 0, 0};   // pulls, bitmap hits, items visited, pairs in range (= draws), infections
+#endif
+#ifdef CABS_GRAPH_P5_SCALAR
+      uint32_t a_nx = 0;
+      int x_nx = 0, y_nx = 0;
+      if (tid < n) { a_nx = S.attr[tid]; if (nsrc) { x_nx = S.px[tid]; y_nx = S.py[tid]; } }
+      for (int base = 0; base < n; base += kThreads) {
+        const int i = base + tid;
+        uint32_t a = a_nx;
+        const int x = x_nx, y = y_nx;
+        {
+          const int inx = i + kThreads;
+          if (inx < n) { a_nx = S.attr[inx]; if (nsrc) { x_nx = S.px[inx]; y_nx = S.py[inx]; } }
+        }
+        if (i < n) {
+          if (nsrc && a_status(a) == S_ &&
+              (GT_COUNT(0), pull_contact(S, sh.sbits, S.cell_keys, S.cell_count, S.cell_items, cmask, eshift, qmask, i, x, y,
+                                         (uint32_t)it GT_PULL_ARG))) {
+            GT_COUNT(4);
+            a = (a & ~3u) | I_;
+            S.attr[i] = a;
+          }
+          c_st += 1ull << (16 * a_status(a));
+          if (a_status(a) != D_ && a_sev(a) != SEV_E_) c_sev += 1ull << (16 * (a_sev(a) - 1));
+        }
+        __syncwarp();
+      }
+#else
+      // every thread of the block makes the same number of trips (guards inside), and the warp is brought back
+      // together after every person: a lane that had a lookup to do must not run the rest of the loop on its own
+      for (int base = 0; base < n; base += kThreads * 4) {
+        const int i0 = base + tid * 4;
+        uint4 A4 = make_uint4(0u, 0u, 0u, 0u);
+        int4 X4 = make_int4(0, 0, 0, 0), Y4 = X4;
+        if (i0 < n) {
+          A4 = load4<uint4, uint32_t>(S.attr, i0, n, 0u);
+          if (nsrc) { X4 = load4<int4, int>(S.px, i0, n, 0); Y4 = load4<int4, int>(S.py, i0, n, 0); }
+        }
+        bool changed = false;
+        if (nsrc) {
+          // the Susceptible persons of the group, one after the other (the warp makes as many trips as its busiest lane)
+          unsigned todo = (a_status(A4.x) == S_ ? 1u : 0u) | (a_status(A4.y) == S_ ? 2u : 0u) |
+                          (a_status(A4.z) == S_ ? 4u : 0u) | (a_status(A4.w) == S_ ? 8u : 0u);
+          if (i0 + 3 >= n) todo &= i0 < n ? (1u << (n - i0)) - 1u : 0u;
+          while (__any_sync(0xffffffffu, todo != 0u)) {
+            if (todo) {
+              const int k = __ffs(todo) - 1;
+              todo &= todo - 1u;
+              GT_COUNT(0);
+              if (pull_contact(S, sh.sbits, S.cell_keys, S.cell_count, S.cell_items, cmask, eshift, qmask, i0 + k,
+                               vget(X4, k), vget(Y4, k), (uint32_t)it GT_PULL_ARG)) {
+                GT_COUNT(4);
+                vset(A4, k, (vget(A4, k) & ~3u) | I_);   // contact() rewrites the status only (graph_abs.py:297-298)
+                changed = true;
+              }
             }
           }
         }
-        __syncthreads();
-      }
-    }
-
-    // ================= phase 5: statistics (graph_abs.py:302-324) =================
-    {
-      unsigned c_st[4] = {0, 0, 0, 0}, c_sev[3] = {0, 0, 0};
-      for (int i = tid; i < n; i += kThreads) {
-        uint32_t a = S.attr[i];
-        if (a & kNew) {                       // contact() rewrote the status (only the status, graph_abs.py:297-298)
-          a = (a & ~(kNew | 3u)) | I_;
-          S.attr[i] = a;
+        if (i0 < n) {
+          const uint32_t a4[4] = {A4.x, A4.y, A4.z, A4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t a = a4[k];
+            if (i0 + k < n) {
+              c_st += 1ull << (16 * a_status(a));
+              if (a_status(a) != D_ && a_sev(a) != SEV_E_) c_sev += 1ull << (16 * (a_sev(a) - 1));
+            }
+          }
         }
-        c_st[a_status(a)]++;
-        if (a_status(a) != D_ && a_sev(a) != SEV_E_) c_sev[a_sev(a) - 1]++;
+        if (changed) store4<uint4, uint32_t>(S.attr, i0, n, A4);
       }
+      __syncwarp();
+#endif
+#ifdef CABS_GRAPH_TIMERS
+      for (int k = 0; k < 5; ++k) {
+        const unsigned v = __reduce_add_sync(0xffffffffu, gt_cnt[k]);
+        if (lane == 0 && v) atomicAdd(&g_graph_phase_clk[3][k], (unsigned long long)v);
+      }
+      if (tid == 0) atomicAdd(&g_graph_phase_clk[3][5], (unsigned long long)nsrc);
+      {
+        const unsigned v = __reduce_max_sync(0xffffffffu, gt_cnt[2]);
+        if (lane == 0 && v) atomicMax(&g_graph_phase_clk[3][6], (unsigned long long)v);
+      }
+#endif
       long long q[5] = {0, 0, 0, 0, 0};
       for (int h = tid; h < nh; h += kThreads) {
         const int s = S.hstratum[h];
-        if (s >= 0 && s < 5) q[s] += S.hrec[h].wealth;
+        const long long wv = S.hrec[h].wealth;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) q[k] += s == k ? wv : 0ll;
       }
       if (tid < 8) sh.cnt[tid] = 0;
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const unsigned v = __reduce_add_sync(0xffffffffu, c_st[k]);
+        const unsigned v = __reduce_add_sync(0xffffffffu, (unsigned)(c_st >> (16 * k)) & 0xFFFFu);
         if (lane == 0 && v) atomicAdd(&sh.cnt[k], v);
       }
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const unsigned v = __reduce_add_sync(0xffffffffu, c_sev[k]);
+        const unsigned v = __reduce_add_sync(0xffffffffu, (unsigned)(c_sev >> (16 * k)) & 0xFFFFu);
         if (lane == 0 && v) atomicAdd(&sh.cnt[4 + k], v);
       }
+#pragma unroll
       for (int k = 0; k < 5; ++k) {
         const long long t = block_sum(q[k], sh.red);
         if (tid == 0) sh.acc[k] = t;
@@ -803,6 +1107,7 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
       prev_hs = __dadd_rn(__ddiv_rn((double)sh.cnt[6], S.pop_size), __ddiv_rn((double)sh.cnt[5], S.pop_size));
       __syncthreads();
     }
+    GT_MARK(5);
   }
 
   // ---- write the shared accounts back

@@ -347,7 +347,8 @@ typedef struct cabs_graph_config {
   uint32_t n_sims;
   uint32_t max_persons, max_houses, max_business; /* per simulation */
   uint32_t history_capacity;                      /* statistics rows kept per simulation (ring)            */
-  uint32_t cell_capacity;                         /* cells of the contact grid per simulation (0 = auto)   */
+  uint32_t cell_capacity;                         /* slots of the contact table per simulation: raised to
+                                                   * the next power of two >= 2 x max_persons (0 = that)   */
 } cabs_graph_config;
 
 /* graph_abs.py:13-32 + abs.py:17-49 + common.py:13-27 */
