@@ -44,7 +44,7 @@ struct cabs_graph {
   int *bx = nullptr, *by = nullptr, *bstratum = nullptr, *bstocks = nullptr, *bsales = nullptr, *bnum = nullptr;
   double *bprice = nullptr;
   long long *bwealth = nullptr, *bfixed = nullptr, *bincomes = nullptr;
-  unsigned *cell_count = nullptr;
+  unsigned *cell_count = nullptr, *req_idx = nullptr;
   unsigned long long *cell_keys = nullptr;
   int4 *cell_items = nullptr, *src_list = nullptr;
   double *history = nullptr, *initial_rows = nullptr;
@@ -86,7 +86,7 @@ extern "C" void cabs_graph_destroy(cabs_graph *g) {
   void *ptrs[] = {g->sims, g->px, g->py, g->house, g->employer, g->hire_seq, g->attr, g->pwealth, g->events, g->hrec,
                   g->hstratum, g->hsize, g->hfixed, g->bx, g->by, g->bstratum,
                   g->bstocks, g->bsales, g->bnum, g->bprice, g->bwealth, g->bfixed, g->bincomes, g->cell_count,
-                  g->cell_items, g->src_list, g->cell_keys, g->history, g->initial_rows, g->queue};
+                  g->cell_items, g->src_list, g->cell_keys, g->req_idx, g->history, g->initial_rows, g->queue};
   for (void *p : ptrs) cudaFree(p);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
@@ -132,7 +132,7 @@ static int graph_create_impl(cabs_graph *g, const cabs_graph_config *cfg) {
   GCK(alloc(&g->bx, B)); GCK(alloc(&g->by, B)); GCK(alloc(&g->bstratum, B)); GCK(alloc(&g->bstocks, B));
   GCK(alloc(&g->bsales, B)); GCK(alloc(&g->bnum, B)); GCK(alloc(&g->bprice, B)); GCK(alloc(&g->bwealth, B));
   GCK(alloc(&g->bfixed, B)); GCK(alloc(&g->bincomes, B));
-  GCK(alloc(&g->cell_count, S * ((size_t)cc + 2))); GCK(alloc(&g->cell_keys, S * (size_t)cc)); GCK(alloc(&g->cell_items, P)); GCK(alloc(&g->src_list, P));
+  GCK(alloc(&g->cell_count, S * ((size_t)cc + 4))); GCK(alloc(&g->cell_keys, S * (size_t)cc)); GCK(alloc(&g->cell_items, P)); GCK(alloc(&g->src_list, P)); GCK(alloc(&g->req_idx, P));
   GCK(alloc(&g->history, S * (size_t)g->cfg.history_capacity * kStats));
   GCK(alloc(&g->initial_rows, S * kStats));
   g->host_sims.assign(S, Sim());
@@ -281,9 +281,9 @@ extern "C" int cabs_graph_upload(cabs_graph *g, uint32_t sim, const cabs_graph_w
   s.k0 = (unsigned)(p->seed & 0xFFFFFFFFu); s.k1 = (unsigned)(p->seed >> 32);
   s.iteration = w->iteration;
   s.next_hire_seq = max_seq + 1;
-  s.cell_count = g->cell_count + (size_t)sim * ((size_t)g->cell_cap + 2);
+  s.cell_count = g->cell_count + (size_t)sim * ((size_t)g->cell_cap + 4);   // 16-byte aligned slices
   s.cell_keys = g->cell_keys + (size_t)sim * (size_t)g->cell_cap;
-  s.cell_items = g->cell_items + op; s.src_list = g->src_list + op;
+  s.cell_items = g->cell_items + op; s.src_list = g->src_list + op; s.req_idx = g->req_idx + op;
   s.cell_cap = (int)g->cell_cap;
   s.history = g->history + (size_t)sim * g->cfg.history_capacity * kStats;
   s.hist_cap = (int)g->cfg.history_capacity;
@@ -311,8 +311,10 @@ extern "C" int cabs_graph_run(cabs_graph *g, int iterations) {
     // by hour from a ticket queue over a persistent grid (see k_graph_run)
     if (g->slots == 0) {
       int per_sm = 0, sms = 0;
+      GCK(cudaFuncSetAttribute(k_graph_run<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphDynSmem));
+      GCK(cudaFuncSetAttribute(k_graph_run<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphDynSmem));
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_graph_run<true>, kThreads, 0) != cudaSuccess || per_sm < 1)
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_graph_run<true>, kThreads, kGraphDynSmem) != cudaSuccess || per_sm < 1)
         per_sm = 1;
       g->slots = per_sm * sms;
     }
@@ -322,10 +324,10 @@ extern "C" int cabs_graph_run(cabs_graph *g, int iterations) {
       if (!g->queue) GCK(cudaMalloc(&g->queue, (1 + (size_t)g->cfg.n_sims) * sizeof(int)));
       GCK(cudaMemsetAsync(g->queue, 0, (1 + (size_t)g->cfg.n_sims) * sizeof(int), g->stream));
       const int grid = g->slots < (int)g->cfg.n_sims ? g->slots : (int)g->cfg.n_sims;
-      k_graph_run<true><<<grid, kThreads, 0, g->stream>>>(g->sims, iterations, (int)g->cfg.n_sims,
+      k_graph_run<true><<<grid, kThreads, kGraphDynSmem, g->stream>>>(g->sims, iterations, (int)g->cfg.n_sims,
                                                           reinterpret_cast<unsigned *>(g->queue), g->queue + 1);
     } else {
-      k_graph_run<false><<<g->cfg.n_sims, kThreads, 0, g->stream>>>(g->sims, iterations, (int)g->cfg.n_sims, nullptr, nullptr);
+      k_graph_run<false><<<g->cfg.n_sims, kThreads, kGraphDynSmem, g->stream>>>(g->sims, iterations, (int)g->cfg.n_sims, nullptr, nullptr);
     }
     g->launches++;
   }

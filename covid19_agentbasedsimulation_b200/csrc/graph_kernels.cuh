@@ -34,7 +34,9 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxBusiness = 16;
 constexpr int kBGrid = 32;
-constexpr int kSrcBits = 32768;
+constexpr int kHotCells = 1024;
+constexpr int kSrcBits = 262144;                                     // bits of each of the two contact maps
+constexpr size_t kGraphDynSmem = 2 * (size_t)kSrcBits / 8;           // both maps: dynamic shared memory (64 KB)
 constexpr int kStats = 14;
 
 enum : uint32_t { S_ = 0, I_ = 1, R_ = 2, D_ = 3 };
@@ -99,9 +101,10 @@ struct Sim {
   double prev_infected, prev_hosp_severe;   // memo of the previous executed hour (statistics fractions)
   // contact scratch: the contagious persons of the hour as {x, y, person, infected_time}
   unsigned long long *cell_keys;   // cell_cap: open-addressing table of the cells that hold a source (key = cell)
-  unsigned *cell_count;   // cell_cap + 2: sources per slot of that table, then the end of the slot's run in cell_items
+  unsigned *cell_count;   // cell_cap + 2: sources per slot of that table, then the start of the slot's run in cell_items
   int4 *cell_items;       // n: the sources grouped by cell
   int4 *src_list;         // n: the sources in the order phase 1 met them
+  unsigned *req_idx;      // n: the persons that asked a business for goods this hour
   int cell_cap;
   // output
   double *history;        // hist_cap rows of kStats doubles, row = iteration % hist_cap
@@ -141,6 +144,19 @@ __device__ __forceinline__ V load4(const T *p, int i0, int n, T fill) {
     v.y = i0 + 1 < n ? p[i0 + 1] : fill;
     v.z = i0 + 2 < n ? p[i0 + 2] : fill;
     v.w = fill;
+  }
+  return v;
+}
+// the same through L2 only (data that atomics of this block have just written)
+__device__ __forceinline__ uint4 load4_cg(const unsigned *p, int i0, int n) {
+  uint4 v;
+  if (i0 + 3 < n) {
+    v = __ldcg(reinterpret_cast<const uint4 *>(p + i0));
+  } else {
+    v.x = __ldcg(p + i0);
+    v.y = i0 + 1 < n ? __ldcg(p + i0 + 1) : 0u;
+    v.z = i0 + 2 < n ? __ldcg(p + i0 + 2) : 0u;
+    v.w = 0u;
   }
   return v;
 }
@@ -186,9 +202,13 @@ struct Shared {
   // (network/agents.py:101-103), so the hour's check-ins are COUNTED with native 32-bit shared atomics and charged once
   // (a 64-bit shared atomicAdd is a compare-and-swap loop, and 7 000 colleagues hit the same word every working hour)
   unsigned ci_cnt[kMaxBusiness][5];
-  // one bit per hashed cell that holds a source of this hour's contacts: most Susceptible persons learn from these
-  // bits (shared memory) that nobody is near and never touch the bucket table
-  unsigned sbits[kSrcBits / 32];
+  // purchase requests of the hour: quantity asked of every business, the persons who asked (Sim::req_idx), and the
+  // businesses whose stock at the start of the hour does not cover what was asked (only those need the person order)
+  unsigned req_q[kMaxBusiness];
+  unsigned n_req, scarce;
+  // the first cells phase 4 meets, counted in shared memory (see there)
+  unsigned long long hot_key[kHotCells];
+  unsigned hot_cnt[kHotCells];
   unsigned n_contagious;
   unsigned cnt[8];
   int sel;                   // result slot of block-wide selections
@@ -249,9 +269,15 @@ __device__ __forceinline__ unsigned cell_hash(int cx, int cy) {
   h *= 0x2C1B3C6Du;
   return h ^ (h >> 13);
 }
-// bit of a cell in the shared "a source is here" map: the cell coordinates modulo 256 x 128 (no hash to compute for
-// the nine cells a Susceptible person tests every hour; aliases only cost a lookup in the table)
-__device__ __forceinline__ unsigned cell_bit(int cx, int cy) { return ((unsigned)(cy & 127) << 8) | (unsigned)(cx & 255); }
+// Two bit maps in (dynamic) shared memory, 512 x 512 cells each, indexed by the cell coordinates modulo 512 (nothing to
+// hash for the cells a Susceptible person tests every hour; an alias only costs a lookup in the table):
+//   sbits  the cell holds a source of this hour's contacts
+//   nbits  some cell within reach of this one holds a source (every source sets the up to nine bits around it): ONE
+//          test tells most Susceptible persons that nobody is near.
+// 64 KB per block on purpose: the loads of this kernel stream (L1 hit rate < 3 %), so the space is worth more as a
+// filter than as cache -- with 4 KB maps a quarter of the persons of a lockdown went to the table in L2 every hour
+// because of aliases (profiles/r2_graph_phase_times_pull.log).
+__device__ __forceinline__ unsigned cell_bit(int cx, int cy) { return ((unsigned)(cy & 511) << 9) | (unsigned)(cx & 511); }
 __device__ __forceinline__ bool is_source(const Sim &S, uint32_t a) {
   // Infected persons whose infected_time can fall inside the window for some (low, up) of graph_abs.py:289-290
   return a_status(a) == I_ && (int)a_time(a) >= S.incubation - 1 && (int)a_time(a) <= S.contagion_time;
@@ -260,12 +286,17 @@ __device__ __forceinline__ bool is_source(const Sim &S, uint32_t a) {
 // nested loops the compiler reconverges a warp only at the exit of the CALLER's person loop, and the lanes that had a
 // lookup to do ran the rest of the hour one or two at a time (measured: 1.9 active lanes per instruction, 17 x the
 // instructions of the converged loop, profiles/r2_graph_divergence.md).
-__device__ __forceinline__ bool pull_contact(const Sim &S, const unsigned *sbits, const unsigned long long *keys,
+__device__ __forceinline__ bool pull_contact(const Sim &S, const unsigned *sbits, const unsigned *nbits,
+                                             const unsigned long long *keys,
                                              const unsigned *table, const int4 *items, unsigned mask, int eshift,
                                              unsigned qmask, int i, int x, int y, uint32_t it GT_PULL_PARAM) {
   const int cx = x >> eshift, cy = y >> eshift;
   const long long T = S.T;
   bool infected = false;
+  {
+    const unsigned nb0 = cell_bit(cx, cy);
+    if (!((nbits[nb0 >> 5] >> (nb0 & 31u)) & 1u)) qmask = 0u;      // nobody in any cell around this one
+  }
   // qmask: the cells of the 3 x 3 neighbourhood that can hold somebody within reach.  With cells of edge 1 (reach 1,
   // every shipped scenario) that is a property of the offset alone -- the diagonals are out -- and was worked out once
   // per hour; with larger cells it depends on where in its cell the person stands and is tested below.
@@ -290,8 +321,8 @@ __device__ __forceinline__ bool pull_contact(const Sim &S, const unsigned *sbits
         kk = __ldcg(keys + b);
       }
       if (kk == key) {
-        const unsigned je = __ldcg(table + b);     // table[b]: END of the run of slot b
-        unsigned k = b ? __ldcg(table + b - 1) : 0u;
+        const unsigned je = __ldcg(table + b + 1);     // table[b]: start of the run of slot b, table[b + 1]: its end
+        unsigned k = __ldcg(table + b);
         for (; k < je && !infected; ++k) {
           const int4 c = items[k];
           GT_COUNT(2);
@@ -404,6 +435,8 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
   // the descriptor (pointers, parameters) is read by every thread all the time: keep a copy in shared memory
   __shared__ Sim S;
   __shared__ Shared sh;
+  extern __shared__ unsigned s_maps[];                       // kGraphDynSmem bytes: the two contact maps
+  unsigned *const s_sbits = s_maps, *const s_nbits = s_maps + kSrcBits / 32;
   __shared__ unsigned s_task;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (bool first_pass = true;; first_pass = false) {
@@ -490,7 +523,8 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
     const bool crit_active = prev_hs >= S.critical_limit;                        // network/agents.py:389-390
     const bool monthly = it > 1 && new_month;
     const bool contacts_on = S.T >= 0;
-    if (tid == 0) sh.n_contagious = 0;
+    if (tid == 0) sh.n_contagious = sh.n_req = sh.scarce = 0u;
+    if (tid < kMaxBusiness) sh.req_q[tid] = 0u;
     if (tid < kMaxBusiness * 5) (&sh.ci_cnt[0][0])[tid] = 0u;
     __syncthreads();
 
@@ -615,8 +649,11 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
               have = b >> 2;
             }
             const uint32_t w = (b & 3) == 0 ? q4.x : (b & 3) == 1 ? q4.y : (b & 3) == 2 ? q4.z : q4.w;
-            ev |= (unsigned long long)(1u + mulhi_pick(w, 9u)) << (4 * b);            // np.random.randint(1, 10)
+            const unsigned qty = 1u + mulhi_pick(w, 9u);                              // np.random.randint(1, 10)
+            ev |= (unsigned long long)qty << (4 * b);
+            atomicAdd(&sh.req_q[b], qty);
           }
+          if (have >= 0) S.req_idx[atomicAdd(&sh.n_req, 1u)] = (unsigned)i;           // asked somebody for goods
         }
         // ---- the sources of this hour's contacts (graph_abs.py:278-290): position and infected_time are final here
         if (contacts_on && is_source(S, a)) {
@@ -646,9 +683,43 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
     __syncthreads();
     if (tid < nb) {   // Business.checkin (network/agents.py:101-103): expenses / 720 of every employee that came in
       long long total = 0;
-      for (int k = 0; k < 5; ++k)
+      unsigned came = 0;
+      for (int k = 0; k < 5; ++k) {
         total += (long long)sh.ci_cnt[tid][k] * fx(__ddiv_rn(__dmul_rn(S.bi[k], S.min_expense), 720.0), scale);
+        came += sh.ci_cnt[tid][k];
+      }
       sh.bwealth[tid] -= total;
+      // Stocks (network/agents.py:82-93,101-102): a check-in adds one unit, a request takes min(quantity, stock) -- the
+      // only order-dependent rule of the person loop.  A business whose stock at the START of the hour covers everything
+      // asked of it this hour serves every request in full whatever the order (check-ins only add): settled here in
+      // one step.  The others are resolved in person order by phase 2.
+      const unsigned asked = sh.req_q[tid];
+      if (sh.bstocks[tid] >= 0 && (unsigned)sh.bstocks[tid] >= asked) {
+        sh.bstocks[tid] += (int)came - (int)asked;
+        sh.bsales[tid] += (int)asked;
+      } else {
+        atomicOr(&sh.scarce, 1u << tid);
+      }
+    }
+    __syncthreads();
+    {
+      const unsigned scarce = sh.scarce, nreq = sh.n_req;
+      for (unsigned t = tid; t < nreq; t += kThreads) {     // Business.supply for the requests served in full
+        const int i = (int)S.req_idx[t];
+        unsigned long long e = S.events[i];
+        const uint32_t a = S.attr[i];
+        const int h = S.house[i];
+        while (e) {
+          const int b = (__ffsll((long long)e) - 1) >> 2;
+          const unsigned nib = (unsigned)(e >> (4 * b)) & 15u;
+          e &= ~(15ull << (4 * b));
+          if (nib > 9u || ((scarce >> b) & 1u)) continue;
+          const long long value = fx(__dmul_rn(__dmul_rn(sh.bprice[b], (double)a_stratum(a)), (double)nib), scale);
+          person_demand(S, i, h, value);
+          atom_add(&sh.bwealth[b], value);
+          atom_add(&sh.bincomes[b], value);
+        }
+      }
     }
     __syncthreads();
     GT_MARK(1);
@@ -658,7 +729,8 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
     // persons the businesses that got a request are scanned in person order (their check-ins included); for every
     // other business the check-ins of the chunk are simply counted.  `present_req` rotates through three slots so
     // that one barrier per chunk is enough (slot k+1 is cleared while chunk k-1 may still be read and chunk k is set).
-    {
+    if (sh.scarce) {
+      const unsigned scarce = sh.scarce;
       if (tid < 3) sh.present_req[tid] = 0u;
       __syncthreads();
       unsigned long long ev_next = tid < n ? S.events[tid] : 0ull;
@@ -675,6 +747,8 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
           if (nib == 15u) ci |= 1u << b; else req |= 1u << b;
           e &= ~(15ull << (4 * b));
         }
+        req &= scarce;      // the other businesses were settled after phase 1
+        ci &= scarce;
         const unsigned wreq = __reduce_or_sync(0xffffffffu, req);
         unsigned wci = __reduce_or_sync(0xffffffffu, ci);
         if (lane == 0 && wreq) atomicOr(&sh.present_req[slot], wreq);
@@ -918,10 +992,22 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
     while (cmask + 1u < 2u * nsrc && 2u * (cmask + 1u) <= (unsigned)S.cell_cap) cmask = 2u * cmask + 1u;
     if (nsrc) {
       const int nbuckets = (int)cmask + 1;
-      for (int c = tid; c <= nbuckets; c += kThreads) S.cell_count[c] = 0;
-      for (int c = tid; c < nbuckets; c += kThreads) S.cell_keys[c] = kEmptyCell;
-      for (int c = tid; c < kSrcBits / 32; c += kThreads) sh.sbits[c] = 0u;
+      for (int c = tid * 4; c <= nbuckets; c += kThreads * 4)      // nbuckets is a multiple of 256
+        store4<uint4, unsigned>(S.cell_count, c, nbuckets + 1, make_uint4(0u, 0u, 0u, 0u));
+      for (int c = tid * 2; c < nbuckets; c += kThreads * 2)
+        *reinterpret_cast<ulonglong2 *>(S.cell_keys + c) = make_ulonglong2(kEmptyCell, kEmptyCell);
+      for (int c = tid * 4; c < 2 * kSrcBits / 32; c += kThreads * 4)
+        *reinterpret_cast<uint4 *>(s_maps + c) = make_uint4(0u, 0u, 0u, 0u);
+      for (int c = tid; c < kHotCells; c += kThreads) {
+        sh.hot_key[c] = kEmptyCell;
+        sh.hot_cnt[c] = 0u;
+      }
       __syncthreads();
+      // ---- count: every source gets its RANK inside its cell (kept in the upper bits of the record's last word).
+      // Thousands of sources share one cell at a workplace or at the hospital; their increments of one counter in
+      // global memory are served one after the other by the L2 (milliseconds per hour at the peak of an epidemic).
+      // The first kHotCells cells the block meets are therefore counted in shared memory -- the big piles are among the
+      // first few hundred records with near certainty -- and handed to the table once, with their totals.
       for (unsigned base = 0; base < nsrc; base += kThreads) {
         const unsigned t = base + tid;
         if (t < nsrc) {
@@ -929,41 +1015,89 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
           const int ccx = r.x >> eshift, ccy = r.y >> eshift;
           const unsigned h = cell_hash(ccx, ccy), hb = cell_bit(ccx, ccy);
           const unsigned long long key = cell_key(ccx, ccy);
-          unsigned b = h & cmask;
-          unsigned long long prev = atomicCAS(&S.cell_keys[b], kEmptyCell, key);   // claim the cell's slot or find it
-          while (prev != kEmptyCell && prev != key) {
-            b = (b + 1u) & cmask;
-            prev = atomicCAS(&S.cell_keys[b], kEmptyCell, key);
+          unsigned rank = 0xFFFFFFFFu;
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) {            // a cell is either always found here or never (slots are not freed)
+            const unsigned slot = ((h >> 12) + pr) & (kHotCells - 1);
+            if (rank == 0xFFFFFFFFu) {
+              const unsigned long long prev = atomicCAS(&sh.hot_key[slot], kEmptyCell, key);
+              if (prev == kEmptyCell || prev == key) rank = atomicAdd(&sh.hot_cnt[slot], 1u);
+            }
           }
-          atomicAdd(&S.cell_count[b], 1u);
-          atomicOr(&sh.sbits[hb >> 5], 1u << (hb & 31u));
+          if (rank == 0xFFFFFFFFu) {
+            unsigned b = h & cmask;
+            unsigned long long prev = atomicCAS(&S.cell_keys[b], kEmptyCell, key);   // claim the cell's slot or find it
+            while (prev != kEmptyCell && prev != key) {
+              b = (b + 1u) & cmask;
+              prev = atomicCAS(&S.cell_keys[b], kEmptyCell, key);
+            }
+            rank = atomicAdd(&S.cell_count[b], 1u);
+          }
+          S.src_list[t].w = r.w | (int)(rank << 8);
+          if (!((s_sbits[hb >> 5] >> (hb & 31u)) & 1u)) {        // first source seen in this cell (or a benign race)
+            atomicOr(&s_sbits[hb >> 5], 1u << (hb & 31u));
+            for (unsigned qm = qmask; qm; qm &= qm - 1u) {        // qmask is symmetric: the cells that can reach this one
+              const int q = __ffs(qm) - 1, oy = (q * 11) >> 5;
+              const unsigned nbq = cell_bit(ccx + (q - 3 * oy) - 1, ccy + oy - 1);
+              atomicOr(&s_nbits[nbq >> 5], 1u << (nbq & 31u));
+            }
+          }
         }
         __syncwarp();
       }
       __syncthreads();
-      // exclusive scan of cell_count[0..nbuckets] (chunked, running carry)
-      unsigned carry = 0;
-      for (int base = 0; base <= nbuckets; base += kThreads) {
-        const int c = base + tid;
-        const unsigned v = c <= nbuckets ? __ldcg(S.cell_count + c) : 0u;
-        unsigned inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += t;
+      for (int c = tid; c < kHotCells; c += kThreads) {          // the cells counted in shared memory enter the table
+        const unsigned long long key = sh.hot_key[c];
+        if (key != kEmptyCell) {
+          unsigned b = cell_hash((int)(unsigned)(key >> 32), (int)(unsigned)key) & cmask;
+          unsigned long long prev = atomicCAS(&S.cell_keys[b], kEmptyCell, key);
+          while (prev != kEmptyCell && prev != key) {
+            b = (b + 1u) & cmask;
+            prev = atomicCAS(&S.cell_keys[b], kEmptyCell, key);
+          }
+          atomicAdd(&S.cell_count[b], sh.hot_cnt[c]);
         }
-        if (lane == 31) sh.wa[wid][0] = (int)inc;
+      }
+      __syncthreads();
+      // exclusive scan of cell_count[0..nbuckets]: cell_count[b] = start of the run of slot b.  Every warp owns one
+      // contiguous slab: it sums it, the 16 sums are combined, then it walks the slab again with the running total in a
+      // register -- two streaming passes with independent 16-byte loads and no block-wide barrier per tile (a scan that
+      // synchronises the block every 512 entries spends a memory round trip per tile: 1 ms of the hour at 2^18 slots).
+      {
+        const int entries = nbuckets + 1;
+        const int slab = ((entries + kWarps * 128 - 1) / (kWarps * 128)) * 128;
+        const int w0 = wid * slab, w1 = min(w0 + slab, entries);
+        unsigned sum = 0;
+        for (int base = w0; base < w1; base += 128) {
+          const int c = base + lane * 4;
+          if (c < entries) {
+            const uint4 v = load4_cg(S.cell_count, c, entries);
+            sum += v.x + v.y + v.z + v.w;
+          }
+        }
+        sum = __reduce_add_sync(0xffffffffu, sum);
+        if (lane == 0) sh.wa[wid][0] = (int)sum;
         __syncthreads();
-        unsigned before = carry, total = 0;
-        for (int k = 0; k < kWarps; ++k) {
-          if (k < wid) before += (unsigned)sh.wa[k][0];
-          total += (unsigned)sh.wa[k][0];
+        unsigned carry = 0;
+        for (int k = 0; k < wid; ++k) carry += (unsigned)sh.wa[k][0];
+        for (int base = w0; base < w1; base += 128) {
+          const int c = base + lane * 4;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (c < entries) v = load4_cg(S.cell_count, c, entries);
+          const unsigned mine = v.x + v.y + v.z + v.w;
+          unsigned inc = mine;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+          }
+          const unsigned e0 = carry + inc - mine;
+          if (c < entries) store4<uint4, unsigned>(S.cell_count, c, entries, make_uint4(e0, e0 + v.x, e0 + v.x + v.y, e0 + v.x + v.y + v.z));
+          carry += __shfl_sync(0xffffffffu, inc, 31);
         }
-        if (c <= nbuckets) S.cell_count[c] = before + inc - v;
-        carry += total;
         __syncthreads();
       }
-      // fill: cell_count[b] is advanced to the end of the run of slot b, i.e. becomes the start of slot b + 1
+      // fill: start of the cell's run + the rank taken above (no atomics)
       for (unsigned base = 0; base < nsrc; base += kThreads) {
         const unsigned t = base + tid;
         if (t < nsrc) {
@@ -972,7 +1106,7 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
           const unsigned long long key = cell_key(ccx, ccy);
           unsigned b = cell_hash(ccx, ccy) & cmask;
           while (__ldcg(S.cell_keys + b) != key) b = (b + 1u) & cmask;
-          S.cell_items[atomicAdd(&S.cell_count[b], 1u)] = r;
+          S.cell_items[__ldcg(S.cell_count + b) + ((unsigned)r.w >> 8)] = make_int4(r.x, r.y, r.z, r.w & 255);
         }
         __syncwarp();
       }
@@ -1001,7 +1135,7 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
         }
         if (i < n) {
           if (nsrc && a_status(a) == S_ &&
-              (GT_COUNT(0), pull_contact(S, sh.sbits, S.cell_keys, S.cell_count, S.cell_items, cmask, eshift, qmask, i, x, y,
+              (GT_COUNT(0), pull_contact(S, s_sbits, s_nbits, S.cell_keys, S.cell_count, S.cell_items, cmask, eshift, qmask, i, x, y,
                                          (uint32_t)it GT_PULL_ARG))) {
             GT_COUNT(4);
             a = (a & ~3u) | I_;
@@ -1034,7 +1168,7 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
               const int k = __ffs(todo) - 1;
               todo &= todo - 1u;
               GT_COUNT(0);
-              if (pull_contact(S, sh.sbits, S.cell_keys, S.cell_count, S.cell_items, cmask, eshift, qmask, i0 + k,
+              if (pull_contact(S, s_sbits, s_nbits, S.cell_keys, S.cell_count, S.cell_items, cmask, eshift, qmask, i0 + k,
                                vget(X4, k), vget(Y4, k), (uint32_t)it GT_PULL_ARG)) {
                 GT_COUNT(4);
                 vset(A4, k, (vget(A4, k) & ~3u) | I_);   // contact() rewrites the status only (graph_abs.py:297-298)
@@ -1069,6 +1203,10 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
         if (lane == 0 && v) atomicMax(&g_graph_phase_clk[3][6], (unsigned long long)v);
       }
 #endif
+#ifdef CABS_GRAPH_TIMERS
+      __syncthreads();
+      GT_MARK(6);     // phase 5, person loop (contacts + counts)
+#endif
       long long q[5] = {0, 0, 0, 0, 0};
       for (int h = tid; h < nh; h += kThreads) {
         const int s = S.hstratum[h];
@@ -1076,6 +1214,10 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
 #pragma unroll
         for (int k = 0; k < 5; ++k) q[k] += s == k ? wv : 0ll;
       }
+#ifdef CABS_GRAPH_TIMERS
+      __syncthreads();
+      GT_MARK(7);     // phase 5, house loop
+#endif
       if (tid < 8) sh.cnt[tid] = 0;
       __syncthreads();
 #pragma unroll

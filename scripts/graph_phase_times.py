@@ -80,6 +80,9 @@ def main():
                 print("   %-18s %5.1f %%  | " % (name, 100 * c[cls].sum() / tot) +
                       " | ".join("%5.1f %%" % (100 * c[cls][k] / tot) for k in range(1, 6)))
             print("   all                         | " + " | ".join("%5.1f %%" % (100 * c[:, k].sum() / tot) for k in range(1, 6)))
+            if c[:3, 6].sum() > 0:
+                print("   phase 5 split: person loop (contacts + counts) %.1f %%, house loop %.1f %%, reductions + row %.1f %%"
+                      % (100 * c[:3, 6].sum() / tot, 100 * c[:3, 7].sum() / tot, 100 * c[:3, 5].sum() / tot))
             ph = len(jobs) * n * 34.0
             k = c[3]
             if k[0] > 0:
