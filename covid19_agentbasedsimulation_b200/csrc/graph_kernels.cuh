@@ -75,7 +75,7 @@ struct Sim {
   unsigned long long *events;   // scratch: one nibble per business (0 none, 1..9 request, 15 check-in)
   // houses: position and the three accounts persons touch every hour share ONE 32-byte sector (a person's house is a
   // random index: as four separate arrays every check-in cost four scattered sectors -- half of the kernel's DRAM
-  // traffic in lockdown and night hours, profiles/r2_graph_summary.md)
+  // traffic in lockdown and night hours, profiles/r2_graph_final_summary.md)
   HouseRec *hrec;
   int *hstratum, *hsize;
   long long *hfixed;
@@ -285,7 +285,7 @@ __device__ __forceinline__ bool is_source(const Sim &S, uint32_t a) {
 // Structured control flow on purpose (flags in the loop conditions, no early return): with a return from inside the
 // nested loops the compiler reconverges a warp only at the exit of the CALLER's person loop, and the lanes that had a
 // lookup to do ran the rest of the hour one or two at a time (measured: 1.9 active lanes per instruction, 17 x the
-// instructions of the converged loop, profiles/r2_graph_divergence.md).
+// instructions of the converged loop, profiles/r2_graph_final_summary.md).
 __device__ __forceinline__ bool pull_contact(const Sim &S, const unsigned *sbits, const unsigned *nbits,
                                              const unsigned long long *keys,
                                              const unsigned *table, const int4 *items, unsigned mask, int eshift,

@@ -1,6 +1,6 @@
 """Scenario x seed ensemble of GraphSimulation sharded over the GPUs of one box (BASELINE.json configs[4], SURVEY.md 8d
 config 5): 7 paper scenarios x `seeds` seeds x `persons` persons.  One process per GPU (torchrun) or a single process;
-simulations are block-distributed over the ranks (network/ensemble.py::shard) and never communicate; at the end every
+simulations are dealt round-robin to the ranks (network/ensemble.py::shard, interleaved: the same scenario mix everywhere) and never communicate; at the end every
 rank reduces its own Min/Sum/SumSq/Max per (scenario, iteration, metric) on the device and the ranks merge those few
 numbers (what batch_experiment writes per scenario, experiments.py:200-208).
 
@@ -56,7 +56,8 @@ def run(args, rank, world, local):
     side = int((n / 0.0012) ** .5)                      # the density of run_batch.py: 300 persons on 500 x 500
     scenarios = sc.PAPER_SCENARIOS
     jobs = [(s, k) for s in range(len(scenarios)) for k in range(seeds)]
-    mine = [jobs[j] for j in shard(len(jobs), rank, world)]
+    # interleaved: every rank gets the same mix of scenarios (their seeds stay consecutive in its list)
+    mine = [jobs[j] for j in shard(len(jobs), rank, world, interleaved=True)]
 
     def make(job):
         s, k = job

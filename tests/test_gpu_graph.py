@@ -108,6 +108,7 @@ def test_ensemble_handle_equals_individual_runs_and_batch_experiment(native_lib,
     from covid19_agentbasedsimulation_b200.network import scenarios as sc
     from covid19_agentbasedsimulation_b200.experiments import batch_experiment
     assert [list(shard(10, r, 4)) for r in range(4)] == [[0, 1, 2], [3, 4, 5], [6, 7], [8, 9]]
+    assert [list(shard(10, r, 4, interleaved=True)) for r in range(4)] == [[0, 4, 8], [1, 5, 9], [2, 6], [3, 7]]
     names = ("scenario1", "scenario2", "scenario3", "scenario4", "scenario6", "scenario8", "scenario10")
     kws = []
     for name in names:
