@@ -85,6 +85,56 @@ def test_built_world_stepwise_equals_batched_equals_oracle(native_lib, scenario,
     assert b.iteration == a.iteration == iters - 1
 
 
+@pytest.mark.parametrize("variant", ["distance3", "distance2", "distance_half", "scarce_stocks", "plentiful_stocks", "crowded_6000"])
+def test_contact_and_stock_paths_equal_oracle(native_lib, variant):
+    """The branches the shipped scenarios do not reach: cells larger than one lattice point (reach 2 and 3: the nearest
+    point of a cell decides whether it is looked up), same-point-only contacts (distance < 1), businesses whose opening
+    stock does not cover the hour's requests (the ordered max-plus scan instead of the one-step settlement) or always
+    does, and a
+    crowded world (several groups per thread, the contact table beyond its smallest size, piles counted in shared
+    memory) -- every column and every statistics row against the oracle."""
+    from covid19_agentbasedsimulation_b200.network.graph_abs import GraphSimulation, GRAPH_STAT_KEYS, default_money_bits
+    from covid19_agentbasedsimulation_b200.network import scenarios as sc
+    from oracle.graph_oracle import GraphOracle
+    kw = dict(sc.global_parameters)
+    kw.update(sc.scenario1)
+    kw.pop("name")
+    n, side, iters = 1200, 120, 72
+    kw.update(initial_infected_perc=0.05)
+    if variant == "distance3":
+        kw.update(contagion_distance=3.0, contagion_rate=0.3)
+    elif variant == "distance2":
+        kw.update(contagion_distance=2.0, contagion_rate=0.4)
+    elif variant == "distance_half":
+        kw.update(contagion_distance=0.5)
+    elif variant == "scarce_stocks":
+        kw.update(business_distance=45)
+    elif variant == "crowded_6000":
+        n, side, iters = 6000, 160, 30
+    kw.update(population_size=n, length=side, height=side)
+    np.random.seed(11)
+    a = GraphSimulation(seed=17, **kw)
+    world, mode, sleep = a.build_world()
+    if variant == "scarce_stocks":
+        world["bstocks"][:] = 0
+    if variant == "plentiful_stocks":       # every request of every hour is covered: the one-step settlement only
+        world["bstocks"][:] = 1000000
+    a.set_world(world, mode, sleep)
+    params = dict(population_size=n, total_wealth=kw["total_wealth"], contagion_distance=kw["contagion_distance"],
+                  contagion_rate=a.contagion_rate, critical_limit=kw["critical_limit"], amplitudes=[10.0, 10.0, 10.0, 0.0],
+                  minimum_income=kw["minimum_income"], minimum_expense=kw["minimum_expense"],
+                  business_distance=kw["business_distance"], incubation_time=5, contagion_time=10, recovering_time=20,
+                  mode=mode, sleep=sleep, money_bits=default_money_bits(kw["total_wealth"]))
+    orc = GraphOracle(oracle_world(world, params), seed=17)
+    rows = a.run(iters)
+    for it in range(iters):
+        o = orc.execute()
+        assert rows[it].tolist() == [o[k] for k in GRAPH_STAT_KEYS], (variant, it)
+    _compare_state(a, orc)
+    if variant == "scarce_stocks":
+        assert int(np.asarray(a.world()["bsales"]).sum()) > 0      # requests were served out of checked-in stock
+
+
 def test_entities_are_materialised_like_the_reference_lists(native_lib):
     from covid19_agentbasedsimulation_b200.network.graph_abs import GraphSimulation
     from covid19_agentbasedsimulation_b200.network import scenarios as sc
