@@ -34,9 +34,12 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxBusiness = 16;
 constexpr int kBGrid = 32;
-constexpr int kHotCells = 1024;
+// Shared memory budget: two blocks per SM within 192 KB (measured: a build whose blocks needed 205 KB between them ran the
+// ensemble bench at 1.77e10 instead of 2.45e10 agent-updates/s)
+constexpr int kHotCells = 512;
 constexpr int kSrcBits = 262144;                                     // bits of each of the two contact maps
-constexpr size_t kGraphDynSmem = 2 * (size_t)kSrcBits / 8;           // both maps: dynamic shared memory (64 KB)
+constexpr int kWantBits = 131072;                                    // bits of the "a Susceptible person is near" map
+constexpr size_t kGraphDynSmem = (2 * (size_t)kSrcBits + kWantBits) / 8;   // the three maps: dynamic shared memory (80 KB)
 constexpr int kStats = 14;
 
 enum : uint32_t { S_ = 0, I_ = 1, R_ = 2, D_ = 3 };
@@ -99,6 +102,7 @@ struct Sim {
   int iteration;          // graph_abs.py:25 starts at -1
   int next_hire_seq;
   double prev_infected, prev_hosp_severe;   // memo of the previous executed hour (statistics fractions)
+  unsigned prev_susceptible, prev_sources;  // ... its Susceptible persons and contact sources (a scheduling hint only)
   // contact scratch: the contagious persons of the hour as {x, y, person, infected_time}
   unsigned long long *cell_keys;   // cell_cap: open-addressing table of the cells that hold a source (key = cell)
   unsigned *cell_count;   // cell_cap + 2: sources per slot of that table, then the start of the slot's run in cell_items
@@ -278,6 +282,26 @@ __device__ __forceinline__ unsigned cell_hash(int cx, int cy) {
 // filter than as cache -- with 4 KB maps a quarter of the persons of a lockdown went to the table in L2 every hour
 // because of aliases (profiles/r2_graph_phase_times_pull.log).
 __device__ __forceinline__ unsigned cell_bit(int cx, int cy) { return ((unsigned)(cy & 511) << 9) | (unsigned)(cx & 511); }
+// A third map (256 x 512 cells) for the hours in which the sources outnumber the Susceptible persons five to one (the
+// peak of an unmitigated epidemic: 87 % of the persons are sources, 5 % can still be infected): phase 1 has every
+// Susceptible person mark the cells within its reach, and a source whose cell is not marked -- nobody it could infect
+// is near -- never enters the table.  Building the table for all of them was 45 MB of random sector traffic per
+// simulation and hour, three quarters of such an hour.
+__device__ __forceinline__ unsigned want_bit(int cx, int cy) { return ((unsigned)(cy & 255) << 9) | (unsigned)(cx & 511); }
+// contact geometry: cell edge = power of two >= reach; which of the 3 x 3 cells can be within reach at all (with cells
+// of edge 1 that is a property of the offset alone)
+__device__ __forceinline__ void contact_geometry(const Sim &S, int &eshift, unsigned &qmask) {
+  eshift = 0;
+  while ((1 << eshift) < S.reach && eshift < 30) ++eshift;
+  qmask = 0x1FFu;
+  if (eshift == 0) {
+    qmask = 0u;
+    for (int q = 0; q < 9; ++q) {
+      const long long ox = q % 3 - 1, oy = q / 3 - 1;
+      if (ox * ox + oy * oy <= (long long)S.T) qmask |= 1u << q;
+    }
+  }
+}
 __device__ __forceinline__ bool is_source(const Sim &S, uint32_t a) {
   // Infected persons whose infected_time can fall inside the window for some (low, up) of graph_abs.py:289-290
   return a_status(a) == I_ && (int)a_time(a) >= S.incubation - 1 && (int)a_time(a) <= S.contagion_time;
@@ -435,8 +459,8 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
   // the descriptor (pointers, parameters) is read by every thread all the time: keep a copy in shared memory
   __shared__ Sim S;
   __shared__ Shared sh;
-  extern __shared__ unsigned s_maps[];                       // kGraphDynSmem bytes: the two contact maps
-  unsigned *const s_sbits = s_maps, *const s_nbits = s_maps + kSrcBits / 32;
+  extern __shared__ unsigned s_maps[];                       // kGraphDynSmem bytes: the three contact maps
+  unsigned *const s_sbits = s_maps, *const s_nbits = s_maps + kSrcBits / 32, *const s_want = s_maps + 2 * kSrcBits / 32;
   __shared__ unsigned s_task;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (bool first_pass = true;; first_pass = false) {
@@ -503,6 +527,7 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
 
   int it = S.iteration;
   double prev_infected = S.prev_infected, prev_hs = S.prev_hosp_severe;
+  unsigned prev_susceptible = S.prev_susceptible, prev_sources = S.prev_sources;
 
   for (int step = 0; step < hours; ++step) {
     ++it;                                                                       // graph_abs.py:192
@@ -519,10 +544,19 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
       continue;
     }
     GT_BEGIN();
+    const bool contacts_on = S.T >= 0;
     const bool lock_all = S.mode == MODE_LOCKDOWN || (S.mode == MODE_CONDITIONAL && prev_infected > 0.05);
     const bool crit_active = prev_hs >= S.critical_limit;                        // network/agents.py:389-390
     const bool monthly = it > 1 && new_month;
-    const bool contacts_on = S.T >= 0;
+    // sources that nobody can catch anything from are left out of the table when they are the many (decided from the
+    // previous hour's counts: a hint, the result does not depend on it)
+#ifdef CABS_NO_WANT_FILTER
+    const bool want_filter = false;
+#else
+    const bool want_filter = contacts_on && prev_sources > 5u * prev_susceptible;
+#endif
+    if (want_filter)
+      for (int c = tid * 4; c < kWantBits / 32; c += kThreads * 4) *reinterpret_cast<uint4 *>(s_want + c) = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) sh.n_contagious = sh.n_req = sh.scarce = 0u;
     if (tid < kMaxBusiness) sh.req_q[tid] = 0u;
     if (tid < kMaxBusiness * 5) (&sh.ci_cnt[0][0])[tid] = 0u;
@@ -654,6 +688,17 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
             atomicAdd(&sh.req_q[b], qty);
           }
           if (have >= 0) S.req_idx[atomicAdd(&sh.n_req, 1u)] = (unsigned)i;           // asked somebody for goods
+        }
+        if (want_filter && a_status(a) == S_) {     // the cells a source must be in to reach this person
+          int eshift;
+          unsigned qmask;
+          contact_geometry(S, eshift, qmask);
+          const int cx = x >> eshift, cy = y >> eshift;
+          for (unsigned qm = qmask; qm; qm &= qm - 1u) {
+            const int q = __ffs(qm) - 1, oy = (q * 11) >> 5;
+            const unsigned wb = want_bit(cx + (q - 3 * oy) - 1, cy + oy - 1);
+            if (!((s_want[wb >> 5] >> (wb & 31u)) & 1u)) atomicOr(&s_want[wb >> 5], 1u << (wb & 31u));
+          }
         }
         // ---- the sources of this hour's contacts (graph_abs.py:278-290): position and infected_time are final here
         if (contacts_on && is_source(S, a)) {
@@ -978,16 +1023,9 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
     GT_MARK(3);
     // ================= phase 4: contacts, the sources grouped by hashed cell (graph_abs.py:256-300) =================
     const unsigned nsrc = sh.n_contagious;
-    int eshift = 0;
-    while ((1 << eshift) < S.reach && eshift < 30) ++eshift;
-    unsigned qmask = 0x1FFu;                                  // which of the 3 x 3 cells can be within reach at all
-    if (eshift == 0) {
-      qmask = 0u;
-      for (int q = 0; q < 9; ++q) {
-        const long long ox = q % 3 - 1, oy = q / 3 - 1;
-        if (ox * ox + oy * oy <= (long long)S.T) qmask |= 1u << q;
-      }
-    }
+    int eshift;
+    unsigned qmask;
+    contact_geometry(S, eshift, qmask);
     unsigned cmask = 255u;                                    // slots: a power of two >= 2 x sources (<= cell_cap)
     while (cmask + 1u < 2u * nsrc && 2u * (cmask + 1u) <= (unsigned)S.cell_cap) cmask = 2u * cmask + 1u;
     if (nsrc) {
@@ -1013,6 +1051,9 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
         if (t < nsrc) {
           const int4 r = S.src_list[t];
           const int ccx = r.x >> eshift, ccy = r.y >> eshift;
+          const unsigned wb = want_bit(ccx, ccy);
+          const bool wanted = !want_filter || ((s_want[wb >> 5] >> (wb & 31u)) & 1u);
+          if (wanted) {
           const unsigned h = cell_hash(ccx, ccy), hb = cell_bit(ccx, ccy);
           const unsigned long long key = cell_key(ccx, ccy);
           unsigned rank = 0xFFFFFFFFu;
@@ -1041,6 +1082,9 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
               const unsigned nbq = cell_bit(ccx + (q - 3 * oy) - 1, ccy + oy - 1);
               atomicOr(&s_nbits[nbq >> 5], 1u << (nbq & 31u));
             }
+          }
+          } else {
+            S.src_list[t].w = -1;                 // not in the table: the fill skips it
           }
         }
         __syncwarp();
@@ -1100,8 +1144,8 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
       // fill: start of the cell's run + the rank taken above (no atomics)
       for (unsigned base = 0; base < nsrc; base += kThreads) {
         const unsigned t = base + tid;
-        if (t < nsrc) {
-          const int4 r = S.src_list[t];
+        const int4 r = t < nsrc ? S.src_list[t] : make_int4(0, 0, 0, -1);
+        if (r.w != -1) {
           const int ccx = r.x >> eshift, ccy = r.y >> eshift;
           const unsigned long long key = cell_key(ccx, ccy);
           unsigned b = cell_hash(ccx, ccy) & cmask;
@@ -1247,6 +1291,8 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
       __syncthreads();
       prev_infected = __ddiv_rn((double)sh.cnt[1], S.pop_size);
       prev_hs = __dadd_rn(__ddiv_rn((double)sh.cnt[6], S.pop_size), __ddiv_rn((double)sh.cnt[5], S.pop_size));
+      prev_susceptible = sh.cnt[0];
+      prev_sources = nsrc;
       __syncthreads();
     }
     GT_MARK(5);
@@ -1264,6 +1310,8 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
     G.iteration = it;
     G.prev_infected = prev_infected;
     G.prev_hosp_severe = prev_hs;
+    G.prev_susceptible = prev_susceptible;
+    G.prev_sources = prev_sources;
   }
   if (kQueue) {   // publish the hour: everything this block wrote, then the progress counter
     __threadfence();

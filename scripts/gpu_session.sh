@@ -1,15 +1,11 @@
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 | tee gpurun_out/gputests_r2_final.log
-timeout 900 python bench.py > gpurun_out/bench_r2_final.json 2> gpurun_out/bench_r2_final.err || tail -5 gpurun_out/bench_r2_final.err
-timeout 600 python bench.py --workload ensemble > gpurun_out/ens_r2_final.json 2> gpurun_out/ens_r2_final.err || tail -5 gpurun_out/ens_r2_final.err
-bash scripts/profile_step.sh r2_final > gpurun_out/profile_r2_final.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_graph_run --launch-skip 1 --launch-count 1 -f -o gpurun_out/prof_graph_r2_final python scripts/graph_phase_times.py --scenario 0 --seeds 296 --days 2 > gpurun_out/ncu_graph_r2_final.log 2>&1
-tail -2 gpurun_out/ncu_graph_r2_final.log
+timeout 1500 python -m pytest tests/test_gpu_graph.py -m gpu -q -x 2>&1 | tail -3 | tee gpurun_out/gputests_graph.log
+CABS_GRAPH_QUEUE=1 timeout 1500 python -m pytest tests/test_gpu_graph.py -m gpu -q -x 2>&1 | tail -2
+for s in 0 2; do
+scripts/with_variant.sh build/variants_graph/graph_timers.so python scripts/graph_phase_times.py --scenario $s --seeds 296 --days 2,10,14 2>&1 | grep -v Warning
+done | tee gpurun_out/graph_phase_times_by_scenario12.log
+timeout 600 python bench.py --workload ensemble > gpurun_out/ens_r2_n.json 2> gpurun_out/ens_r2_n.err || tail -5 gpurun_out/ens_r2_n.err
 python - <<'PY'
 import json
-d=json.loads(open("gpurun_out/bench_r2_final.json").read().strip().splitlines()[-1])
-print("value %.4g ms/step %.4f frac %.3f e2e %.4g" % (d["value"], d["ms_per_step"], d["roofline"]["frac"], d["e2e"]["value"]))
-print({k: round(v["avg_ms"],4) for k,v in d["roofline"]["kernels"].items()})
-print({k: (v if not isinstance(v, dict) else {kk: vv for kk, vv in list(v.items())[:6]}) for k, v in d.get("other_configs", {}).items()})
-d=json.loads(open("gpurun_out/ens_r2_final.json").read().strip().splitlines()[-1])
-print("ensemble value %.4g ms/iter %.3f frac80 %.3f" % (d["value"], d["ms_per_step"], d["roofline"]["frac"]))
+d=json.loads(open("gpurun_out/ens_r2_n.json").read().strip().splitlines()[-1])
+print("ensemble value %.4g ms/iter %.3f frac80 %.3f" % (d["value"], d["ms_per_step"], d["roofline"]["frac"]), d["final_infected_avg_std_by_scenario"][:2])
 PY

@@ -85,12 +85,13 @@ def test_built_world_stepwise_equals_batched_equals_oracle(native_lib, scenario,
     assert b.iteration == a.iteration == iters - 1
 
 
-@pytest.mark.parametrize("variant", ["distance3", "distance2", "distance_half", "scarce_stocks", "plentiful_stocks", "crowded_6000"])
+@pytest.mark.parametrize("variant", ["distance3", "distance2", "distance_half", "scarce_stocks", "plentiful_stocks", "crowded_6000", "peak_filter"])
 def test_contact_and_stock_paths_equal_oracle(native_lib, variant):
     """The branches the shipped scenarios do not reach: cells larger than one lattice point (reach 2 and 3: the nearest
     point of a cell decides whether it is looked up), same-point-only contacts (distance < 1), businesses whose opening
     stock does not cover the hour's requests (the ordered max-plus scan instead of the one-step settlement) or always
-    does, and a
+    does, the
+    peak of an epidemic (sources filtered by the cells the last Susceptible persons can reach), and a
     crowded world (several groups per thread, the contact table beyond its smallest size, piles counted in shared
     memory) -- every column and every statistics row against the oracle."""
     from covid19_agentbasedsimulation_b200.network.graph_abs import GraphSimulation, GRAPH_STAT_KEYS, default_money_bits
@@ -111,6 +112,8 @@ def test_contact_and_stock_paths_equal_oracle(native_lib, variant):
         kw.update(business_distance=45)
     elif variant == "crowded_6000":
         n, side, iters = 6000, 160, 30
+    elif variant == "peak_filter":          # nine days: from day 5 on the sources outnumber the Susceptible 5 : 1 and
+        n, side, iters = 800, 100, 216      # only those a Susceptible person can reach enter the contact table
     kw.update(population_size=n, length=side, height=side)
     np.random.seed(11)
     a = GraphSimulation(seed=17, **kw)
