@@ -34,8 +34,8 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxBusiness = 16;
 constexpr int kBGrid = 32;
-// Shared memory budget: two blocks per SM within 192 KB (measured: a build whose blocks needed 205 KB between them ran the
-// ensemble bench at 1.77e10 instead of 2.45e10 agent-updates/s)
+// Shared memory budget: two blocks per SM within the 196 KB carveout, which leaves 60 KB of L1 (a build whose blocks needed
+// 205 KB between them got the 228 KB carveout, 28 KB of L1, and ran the ensemble bench at 1.77e10 instead of 2.45e10)
 constexpr int kHotCells = 512;
 constexpr int kSrcBits = 262144;                                     // bits of each of the two contact maps
 constexpr int kWantBits = 131072;                                    // bits of the "a Susceptible person is near" map
