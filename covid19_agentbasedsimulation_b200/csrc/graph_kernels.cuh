@@ -37,9 +37,11 @@ constexpr int kBGrid = 32;
 // Shared memory budget: two blocks per SM within the 196 KB carveout, which leaves 60 KB of L1 (a build whose blocks needed
 // 205 KB between them got the 228 KB carveout, 28 KB of L1, and ran the ensemble bench at 1.77e10 instead of 2.45e10)
 constexpr int kHotCells = 512;
-constexpr int kSrcBits = 262144;                                     // bits of each of the two contact maps
-constexpr int kWantBits = 131072;                                    // bits of the "a Susceptible person is near" map
-constexpr size_t kGraphDynSmem = (2 * (size_t)kSrcBits + kWantBits) / 8;   // the three maps: dynamic shared memory (80 KB)
+#ifndef CABS_MAP_BITS
+#define CABS_MAP_BITS 262144
+#endif
+constexpr int kSrcBits = CABS_MAP_BITS;                              // bits of each contact map (a power of two >= 512)
+constexpr size_t kGraphDynSmem = 2 * (size_t)kSrcBits / 8;           // two maps of 32 KB: dynamic shared memory
 constexpr int kStats = 14;
 
 enum : uint32_t { S_ = 0, I_ = 1, R_ = 2, D_ = 3 };
@@ -281,13 +283,17 @@ __device__ __forceinline__ unsigned cell_hash(int cx, int cy) {
 // 64 KB per block on purpose: the loads of this kernel stream (L1 hit rate < 3 %), so the space is worth more as a
 // filter than as cache -- with 4 KB maps a quarter of the persons of a lockdown went to the table in L2 every hour
 // because of aliases (profiles/r2_graph_phase_times_pull.log).
-__device__ __forceinline__ unsigned cell_bit(int cx, int cy) { return ((unsigned)(cy & 511) << 9) | (unsigned)(cx & 511); }
-// A third map (256 x 512 cells) for the hours in which the sources outnumber the Susceptible persons five to one (the
-// peak of an unmitigated epidemic: 87 % of the persons are sources, 5 % can still be infected): phase 1 has every
-// Susceptible person mark the cells within its reach, and a source whose cell is not marked -- nobody it could infect
-// is near -- never enters the table.  Building the table for all of them was 45 MB of random sector traffic per
-// simulation and hour, three quarters of such an hour.
-__device__ __forceinline__ unsigned want_bit(int cx, int cy) { return ((unsigned)(cy & 255) << 9) | (unsigned)(cx & 511); }
+__device__ __forceinline__ unsigned cell_bit(int cx, int cy) {
+  return (((unsigned)cy << 9) | ((unsigned)cx & 511u)) & (unsigned)(kSrcBits - 1);     // 512 columns x kSrcBits / 512 rows
+}
+// In the hours in which the sources outnumber the Susceptible persons five to one (the peak of an unmitigated epidemic:
+// 87 % of the persons are sources, 5 % can still be infected) phase 1 has every Susceptible person mark the cells within
+// its reach -- in the memory of the `sbits` map, which nobody needs before phase 4 -- and a source whose cell is not
+// marked (nobody it could infect is near) never enters the table.  Building the table for all of them was 45 MB of
+// random sector traffic per simulation and hour, three quarters of such an hour.
+// NOTE sbits and nbits must use the SAME cell -> bit mapping: a source dilates into nbits only when it is the first to
+// set its sbits bit, which is right because cells that alias in one map alias, with all their neighbours, in the other
+// (a build with a smaller sbits map infected fewer persons).
 // contact geometry: cell edge = power of two >= reach; which of the 3 x 3 cells can be within reach at all (with cells
 // of edge 1 that is a property of the offset alone)
 __device__ __forceinline__ void contact_geometry(const Sim &S, int &eshift, unsigned &qmask) {
@@ -459,8 +465,8 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
   // the descriptor (pointers, parameters) is read by every thread all the time: keep a copy in shared memory
   __shared__ Sim S;
   __shared__ Shared sh;
-  extern __shared__ unsigned s_maps[];                       // kGraphDynSmem bytes: the three contact maps
-  unsigned *const s_sbits = s_maps, *const s_nbits = s_maps + kSrcBits / 32, *const s_want = s_maps + 2 * kSrcBits / 32;
+  extern __shared__ unsigned s_maps[];                       // kGraphDynSmem bytes: the contact maps
+  unsigned *const s_nbits = s_maps, *const s_sbits = s_maps + kSrcBits / 32, *const s_want = s_sbits;
   __shared__ unsigned s_task;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (bool first_pass = true;; first_pass = false) {
@@ -556,7 +562,7 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
     const bool want_filter = contacts_on && prev_sources > 5u * prev_susceptible;
 #endif
     if (want_filter)
-      for (int c = tid * 4; c < kWantBits / 32; c += kThreads * 4) *reinterpret_cast<uint4 *>(s_want + c) = make_uint4(0u, 0u, 0u, 0u);
+      for (int c = tid * 4; c < kSrcBits / 32; c += kThreads * 4) *reinterpret_cast<uint4 *>(s_want + c) = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) sh.n_contagious = sh.n_req = sh.scarce = 0u;
     if (tid < kMaxBusiness) sh.req_q[tid] = 0u;
     if (tid < kMaxBusiness * 5) (&sh.ci_cnt[0][0])[tid] = 0u;
@@ -696,7 +702,7 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
           const int cx = x >> eshift, cy = y >> eshift;
           for (unsigned qm = qmask; qm; qm &= qm - 1u) {
             const int q = __ffs(qm) - 1, oy = (q * 11) >> 5;
-            const unsigned wb = want_bit(cx + (q - 3 * oy) - 1, cy + oy - 1);
+            const unsigned wb = cell_bit(cx + (q - 3 * oy) - 1, cy + oy - 1);
             if (!((s_want[wb >> 5] >> (wb & 31u)) & 1u)) atomicOr(&s_want[wb >> 5], 1u << (wb & 31u));
           }
         }
@@ -1028,6 +1034,14 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
     contact_geometry(S, eshift, qmask);
     unsigned cmask = 255u;                                    // slots: a power of two >= 2 x sources (<= cell_cap)
     while (cmask + 1u < 2u * nsrc && 2u * (cmask + 1u) <= (unsigned)S.cell_cap) cmask = 2u * cmask + 1u;
+    if (nsrc && want_filter) {      // the marks live in the memory of sbits: settle every source before that map is reset
+      for (unsigned t = tid; t < nsrc; t += kThreads) {
+        const int4 r = S.src_list[t];
+        const unsigned wb = cell_bit(r.x >> eshift, r.y >> eshift);
+        if (!((s_want[wb >> 5] >> (wb & 31u)) & 1u)) S.src_list[t].w = -1;     // not in the table: nobody can reach it
+      }
+      __syncthreads();
+    }
     if (nsrc) {
       const int nbuckets = (int)cmask + 1;
       for (int c = tid * 4; c <= nbuckets; c += kThreads * 4)      // nbuckets is a multiple of 256
@@ -1051,9 +1065,7 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
         if (t < nsrc) {
           const int4 r = S.src_list[t];
           const int ccx = r.x >> eshift, ccy = r.y >> eshift;
-          const unsigned wb = want_bit(ccx, ccy);
-          const bool wanted = !want_filter || ((s_want[wb >> 5] >> (wb & 31u)) & 1u);
-          if (wanted) {
+          if (r.w != -1) {
           const unsigned h = cell_hash(ccx, ccy), hb = cell_bit(ccx, ccy);
           const unsigned long long key = cell_key(ccx, ccy);
           unsigned rank = 0xFFFFFFFFu;
@@ -1083,8 +1095,6 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
               atomicOr(&s_nbits[nbq >> 5], 1u << (nbq & 31u));
             }
           }
-          } else {
-            S.src_list[t].w = -1;                 // not in the table: the fill skips it
           }
         }
         __syncwarp();
