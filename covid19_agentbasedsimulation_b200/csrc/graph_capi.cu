@@ -313,10 +313,9 @@ extern "C" int cabs_graph_run(cabs_graph *g, int iterations) {
       int per_sm = 0, sms = 0;
       GCK(cudaFuncSetAttribute(k_graph_run<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphDynSmem));
       GCK(cudaFuncSetAttribute(k_graph_run<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphDynSmem));
-      // two blocks of 15.6 KB static + 64 KB dynamic (+ 1 KB reserved each) = 161 KB per SM: the driver picks the 164 KB
-      // carveout, which leaves 92 KB of L1.  L1 matters here: with the 228 KB carveout (28 KB of L1) the same kernel ran
-      // 8-45 % slower -- measured twice: with a carveout hint that rounded up to it, and with a build whose two blocks
-      // needed 205 KB (profiles/r2_graph_ab_carveout_{1,2}.log)
+      // one block of 1 024 threads per SM: 18.8 KB static + 64 KB dynamic (+ 1 KB reserved) -> the 100 KB carveout, 156 KB
+      // of L1.  The carveout is left to the driver; L1 matters here (two 512-thread blocks: 164 KB carveout 2.63e10
+      // agent-updates/s on the bench, 196 KB 2.43e10, 228 KB 1.77e10: profiles/r2_graph_ab_carveout_{1,2}.log)
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_graph_run<true>, kThreads, kGraphDynSmem) != cudaSuccess || per_sm < 1)
         per_sm = 1;

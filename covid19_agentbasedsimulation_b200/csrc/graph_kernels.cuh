@@ -30,12 +30,21 @@
 namespace cabs {
 namespace graph {
 
-constexpr int kThreads = 512;
+// One block of 1 024 threads per SM (64 registers each: the whole register file).  Two blocks of 512 share the issue slots
+// and the L1 of an SM less well than one block twice the size -- 296 simulations x 10^5 persons, day 2 of "do nothing":
+// 50.2 ms per 48 hours with 2 x 512 (static schedule), 33.7 ms with 1 x 1024 (the same simulations drawn from the task
+// queue by 148 blocks); the 896-simulation bench 2.63e10 -> 2.70e10 agent-updates/s.  -DCABS_GRAPH_THREADS=512 restores
+// the old shape.
+#ifndef CABS_GRAPH_THREADS
+#define CABS_GRAPH_THREADS 1024
+#endif
+constexpr int kThreads = CABS_GRAPH_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxBusiness = 16;
 constexpr int kBGrid = 32;
-// Shared memory budget: two blocks per SM within the 196 KB carveout, which leaves 60 KB of L1 (a build whose blocks needed
-// 205 KB between them got the 228 KB carveout, 28 KB of L1, and ran the ensemble bench at 1.77e10 instead of 2.45e10)
+// Shared memory budget: what is not shared memory is L1, and L1 matters to this kernel (with two blocks of 512 threads per
+// SM: 164 KB carveout 2.63e10 agent-updates/s on the bench, 196 KB 2.43e10, 228 KB 1.77e10).  One block of 1 024 threads
+// needs 84 KB (100 KB carveout, 156 KB of L1); maps twice the size filter better but cost more than they save (2.63e10).
 constexpr int kHotCells = 512;
 #ifndef CABS_MAP_BITS
 #define CABS_MAP_BITS 262144
@@ -450,17 +459,17 @@ __device__ __forceinline__ void fire(const Sim &S, Shared &sh, int b, uint32_t i
 // ---------------------------------------------------------------------------------------------------
 // Two schedules of the same hour code:
 //   kQueue = false   block b owns simulation b for the whole run (grid = n_sims): nothing is shared between blocks;
-//                    right whenever the simulations fit the GPU at once (2 blocks per SM).
+//                    right whenever the simulations fit the GPU at once (one block per SM).
 //   kQueue = true    a persistent grid (one block per resident slot) draws (simulation, hour) tasks from a ticket
 //                    counter, hour-major: task t = hour * n_sims + simulation.  A simulation's hours still run in order
 //                    (a worker waits until `progress[simulation]` says the hour before is done -- it was handed out
 //                    n_sims tickets earlier, to a worker that is running, so the wait cannot deadlock), but which
-//                    block runs which hour is decided as blocks become free.  An ensemble of 896 simulations on 296
-//                    slots is then 3.03 slots' worth of time instead of 4 rounds (the fourth round of the static
+//                    block runs which hour is decided as blocks become free.  An ensemble of 896 simulations on 148
+//                    slots is then 6.05 slots' worth of time instead of 7 rounds (the last round of the static
 //                    schedule runs 8 blocks on an otherwise idle GPU).  Between tasks the accounts go back to global
 //                    memory (a few hundred bytes); results are identical bit for bit.
 template <bool kQueue>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1024 / kThreads)
 k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progress) {
   // the descriptor (pointers, parameters) is read by every thread all the time: keep a copy in shared memory
   __shared__ Sim S;
