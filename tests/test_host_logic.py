@@ -126,3 +126,17 @@ def test_constants_match_oracle_tables():
     assert common.age_severe_probs == seq_oracle.AGE_SEVERE
     assert common.age_death_probs == seq_oracle.AGE_DEATH
     assert common.basic_income.tolist() == seq_oracle.BASIC_INCOME.tolist() == [1.0, 2.0, 3.25, 5.0, 13.75]
+
+
+def test_shard_block_and_interleaved():
+    """network/ensemble.py::shard: every job exactly once; interleaved keeps a scenario-major list scenario-major."""
+    from covid19_agentbasedsimulation_b200.network.ensemble import shard
+    assert [list(shard(10, r, 4)) for r in range(4)] == [[0, 1, 2], [3, 4, 5], [6, 7], [8, 9]]
+    assert [list(shard(10, r, 4, interleaved=True)) for r in range(4)] == [[0, 4, 8], [1, 5, 9], [2, 6], [3, 7]]
+    jobs = [(s, k) for s in range(7) for k in range(16)]
+    for world in (1, 2, 3, 8):
+        parts = [[jobs[j] for j in shard(len(jobs), r, world, interleaved=True)] for r in range(world)]
+        assert sorted(sum(parts, [])) == jobs
+        for mine in parts:
+            assert mine == sorted(mine)                                  # the seeds of a scenario stay consecutive
+            assert max(sum(1 for s, _ in mine if s == sc) for sc in range(7)) <= -(-16 // world) + 1
