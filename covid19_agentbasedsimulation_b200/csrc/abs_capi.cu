@@ -75,6 +75,9 @@ struct cabs_sim {
   unsigned *seq_round = nullptr;   // "labels lowered in round r" counters of the cooperative relaxation (3 slots)
   int seq_grid = 0;                // its grid: every block resident (0: no cooperative launch, host-driven rounds)
   cudaStream_t own_stream = nullptr;
+  cudaStream_t side = nullptr;           // direct slab mode: the global half of the closing runs here, next to pass A
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_close = true;                // CABS_SLAB_SERIAL_CLOSE=1: the closing stays in the main stream (A/B timing)
   Ctl *ctl = nullptr;
   Ctl *host_ctl = nullptr;      // pinned mirror: statistics, error bits and trigger-rewritten attributes in ONE copy + ONE sync
   StatRecord *history = nullptr;
@@ -203,6 +206,9 @@ extern "C" void cabs_destroy(cabs_sim *sim) {
   if (sim->slab_graph) cudaGraphExecDestroy(sim->slab_graph);
   for (cudaEvent_t e : sim->events) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
+  if (sim->side) cudaStreamDestroy(sim->side);
+  if (sim->ev_fork) cudaEventDestroy(sim->ev_fork);
+  if (sim->ev_join) cudaEventDestroy(sim->ev_join);
   if (sim->stream) cudaStreamDestroy(sim->stream);
   delete sim;
 }
@@ -219,6 +225,9 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
   sim->num_sms = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
   sim->own_stream = sim->stream;
+  CK(cudaStreamCreateWithFlags(&sim->side, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&sim->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&sim->ev_join, cudaEventDisableTiming));
   // pass B: shared memory for CABS_B_MINBLOCKS resident blocks (ring + partial sums + Infected list + 2 KB of static
   // and reserved space each) and the REST of the 256 KB to L1 -- its cell-start gather is the most expensive part of
   // the kernel (measured without it: 0.109 ms against 0.144 ms) and lives on L1 hits
@@ -247,6 +256,8 @@ static int create_impl(cabs_sim *sim, const cabs_config *cfg) {
     sim->use_pdl = pdl && pdl[0] == '1';
     // Folding the emigrants' update + pack into pass A and the ghost contacts into the local contact launch saves two
     // launches per step but doubles pass A's registers: 2 GPUs 0.391 ms/step against 0.297 ms.
+    const char *serial = getenv("CABS_SLAB_SERIAL_CLOSE");
+    sim->side_close = !(serial && serial[0] == '1');
     const char *fused = getenv("CABS_SLAB_FUSED");
     sim->slab_unfused = !(fused && fused[0] == '1');
   }
@@ -644,7 +655,7 @@ static int slab_phase(cabs_sim *sim, int phase) {
     rows = (long long *)sl.stats_rows;
   }
   switch (phase) {
-    case 0:
+    case 0: {
       if (!kAdvance) {
         LAUNCH_PDLN(k_bbox, nb, 256, sim->ctl, sim->hot[c]);
         LAUNCH_PDLN(k_replan, 1, 32, sim->ctl, 1);
@@ -660,16 +671,37 @@ static int slab_phase(cabs_sim *sim, int phase) {
                       (const double *)sim->sqrt_tab, D, sim->late_pending ? 1 : 0);
         break;
       }
+      // Pass A needs nothing global; pass B and the emigrants' update need the critical-limit flag the global half of
+      // the previous step's closing sets.  That half (one thread waiting for every rank's statistics row) runs on a
+      // second stream NEXT TO pass A -- forked and joined with events, so a captured graph carries it as a parallel
+      // branch -- instead of between pass A and the pack: its wait for the slowest rank is off the critical path.
+      const bool fork_close = sim->direct && sim->late_pending && sim->side_close && !sim->profiling && !sim->use_pdl;
+      if (fork_close) {
+        SlabDirect G;
+        memset(&G, 0, sizeof G);
+        G.self = sim->blocks[sl.rank];
+        G.seq = sim->late_offset;
+        G.enabled = 1;
+        CK(cudaEventRecord(sim->ev_fork, sim->stream));
+        CK(cudaStreamWaitEvent(sim->side, sim->ev_fork, 0));
+        k_slab_close_global<<<1, 32, 0, sim->side>>>(sim->ctl, sim->history, sim->late_record, G);
+        sim->launches++;
+        CK(cudaEventRecord(sim->ev_join, sim->side));
+        sim->late_pending = false;
+      }
       LAUNCH_PDL_AS(kAdvance ? "k_move_count<true>" : "k_move_count<false>", (k_move_count<kAdvance, false>), nb, 256,
                     sim->ctl, sim->hot[c], sim->aux, sim->cells[t], sim->tile_state, sim->emig_list, sim->sp, nullptr,
                     nullptr, nullptr, nullptr, SlabDirect(), 0);
-      {   // pass A needed nothing global; pass B and the emigrants' update need the critical-limit flag
+      if (fork_close) {
+        CK(cudaStreamWaitEvent(sim->stream, sim->ev_join, 0));
+      } else {
         const int rc = flush_late_close(sim);
         if (rc != CABS_OK) return rc;
       }
       LAUNCH_PDL_AS("k_pack_emigrants", k_pack_emigrants<kAdvance>, nbs, 256, sim->ctl, sim->hot[c], sim->w[c], sim->aux,
                 sim->emig_list, ms[0], ms[1], sim->sqrt_tab, D);
       break;
+    }
     case 1: {
       SlabDirect C;   // the rows the global closing reads: the build that was closed locally (sequence offset 0)
       memset(&C, 0, sizeof C);
