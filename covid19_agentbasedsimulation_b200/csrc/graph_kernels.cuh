@@ -63,7 +63,7 @@ constexpr uint32_t kGovId = 0xFFFFFFFFu, kBusinessId0 = 0xFFFF0000u;
 
 // person attribute word: status[1:0] severity[3:2] stratum[6:4] new[7] infected_time[15:8] age[23:16]
 //                        active[24] isolated[25]
-constexpr uint32_t kNew = 0x80u, kActive = 1u << 24, kIsolated = 1u << 25;
+constexpr uint32_t kActive = 1u << 24, kIsolated = 1u << 25;   // bit 7 ("new") is not used by the pull design
 __device__ __forceinline__ uint32_t a_status(uint32_t a) { return a & 3u; }
 __device__ __forceinline__ uint32_t a_sev(uint32_t a) { return (a >> 2) & 3u; }
 __device__ __forceinline__ uint32_t a_stratum(uint32_t a) { return (a >> 4) & 7u; }
@@ -565,11 +565,7 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
     const bool monthly = it > 1 && new_month;
     // sources that nobody can catch anything from are left out of the table when they are the many (decided from the
     // previous hour's counts: a hint, the result does not depend on it)
-#ifdef CABS_NO_WANT_FILTER
-    const bool want_filter = false;
-#else
     const bool want_filter = contacts_on && prev_sources > 5u * prev_susceptible;
-#endif
     if (want_filter)
       for (int c = tid * 4; c < kSrcBits / 32; c += kThreads * 4) *reinterpret_cast<uint4 *>(s_want + c) = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) sh.n_contagious = sh.n_req = sh.scarce = 0u;
@@ -1184,32 +1180,6 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
 #ifdef CABS_GRAPH_TIMERS
       unsigned gt_cnt[5] = {0, 0, 0, 0, 0};   // pulls, bitmap hits, items visited, pairs in range (= draws), infections
 #endif
-#ifdef CABS_GRAPH_P5_SCALAR
-      uint32_t a_nx = 0;
-      int x_nx = 0, y_nx = 0;
-      if (tid < n) { a_nx = S.attr[tid]; if (nsrc) { x_nx = S.px[tid]; y_nx = S.py[tid]; } }
-      for (int base = 0; base < n; base += kThreads) {
-        const int i = base + tid;
-        uint32_t a = a_nx;
-        const int x = x_nx, y = y_nx;
-        {
-          const int inx = i + kThreads;
-          if (inx < n) { a_nx = S.attr[inx]; if (nsrc) { x_nx = S.px[inx]; y_nx = S.py[inx]; } }
-        }
-        if (i < n) {
-          if (nsrc && a_status(a) == S_ &&
-              (GT_COUNT(0), pull_contact(S, s_sbits, s_nbits, S.cell_keys, S.cell_count, S.cell_items, cmask, eshift, qmask, i, x, y,
-                                         (uint32_t)it GT_PULL_ARG))) {
-            GT_COUNT(4);
-            a = (a & ~3u) | I_;
-            S.attr[i] = a;
-          }
-          c_st += 1ull << (16 * a_status(a));
-          if (a_status(a) != D_ && a_sev(a) != SEV_E_) c_sev += 1ull << (16 * (a_sev(a) - 1));
-        }
-        __syncwarp();
-      }
-#else
       // every thread of the block makes the same number of trips (guards inside), and the warp is brought back
       // together after every person: a lane that had a lookup to do must not run the rest of the loop on its own
       for (int base = 0; base < n; base += kThreads * 4) {
@@ -1254,7 +1224,6 @@ k_graph_run(Sim *sims, int iterations, int n_sims, unsigned *ticket, int *progre
         if (changed) store4<uint4, uint32_t>(S.attr, i0, n, A4);
       }
       __syncwarp();
-#endif
 #ifdef CABS_GRAPH_TIMERS
       for (int k = 0; k < 5; ++k) {
         const unsigned v = __reduce_add_sync(0xffffffffu, gt_cnt[k]);
