@@ -1865,8 +1865,8 @@ __device__ void close_global(Ctl *ctl, const long long *rows, StatRecord *histor
       ymin = min(ymin, (int)r[13]);
       ymax = max(ymax, (int)r[14]);
     }
-    ctl->err |= (unsigned)r[15];  // an exchange overflow anywhere invalidates the run everywhere
-  }
+    if (r[15]) atomicOr(&ctl->err, (unsigned)r[15]);  // an exchange overflow anywhere invalidates the run everywhere
+  }                                                   // (atomic: pass A of the next build may be running beside this)
   cur.cnt[ST_S] -= newinf;  // infections of the contact phase (abs.py:153)
   cur.cnt[ST_I] += newinf;
   cur.new_infections = newinf;

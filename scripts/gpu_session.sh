@@ -1,11 +1,12 @@
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -3 | tee gpurun_out/gputests_r2_final.log
-timeout 900 python bench.py > gpurun_out/bench_r2_final.json 2> gpurun_out/bench_r2_final.err || tail -5 gpurun_out/bench_r2_final.err
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r2_final_reference.json 2> gpurun_out/bench_r2_final_reference.err || tail -5 gpurun_out/bench_r2_final_reference.err
+timeout 900 python -m pytest tests/test_gpu_slabs.py -q -x -k "two_process" 2>&1 | tail -3
+run2(){ python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 200 --warmup 10 --no-cpu-baseline --no-other-configs "$@"; }
+run2 > gpurun_out/bench_2gpu_edgefirst.json 2> gpurun_out/bench_2gpu_edgefirst.err || tail -5 gpurun_out/bench_2gpu_edgefirst.err
+CABS_SLAB_EDGE_FIRST=0 run2 > gpurun_out/bench_2gpu_noedge.json 2> gpurun_out/bench_2gpu_noedge.err || tail -5 gpurun_out/bench_2gpu_noedge.err
 python - <<'PY'
 import json
-d=json.loads(open("gpurun_out/bench_r2_final.json").read().strip().splitlines()[-1])
-print("value %.4g ms/step %.4f frac %.3f e2e %.4g launches %s" % (d["value"], d["ms_per_step"], d["roofline"]["frac"], d["e2e"]["value"], d["gpu_launches"]))
-d=json.loads(open("gpurun_out/bench_r2_final_reference.json").read().strip().splitlines()[-1])
-print("reference arm:", {k: d[k] for k in ("impl","value","unit","n_gpus","steps") if k in d}, d.get("cpu_baseline",{}).get("kind"), d.get("cpu_baseline",{}).get("cores"))
+for f in ("edgefirst","noedge"):
+    try:
+        d=json.loads(open("gpurun_out/bench_2gpu_%s.json"%f).read().strip().splitlines()[-1])
+        print(f, "ms/step %.4f value %.4g invariance %s" % (d["ms_per_step"], d["value"], d.get("slab_invariance")), d.get("slab_invariance_detail"), d.get("final_stats"))
+    except Exception as e: print(f, "failed", e)
 PY
